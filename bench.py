@@ -1,0 +1,515 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native fast-pauli hot path.
+
+Metric (BASELINE.json): PauliOp.apply amplitude*strings/s and HBM GB/s (% of roofline).
+
+Workload at every N (weak scaling, one rank per GPU, no data-path collective): BASELINE config 2,
+    PauliString.apply_batch + PauliString.expectation_value, 20 qubits, batch 256 per GPU, complex128
+(4 GiB in + 4 GiB out per GPU; a PauliString is the one-string PauliOp, and both calls run the same
+kernels PauliOp.apply / expectation_value use).  One "step" = one apply_batch + one expectation_value
+over the whole resident batch = 2 * dim * n_states amplitude*strings per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extras] [--no-cpu-baseline]
+
+For N > 1 launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ...
+Rank 0 prints exactly one JSON line on stdout.
+
+--impl reference times the reference's own OpenMP CPU implementation (oracle/_ref, compiled from the unmodified
+reference headers; falls back to the plain-C port) on the host cores for the same metric/config, each step a
+bounded column sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_QUBITS = 20
+BATCH = 256
+DTYPE = np.complex128
+SEED = 18
+STRING_SEED = 1234
+METRIC = "PauliOp.apply amplitude*strings/s (PauliString.apply_batch + expectation_value, 20 qubits, batch 256/GPU, complex128)"
+UNIT = "amplitude*strings/s"
+
+
+def make_string(n: int, seed: int = STRING_SEED) -> str:
+    """One i.i.d. uniform IXYZ string (tests/benchmarks/test_qiskit_adv.py:122-125 style), fixed seed."""
+    rng = np.random.default_rng(seed)
+    s = "".join(np.array(list("IXYZ"))[rng.integers(0, 4, size=n)])
+    if "X" not in s and "Y" not in s:  # keep the gather non-trivial
+        s = "X" + s[1:]
+    return s
+
+
+def peaks() -> dict:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": float(p["hbm_gbs"]), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.path = f"/tmp/fp_clocks_{os.getpid()}.csv"
+
+    def start(self) -> None:
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+            self.fh.close()
+            sm, smax, reasons = [], [], set()
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower() == "active":
+                        reasons.add(name)
+            if sm:
+                out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+            os.unlink(self.path)
+        except Exception as e:  # clocks are evidence, never a reason to lose the measurement
+            out["error"] = str(e)
+        return out
+
+
+# ------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step(backend, string: str, n: int, cols: int, par: bool = True) -> tuple[float, float]:
+    """One bounded step of the reference CPU path: apply_batch + expectation_value on `cols` columns.
+    Returns (seconds, amplitude*strings processed)."""
+    from __graft_entry__ import load_package
+
+    load_package()  # only for the host twin of the input generator; no GPU work on this arm
+    from fast_pauli_b200.synth import uniform_host
+
+    dim = 1 << n
+    psi = getattr(cpu_reference_step, "_psi", None)
+    if psi is None or psi.shape != (dim, cols):
+        psi = uniform_host((dim, cols), DTYPE, seed=SEED)
+        cpu_reference_step._psi = psi
+        cpu_reference_step._out = np.zeros_like(psi)
+        cpu_reference_step._ev = np.zeros(cols, dtype=DTYPE)
+    out, ev = cpu_reference_step._out, cpu_reference_step._ev
+    t0 = time.perf_counter()
+    backend.string_apply(string, psi, 0.75 - 0.5j, out=out, par=par)
+    backend.string_expval(string, psi, 0.75 - 0.5j, out=ev, par=par)
+    dt = time.perf_counter() - t0
+    return dt, 2.0 * dim * cols
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # under torchrun only rank 0 measures the CPU arm; the others exit 0 without work
+    from oracle import oracle as orc
+
+    be = orc.reference() or orc.port()
+    string = make_string(N_QUBITS)
+    cols = 16  # bounded sample: 16 of the 256 columns per step (work is exactly linear in the batch)
+    threads = be.max_threads()
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_reference_step(be, string, N_QUBITS, cols)
+    times, work = [], 0.0
+    for _ in range(args.steps):
+        dt, w = cpu_reference_step(be, string, N_QUBITS, cols)
+        times.append(dt)
+        work += w
+    total = sum(times)
+    value = work / total
+    sample = (f"{cols} of {BATCH} batch columns per step (work is linear in the batch); "
+              f"{'unmodified reference headers, std::execution::par' if be.kind == 'reference' else 'plain-C port, OpenMP'}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+        "config": {"workload": "BASELINE config 2: PauliString.apply_batch + expectation_value, 20 qubits, complex128",
+                   "n_qubits": N_QUBITS, "batch_per_step": cols, "string": string},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": be.kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def timed_ms(fp, ctx, fn, iters: int, warmup: int = 1) -> float:
+    import ctypes as C
+
+    for _ in range(warmup):
+        fn()
+    ctx.sync()
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    fp.lib.fp_event_create(C.byref(e0))
+    fp.lib.fp_event_create(C.byref(e1))
+    fp.lib.fp_event_record(ctx._h, e0)
+    for _ in range(iters):
+        fn()
+    fp.lib.fp_event_record(ctx._h, e1)
+    ms = C.c_float()
+    fp.lib.fp_event_elapsed_ms(e0, e1, C.byref(ms))
+    fp.lib.fp_event_destroy(e0)
+    fp.lib.fp_event_destroy(e1)
+    return ms.value / iters
+
+
+def run_extras(fp, ctx, hbm_peak: float) -> dict:
+    """Device-resident timings of the other BASELINE configs (reported beside the headline, never as `value`)."""
+    from fast_pauli_b200.synth import random_strings as rand_strings
+
+    out = {}
+    rng = np.random.default_rng(STRING_SEED)
+
+    def guard(name, f):
+        try:
+            out[name] = f()
+        except Exception as e:  # an extra must never cost the headline line
+            out[name] = {"error": f"{type(e).__name__}: {e}"}
+
+    # PauliOp.apply, 20 qubits, batch 64, complex128: (i) 64 strings over 8 x-masks (HBM-bound), (ii) 64 random strings
+    def op20():
+        n, B = 20, 64
+        psi = ctx.uniform((1 << n, B), DTYPE, seed=SEED)
+        res = {}
+        xs = rand_strings(rng, n, 8)
+        few = []
+        for s in xs:  # 8 z-variants per x-mask: swap X<->Y and I<->Z at random positions keeps the x-mask
+            for _ in range(8):
+                t = list(s)
+                for q in range(n):
+                    if rng.random() < 0.5:
+                        t[q] = {"X": "Y", "Y": "X", "I": "Z", "Z": "I"}[t[q]]
+                few.append("".join(t))
+        for tag, strings in (("few_group_64_strings_8_xmasks", few), ("random_64_strings", rand_strings(rng, n, 64))):
+            h = rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))
+            op = fp.PauliOp(h, strings, ctx=ctx)
+            info = op.plan_info()
+            y = op.apply(psi)
+            ms = timed_ms(fp, ctx, lambda: fp.lib.fp_op_apply(ctx._h, op._plan(DTYPE), _vp(y.ptr), _vp(psi.ptr),
+                                                                _sz(1 << n), _sz(B), 0), 5)
+            amps = (1 << n) * B
+            res[tag] = {"ms": ms, "amp_strings_per_s": amps * len(strings) / (ms * 1e-3),
+                        "algorithmic_GBps": amps * 32 / (ms * 1e-3) / 1e9,
+                        "hbm_frac": amps * 32 / (ms * 1e-3) / 1e9 / hbm_peak, "x_groups": info["n_x_groups"]}
+            del op
+        return res
+
+    # config 3: PauliOp.apply (batch), 16 qubits, 2000 strings weight <= 4, batch 1024, complex128
+    def cfg3():
+        n, B, S = 16, 1024, 2000
+        strings = rand_strings(rng, n, S, max_weight=4)
+        h = rng.uniform(-1, 1, S) + 1j * rng.uniform(-1, 1, S)
+        psi = ctx.uniform((1 << n, B), DTYPE, seed=SEED)
+        op = fp.PauliOp(h, strings, ctx=ctx)
+        info = op.plan_info()
+        y = op.apply(psi)
+        ms = timed_ms(fp, ctx, lambda: fp.lib.fp_op_apply(ctx._h, op._plan(DTYPE), _vp(y.ptr), _vp(psi.ptr),
+                                                            _sz(1 << n), _sz(B), 0), 3)
+        amps = (1 << n) * B
+        return {"ms": ms, "amp_strings_per_s": amps * S / (ms * 1e-3), "x_groups": info["n_x_groups"],
+                "packed_strings": info["n_packed_strings"], "algorithmic_GBps": amps * 32 / (ms * 1e-3) / 1e9,
+                "fp64_TFLOPs": 8.0 * info["n_x_groups"] * amps / (ms * 1e-3) / 1e12}
+
+    # config 4: SummedPauliOp.apply_weighted + expectation_value, 12 qubits, 10k strings x 64 ops, batch 4096, complex64
+    def cfg4():
+        n, B, S, K = 12, 4096, 10000, 64
+        strings = rand_strings(rng, n, S)
+        hk = (rng.uniform(-1, 1, (S, K)) + 1j * rng.uniform(-1, 1, (S, K))).astype(np.complex64)
+        psi = ctx.uniform((1 << n, B), np.complex64, seed=SEED)
+        data = ctx.to_device(rng.random((K, B)).astype(np.float32))
+        sop = fp.SummedPauliOp(strings, hk, ctx=ctx)
+        plan = sop._plan(np.complex64)
+        y = ctx.empty((1 << n, B), np.complex64)
+        ev = ctx.empty((K, B), np.complex64)
+        ms_w = timed_ms(fp, ctx, lambda: fp.lib.fp_sop_apply_weighted(ctx._h, plan, _vp(y.ptr), _vp(psi.ptr),
+                                                                      _vp(data.ptr), 0, _sz(1 << n), _sz(B), 0), 2)
+        ms_e = timed_ms(fp, ctx, lambda: fp.lib.fp_sop_expval(ctx._h, plan, _vp(ev.ptr), _vp(psi.ptr), _sz(1 << n),
+                                                              _sz(B), 0), 2)
+        amps = (1 << n) * B
+        return {"apply_weighted_ms": ms_w, "expectation_value_ms": ms_e,
+                "apply_weighted_amp_strings_per_s": amps * S / (ms_w * 1e-3),
+                "expectation_value_amp_strings_per_s": amps * S / (ms_e * 1e-3)}
+
+    ctx.set_async(True)
+    guard("pauli_op_apply_20q_b64_c128", op20)
+    guard("config3_pauli_op_apply_16q_2000strings_b1024_c128", cfg3)
+    guard("config4_summed_12q_10k_strings_64ops_b4096_c64", cfg4)
+    ctx.sync()
+    ctx.set_async(False)
+    return out
+
+
+def _vp(p):
+    import ctypes as C
+
+    return C.c_void_p(p)
+
+
+def _sz(v):
+    import ctypes as C
+
+    return C.c_size_t(v)
+
+
+def run_ours(args) -> None:
+    import ctypes as C
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    os.environ.setdefault("FASTPAULI_DEVICE", str(local_rank))
+
+    dist = None
+    torch = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from __graft_entry__ import load_package
+
+    fp = load_package()  # raises ImportError if the CUDA extension is missing: no fallback
+    ctx = fp.Context(local_rank)
+    pk = peaks()
+
+    n, B = N_QUBITS, BATCH
+    dim = 1 << n
+    string = make_string(n)
+    coeff = np.array([0.75 - 0.5j], dtype=DTYPE)
+    codes, _ = fp._encode([string])
+    # batch shard of this rank: columns [rank*B, (rank+1)*B) of the global (dim, B*world) batch -- the generator is
+    # counter based, so give every rank a distinct stream offset
+    psi = ctx.uniform((dim, B), DTYPE, seed=SEED + rank)
+    out = ctx.empty((dim, B), DTYPE)
+    ev = ctx.empty((B,), DTYPE)
+    ctx.set_async(True)
+
+    def apply_call():
+        rc = fp.lib.fp_string_apply(ctx._h, fp.FP_C128, n, _vp(codes.ctypes.data), _vp(coeff.ctypes.data), _vp(out.ptr),
+                                    _vp(psi.ptr), _sz(dim), _sz(B), 0)
+        if rc:
+            raise RuntimeError(fp.lib.fp_last_error().decode())
+
+    def expval_call():
+        rc = fp.lib.fp_string_expval(ctx._h, fp.FP_C128, n, _vp(codes.ctypes.data), _vp(coeff.ctypes.data), _vp(ev.ptr),
+                                     _vp(psi.ptr), _sz(dim), _sz(B), 0)
+        if rc:
+            raise RuntimeError(fp.lib.fp_last_error().decode())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        ctx.sync()
+        if torch is not None:
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        apply_call()
+        expval_call()
+    barrier()
+
+    K = args.steps
+    evs = []
+    for _ in range(3 * K + 1):
+        e = C.c_void_p()
+        fp.lib.fp_event_create(C.byref(e))
+        evs.append(e)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    l0 = ctx.launch_count
+    fp.lib.fp_event_record(ctx._h, evs[0])
+    for k in range(K):
+        apply_call()
+        fp.lib.fp_event_record(ctx._h, evs[3 * k + 1])
+        expval_call()
+        fp.lib.fp_event_record(ctx._h, evs[3 * k + 2])
+    fp.lib.fp_event_record(ctx._h, evs[3 * K])
+    barrier()
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else {}
+
+    def el(a, b) -> float:
+        ms = C.c_float()
+        fp.lib.fp_event_elapsed_ms(evs[a], evs[b], C.byref(ms))
+        return float(ms.value)
+
+    total_ms = el(0, 3 * K)
+    apply_ms = [el(3 * k if k == 0 else 3 * k - 1, 3 * k + 1) for k in range(K)]
+    expval_ms = [el(3 * k + 1, 3 * k + 2) for k in range(K)]
+    if dist is not None:
+        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = world * 2.0 * dim * B / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (the streaming apply): algorithmic bytes = dim*B*16 B read + 16 B written
+    apply_avg = sum(apply_ms) / K
+    expval_avg = sum(expval_ms) / K
+    alg_bytes = dim * B * 32.0
+    achieved = alg_bytes / (apply_avg * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("string_apply_c128_20q_b256_bytes")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "op_kernel<double,EPV=1,V=4,MODE=0,INLINE1> (PauliString.apply_batch)",
+                "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                "traffic": traffic, "peak_source": pk["source"], "algorithmic_bytes_per_launch": alg_bytes,
+                "avg_launch_ms": apply_avg,
+                "second_kernel": {"kernel": "expval_pairs_kernel<double,1,4,1> (PauliString.expectation_value)",
+                                  "algorithmic_bytes_per_launch": dim * B * 16.0, "avg_launch_ms": expval_avg,
+                                  "achieved": dim * B * 16.0 / (expval_avg * 1e-3) / 1e9,
+                                  "frac": dim * B * 16.0 / (expval_avg * 1e-3) / 1e9 / pk["hbm_gbs"]}}
+
+    # ---- end to end through the public C ABI with pinned HOST buffers (H2D + kernel + D2H inside the call)
+    ctx.set_async(False)
+    e2e = None
+    try:
+        h_in = ctx.pinned_empty((dim, B), DTYPE)
+        h_out = ctx.pinned_empty((dim, B), DTYPE)
+        h_ev = ctx.pinned_empty((B,), DTYPE)
+        fp.lib.fp_memcpy(ctx._h, _vp(h_in.ctypes.data), _vp(psi.ptr), _sz(h_in.nbytes))
+
+        def e2e_step():
+            rc = fp.lib.fp_string_apply(ctx._h, fp.FP_C128, n, _vp(codes.ctypes.data), _vp(coeff.ctypes.data),
+                                        _vp(h_out.ctypes.data), _vp(h_in.ctypes.data), _sz(dim), _sz(B), 0)
+            rc |= fp.lib.fp_string_expval(ctx._h, fp.FP_C128, n, _vp(codes.ctypes.data), _vp(coeff.ctypes.data),
+                                          _vp(h_ev.ctypes.data), _vp(h_in.ctypes.data), _sz(dim), _sz(B), 0)
+            if rc:
+                raise RuntimeError(fp.lib.fp_last_error().decode())
+
+        Ke = max(2, min(K, 5))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * 2.0 * dim * B * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * h_in.nbytes,
+               "d2h_bytes_per_step": h_out.nbytes + h_ev.nbytes, "steps": Ke, "ms_per_step": 1e3 * dt / Ke,
+               "path": "fp_string_apply + fp_string_expval with pinned host pointers"}
+        # keep the device result honest: the host copy of the output must equal the device-resident one
+        chk = out.get_rows(12345, 12346)
+        if not np.array_equal(chk, h_out[12345:12346]):
+            e2e["warning"] = "host-staged result differs from device-resident result"
+        ctx.pinned_free(h_in)
+        ctx.pinned_free(h_out)
+        ctx.pinned_free(h_ev)
+    except Exception as ex:
+        e2e = {"value": None, "unit": UNIT, "error": f"{type(ex).__name__}: {ex}", "h2d_bytes_per_step": None,
+               "d2h_bytes_per_step": None}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            from oracle import oracle as orc
+
+            be = orc.reference() or orc.port()
+            cols = 16
+            cpu_reference_step(be, string, n, cols)  # warm-up
+            best, spent, reps = None, 0.0, 0
+            while spent < 10.0 and reps < 20:
+                dt, w = cpu_reference_step(be, string, n, cols)
+                spent += dt
+                reps += 1
+                best = dt if best is None else min(best, dt)
+            cpu_baseline = {"value": 2.0 * dim * cols / best, "unit": UNIT, "cores": be.max_threads(), "kind": be.kind,
+                            "sample": f"{cols} of {B} batch columns, best of {spent:.1f} s of repeats; "
+                                      f"{'unmodified reference headers (std::execution::par)' if be.kind == 'reference' else 'plain-C port + OpenMP'}"}
+        except Exception as ex:
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {ex}"}
+
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        del out
+        extras = run_extras(fp, ctx, pk["hbm_gbs"])
+
+    if dist is not None:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 (complex128)", "data": "synthetic",
+            "config": {"workload": "BASELINE config 2: PauliString.apply_batch + PauliString.expectation_value, "
+                                   "20 qubits, batch 256 per GPU, complex128, batch-axis sharded (no collective)",
+                       "n_qubits": n, "batch_per_gpu": B, "global_batch": B * world, "string": string,
+                       "state_bytes_per_gpu": dim * B * 16,
+                       "l2": "inputs (4 GiB per GPU) are 32x larger than L2; no flush needed",
+                       "input_generator": f"counter-based splitmix64 U[0,1)+iU[0,1), seed {SEED}+rank"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "extras": extras,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,581 @@
+"""fast_pauli_b200 -- Python face of the B200-native fast-pauli hot path.
+
+This module is the ctypes binding a fast-pauli maintainer would add over the C ABI in
+``include/fastpauli_b200.h``.  It mirrors the *signatures and behaviour* of the
+reference's nanobind classes for the hot path only:
+
+=====================================  ==========================================================
+reference (fast_pauli/cpp/src/include)  here
+=====================================  ==========================================================
+``PauliString.apply(states, coeff)``    ``__pauli_string_bindings.hpp:131-159``
+``PauliString.expectation_value``       ``__pauli_string_bindings.hpp:182-211``
+``PauliOp.apply / expectation_value``   ``__pauli_op_bindings.hpp:489-567``
+``SummedPauliOp.apply / apply_weighted  ``__summed_pauli_op_bindings.hpp:156-274``
+/ expectation_value``
+=====================================  ==========================================================
+
+All compute happens in hand-written sm_100a kernels inside ``lib/libfastpauli_b200.so``.  There is **no CPU
+fallback**: importing works anywhere (so symbols can be checked without a GPU) but the first compute call
+without a CUDA device raises ``RuntimeError``; a missing shared library raises ``ImportError`` at import time.
+
+Array arguments may be numpy arrays (host; staged through the GPU inside the call, result returned as a new
+numpy array) or device-resident: a :class:`DeviceArray` or any object exposing ``__cuda_array_interface__``
+(e.g. a CUDA ``torch.Tensor``), in which case the result is a :class:`DeviceArray` on the same GPU.
+complex64 inputs stay complex64 (the reference's C++ templates support it, its Python bindings do not);
+every other dtype is converted to complex128 like nanobind does for the reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Iterable, Sequence
+
+import numpy as np
+
+__all__ = ["PauliString", "PauliOp", "SummedPauliOp", "DeviceArray", "Context", "lib", "default_context"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libfastpauli_b200.so")
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or `make -C fast-pauli_b200` (there is no Python/CPU fallback)"
+    )
+lib = C.CDLL(_LIB_PATH)
+lib.fp_last_error.restype = C.c_char_p
+
+FP_C64, FP_C128 = 0, 1
+_STATUS_EXC = {1: ValueError, 2: RuntimeError, 3: RuntimeError, 4: MemoryError, 5: NotImplementedError}
+_CODE = {"I": 0, "X": 1, "Y": 2, "Z": 3}
+_LETTER = "IXYZ"
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise _STATUS_EXC.get(rc, RuntimeError)(lib.fp_last_error().decode())
+
+
+def _dtype_code(dtype) -> int:
+    return FP_C64 if np.dtype(dtype) == np.complex64 else FP_C128
+
+
+def _encode(strings: Iterable[str]) -> tuple[np.ndarray, int]:
+    strings = [str(s) for s in strings]
+    n = len(strings[0]) if strings else 0
+    codes = np.zeros((len(strings), n), dtype=np.uint8)
+    for s, st in enumerate(strings):
+        if len(st) != n:
+            raise ValueError("All PauliStrings must have the same size")  # PO:588
+        for q, ch in enumerate(st):
+            if ch not in _CODE:
+                raise ValueError(f"Invalid Pauli character {ch}")  # PS:194
+            codes[s, q] = _CODE[ch]
+    return codes, n
+
+
+# --------------------------------------------------------------------------------------------- context
+class Context:
+    """One GPU + stream + scratch (``fp_ctx``)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(lib.fp_ctx_create(C.c_int(device), C.byref(self._h)))
+        self.device = device
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.fp_ctx_destroy(h)
+
+    def sync(self) -> None:
+        _check(lib.fp_ctx_sync(self._h))
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        _check(lib.fp_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_async(self, flag: bool) -> None:
+        _check(lib.fp_ctx_set_async(self._h, C.c_int(bool(flag))))
+
+    def set_tensor_core(self, flag: bool) -> None:
+        _check(lib.fp_ctx_set_tensor_core(self._h, C.c_int(bool(flag))))
+
+    def set_l2_budget(self, nbytes: int) -> None:
+        _check(lib.fp_ctx_set_l2_budget(self._h, C.c_size_t(nbytes)))
+
+    @property
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        _check(lib.fp_ctx_launch_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def mem_info(self) -> tuple[int, int]:
+        f, t = C.c_size_t(), C.c_size_t()
+        _check(lib.fp_device_mem_info(self._h, C.byref(f), C.byref(t)))
+        return int(f.value), int(t.value)
+
+    # -- arrays
+    def empty(self, shape, dtype=np.complex128) -> "DeviceArray":
+        return DeviceArray(self, shape, dtype)
+
+    def zeros(self, shape, dtype=np.complex128) -> "DeviceArray":
+        a = DeviceArray(self, shape, dtype)
+        _check(lib.fp_memset(self._h, C.c_void_p(a.ptr), C.c_int(0), C.c_size_t(a.nbytes)))
+        return a
+
+    def to_device(self, host: np.ndarray) -> "DeviceArray":
+        host = np.ascontiguousarray(host)
+        a = DeviceArray(self, host.shape, host.dtype)
+        _check(lib.fp_memcpy(self._h, C.c_void_p(a.ptr), host.ctypes.data_as(C.c_void_p), C.c_size_t(a.nbytes)))
+        return a
+
+    def uniform(self, shape, dtype=np.complex128, seed: int = 18, first: int = 0) -> "DeviceArray":
+        """Counter-based U[0,1)+iU[0,1) amplitudes generated on the device (``fp_fill_uniform``)."""
+        a = DeviceArray(self, shape, dtype)
+        _check(lib.fp_fill_uniform(self._h, C.c_int(_dtype_code(dtype)), C.c_void_p(a.ptr),
+                                   C.c_uint64(a.size), C.c_uint64(first), C.c_uint64(seed)))
+        return a
+
+    def pinned_empty(self, shape, dtype=np.complex128) -> np.ndarray:
+        """numpy array backed by pinned (page-locked) host memory."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) if np.ndim(shape) else int(shape)
+        p = C.c_void_p()
+        _check(lib.fp_host_malloc(self._h, C.c_size_t(max(n * dtype.itemsize, 16)), C.byref(p)))
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+        _PINNED[arr.ctypes.data] = (self, p.value)
+        return arr
+
+    def pinned_free(self, arr: np.ndarray) -> None:
+        ent = _PINNED.pop(arr.ctypes.data, None)
+        if ent:
+            lib.fp_host_free(self._h, C.c_void_p(ent[1]))
+
+
+_PINNED: dict[int, tuple] = {}
+_default_ctx: Context | None = None
+_default_lock = threading.Lock()
+
+
+def default_context() -> Context:
+    """Process-wide context on ``FASTPAULI_DEVICE`` (default: ``LOCAL_RANK`` or 0)."""
+    global _default_ctx
+    with _default_lock:
+        if _default_ctx is None:
+            dev = int(os.environ.get("FASTPAULI_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+            _default_ctx = Context(dev)
+        return _default_ctx
+
+
+class DeviceArray:
+    """A C-contiguous array in HBM owned by a :class:`Context` (or a zero-copy view of foreign device memory)."""
+
+    def __init__(self, ctx: Context, shape, dtype=np.complex128, ptr: int | None = None, owner=None):
+        self.ctx = ctx
+        self.shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.size = int(np.prod(self.shape)) if self.shape else 1
+        self.nbytes = self.size * self.dtype.itemsize
+        self._owner = owner
+        if ptr is None:
+            p = C.c_void_p()
+            _check(lib.fp_device_malloc(ctx._h, C.c_size_t(max(self.nbytes, 16)), C.byref(p)))
+            self.ptr = int(p.value)
+            self._owned = True
+        else:
+            self.ptr = int(ptr)
+            self._owned = False
+
+    def __del__(self):
+        if getattr(self, "_owned", False) and self.ctx._h:
+            lib.fp_device_free(self.ctx._h, C.c_void_p(self.ptr))
+            self._owned = False
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    @property
+    def __cuda_array_interface__(self) -> dict:
+        return {"shape": self.shape, "typestr": self.dtype.str, "data": (self.ptr, False), "version": 3,
+                "strides": None}
+
+    def get(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=self.dtype)
+        _check(lib.fp_memcpy(self.ctx._h, out.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr),
+                             C.c_size_t(self.nbytes)))
+        return out
+
+    def get_rows(self, r0: int, r1: int) -> np.ndarray:
+        """Rows [r0, r1) of a 2-D (or 1-D) array as a host copy."""
+        row_elems = int(np.prod(self.shape[1:])) if self.ndim > 1 else 1
+        out = np.empty((r1 - r0,) + self.shape[1:], dtype=self.dtype)
+        _check(lib.fp_memcpy(self.ctx._h, out.ctypes.data_as(C.c_void_p),
+                             C.c_void_p(self.ptr + r0 * row_elems * self.dtype.itemsize), C.c_size_t(out.nbytes)))
+        return out
+
+    def set(self, host: np.ndarray) -> None:
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        assert host.size == self.size
+        _check(lib.fp_memcpy(self.ctx._h, C.c_void_p(self.ptr), host.ctypes.data_as(C.c_void_p),
+                             C.c_size_t(self.nbytes)))
+
+
+# --------------------------------------------------------------------------------------------- argument plumbing
+class _Arg:
+    """Normalised array argument: pointer + shape + dtype, host or device."""
+
+    __slots__ = ("ptr", "shape", "dtype", "on_device", "keep", "ctx")
+
+    def __init__(self, obj, ctx: Context, want_real: bool = False):
+        self.ctx = ctx
+        if isinstance(obj, DeviceArray):
+            self.ptr, self.shape, self.dtype, self.on_device, self.keep = obj.ptr, obj.shape, obj.dtype, True, obj
+            return
+        cai = getattr(obj, "__cuda_array_interface__", None)
+        if cai is not None and not isinstance(obj, np.ndarray):
+            if cai.get("strides") not in (None,) and not _is_c_contiguous(cai):
+                raise ValueError("array must be C-contiguous (row-major)")  # NB:55-74
+            self.ptr, self.shape = int(cai["data"][0]), tuple(cai["shape"])
+            self.dtype, self.on_device, self.keep = np.dtype(cai["typestr"]), True, obj
+            return
+        arr = np.asarray(obj)
+        if want_real:
+            if arr.dtype not in (np.float32, np.float64):
+                arr = arr.astype(np.float64)
+        elif arr.dtype not in (np.complex64, np.complex128):
+            arr = arr.astype(np.complex128)  # nanobind converts implicitly (PY_PS:185,191 pass float/int arrays)
+        if not arr.flags.c_contiguous:
+            raise ValueError("array must be C-contiguous (row-major)")  # NB:55-74
+        self.ptr, self.shape, self.dtype, self.on_device, self.keep = arr.ctypes.data, arr.shape, arr.dtype, False, arr
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+
+def _is_c_contiguous(cai: dict) -> bool:
+    shape, strides = cai["shape"], cai["strides"]
+    item = np.dtype(cai["typestr"]).itemsize
+    expect = item
+    for s, st in zip(reversed(shape), reversed(strides)):
+        if s != 1 and st != expect:
+            return False
+        expect *= s
+    return True
+
+
+def _alloc_like(arg: _Arg, shape, dtype):
+    """Zeroed output like the reference's owning_ndarray_from_shape (NB:149-172): host -> numpy, device -> DeviceArray."""
+    if arg.on_device:
+        return arg.ctx.empty(shape, dtype)  # the kernels overwrite (accumulate=0): no need to zero
+    return np.empty(shape, dtype=dtype)
+
+
+def _ptr(o) -> C.c_void_p:
+    return C.c_void_p(o.ptr if isinstance(o, DeviceArray) else o.ctypes.data)
+
+
+def _coef_buf(c, dtype) -> np.ndarray:
+    return np.array([complex(c)], dtype=dtype)
+
+
+# --------------------------------------------------------------------------------------------- PauliString
+class PauliString:
+    """Tensor product of Pauli matrices (reference: ``struct PauliString``, __pauli_string.hpp:126-206)."""
+
+    def __init__(self, string: "str | PauliString" = "", ctx: Context | None = None):
+        string = str(string)
+        self._codes, self._n = _encode([string])
+        self.string = string
+        self._ctx = ctx
+
+    # -- properties mirrored from the bindings (__pauli_string_bindings.hpp:120-129)
+    @property
+    def n_qubits(self) -> int:
+        return self._n
+
+    @property
+    def dim(self) -> int:
+        return (1 << self._n) if self._n else 0
+
+    @property
+    def weight(self) -> int:
+        return int(np.count_nonzero(self._codes))
+
+    def __str__(self) -> str:
+        return self.string
+
+    def __repr__(self) -> str:
+        return f'PauliString("{self.string}")'
+
+    def __eq__(self, other) -> bool:
+        return isinstance(other, PauliString) and other.string == self.string
+
+    def __hash__(self) -> int:
+        return hash(self.string)
+
+    def clone(self) -> "PauliString":
+        return PauliString(self.string, self._ctx)
+
+    def _context(self) -> Context:
+        return self._ctx or default_context()
+
+    def apply(self, states, coeff: complex = 1.0):
+        """``coeff * P |psi_t>`` for a 1-D state or a (dim, n_states) batch (B_PS:131-159).
+
+        Mirrors a quirk of the reference binding: for a 1-D state the ``coeff`` argument is NOT applied
+        (``__pauli_string_bindings.hpp:142`` calls ``apply`` without ``c``); 2-D honours it.
+        """
+        ctx = self._context()
+        a = _Arg(states, ctx)
+        if a.ndim not in (1, 2):
+            raise ValueError(f"apply: expected 1 or 2 dimensions, got {a.ndim}")
+        if a.ndim == 1:
+            coeff = 1.0
+        B = 1 if a.ndim == 1 else a.shape[1]
+        out = _alloc_like(a, a.shape, a.dtype)
+        c = _coef_buf(coeff, a.dtype)
+        _check(lib.fp_string_apply(ctx._h, C.c_int(_dtype_code(a.dtype)), C.c_int(self._n),
+                                   self._codes.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p), _ptr(out),
+                                   C.c_void_p(a.ptr), C.c_size_t(a.shape[0]), C.c_size_t(B), C.c_int(0)))
+        return out
+
+    def expectation_value(self, states, coeff: complex = 1.0):
+        """``<psi_t| coeff P |psi_t>``: 1-D state -> shape (1,), batch -> (n_states,) (B_PS:182-211)."""
+        ctx = self._context()
+        a = _Arg(states, ctx)
+        if a.ndim not in (1, 2):
+            raise ValueError(f"expectation_value: expected 1 or 2 dimensions, got {a.ndim}")
+        B = 1 if a.ndim == 1 else a.shape[1]
+        out = _alloc_like(a, (B,), a.dtype)
+        c = _coef_buf(coeff, a.dtype)
+        _check(lib.fp_string_expval(ctx._h, C.c_int(_dtype_code(a.dtype)), C.c_int(self._n),
+                                    self._codes.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p), _ptr(out),
+                                    C.c_void_p(a.ptr), C.c_size_t(a.shape[0]), C.c_size_t(B), C.c_int(0)))
+        return out
+
+
+# --------------------------------------------------------------------------------------------- PauliOp
+class PauliOp:
+    """Weighted sum of Pauli strings ``sum_i h_i P_i`` (reference: ``struct PauliOp``, __pauli_op.hpp:38-97).
+
+    The packed, x-mask-grouped device plan (``fp_op``) is built lazily per dtype and reused across calls.
+    """
+
+    def __init__(self, coeffs: Sequence[complex] | np.ndarray | None = None,
+                 strings: Sequence["str | PauliString"] | None = None, ctx: Context | None = None):
+        if strings is None and coeffs is not None and len(coeffs) and isinstance(coeffs[0], (str, PauliString)):
+            strings, coeffs = coeffs, None  # PauliOp(strings): coefficients default to one (PO:59-80)
+        strings = [str(s) for s in (strings or [])]
+        self._coeffs = np.ones(len(strings), np.complex128) if coeffs is None else \
+            np.array(coeffs, dtype=np.complex128).reshape(-1)
+        if len(self._coeffs) != len(strings):
+            raise ValueError("coeffs and pauli_strings must have the same size")  # PO:92-95
+        self._codes, self._n = _encode(strings)
+        self._strings = strings
+        self._ctx = ctx
+        self._plans: dict[int, C.c_void_p] = {}
+
+    def __del__(self):
+        self._drop_plans()
+
+    def _drop_plans(self) -> None:
+        for h in getattr(self, "_plans", {}).values():
+            lib.fp_op_destroy(h)
+        self._plans = {}
+
+    # -- properties (__pauli_op_bindings.hpp)
+    @property
+    def dim(self) -> int:
+        return (1 << self._n) if (self._strings and self._n) else 0
+
+    @property
+    def n_qubits(self) -> int:
+        return self._n if self._strings else 0
+
+    @property
+    def n_pauli_strings(self) -> int:
+        return len(self._strings)
+
+    @property
+    def coeffs(self) -> np.ndarray:
+        return self._coeffs.copy()
+
+    @property
+    def pauli_strings(self) -> list[PauliString]:
+        return [PauliString(s) for s in self._strings]
+
+    @property
+    def pauli_strings_as_str(self) -> list[str]:
+        return list(self._strings)
+
+    def scale(self, factors) -> None:
+        """Scale each term (PO:142-158); drops the cached device plans."""
+        f = np.asarray(factors, dtype=np.complex128)
+        if f.ndim and f.shape != self._coeffs.shape:
+            raise ValueError("factors must have the same length as the number of PauliStrings")
+        self._coeffs = self._coeffs * f
+        self._drop_plans()
+
+    def clone(self) -> "PauliOp":
+        return PauliOp(self._coeffs.copy(), list(self._strings), self._ctx)
+
+    def _context(self) -> Context:
+        return self._ctx or default_context()
+
+    def _plan(self, dtype) -> C.c_void_p:
+        code = _dtype_code(dtype)
+        if code not in self._plans:
+            h = C.c_void_p()
+            coeffs = np.ascontiguousarray(self._coeffs, dtype=dtype)
+            _check(lib.fp_op_create(self._context()._h, C.c_int(code), C.c_int(self._n),
+                                    C.c_size_t(len(self._strings)), self._codes.ctypes.data_as(C.c_void_p),
+                                    coeffs.ctypes.data_as(C.c_void_p), C.byref(h)))
+            self._plans[code] = h
+        return self._plans[code]
+
+    def plan_info(self, dtype=np.complex128) -> dict:
+        d, n, s, p, g = C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        _check(lib.fp_op_info(self._plan(dtype), C.byref(d), C.byref(n), C.byref(s), C.byref(p), C.byref(g)))
+        return {"n_qubits": n.value, "n_strings": s.value, "n_packed_strings": p.value, "n_x_groups": g.value}
+
+    def apply(self, states):
+        """``(sum_i h_i P_i) |psi_t>`` for a 1-D state or (dim, n_states) batch (B_PO:489-516)."""
+        ctx = self._context()
+        a = _Arg(states, ctx)
+        if a.ndim not in (1, 2):
+            raise ValueError(f"apply: expected 1 or 2 dimensions, got {a.ndim}")
+        B = 1 if a.ndim == 1 else a.shape[1]
+        out = _alloc_like(a, a.shape, a.dtype)
+        _check(lib.fp_op_apply(ctx._h, self._plan(a.dtype), _ptr(out), C.c_void_p(a.ptr), C.c_size_t(a.shape[0]),
+                               C.c_size_t(B), C.c_int(0)))
+        return out
+
+    def expectation_value(self, states):
+        """``<psi_t| sum_i h_i P_i |psi_t>`` (B_PO:537-567)."""
+        ctx = self._context()
+        a = _Arg(states, ctx)
+        if a.ndim not in (1, 2):
+            raise ValueError(f"expectation_value: expected 1 or 2 dimensions, got {a.ndim}")
+        B = 1 if a.ndim == 1 else a.shape[1]
+        out = _alloc_like(a, (B,), a.dtype)
+        _check(lib.fp_op_expval(ctx._h, self._plan(a.dtype), _ptr(out), C.c_void_p(a.ptr), C.c_size_t(a.shape[0]),
+                                C.c_size_t(B), C.c_int(0)))
+        return out
+
+
+# --------------------------------------------------------------------------------------------- SummedPauliOp
+class SummedPauliOp:
+    """``A_k = sum_i h_ik P_i`` for k = 0..n_operators-1 (reference: __summed_pauli_op.hpp:37-145).
+
+    ``coeffs`` is (n_pauli_strings, n_operators) like the reference constructor (B_SPO:60-84).
+    """
+
+    def __init__(self, strings: Sequence["str | PauliString"], coeffs: np.ndarray, ctx: Context | None = None):
+        strings = [str(s) for s in strings]
+        coeffs = np.array(coeffs, dtype=np.complex128)
+        if coeffs.ndim == 1 and len(strings):
+            coeffs = coeffs.reshape(len(strings), -1)  # flat (n_strings * n_operators) form, SPO:83-92
+        if coeffs.ndim != 2 or coeffs.shape[0] != len(strings):
+            raise ValueError("The number of PauliStrings must match the number of rows in the coeffs matrix")  # SPO:60-64
+        if not strings:
+            raise ValueError("SummedPauliOp needs at least one PauliString")
+        self._codes, self._n = _encode(strings)
+        self._strings = strings
+        self._coeffs = np.ascontiguousarray(coeffs)
+        self._ctx = ctx
+        self._plans: dict[int, C.c_void_p] = {}
+
+    def __del__(self):
+        for h in getattr(self, "_plans", {}).values():
+            lib.fp_sop_destroy(h)
+        self._plans = {}
+
+    @property
+    def dim(self) -> int:
+        return 1 << self._n if self._n else 0
+
+    @property
+    def n_qubits(self) -> int:
+        return self._n
+
+    @property
+    def n_operators(self) -> int:
+        return self._coeffs.shape[1]
+
+    @property
+    def n_pauli_strings(self) -> int:
+        return len(self._strings)
+
+    @property
+    def coeffs(self) -> np.ndarray:
+        """(n_operators, n_pauli_strings): the reference getter returns the transpose (B_SPO:113-135)."""
+        return self._coeffs.T.copy()
+
+    @property
+    def pauli_strings(self) -> list[PauliString]:
+        return [PauliString(s) for s in self._strings]
+
+    def clone(self) -> "SummedPauliOp":
+        return SummedPauliOp(list(self._strings), self._coeffs.copy(), self._ctx)
+
+    def _context(self) -> Context:
+        return self._ctx or default_context()
+
+    def _plan(self, dtype) -> C.c_void_p:
+        code = _dtype_code(dtype)
+        if code not in self._plans:
+            h = C.c_void_p()
+            coeffs = np.ascontiguousarray(self._coeffs, dtype=dtype)
+            _check(lib.fp_sop_create(self._context()._h, C.c_int(code), C.c_int(self._n),
+                                     C.c_size_t(len(self._strings)), self._codes.ctypes.data_as(C.c_void_p),
+                                     C.c_size_t(coeffs.shape[1]), coeffs.ctypes.data_as(C.c_void_p), C.byref(h)))
+            self._plans[code] = h
+        return self._plans[code]
+
+    def apply(self, states):
+        """``sum_k A_k |psi_t>`` (B_SPO:156-182)."""
+        ctx = self._context()
+        a = _Arg(states, ctx)
+        if a.ndim not in (1, 2):
+            raise ValueError(f"apply: expected 1 or 2 dimensions, got {a.ndim}")
+        B = 1 if a.ndim == 1 else a.shape[1]
+        out = _alloc_like(a, a.shape, a.dtype)
+        _check(lib.fp_sop_apply(ctx._h, self._plan(a.dtype), _ptr(out), C.c_void_p(a.ptr), C.c_size_t(a.shape[0]),
+                                C.c_size_t(B), C.c_int(0)))
+        return out
+
+    def apply_weighted(self, states, data):
+        """``sum_k x_kt A_k |psi_t>`` with real weights ``data`` of shape (n_operators, n_states) (B_SPO:199-228)."""
+        ctx = self._context()
+        a = _Arg(states, ctx)
+        d = _Arg(data, ctx, want_real=True)
+        if a.ndim not in (1, 2):
+            raise ValueError(f"apply_weighted: expected 1 or 2 dimensions, got {a.ndim}")
+        B = 1 if a.ndim == 1 else a.shape[1]
+        dshape = d.shape if d.ndim == 2 else (d.shape[0], 1)
+        if d.ndim not in (1, 2) or d.ndim != a.ndim or dshape != (self.n_operators, B):  # SPO:389-394
+            raise ValueError("data(k,t) must have the same number of operators as the SummedPauliOp "
+                             "and the same number of states as the input states")
+        if d.dtype not in (np.float32, np.float64):
+            raise ValueError("data must be float32 or float64")
+        out = _alloc_like(a, a.shape, a.dtype)
+        _check(lib.fp_sop_apply_weighted(ctx._h, self._plan(a.dtype), _ptr(out), C.c_void_p(a.ptr),
+                                         C.c_void_p(d.ptr), C.c_int(d.dtype == np.float64),
+                                         C.c_size_t(a.shape[0]), C.c_size_t(B), C.c_int(0)))
+        return out
+
+    def expectation_value(self, states):
+        """``<psi_t| A_k |psi_t>``: 1-D state -> (n_operators,), batch -> (n_operators, n_states) (B_SPO:246-274)."""
+        ctx = self._context()
+        a = _Arg(states, ctx)
+        if a.ndim not in (1, 2):
+            raise ValueError(f"expectation_value: expected 1 or 2 dimensions, got {a.ndim}")
+        B = 1 if a.ndim == 1 else a.shape[1]
+        shape = (self.n_operators,) if a.ndim == 1 else (self.n_operators, B)
+        out = _alloc_like(a, shape, a.dtype)
+        _check(lib.fp_sop_expval(ctx._h, self._plan(a.dtype), _ptr(out), C.c_void_p(a.ptr), C.c_size_t(a.shape[0]),
+                                 C.c_size_t(B), C.c_int(0)))
+        return out

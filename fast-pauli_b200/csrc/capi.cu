@@ -1,0 +1,1506 @@
+// C ABI of the B200-native fast-pauli hot path (declared in include/fastpauli_b200.h).
+//
+// Host-side responsibilities only: argument checks that mirror the reference's std::invalid_argument sites,
+// host/device pointer staging, plan packing (pack.hpp), geometry selection and kernel launches (kernels.cuh).
+// No compute happens on the host and there is no CPU fallback: without a CUDA device every compute call fails.
+#include "../../include/fastpauli_b200.h"
+
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+#include "pack.hpp"
+
+using namespace fpk;
+
+// ================================================================ errors
+namespace
+{
+thread_local std::string g_err;
+
+int set_err(int code, std::string msg)
+{
+    g_err = std::move(msg);
+    return code;
+}
+
+#define FP_CU(call)                                                                                                    \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess)                                                                                         \
+        {                                                                                                              \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? FP_OUT_OF_MEMORY                                           \
+                        : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? FP_NO_DEVICE                \
+                                                                                         : FP_CUDA_ERROR;              \
+            return set_err(code_, std::string(#call) + ": " + cudaGetErrorString(e_));                                 \
+        }                                                                                                              \
+    } while (0)
+
+#define FP_TRY(expr)                                                                                                   \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        int rc_ = (expr);                                                                                              \
+        if (rc_ != FP_OK)                                                                                              \
+            return rc_;                                                                                                \
+    } while (0)
+
+struct Scratch
+{
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return FP_OK;
+        if (p)
+        {
+            cudaFree(p);
+            p = nullptr;
+            cap = 0;
+        }
+        size_t want = bytes + (bytes >> 3); // 12.5 % headroom so slowly growing calls do not reallocate every time
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess)
+        {
+            (void)cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess)
+        {
+            (void)cudaGetLastError();
+            p = nullptr;
+            return set_err(FP_OUT_OF_MEMORY, "device scratch allocation of " + std::to_string(bytes) + " bytes failed");
+        }
+        cap = want;
+        return FP_OK;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+} // namespace
+
+// ================================================================ opaque types
+struct fp_ctx
+{
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    bool async = false;
+    bool tensor_core = true;
+    uint64_t launches = 0;
+    size_t l2_budget = 40ull << 20;
+    Scratch stage_in, stage_out, stage_data, partials, work_a, work_b, meta;
+    std::mutex mu;
+};
+
+struct fp_event
+{
+    cudaEvent_t ev = nullptr;
+};
+
+template <typename T> struct DeviceOp
+{
+    PackedOp<T> host;
+    uint64_t *gx = nullptr;
+    uint32_t *gstart = nullptr;
+    uint64_t *sz = nullptr;
+    Cx<T> *sc = nullptr;
+    uint8_t *sodd = nullptr;
+    PairChunk *chunks = nullptr; // strings of each group in chunks of <= kPairMS (paired expectation kernel)
+    uint32_t n_chunks = 0;
+    bool any_diag = false;
+
+    OpView<T> view() const
+    {
+        OpView<T> v{};
+        v.gx = gx;
+        v.gstart = gstart;
+        v.sz = sz;
+        v.scoef = sc;
+        v.G = static_cast<uint32_t>(host.gx.size());
+        if (host.sz.size() == 1)
+        {
+            v.x0 = host.gx[0];
+            v.z0 = host.sz[0];
+            v.c0 = Cx<T>{host.sc[0].real(), host.sc[0].imag()};
+        }
+        return v;
+    }
+    void release()
+    {
+        cudaFree(gx);
+        cudaFree(gstart);
+        cudaFree(sz);
+        cudaFree(sc);
+        cudaFree(sodd);
+        cudaFree(chunks);
+        gx = nullptr;
+        gstart = nullptr;
+        sz = nullptr;
+        sc = nullptr;
+        sodd = nullptr;
+        chunks = nullptr;
+    }
+};
+
+constexpr int kPairMS = 4;
+
+struct fp_op
+{
+    int dtype = FP_C128;
+    int device = 0;
+    int n_qubits = 0;
+    size_t n_strings = 0;
+    DeviceOp<float> f;
+    DeviceOp<double> d;
+};
+
+struct fp_sop
+{
+    int dtype = FP_C128;
+    int device = 0;
+    int n_qubits = 0;
+    size_t n_strings = 0, n_ops = 0;
+    fp_op *summed = nullptr; // PauliOp with c_j = sum_k coeffs(j,k)  (SummedPauliOp::apply)
+    fp_op *strings = nullptr; // unmerged packed strings (unit coefficients) for apply_weighted / expectation_value
+    void *A_w = nullptr;      // [2S x K] planar (-i)^nY coeffs, rows in packed order        (W = A_w * data)
+    void *A_e = nullptr;      // [2K x S] planar coeffs * (-i)^nY * pair factor, transposed  (out = A_e * E)
+};
+
+// ================================================================ helpers
+namespace
+{
+template <typename T> int upload_vec(T **dst, std::vector<T> const &v)
+{
+    void *p = nullptr;
+    size_t bytes = v.size() * sizeof(T);
+    if (bytes == 0)
+    {
+        FP_CU(cudaMalloc(&p, 16));
+    }
+    else
+    {
+        FP_CU(cudaMalloc(&p, bytes));
+        FP_CU(cudaMemcpy(p, v.data(), bytes, cudaMemcpyHostToDevice));
+    }
+    *dst = static_cast<T *>(p);
+    return FP_OK;
+}
+
+template <typename T> int upload_op(DeviceOp<T> &d)
+{
+    FP_TRY(upload_vec(&d.gx, d.host.gx));
+    FP_TRY(upload_vec(&d.gstart, d.host.gstart));
+    FP_TRY(upload_vec(&d.sz, d.host.sz));
+    {
+        std::vector<Cx<T>> sc(d.host.sc.size());
+        for (size_t i = 0; i < sc.size(); ++i)
+            sc[i] = Cx<T>{d.host.sc[i].real(), d.host.sc[i].imag()};
+        FP_TRY(upload_vec(&d.sc, sc));
+    }
+    FP_TRY(upload_vec(&d.sodd, d.host.sodd));
+    std::vector<PairChunk> chunks;
+    d.any_diag = false;
+    for (size_t g = 0; g + 1 < d.host.gstart.size(); ++g)
+    {
+        uint64_t x = d.host.gx[g];
+        uint32_t hbit = 0;
+        if (x)
+            hbit = 63u - static_cast<uint32_t>(__builtin_clzll(x));
+        else
+            d.any_diag = true;
+        for (uint32_t s = d.host.gstart[g]; s < d.host.gstart[g + 1]; s += kPairMS)
+        {
+            PairChunk c;
+            c.x = x;
+            c.s0 = s;
+            c.count = std::min<uint32_t>(kPairMS, d.host.gstart[g + 1] - s);
+            c.hbit = hbit;
+            c.diag = x == 0;
+            chunks.push_back(c);
+        }
+    }
+    d.n_chunks = static_cast<uint32_t>(chunks.size());
+    FP_TRY(upload_vec(&d.chunks, chunks));
+    return FP_OK;
+}
+
+bool is_device_ptr(void const *p)
+{
+    if (!p)
+        return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// A caller buffer, used in place when it lives on the device, staged through scratch when it lives on the host.
+struct Staged
+{
+    void *dev = nullptr;
+    void *host = nullptr;
+    size_t bytes = 0;
+    bool staged = false;
+};
+
+int stage_in(fp_ctx *ctx, Scratch &scratch, void const *p, size_t bytes, bool copy, Staged &s)
+{
+    s.bytes = bytes;
+    if (bytes == 0)
+    {
+        s.dev = const_cast<void *>(p);
+        return FP_OK;
+    }
+    if (!p)
+        return set_err(FP_INVALID_ARGUMENT, "null data pointer");
+    if (is_device_ptr(p))
+    {
+        s.dev = const_cast<void *>(p);
+        return FP_OK;
+    }
+    FP_TRY(scratch.ensure(bytes));
+    s.dev = scratch.p;
+    s.host = const_cast<void *>(p);
+    s.staged = true;
+    if (copy)
+        FP_CU(cudaMemcpyAsync(s.dev, p, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return FP_OK;
+}
+
+int stage_back(fp_ctx *ctx, Staged &s)
+{
+    if (s.staged && s.bytes)
+        FP_CU(cudaMemcpyAsync(s.host, s.dev, s.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return FP_OK;
+}
+
+int finish(fp_ctx *ctx, bool any_staged)
+{
+    FP_CU(cudaGetLastError());
+    if (any_staged || !ctx->async)
+        FP_CU(cudaStreamSynchronize(ctx->stream));
+    return FP_OK;
+}
+
+struct DeviceGuard
+{
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev)
+            cudaSetDevice(dev);
+        else
+            prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+size_t csize(int dtype)
+{
+    return dtype == FP_C128 ? 16 : 8;
+}
+
+int check_dtype(int dtype)
+{
+    if (dtype != FP_C64 && dtype != FP_C128)
+        return set_err(FP_INVALID_ARGUMENT, "dtype must be FP_C64 or FP_C128");
+    return FP_OK;
+}
+
+uint64_t dim_of(int n)
+{
+    return n > 0 ? (1ull << n) : 0; // PS:266-269: an empty string has dim 0
+}
+
+// ---------------------------------------------------------------- geometry
+struct GeomSel
+{
+    Geom g{};
+    int V = 4;
+    uint64_t grid = 0;
+};
+
+// rows: rows the kernel iterates over (dim, or dim/2 pair-rows); dim: rows of the state (L2 working set)
+GeomSel choose_geom(fp_ctx const *ctx, uint64_t rows, uint64_t dim, uint64_t rowvecs, size_t vec_bytes, bool multi_group,
+                    bool reduce, uint64_t n_chunks = 1)
+{
+    GeomSel s;
+    uint32_t tw = 1;
+    while (tw < rowvecs && tw < static_cast<uint32_t>(kThreads))
+        tw <<= 1;
+    if (multi_group)
+    {
+        // batch-tile the sweep so dim x tile stays L2-resident while all x-groups gather from it;
+        // never go below one 64-byte DRAM granule per row
+        uint32_t floor_tw = static_cast<uint32_t>(std::max<size_t>(1, 64 / vec_bytes));
+        while (tw > floor_tw && dim * tw * vec_bytes > ctx->l2_budget)
+            tw >>= 1;
+    }
+    uint32_t log2tw = 0;
+    while ((1u << log2tw) < tw)
+        ++log2tw;
+    uint32_t const TY = kThreads / tw;
+    uint32_t const nct = static_cast<uint32_t>((rowvecs + tw - 1) / tw);
+    int V = 4;
+    {
+        uint64_t blocks4 = ((rows + TY * 4ull - 1) / (TY * 4ull)) * nct * n_chunks;
+        if (rows < TY * 4ull || blocks4 < static_cast<uint64_t>(ctx->sm_count) * 2)
+            V = 1;
+    }
+    uint64_t const rows_per_iter = static_cast<uint64_t>(TY) * V;
+    uint64_t const n_row_iters = (rows + rows_per_iter - 1) / rows_per_iter;
+    s.V = V;
+    s.g.N = rows;
+    s.g.rowvecs = rowvecs;
+    s.g.nColTiles = nct;
+    s.g.log2TW = log2tw;
+    if (!reduce)
+    {
+        s.g.iters = 1;
+        s.g.nRowBlocks = n_row_iters;
+    }
+    else
+    {
+        uint64_t const target = static_cast<uint64_t>(ctx->sm_count) * 8;
+        uint64_t const fixed = static_cast<uint64_t>(nct) * n_chunks;
+        uint64_t want_rb = std::max<uint64_t>(1, (target + fixed - 1) / fixed);
+        uint64_t iters = std::max<uint64_t>(1, n_row_iters / want_rb);
+        iters = std::min<uint64_t>(iters, 1024);
+        s.g.iters = static_cast<uint32_t>(iters);
+        s.g.nRowBlocks = (n_row_iters + iters - 1) / iters;
+    }
+    s.grid = s.g.nRowBlocks * s.g.nColTiles * n_chunks;
+    return s;
+}
+
+template <typename T> int pick_epv(void const *a, void const *b, uint64_t B)
+{
+    if (sizeof(T) == 8)
+        return 1;
+    bool aligned = (reinterpret_cast<uintptr_t>(a) % 16 == 0) && (reinterpret_cast<uintptr_t>(b) % 16 == 0);
+    return (B % 2 == 0 && aligned) ? 2 : 1;
+}
+
+int check_align(void const *p, size_t align, char const *what)
+{
+    if (reinterpret_cast<uintptr_t>(p) % align)
+        return set_err(FP_INVALID_ARGUMENT, std::string(what) + " must be " + std::to_string(align) + "-byte aligned");
+    return FP_OK;
+}
+
+int check_grid(uint64_t grid)
+{
+    if (grid == 0 || grid > 0x7fffffffull)
+        return set_err(FP_UNSUPPORTED, "problem too large for a single launch (grid " + std::to_string(grid) + ")");
+    return FP_OK;
+}
+
+// ---------------------------------------------------------------- launchers (all pointers are device pointers here)
+template <typename T, int EPV, int MODE, bool INLINE1>
+void launch_op_v(fp_ctx *ctx, GeomSel const &gs, OpView<T> const &view, void const *in, void *out, void *partials,
+                 int beta)
+{
+    auto const *din = static_cast<CVec<T, EPV> const *>(in);
+    auto *dout = static_cast<CVec<T, EPV> *>(out);
+    auto *dpart = static_cast<Cx<T> *>(partials);
+    dim3 grid(static_cast<unsigned>(gs.grid));
+    if (gs.V == 4)
+        op_kernel<T, EPV, 4, MODE, INLINE1><<<grid, kThreads, 0, ctx->stream>>>(view, gs.g, din, dout, dpart, beta);
+    else
+        op_kernel<T, EPV, 1, MODE, INLINE1><<<grid, kThreads, 0, ctx->stream>>>(view, gs.g, din, dout, dpart, beta);
+    ctx->launches++;
+}
+
+template <typename T>
+int run_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const *in, uint64_t dim, uint64_t B, int beta)
+{
+    if (dim == 0 || B == 0)
+        return FP_OK;
+    if (op.host.sz.empty())
+    {
+        // operator with no strings acts as zero (cannot happen through the checked entry points: dim() == 0)
+        if (!beta)
+            FP_CU(cudaMemsetAsync(out, 0, dim * B * 2 * sizeof(T), ctx->stream));
+        return FP_OK;
+    }
+    FP_TRY(check_align(in, 2 * sizeof(T), "states"));
+    FP_TRY(check_align(out, 2 * sizeof(T), "new_states"));
+    int const epv = pick_epv<T>(in, out, B);
+    uint64_t const rowvecs = B / epv;
+    bool const single = op.host.sz.size() == 1;
+    GeomSel gs = choose_geom(ctx, dim, dim, rowvecs, 2 * sizeof(T) * epv, op.host.gx.size() > 1, false);
+    FP_TRY(check_grid(gs.grid));
+    OpView<T> view = op.view();
+    if constexpr (sizeof(T) == 4)
+    {
+        if (epv == 2)
+        {
+            if (single)
+                launch_op_v<T, 2, 0, true>(ctx, gs, view, in, out, nullptr, beta);
+            else
+                launch_op_v<T, 2, 0, false>(ctx, gs, view, in, out, nullptr, beta);
+            return FP_OK;
+        }
+    }
+    if (single)
+        launch_op_v<T, 1, 0, true>(ctx, gs, view, in, out, nullptr, beta);
+    else
+        launch_op_v<T, 1, 0, false>(ctx, gs, view, in, out, nullptr, beta);
+    return FP_OK;
+}
+
+template <typename T>
+int run_op_expval(fp_ctx *ctx, DeviceOp<T> const &op, void *out /* B complex, device */, void const *in, uint64_t dim,
+                  uint64_t B, int beta)
+{
+    if (B == 0)
+        return FP_OK;
+    if (dim == 0 || op.host.sz.empty())
+    {
+        if (!beta)
+            FP_CU(cudaMemsetAsync(out, 0, B * 2 * sizeof(T), ctx->stream));
+        return FP_OK;
+    }
+    FP_TRY(check_align(in, 2 * sizeof(T), "states"));
+    int const epv = pick_epv<T>(in, in, B);
+    uint64_t const rowvecs = B / epv;
+    GeomSel gs = choose_geom(ctx, dim, dim, rowvecs, 2 * sizeof(T) * epv, op.host.gx.size() > 1, true);
+    FP_TRY(check_grid(gs.grid));
+    uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
+    if (B > 0xfffffff0ull)
+        return set_err(FP_UNSUPPORTED, "n_states too large");
+    gs.g.Bpad = Bpad;
+    FP_TRY(ctx->partials.ensure(gs.g.nRowBlocks * Bpad * 2 * sizeof(T)));
+    OpView<T> view = op.view();
+    bool done = false;
+    if constexpr (sizeof(T) == 4)
+    {
+        if (epv == 2)
+        {
+            launch_op_v<T, 2, 1, false>(ctx, gs, view, in, nullptr, ctx->partials.p, 0);
+            done = true;
+        }
+    }
+    if (!done)
+        launch_op_v<T, 1, 1, false>(ctx, gs, view, in, nullptr, ctx->partials.p, 0);
+    unsigned fgrid = static_cast<unsigned>((B + 127) / 128);
+    finalize_complex_kernel<T><<<fgrid, 128, 0, ctx->stream>>>(static_cast<Cx<T> const *>(ctx->partials.p),
+                                                                 gs.g.nRowBlocks, Bpad, B, static_cast<Cx<T> *>(out),
+                                                                 beta);
+    ctx->launches++;
+    return FP_OK;
+}
+
+template <typename T, int EPV, int MS>
+void launch_pairs_v(fp_ctx *ctx, GeomSel const &gs, PairChunk const *chunks, uint64_t const *sz, uint8_t const *sodd,
+                    PairChunk inl, uint64_t inl_z, uint32_t inl_odd, int use_inline, uint64_t dim, void const *in,
+                    T *partials, uint64_t slot_stride)
+{
+    auto const *din = static_cast<CVec<T, EPV> const *>(in);
+    dim3 grid(static_cast<unsigned>(gs.grid));
+    if (gs.V == 4)
+        expval_pairs_kernel<T, EPV, 4, MS><<<grid, kThreads, 0, ctx->stream>>>(
+            chunks, sz, sodd, inl, inl_z, inl_odd, use_inline, gs.g, dim, din, partials, slot_stride);
+    else
+        expval_pairs_kernel<T, EPV, 1, MS><<<grid, kThreads, 0, ctx->stream>>>(
+            chunks, sz, sodd, inl, inl_z, inl_odd, use_inline, gs.g, dim, din, partials, slot_stride);
+    ctx->launches++;
+}
+
+// PauliString::expectation_value through the paired kernel: each amplitude is read once.
+template <typename T>
+int run_string_expval(fp_ctx *ctx, StringMasks const &mk, std::complex<T> coeff, void *out, void const *in,
+                      uint64_t dim, uint64_t B, int beta)
+{
+    if (B == 0)
+        return FP_OK;
+    if (dim == 0)
+    {
+        if (!beta)
+            FP_CU(cudaMemsetAsync(out, 0, B * 2 * sizeof(T), ctx->stream));
+        return FP_OK;
+    }
+    FP_TRY(check_align(in, 2 * sizeof(T), "states"));
+    int const epv = pick_epv<T>(in, in, B);
+    uint64_t const rowvecs = B / epv;
+    PairChunk ch{};
+    ch.x = mk.x;
+    ch.s0 = 0;
+    ch.count = 1;
+    ch.diag = mk.x == 0;
+    ch.hbit = mk.x ? 63u - static_cast<uint32_t>(__builtin_clzll(mk.x)) : 0;
+    uint64_t const rows = ch.diag ? dim : dim / 2;
+    GeomSel gs = choose_geom(ctx, rows, dim, rowvecs, 2 * sizeof(T) * epv, false, true);
+    FP_TRY(check_grid(gs.grid));
+    uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
+    gs.g.Bpad = Bpad;
+    uint64_t const slot_stride = gs.g.nRowBlocks * Bpad;
+    FP_TRY(ctx->partials.ensure(slot_stride * sizeof(T)));
+    T *part = static_cast<T *>(ctx->partials.p);
+    bool done = false;
+    if constexpr (sizeof(T) == 4)
+    {
+        if (epv == 2)
+        {
+            launch_pairs_v<T, 2, 1>(ctx, gs, nullptr, nullptr, nullptr, ch, mk.z, mk.ny & 1u, 1, dim, in, part,
+                                    slot_stride);
+            done = true;
+        }
+    }
+    if (!done)
+        launch_pairs_v<T, 1, 1>(ctx, gs, nullptr, nullptr, nullptr, ch, mk.z, mk.ny & 1u, 1, dim, in, part, slot_stride);
+    // factor = coeff * (-i)^nY * (1 | 2 | 2i)
+    std::complex<double> f = times_phase(std::complex<double>(coeff.real(), coeff.imag()), mk.ny);
+    if (!ch.diag)
+        f *= (mk.ny & 1u) ? std::complex<double>(0, 2) : std::complex<double>(2, 0);
+    unsigned fgrid = static_cast<unsigned>((B + 127) / 128);
+    finalize_pairs_string_kernel<T><<<fgrid, 128, 0, ctx->stream>>>(part, gs.g.nRowBlocks, Bpad, B, f.real(), f.imag(),
+                                                                      static_cast<Cx<T> *>(out), beta);
+    ctx->launches++;
+    return FP_OK;
+}
+
+// C[M x N] = A[M x Kd] * Bm[Kd x N]  (+ split-K planes)
+template <typename T, typename DT>
+int run_gemm(fp_ctx *ctx, T const *A, DT const *Bm, T *C, uint32_t M, uint64_t N, uint32_t Kd, uint32_t splitK,
+             uint32_t kchunk)
+{
+    if (M == 0 || N == 0)
+        return FP_OK;
+    if constexpr (std::is_same<T, float>::value && std::is_same<DT, float>::value)
+    {
+        if (ctx->tensor_core && gemm_tc_supported(M, N, Kd, splitK))
+        {
+            int rc = gemm_tc_3xtf32(ctx->stream, A, Bm, C, M, N, Kd, splitK, kchunk);
+            if (rc == 0)
+            {
+                ctx->launches++;
+                return FP_OK;
+            }
+        }
+    }
+    dim3 grid(static_cast<unsigned>((N + 63) / 64), (M + 63) / 64, splitK);
+    if (grid.y > 65535 || grid.z > 65535)
+        return set_err(FP_UNSUPPORTED, "contraction too large");
+    gemm_simt_kernel<T, DT><<<grid, 256, 0, ctx->stream>>>(A, Bm, C, M, N, Kd, kchunk);
+    ctx->launches++;
+    return FP_OK;
+}
+
+// ---------------------------------------------------------------- typed front-ends over fp_op
+template <typename T> DeviceOp<T> &dop(fp_op *op);
+template <> DeviceOp<float> &dop<float>(fp_op *op)
+{
+    return op->f;
+}
+template <> DeviceOp<double> &dop<double>(fp_op *op)
+{
+    return op->d;
+}
+template <typename T> DeviceOp<T> const &dop(fp_op const *op)
+{
+    return dop<T>(const_cast<fp_op *>(op));
+}
+
+template <typename T>
+int op_create_t(fp_ctx *ctx, int dtype, int n, size_t S, uint8_t const *codes, std::complex<T> const *coeffs,
+                bool merge, fp_op **out)
+{
+    std::unique_ptr<fp_op> op(new fp_op);
+    op->dtype = dtype;
+    op->device = ctx->device;
+    op->n_qubits = n;
+    op->n_strings = S;
+    try
+    {
+        dop<T>(op.get()).host = pack_op<T>(n, S, codes, coeffs, merge);
+    }
+    catch (std::invalid_argument const &e)
+    {
+        return set_err(FP_INVALID_ARGUMENT, e.what());
+    }
+    int rc = upload_op(dop<T>(op.get()));
+    if (rc != FP_OK)
+    {
+        dop<T>(op.get()).release();
+        return rc;
+    }
+    *out = op.release();
+    return FP_OK;
+}
+
+int op_check(fp_ctx *ctx, fp_op const *op)
+{
+    if (!ctx || !op)
+        return set_err(FP_INVALID_ARGUMENT, "null context or operator");
+    if (op->device != ctx->device)
+        return set_err(FP_INVALID_ARGUMENT, "operator plan was created on a different device than the context");
+    return FP_OK;
+}
+
+} // namespace
+
+// ================================================================ extern "C"
+extern "C"
+{
+
+    const char *fp_last_error(void)
+    {
+        return g_err.c_str();
+    }
+
+    int fp_version(void)
+    {
+        return 100; // 0.1.0
+    }
+
+    int fp_device_count(int *count)
+    {
+        if (!count)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        *count = 0;
+        cudaError_t e = cudaGetDeviceCount(count);
+        if (e != cudaSuccess)
+        {
+            (void)cudaGetLastError();
+            *count = 0;
+            return set_err(FP_NO_DEVICE, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+        }
+        return FP_OK;
+    }
+
+    int fp_ctx_create(int device, fp_ctx **out)
+    {
+        if (!out)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        *out = nullptr;
+        int n = 0;
+        FP_TRY(fp_device_count(&n));
+        if (n == 0)
+            return set_err(FP_NO_DEVICE, "no CUDA device visible: fastpauli_b200 has no CPU fallback");
+        if (device < 0 || device >= n)
+            return set_err(FP_INVALID_ARGUMENT, "device index out of range");
+        FP_CU(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        FP_CU(cudaGetDeviceProperties(&prop, device));
+        std::unique_ptr<fp_ctx> ctx(new fp_ctx);
+        ctx->device = device;
+        ctx->sm_count = prop.multiProcessorCount;
+        if (prop.l2CacheSize > 0)
+            ctx->l2_budget = static_cast<size_t>(prop.l2CacheSize) / 3; // one die's worth of L2 minus headroom
+        if (char const *env = getenv("FASTPAULI_L2_BUDGET"))
+            ctx->l2_budget = strtoull(env, nullptr, 10);
+        if (char const *env = getenv("FASTPAULI_TENSOR_CORE"))
+            ctx->tensor_core = atoi(env) != 0;
+        if (prop.major != 10)
+            ctx->tensor_core = false; // tcgen05 exists on sm_100 only
+        FP_CU(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        ctx->stream = ctx->own_stream;
+        *out = ctx.release();
+        return FP_OK;
+    }
+
+    int fp_ctx_destroy(fp_ctx *ctx)
+    {
+        if (!ctx)
+            return FP_OK;
+        DeviceGuard g(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        for (Scratch *s : {&ctx->stage_in, &ctx->stage_out, &ctx->stage_data, &ctx->partials, &ctx->work_a, &ctx->work_b,
+                           &ctx->meta})
+            s->release();
+        if (ctx->own_stream)
+            cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return FP_OK;
+    }
+
+    int fp_ctx_device(const fp_ctx *ctx, int *device)
+    {
+        if (!ctx || !device)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        *device = ctx->device;
+        return FP_OK;
+    }
+
+    int fp_ctx_set_stream(fp_ctx *ctx, void *cuda_stream)
+    {
+        if (!ctx)
+            return set_err(FP_INVALID_ARGUMENT, "null context");
+        ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+        return FP_OK;
+    }
+
+    int fp_ctx_set_async(fp_ctx *ctx, int async)
+    {
+        if (!ctx)
+            return set_err(FP_INVALID_ARGUMENT, "null context");
+        ctx->async = async != 0;
+        return FP_OK;
+    }
+
+    int fp_ctx_set_tensor_core(fp_ctx *ctx, int enable)
+    {
+        if (!ctx)
+            return set_err(FP_INVALID_ARGUMENT, "null context");
+        ctx->tensor_core = enable != 0;
+        return FP_OK;
+    }
+
+    int fp_ctx_set_l2_budget(fp_ctx *ctx, size_t bytes)
+    {
+        if (!ctx || bytes == 0)
+            return set_err(FP_INVALID_ARGUMENT, "null context or zero budget");
+        ctx->l2_budget = bytes;
+        return FP_OK;
+    }
+
+    int fp_ctx_sync(fp_ctx *ctx)
+    {
+        if (!ctx)
+            return set_err(FP_INVALID_ARGUMENT, "null context");
+        DeviceGuard g(ctx->device);
+        FP_CU(cudaStreamSynchronize(ctx->stream));
+        return FP_OK;
+    }
+
+    int fp_ctx_launch_count(const fp_ctx *ctx, uint64_t *count)
+    {
+        if (!ctx || !count)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        *count = ctx->launches;
+        return FP_OK;
+    }
+
+    // ------------------------------------------------------------ memory / timing
+    int fp_device_malloc(fp_ctx *ctx, size_t bytes, void **ptr)
+    {
+        if (!ctx || !ptr)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        DeviceGuard g(ctx->device);
+        *ptr = nullptr;
+        FP_CU(cudaMalloc(ptr, bytes ? bytes : 16));
+        return FP_OK;
+    }
+    int fp_device_free(fp_ctx *ctx, void *ptr)
+    {
+        if (!ctx)
+            return set_err(FP_INVALID_ARGUMENT, "null context");
+        DeviceGuard g(ctx->device);
+        FP_CU(cudaFree(ptr));
+        return FP_OK;
+    }
+    int fp_host_malloc(fp_ctx *ctx, size_t bytes, void **ptr)
+    {
+        if (!ctx || !ptr)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        DeviceGuard g(ctx->device);
+        *ptr = nullptr;
+        FP_CU(cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocDefault));
+        return FP_OK;
+    }
+    int fp_host_free(fp_ctx *ctx, void *ptr)
+    {
+        if (!ctx)
+            return set_err(FP_INVALID_ARGUMENT, "null context");
+        DeviceGuard g(ctx->device);
+        FP_CU(cudaFreeHost(ptr));
+        return FP_OK;
+    }
+    int fp_memcpy_async(fp_ctx *ctx, void *dst, const void *src, size_t bytes)
+    {
+        if (!ctx)
+            return set_err(FP_INVALID_ARGUMENT, "null context");
+        DeviceGuard g(ctx->device);
+        if (bytes)
+            FP_CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+        return FP_OK;
+    }
+    int fp_memcpy(fp_ctx *ctx, void *dst, const void *src, size_t bytes)
+    {
+        FP_TRY(fp_memcpy_async(ctx, dst, src, bytes));
+        return fp_ctx_sync(ctx);
+    }
+    int fp_memset(fp_ctx *ctx, void *dst, int value, size_t bytes)
+    {
+        if (!ctx)
+            return set_err(FP_INVALID_ARGUMENT, "null context");
+        DeviceGuard g(ctx->device);
+        if (bytes)
+            FP_CU(cudaMemsetAsync(dst, value, bytes, ctx->stream));
+        return FP_OK;
+    }
+    int fp_device_mem_info(fp_ctx *ctx, size_t *free_bytes, size_t *total_bytes)
+    {
+        if (!ctx || !free_bytes || !total_bytes)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        DeviceGuard g(ctx->device);
+        FP_CU(cudaMemGetInfo(free_bytes, total_bytes));
+        return FP_OK;
+    }
+    int fp_event_create(fp_event **ev)
+    {
+        if (!ev)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        std::unique_ptr<fp_event> e(new fp_event);
+        FP_CU(cudaEventCreate(&e->ev));
+        *ev = e.release();
+        return FP_OK;
+    }
+    int fp_event_destroy(fp_event *ev)
+    {
+        if (ev)
+        {
+            cudaEventDestroy(ev->ev);
+            delete ev;
+        }
+        return FP_OK;
+    }
+    int fp_event_record(fp_ctx *ctx, fp_event *ev)
+    {
+        if (!ctx || !ev)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        DeviceGuard g(ctx->device);
+        FP_CU(cudaEventRecord(ev->ev, ctx->stream));
+        return FP_OK;
+    }
+    int fp_event_elapsed_ms(fp_event *start, fp_event *stop, float *ms)
+    {
+        if (!start || !stop || !ms)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        FP_CU(cudaEventSynchronize(stop->ev));
+        FP_CU(cudaEventElapsedTime(ms, start->ev, stop->ev));
+        return FP_OK;
+    }
+
+    int fp_fill_uniform(fp_ctx *ctx, int dtype, void *dst, uint64_t n_complex, uint64_t first_complex, uint64_t seed)
+    {
+        if (!ctx || (!dst && n_complex))
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        FP_TRY(check_dtype(dtype));
+        if (n_complex == 0)
+            return FP_OK;
+        DeviceGuard g(ctx->device);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Staged s;
+        FP_TRY(stage_in(ctx, ctx->stage_out, dst, n_complex * csize(dtype), false, s));
+        uint64_t n_real = 2 * n_complex;
+        unsigned grid = static_cast<unsigned>(std::min<uint64_t>((n_real + 255) / 256, ctx->sm_count * 32ull));
+        if (dtype == FP_C128)
+            fill_uniform_kernel<double>
+                <<<grid, 256, 0, ctx->stream>>>(static_cast<double *>(s.dev), n_real, 2 * first_complex, seed);
+        else
+            fill_uniform_kernel<float>
+                <<<grid, 256, 0, ctx->stream>>>(static_cast<float *>(s.dev), n_real, 2 * first_complex, seed);
+        ctx->launches++;
+        FP_TRY(stage_back(ctx, s));
+        return finish(ctx, s.staged);
+    }
+
+    // ------------------------------------------------------------ PauliString
+    int fp_string_apply(fp_ctx *ctx, int dtype, int n_qubits, const uint8_t *codes, const void *coeff, void *out,
+                        const void *in, size_t dim, size_t n_states, int accumulate)
+    {
+        if (!ctx || (!codes && n_qubits > 0) || !coeff)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        FP_TRY(check_dtype(dtype));
+        if (n_qubits < 0 || n_qubits > 62)
+            return set_err(FP_INVALID_ARGUMENT, "n_qubits must be in [0, 62]");
+        StringMasks mk;
+        try
+        {
+            mk = make_masks(n_qubits, codes);
+        }
+        catch (std::invalid_argument const &e)
+        {
+            return set_err(FP_INVALID_ARGUMENT, e.what());
+        }
+        if (dim != dim_of(n_qubits)) // PS:275-278, PS:347-353
+            return set_err(FP_INVALID_ARGUMENT, "[PauliString] states shape (" + std::to_string(dim) +
+                                                    ") must match the dimension of the operators (" +
+                                                    std::to_string(dim_of(n_qubits)) + ")");
+        if (dim == 0 || n_states == 0)
+            return FP_OK;
+        DeviceGuard g(ctx->device);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        size_t const bytes = dim * n_states * csize(dtype);
+        Staged sin, sout;
+        FP_TRY(stage_in(ctx, ctx->stage_in, in, bytes, true, sin));
+        FP_TRY(stage_in(ctx, ctx->stage_out, out, bytes, accumulate != 0, sout));
+        int rc;
+        if (dtype == FP_C128)
+        {
+            DeviceOp<double> op;
+            auto c = *static_cast<std::complex<double> const *>(coeff);
+            op.host.gx = {mk.x};
+            op.host.gstart = {0, 1};
+            op.host.sz = {mk.z};
+            op.host.sc = {times_phase(c, mk.ny)};
+            rc = run_op_apply<double>(ctx, op, sout.dev, sin.dev, dim, n_states, accumulate);
+        }
+        else
+        {
+            DeviceOp<float> op;
+            auto c = *static_cast<std::complex<float> const *>(coeff);
+            op.host.gx = {mk.x};
+            op.host.gstart = {0, 1};
+            op.host.sz = {mk.z};
+            op.host.sc = {times_phase(c, mk.ny)};
+            rc = run_op_apply<float>(ctx, op, sout.dev, sin.dev, dim, n_states, accumulate);
+        }
+        FP_TRY(rc);
+        FP_TRY(stage_back(ctx, sout));
+        return finish(ctx, sin.staged || sout.staged);
+    }
+
+    int fp_string_expval(fp_ctx *ctx, int dtype, int n_qubits, const uint8_t *codes, const void *coeff, void *out,
+                         const void *in, size_t dim, size_t n_states, int accumulate)
+    {
+        if (!ctx || (!codes && n_qubits > 0) || !coeff)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        FP_TRY(check_dtype(dtype));
+        if (n_qubits < 0 || n_qubits > 62)
+            return set_err(FP_INVALID_ARGUMENT, "n_qubits must be in [0, 62]");
+        StringMasks mk;
+        try
+        {
+            mk = make_masks(n_qubits, codes);
+        }
+        catch (std::invalid_argument const &e)
+        {
+            return set_err(FP_INVALID_ARGUMENT, e.what());
+        }
+        if (dim != dim_of(n_qubits)) // PS:443-446
+            return set_err(FP_INVALID_ARGUMENT, "[PauliString] states shape (" + std::to_string(dim) +
+                                                    ") must match the dimension of the operators (" +
+                                                    std::to_string(dim_of(n_qubits)) + ")");
+        if (n_states == 0)
+            return FP_OK;
+        DeviceGuard g(ctx->device);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Staged sin, sout;
+        FP_TRY(stage_in(ctx, ctx->stage_in, in, dim * n_states * csize(dtype), true, sin));
+        FP_TRY(stage_in(ctx, ctx->stage_out, out, n_states * csize(dtype), accumulate != 0, sout));
+        int rc;
+        if (dtype == FP_C128)
+            rc = run_string_expval<double>(ctx, mk, *static_cast<std::complex<double> const *>(coeff), sout.dev, sin.dev,
+                                           dim, n_states, accumulate);
+        else
+            rc = run_string_expval<float>(ctx, mk, *static_cast<std::complex<float> const *>(coeff), sout.dev, sin.dev,
+                                          dim, n_states, accumulate);
+        FP_TRY(rc);
+        FP_TRY(stage_back(ctx, sout));
+        return finish(ctx, sin.staged || sout.staged);
+    }
+
+    // ------------------------------------------------------------ PauliOp
+    int fp_op_create(fp_ctx *ctx, int dtype, int n_qubits, size_t n_strings, const uint8_t *codes, const void *coeffs,
+                     fp_op **op)
+    {
+        if (!ctx || !op || (n_strings && n_qubits > 0 && !codes) || (n_strings && !coeffs))
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        FP_TRY(check_dtype(dtype));
+        DeviceGuard g(ctx->device);
+        if (dtype == FP_C128)
+            return op_create_t<double>(ctx, dtype, n_qubits, n_strings, codes,
+                                       static_cast<std::complex<double> const *>(coeffs), true, op);
+        return op_create_t<float>(ctx, dtype, n_qubits, n_strings, codes,
+                                  static_cast<std::complex<float> const *>(coeffs), true, op);
+    }
+
+    int fp_op_destroy(fp_op *op)
+    {
+        if (!op)
+            return FP_OK;
+        DeviceGuard g(op->device);
+        op->f.release();
+        op->d.release();
+        delete op;
+        return FP_OK;
+    }
+
+    int fp_op_info(const fp_op *op, int *dtype, int *n_qubits, size_t *n_strings, size_t *n_packed, size_t *n_groups)
+    {
+        if (!op)
+            return set_err(FP_INVALID_ARGUMENT, "null operator");
+        if (dtype)
+            *dtype = op->dtype;
+        if (n_qubits)
+            *n_qubits = op->n_qubits;
+        if (n_strings)
+            *n_strings = op->n_strings;
+        size_t S = op->dtype == FP_C128 ? op->d.host.sz.size() : op->f.host.sz.size();
+        size_t G = op->dtype == FP_C128 ? op->d.host.gx.size() : op->f.host.gx.size();
+        if (n_packed)
+            *n_packed = S;
+        if (n_groups)
+            *n_groups = G;
+        return FP_OK;
+    }
+
+    int fp_op_apply(fp_ctx *ctx, const fp_op *op, void *out, const void *in, size_t dim, size_t n_states, int accumulate)
+    {
+        FP_TRY(op_check(ctx, op));
+        uint64_t const opdim = op->n_strings ? dim_of(op->n_qubits) : 0; // PO:105-115
+        if (dim != opdim)                                              // PO:343-346
+            return set_err(FP_INVALID_ARGUMENT, "[PauliOp] state size must match the dimension of the operators");
+        if (dim == 0 || n_states == 0)
+            return FP_OK;
+        DeviceGuard g(ctx->device);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        size_t const bytes = dim * n_states * csize(op->dtype);
+        Staged sin, sout;
+        FP_TRY(stage_in(ctx, ctx->stage_in, in, bytes, true, sin));
+        FP_TRY(stage_in(ctx, ctx->stage_out, out, bytes, accumulate != 0, sout));
+        if (op->dtype == FP_C128)
+            FP_TRY(run_op_apply<double>(ctx, op->d, sout.dev, sin.dev, dim, n_states, accumulate));
+        else
+            FP_TRY(run_op_apply<float>(ctx, op->f, sout.dev, sin.dev, dim, n_states, accumulate));
+        FP_TRY(stage_back(ctx, sout));
+        return finish(ctx, sin.staged || sout.staged);
+    }
+
+    int fp_op_expval(fp_ctx *ctx, const fp_op *op, void *out, const void *in, size_t dim, size_t n_states,
+                     int accumulate)
+    {
+        FP_TRY(op_check(ctx, op));
+        uint64_t const opdim = op->n_strings ? dim_of(op->n_qubits) : 0;
+        if (dim != opdim) // PO:502-505
+            return set_err(FP_INVALID_ARGUMENT, "[PauliOp] state size must match the dimension of the operators");
+        if (n_states == 0)
+            return FP_OK;
+        DeviceGuard g(ctx->device);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Staged sin, sout;
+        FP_TRY(stage_in(ctx, ctx->stage_in, in, dim * n_states * csize(op->dtype), true, sin));
+        FP_TRY(stage_in(ctx, ctx->stage_out, out, n_states * csize(op->dtype), accumulate != 0, sout));
+        if (op->dtype == FP_C128)
+            FP_TRY(run_op_expval<double>(ctx, op->d, sout.dev, sin.dev, dim, n_states, accumulate));
+        else
+            FP_TRY(run_op_expval<float>(ctx, op->f, sout.dev, sin.dev, dim, n_states, accumulate));
+        FP_TRY(stage_back(ctx, sout));
+        return finish(ctx, sin.staged || sout.staged);
+    }
+
+} // extern "C"
+
+// ================================================================ SummedPauliOp
+namespace
+{
+template <typename T>
+int sop_create_t(fp_ctx *ctx, int dtype, int n, size_t S, uint8_t const *codes, size_t K,
+                 std::complex<T> const *coeffs, fp_sop **out)
+{
+    std::unique_ptr<fp_sop> sop(new fp_sop);
+    sop->dtype = dtype;
+    sop->device = ctx->device;
+    sop->n_qubits = n;
+    sop->n_strings = S;
+    sop->n_ops = K;
+    // (1) SummedPauliOp::apply: c_j = sum_k coeffs(j,k), summed in k order in T like SPO:312-317 / 341-345
+    std::vector<std::complex<T>> csum(S);
+    for (size_t j = 0; j < S; ++j)
+    {
+        std::complex<T> c(0, 0);
+        for (size_t k = 0; k < K; ++k)
+            c += coeffs[j * K + k];
+        csum[j] = c;
+    }
+    FP_TRY(op_create_t<T>(ctx, dtype, n, S, codes, csum.data(), true, &sop->summed));
+    // (2) unmerged packed strings with unit coefficients: masks + order for the W / E matrices
+    std::vector<std::complex<T>> ones(S, std::complex<T>(1, 0));
+    int rc = op_create_t<T>(ctx, dtype, n, S, codes, ones.data(), false, &sop->strings);
+    if (rc != FP_OK)
+    {
+        fp_op_destroy(sop->summed);
+        return rc;
+    }
+    PackedOp<T> const &pk = dop<T>(sop->strings).host;
+    // (3) planar coefficient matrices in packed order
+    std::vector<T> Aw(2 * S * K), Ae(2 * K * S);
+    for (size_t p = 0; p < S; ++p)
+    {
+        size_t j = pk.perm[p];
+        uint32_t ny = pk.sny[p];
+        bool diag = false;
+        // group lookup is not needed: x == 0 iff the string has no X/Y; recompute from the masks
+        {
+            StringMasks mk = make_masks(n, codes + j * static_cast<size_t>(n));
+            diag = mk.x == 0;
+        }
+        for (size_t k = 0; k < K; ++k)
+        {
+            std::complex<T> c = times_phase(coeffs[j * K + k], ny); // coeffs(j,k) * (-i)^nY
+            Aw[p * K + k] = c.real();
+            Aw[(S + p) * K + k] = c.imag();
+            // pair factor of the expectation kernel: 1 (x == 0), 2 (nY even), 2i (nY odd)
+            std::complex<T> e = diag ? c : ((ny & 1u) ? std::complex<T>(-2 * c.imag(), 2 * c.real()) : T(2) * c);
+            Ae[k * S + p] = e.real();
+            Ae[(K + k) * S + p] = e.imag();
+        }
+    }
+    T *dAw = nullptr, *dAe = nullptr;
+    rc = upload_vec(&dAw, Aw);
+    if (rc == FP_OK)
+        rc = upload_vec(&dAe, Ae);
+    if (rc != FP_OK)
+    {
+        cudaFree(dAw);
+        fp_op_destroy(sop->summed);
+        fp_op_destroy(sop->strings);
+        return rc;
+    }
+    sop->A_w = dAw;
+    sop->A_e = dAe;
+    *out = sop.release();
+    return FP_OK;
+}
+
+int sop_check(fp_ctx *ctx, fp_sop const *sop)
+{
+    if (!ctx || !sop)
+        return set_err(FP_INVALID_ARGUMENT, "null context or operator");
+    if (sop->device != ctx->device)
+        return set_err(FP_INVALID_ARGUMENT, "operator plan was created on a different device than the context");
+    return FP_OK;
+}
+
+template <typename T, typename DT>
+int run_sop_weighted(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, DT const *data, uint64_t dim, uint64_t B,
+                     int beta)
+{
+    uint32_t const S = static_cast<uint32_t>(sop->n_strings), K = static_cast<uint32_t>(sop->n_ops);
+    DeviceOp<T> const &op = dop<T>(sop->strings);
+    // W[2S x B] = A_w[2S x K] * data[K x B]                                   (SPO:413-432, the tensor-core step)
+    FP_TRY(ctx->work_a.ensure(2ull * S * B * sizeof(T)));
+    T *W = static_cast<T *>(ctx->work_a.p);
+    FP_TRY((run_gemm<T, DT>(ctx, static_cast<T const *>(sop->A_w), data, W, 2 * S, B, K, 1, K ? K : 1)));
+    FP_TRY(check_align(in, 2 * sizeof(T), "states"));
+    FP_TRY(check_align(out, 2 * sizeof(T), "new_states"));
+    int const epv = pick_epv<T>(in, out, B);
+    uint64_t const rowvecs = B / epv;
+    GeomSel gs = choose_geom(ctx, dim, dim, rowvecs, 2 * sizeof(T) * epv, op.host.gx.size() > 1, false);
+    FP_TRY(check_grid(gs.grid));
+    OpView<T> view = op.view();
+    T const *Wre = W, *Wim = W + static_cast<uint64_t>(S) * B;
+    dim3 grid(static_cast<unsigned>(gs.grid));
+    bool done = false;
+    if constexpr (sizeof(T) == 4)
+    {
+        if (epv == 2)
+        {
+            auto const *din = static_cast<CVec<T, 2> const *>(in);
+            auto *dout = static_cast<CVec<T, 2> *>(out);
+            if (gs.V == 4)
+                weighted_apply_kernel<T, 2, 4>
+                    <<<grid, kThreads, 0, ctx->stream>>>(view, gs.g, Wre, Wim, B, din, dout, beta);
+            else
+                weighted_apply_kernel<T, 2, 1>
+                    <<<grid, kThreads, 0, ctx->stream>>>(view, gs.g, Wre, Wim, B, din, dout, beta);
+            done = true;
+        }
+    }
+    if (!done)
+    {
+        auto const *din = static_cast<CVec<T, 1> const *>(in);
+        auto *dout = static_cast<CVec<T, 1> *>(out);
+        if (gs.V == 4)
+            weighted_apply_kernel<T, 1, 4><<<grid, kThreads, 0, ctx->stream>>>(view, gs.g, Wre, Wim, B, din, dout, beta);
+        else
+            weighted_apply_kernel<T, 1, 1><<<grid, kThreads, 0, ctx->stream>>>(view, gs.g, Wre, Wim, B, din, dout, beta);
+    }
+    ctx->launches++;
+    return FP_OK;
+}
+
+template <typename T>
+int run_sop_expval(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, uint64_t dim, uint64_t B, int beta)
+{
+    uint32_t const S = static_cast<uint32_t>(sop->n_strings), K = static_cast<uint32_t>(sop->n_ops);
+    DeviceOp<T> const &op = dop<T>(sop->strings);
+    FP_TRY(check_align(in, 2 * sizeof(T), "states"));
+    int const epv = pick_epv<T>(in, in, B);
+    uint64_t const rowvecs = B / epv;
+    uint64_t const rows = op.any_diag ? dim : dim / 2;
+    GeomSel gs = choose_geom(ctx, rows, dim, rowvecs, 2 * sizeof(T) * epv, false, true, op.n_chunks);
+    FP_TRY(check_grid(gs.grid));
+    uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
+    gs.g.Bpad = Bpad;
+    uint64_t const slot_stride = gs.g.nRowBlocks * Bpad;
+    // stage 1: E(s,t) per packed string                                      (SPO:573-577, paired kernel)
+    FP_TRY(ctx->work_a.ensure(static_cast<uint64_t>(S) * B * sizeof(T)));
+    T *E = static_cast<T *>(ctx->work_a.p);
+    T *part = E;
+    if (gs.g.nRowBlocks > 1 || Bpad != B)
+    {
+        FP_TRY(ctx->partials.ensure(static_cast<uint64_t>(S) * slot_stride * sizeof(T)));
+        part = static_cast<T *>(ctx->partials.p);
+    }
+    PairChunk none{};
+    bool done = false;
+    if constexpr (sizeof(T) == 4)
+    {
+        if (epv == 2)
+        {
+            launch_pairs_v<T, 2, kPairMS>(ctx, gs, op.chunks, op.sz, op.sodd, none, 0, 0, 0, dim, in, part, slot_stride);
+            done = true;
+        }
+    }
+    if (!done)
+        launch_pairs_v<T, 1, kPairMS>(ctx, gs, op.chunks, op.sz, op.sodd, none, 0, 0, 0, dim, in, part, slot_stride);
+    if (part != E)
+    {
+        dim3 fgrid(static_cast<unsigned>((B + 127) / 128), S);
+        if (S > 65535)
+            return set_err(FP_UNSUPPORTED, "too many strings for the expectation finaliser");
+        finalize_pairs_matrix_kernel<T>
+            <<<fgrid, 128, 0, ctx->stream>>>(part, slot_stride, gs.g.nRowBlocks, Bpad, B, E);
+        ctx->launches++;
+    }
+    // stage 2: out[2K x B] = A_e[2K x S] * E[S x B], split over S              (SPO:579-591)
+    uint32_t kchunk = 512;
+    uint32_t splitK = std::max<uint32_t>(1, (S + kchunk - 1) / kchunk);
+    FP_TRY(ctx->work_b.ensure(static_cast<uint64_t>(splitK) * 2 * K * B * sizeof(T)));
+    T *Cst = static_cast<T *>(ctx->work_b.p);
+    FP_TRY((run_gemm<T, T>(ctx, static_cast<T const *>(sop->A_e), E, Cst, 2 * K, B, S, splitK, kchunk)));
+    uint64_t total = static_cast<uint64_t>(K) * B;
+    finalize_sop_expval_kernel<T><<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctx->stream>>>(
+        Cst, splitK, K, B, static_cast<Cx<T> *>(out), beta);
+    ctx->launches++;
+    return FP_OK;
+}
+} // namespace
+
+extern "C"
+{
+
+    int fp_sop_create(fp_ctx *ctx, int dtype, int n_qubits, size_t n_strings, const uint8_t *codes, size_t n_operators,
+                      const void *coeffs, fp_sop **sop)
+    {
+        if (!ctx || !sop || !coeffs || (n_qubits > 0 && !codes))
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        FP_TRY(check_dtype(dtype));
+        if (n_strings == 0) // the reference dereferences pauli_strings.front() (SPO:50): undefined; reject instead
+            return set_err(FP_INVALID_ARGUMENT, "SummedPauliOp needs at least one PauliString");
+        if (n_strings > 0x7fffffffull || n_operators > 0x3fffffffull)
+            return set_err(FP_UNSUPPORTED, "operator too large");
+        DeviceGuard g(ctx->device);
+        if (dtype == FP_C128)
+            return sop_create_t<double>(ctx, dtype, n_qubits, n_strings, codes, n_operators,
+                                        static_cast<std::complex<double> const *>(coeffs), sop);
+        return sop_create_t<float>(ctx, dtype, n_qubits, n_strings, codes, n_operators,
+                                   static_cast<std::complex<float> const *>(coeffs), sop);
+    }
+
+    int fp_sop_destroy(fp_sop *sop)
+    {
+        if (!sop)
+            return FP_OK;
+        DeviceGuard g(sop->device);
+        fp_op_destroy(sop->summed);
+        fp_op_destroy(sop->strings);
+        cudaFree(sop->A_w);
+        cudaFree(sop->A_e);
+        delete sop;
+        return FP_OK;
+    }
+
+    int fp_sop_apply(fp_ctx *ctx, const fp_sop *sop, void *out, const void *in, size_t dim, size_t n_states,
+                     int accumulate)
+    {
+        FP_TRY(sop_check(ctx, sop));
+        if (dim != dim_of(sop->n_qubits))
+            return set_err(FP_INVALID_ARGUMENT, "state size must match the dimension of the operators");
+        return fp_op_apply(ctx, sop->summed, out, in, dim, n_states, accumulate);
+    }
+
+    int fp_sop_apply_weighted(fp_ctx *ctx, const fp_sop *sop, void *out, const void *in, const void *data,
+                              int data_is_f64, size_t dim, size_t n_states, int accumulate)
+    {
+        FP_TRY(sop_check(ctx, sop));
+        if (dim != dim_of(sop->n_qubits)) // SPO:396-399
+            return set_err(FP_INVALID_ARGUMENT, "state size must match the dimension of the operators");
+        if (dim == 0 || n_states == 0)
+            return FP_OK;
+        if (!data && sop->n_ops)
+            return set_err(FP_INVALID_ARGUMENT, "null data pointer");
+        DeviceGuard g(ctx->device);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        size_t const bytes = dim * n_states * csize(sop->dtype);
+        Staged sin, sout, sdat;
+        FP_TRY(stage_in(ctx, ctx->stage_in, in, bytes, true, sin));
+        FP_TRY(stage_in(ctx, ctx->stage_out, out, bytes, accumulate != 0, sout));
+        FP_TRY(stage_in(ctx, ctx->stage_data, data, sop->n_ops * n_states * (data_is_f64 ? 8 : 4), true, sdat));
+        int rc;
+        if (sop->dtype == FP_C128)
+            rc = data_is_f64 ? run_sop_weighted<double, double>(ctx, sop, sout.dev, sin.dev,
+                                                                static_cast<double const *>(sdat.dev), dim, n_states,
+                                                                accumulate)
+                             : run_sop_weighted<double, float>(ctx, sop, sout.dev, sin.dev,
+                                                               static_cast<float const *>(sdat.dev), dim, n_states,
+                                                               accumulate);
+        else
+            rc = data_is_f64 ? run_sop_weighted<float, double>(ctx, sop, sout.dev, sin.dev,
+                                                               static_cast<double const *>(sdat.dev), dim, n_states,
+                                                               accumulate)
+                             : run_sop_weighted<float, float>(ctx, sop, sout.dev, sin.dev,
+                                                              static_cast<float const *>(sdat.dev), dim, n_states,
+                                                              accumulate);
+        FP_TRY(rc);
+        FP_TRY(stage_back(ctx, sout));
+        return finish(ctx, sin.staged || sout.staged || sdat.staged);
+    }
+
+    int fp_sop_expval(fp_ctx *ctx, const fp_sop *sop, void *out, const void *in, size_t dim, size_t n_states,
+                      int accumulate)
+    {
+        FP_TRY(sop_check(ctx, sop));
+        if (dim != dim_of(sop->n_qubits)) // SPO:546-551
+            return set_err(FP_INVALID_ARGUMENT, "states must have the same dimension (" + std::to_string(dim) +
+                                                    ") as the SummedPauliOp (" +
+                                                    std::to_string(dim_of(sop->n_qubits)) + ")");
+        if (n_states == 0 || sop->n_ops == 0)
+            return FP_OK;
+        DeviceGuard g(ctx->device);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Staged sin, sout;
+        FP_TRY(stage_in(ctx, ctx->stage_in, in, dim * n_states * csize(sop->dtype), true, sin));
+        FP_TRY(stage_in(ctx, ctx->stage_out, out, sop->n_ops * n_states * csize(sop->dtype), accumulate != 0, sout));
+        if (sop->dtype == FP_C128)
+            FP_TRY(run_sop_expval<double>(ctx, sop, sout.dev, sin.dev, dim, n_states, accumulate));
+        else
+            FP_TRY(run_sop_expval<float>(ctx, sop, sout.dev, sin.dev, dim, n_states, accumulate));
+        FP_TRY(stage_back(ctx, sout));
+        return finish(ctx, sin.staged || sout.staged);
+    }
+
+    // ------------------------------------------------------------ one-shot entry points (oracle-shaped)
+    int fp_default_ctx(fp_ctx **out)
+    {
+        static std::mutex mu;
+        static fp_ctx *ctx = nullptr;
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ctx)
+        {
+            int dev = 0;
+            if (char const *env = getenv("FASTPAULI_DEVICE"))
+                dev = atoi(env);
+            FP_TRY(fp_ctx_create(dev, &ctx));
+        }
+        *out = ctx;
+        return FP_OK;
+    }
+
+#define FP_DEFINE_ONESHOT(SFX, T, DT)                                                                                  \
+    int fp_string_apply1d_##SFX(int n, const uint8_t *codes, const T *c, T *out, const T *in, size_t dim, int)         \
+    {                                                                                                                  \
+        fp_ctx *ctx;                                                                                                   \
+        FP_TRY(fp_default_ctx(&ctx));                                                                                  \
+        return fp_string_apply(ctx, DT, n, codes, c, out, in, dim, 1, 1);                                              \
+    }                                                                                                                  \
+    int fp_string_apply_##SFX(int n, const uint8_t *codes, const T *c, T *out, const T *in, size_t dim, size_t B, int) \
+    {                                                                                                                  \
+        fp_ctx *ctx;                                                                                                   \
+        FP_TRY(fp_default_ctx(&ctx));                                                                                  \
+        return fp_string_apply(ctx, DT, n, codes, c, out, in, dim, B, 1);                                              \
+    }                                                                                                                  \
+    int fp_string_expval_##SFX(int n, const uint8_t *codes, const T *c, T *out, const T *in, size_t dim, size_t B,     \
+                               int)                                                                                    \
+    {                                                                                                                  \
+        fp_ctx *ctx;                                                                                                   \
+        FP_TRY(fp_default_ctx(&ctx));                                                                                  \
+        return fp_string_expval(ctx, DT, n, codes, c, out, in, dim, B, 1);                                             \
+    }                                                                                                                  \
+    int fp_op_apply_##SFX(int n, size_t S, const uint8_t *codes, const T *coeffs, T *out, const T *in, size_t dim,     \
+                          size_t B, int)                                                                               \
+    {                                                                                                                  \
+        fp_ctx *ctx;                                                                                                   \
+        FP_TRY(fp_default_ctx(&ctx));                                                                                  \
+        fp_op *op = nullptr;                                                                                           \
+        FP_TRY(fp_op_create(ctx, DT, n, S, codes, coeffs, &op));                                                       \
+        int rc = fp_op_apply(ctx, op, out, in, dim, B, 1);                                                             \
+        fp_op_destroy(op);                                                                                             \
+        return rc;                                                                                                     \
+    }                                                                                                                  \
+    int fp_op_apply1d_##SFX(int n, size_t S, const uint8_t *codes, const T *coeffs, T *out, const T *in, size_t dim,   \
+                            int par)                                                                                   \
+    {                                                                                                                  \
+        return fp_op_apply_##SFX(n, S, codes, coeffs, out, in, dim, 1, par);                                           \
+    }                                                                                                                  \
+    int fp_op_expval_##SFX(int n, size_t S, const uint8_t *codes, const T *coeffs, T *out, const T *in, size_t dim,    \
+                           size_t B, int)                                                                              \
+    {                                                                                                                  \
+        fp_ctx *ctx;                                                                                                   \
+        FP_TRY(fp_default_ctx(&ctx));                                                                                  \
+        fp_op *op = nullptr;                                                                                           \
+        FP_TRY(fp_op_create(ctx, DT, n, S, codes, coeffs, &op));                                                       \
+        int rc = fp_op_expval(ctx, op, out, in, dim, B, 1);                                                            \
+        fp_op_destroy(op);                                                                                             \
+        return rc;                                                                                                     \
+    }                                                                                                                  \
+    int fp_sop_apply_##SFX(int n, size_t S, const uint8_t *codes, size_t K, const T *coeffs, T *out, const T *in,      \
+                           size_t dim, size_t B, int)                                                                  \
+    {                                                                                                                  \
+        fp_ctx *ctx;                                                                                                   \
+        FP_TRY(fp_default_ctx(&ctx));                                                                                  \
+        fp_sop *sop = nullptr;                                                                                         \
+        FP_TRY(fp_sop_create(ctx, DT, n, S, codes, K, coeffs, &sop));                                                  \
+        int rc = fp_sop_apply(ctx, sop, out, in, dim, B, 1);                                                           \
+        fp_sop_destroy(sop);                                                                                           \
+        return rc;                                                                                                     \
+    }                                                                                                                  \
+    int fp_sop_apply_weighted_##SFX(int n, size_t S, const uint8_t *codes, size_t K, const T *coeffs, T *out,          \
+                                    const T *in, const void *data, int data_is_f64, size_t dim, size_t B, int)         \
+    {                                                                                                                  \
+        fp_ctx *ctx;                                                                                                   \
+        FP_TRY(fp_default_ctx(&ctx));                                                                                  \
+        fp_sop *sop = nullptr;                                                                                         \
+        FP_TRY(fp_sop_create(ctx, DT, n, S, codes, K, coeffs, &sop));                                                  \
+        int rc = fp_sop_apply_weighted(ctx, sop, out, in, data, data_is_f64, dim, B, 1);                               \
+        fp_sop_destroy(sop);                                                                                           \
+        return rc;                                                                                                     \
+    }                                                                                                                  \
+    int fp_sop_expval_##SFX(int n, size_t S, const uint8_t *codes, size_t K, const T *coeffs, T *out, const T *in,     \
+                            size_t dim, size_t B, int)                                                                 \
+    {                                                                                                                  \
+        fp_ctx *ctx;                                                                                                   \
+        FP_TRY(fp_default_ctx(&ctx));                                                                                  \
+        fp_sop *sop = nullptr;                                                                                         \
+        FP_TRY(fp_sop_create(ctx, DT, n, S, codes, K, coeffs, &sop));                                                  \
+        int rc = fp_sop_expval(ctx, sop, out, in, dim, B, 1);                                                          \
+        fp_sop_destroy(sop);                                                                                           \
+        return rc;                                                                                                     \
+    }
+
+    FP_DEFINE_ONESHOT(c128, double, FP_C128)
+    FP_DEFINE_ONESHOT(c64, float, FP_C64)
+
+} // extern "C"

@@ -1,0 +1,176 @@
+/*
+ * fastpauli_b200 -- C ABI of the B200-native fast-pauli hot path.
+ *
+ * This is the drop-in boundary: the reference (qognitive/fast-pauli) has no
+ * FFI of its own -- its hot path is nine C++ template methods -- so each entry
+ * point below names the reference method whose body it replaces
+ * (paths relative to fast_pauli/cpp/include/ in the reference tree):
+ *
+ *   PS  = __pauli_string.hpp   PO = __pauli_op.hpp   SPO = __summed_pauli_op.hpp
+ *
+ * Conventions (identical to the reference's mdspan arguments):
+ *   - state batches are row-major (dim, n_states) with the batch axis
+ *     contiguous ("transposed" layout, PS:361-363), interleaved (re, im);
+ *     dtype FP_C128 = std::complex<double>, FP_C64 = std::complex<float>;
+ *   - Pauli strings travel as uint8 codes, n_strings x n_qubits, 0:I 1:X 2:Y
+ *     3:Z; codes[s*n + 0] is the left-most character = most significant qubit
+ *     (PS:52-54);
+ *   - every data pointer may be a HOST pointer (pageable or pinned: staged
+ *     through device scratch inside the call) or a DEVICE pointer on the
+ *     context's GPU (used in place); the library never keeps caller pointers;
+ *   - `accumulate` != 0 reproduces the C++ methods' `+=` into the caller's
+ *     buffer (PS:419,432,523,534); 0 overwrites (what the reference's Python
+ *     bindings observe, because they hand in zeroed outputs, NB:149-172);
+ *   - calls are synchronous: they return after the work on the context's
+ *     stream has completed, unless fp_ctx_set_async(ctx, 1) was called, in
+ *     which case calls whose pointers are all device pointers only enqueue;
+ *   - return value: FP_OK or an fp_status code; fp_last_error() holds the
+ *     message (thread-local).  FP_INVALID_ARGUMENT is raised exactly where
+ *     the reference throws std::invalid_argument.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with FP_NO_DEVICE.
+ */
+#ifndef FASTPAULI_B200_H
+#define FASTPAULI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+    typedef enum fp_status
+    {
+        FP_OK = 0,
+        FP_INVALID_ARGUMENT = 1, /* the reference would throw std::invalid_argument */
+        FP_CUDA_ERROR = 2,       /* a CUDA runtime call failed */
+        FP_NO_DEVICE = 3,        /* no usable CUDA device */
+        FP_OUT_OF_MEMORY = 4,
+        FP_UNSUPPORTED = 5
+    } fp_status;
+
+    typedef enum fp_dtype
+    {
+        FP_C64 = 0, /* std::complex<float>  */
+        FP_C128 = 1 /* std::complex<double> */
+    } fp_dtype;
+
+    typedef struct fp_ctx fp_ctx;     /* one GPU + stream + scratch */
+    typedef struct fp_op fp_op;       /* device-resident packed PauliOp (strings grouped by x-mask) */
+    typedef struct fp_sop fp_sop;     /* device-resident packed SummedPauliOp */
+    typedef struct fp_event fp_event; /* CUDA event for timing on the context's stream */
+
+    /* ---- library / context ------------------------------------------------------------------ */
+    const char *fp_last_error(void);
+    int fp_version(void);
+    int fp_device_count(int *count);
+    int fp_ctx_create(int device, fp_ctx **ctx);
+    int fp_ctx_destroy(fp_ctx *ctx);
+    int fp_ctx_device(const fp_ctx *ctx, int *device);
+    /* Run on a caller-owned cudaStream_t (e.g. PyTorch's current stream); NULL restores the context's own stream. */
+    int fp_ctx_set_stream(fp_ctx *ctx, void *cuda_stream);
+    int fp_ctx_set_async(fp_ctx *ctx, int async);
+    int fp_ctx_sync(fp_ctx *ctx);
+    /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+    int fp_ctx_launch_count(const fp_ctx *ctx, uint64_t *count);
+    /* Override the L2 working-set budget (bytes) used to pick the batch-tile width of multi-group kernels. */
+    int fp_ctx_set_l2_budget(fp_ctx *ctx, size_t bytes);
+
+    /* ---- memory / timing helpers (thin wrappers so hosts need not link libcudart) ------------- */
+    int fp_device_malloc(fp_ctx *ctx, size_t bytes, void **ptr);
+    int fp_device_free(fp_ctx *ctx, void *ptr);
+    int fp_host_malloc(fp_ctx *ctx, size_t bytes, void **ptr); /* pinned */
+    int fp_host_free(fp_ctx *ctx, void *ptr);
+    int fp_memcpy(fp_ctx *ctx, void *dst, const void *src, size_t bytes);       /* any direction, synchronous */
+    int fp_memcpy_async(fp_ctx *ctx, void *dst, const void *src, size_t bytes); /* enqueued on the ctx stream */
+    int fp_memset(fp_ctx *ctx, void *dst, int value, size_t bytes);
+    int fp_device_mem_info(fp_ctx *ctx, size_t *free_bytes, size_t *total_bytes);
+    int fp_event_create(fp_event **ev);
+    int fp_event_destroy(fp_event *ev);
+    int fp_event_record(fp_ctx *ctx, fp_event *ev);
+    int fp_event_elapsed_ms(fp_event *start, fp_event *stop, float *ms); /* synchronises on `stop` */
+    /* Fill a device or host buffer with the bench's counter-based U[0,1) amplitudes:
+     * element e (a real scalar; 2 per complex) = splitmix64(seed, first_elem + e) -> [0,1).  On-device generation. */
+    int fp_fill_uniform(fp_ctx *ctx, int dtype, void *dst, uint64_t n_complex, uint64_t first_complex, uint64_t seed);
+
+    /* ---- PauliString (one-shot: the string is three words, no plan needed) -------------------- */
+    /* PauliString::apply, 1-D (PS:296-341) when n_states == 1 and PauliString::apply_batch (PS:377-436):
+     *   out(i,t) (+)= coeff * m[i] * in(i ^ x, t).  Errors: PS:271-283, PS:343-359. */
+    int fp_string_apply(fp_ctx *ctx, int dtype, int n_qubits, const uint8_t *codes, const void *coeff /* 1 complex */,
+                        void *out, const void *in, size_t dim, size_t n_states, int accumulate);
+    /* PauliString::expectation_value (PS:470-538): out[t] (+)= sum_i conj(in(i,t)) coeff m[i] in(i^x,t).
+     * Errors: PS:438-450. */
+    int fp_string_expval(fp_ctx *ctx, int dtype, int n_qubits, const uint8_t *codes, const void *coeff,
+                         void *out /* n_states complex */, const void *in, size_t dim, size_t n_states,
+                         int accumulate);
+
+    /* ---- PauliOp (PO:38-97): sum_s h_s P_s ----------------------------------------------------- */
+    /* Pack (x,z,phase) per string, merge duplicates, group by x-mask, upload.  coeffs: n_strings complex of `dtype`.
+     * Errors: unequal string sizes cannot occur in this encoding; codes > 3 -> P:58-59. */
+    int fp_op_create(fp_ctx *ctx, int dtype, int n_qubits, size_t n_strings, const uint8_t *codes,
+                     const void *coeffs, fp_op **op);
+    int fp_op_destroy(fp_op *op);
+    int fp_op_info(const fp_op *op, int *dtype, int *n_qubits, size_t *n_strings, size_t *n_packed_strings,
+                   size_t *n_groups);
+    /* PauliOp::apply 1-D (PO:362-383, n_states == 1) and 2-D (PO:399-468). Errors: PO:340-351. */
+    int fp_op_apply(fp_ctx *ctx, const fp_op *op, void *out, const void *in, size_t dim, size_t n_states,
+                    int accumulate);
+    /* PauliOp::expectation_value (PO:482-549). Errors: PO:502-505. */
+    int fp_op_expval(fp_ctx *ctx, const fp_op *op, void *out /* n_states complex */, const void *in, size_t dim,
+                     size_t n_states, int accumulate);
+
+    /* ---- SummedPauliOp (SPO:37-145): K operators over one string set, coeffs (n_strings, n_operators) ---- */
+    int fp_sop_create(fp_ctx *ctx, int dtype, int n_qubits, size_t n_strings, const uint8_t *codes,
+                      size_t n_operators, const void *coeffs /* row-major (n_strings, n_operators) complex */,
+                      fp_sop **sop);
+    int fp_sop_destroy(fp_sop *sop);
+    /* SummedPauliOp::apply (SPO:277-349). Errors: SPO:290-293 (+ the dim check the reference omits). */
+    int fp_sop_apply(fp_ctx *ctx, const fp_sop *sop, void *out, const void *in, size_t dim, size_t n_states,
+                     int accumulate);
+    /* SummedPauliOp::apply_weighted (SPO:364-503): data is real (n_operators, n_states), float or double
+     * independently of the state dtype.  Errors: SPO:384-399. */
+    int fp_sop_apply_weighted(fp_ctx *ctx, const fp_sop *sop, void *out, const void *in, const void *data,
+                              int data_is_f64, size_t dim, size_t n_states, int accumulate);
+    /* SummedPauliOp::expectation_value (SPO:520-614): out is (n_operators, n_states) complex. Errors: SPO:539-558. */
+    int fp_sop_expval(fp_ctx *ctx, const fp_sop *sop, void *out, const void *in, size_t dim, size_t n_states,
+                      int accumulate);
+    /* Select the coefficient-contraction engine of apply_weighted / expectation_value for FP_C64 plans:
+     * 0 = FP32 SIMT, 1 = tcgen05 3xTF32 tensor-core path (default when available). */
+    int fp_ctx_set_tensor_core(fp_ctx *ctx, int enable);
+
+    /* ---- one-shot entry points with the oracle's raw signature ---------------------------------
+     * Same argument lists as orc_* (oracle/pauli_oracle.c) and ref_* (oracle/ref_wrapper.cpp) so one
+     * harness drives the reference, the port and the GPU.  They run on a process-wide default context
+     * (device from FASTPAULI_DEVICE, default 0), ACCUMULATE into `out` like the C++ methods, and accept
+     * `par` only for signature compatibility: both execution policies route to the GPU. */
+#define FP_DECLARE_ONESHOT(SFX, T)                                                                                     \
+    int fp_string_apply1d_##SFX(int n, const uint8_t *codes, const T *c, T *out, const T *in, size_t dim, int par);    \
+    int fp_string_apply_##SFX(int n, const uint8_t *codes, const T *c, T *out, const T *in, size_t dim, size_t B,      \
+                              int par);                                                                                \
+    int fp_string_expval_##SFX(int n, const uint8_t *codes, const T *c, T *out, const T *in, size_t dim, size_t B,     \
+                               int par);                                                                               \
+    int fp_op_apply1d_##SFX(int n, size_t S, const uint8_t *codes, const T *coeffs, T *out, const T *in, size_t dim,   \
+                            int par);                                                                                  \
+    int fp_op_apply_##SFX(int n, size_t S, const uint8_t *codes, const T *coeffs, T *out, const T *in, size_t dim,     \
+                          size_t B, int par);                                                                          \
+    int fp_op_expval_##SFX(int n, size_t S, const uint8_t *codes, const T *coeffs, T *out, const T *in, size_t dim,    \
+                           size_t B, int par);                                                                         \
+    int fp_sop_apply_##SFX(int n, size_t S, const uint8_t *codes, size_t K, const T *coeffs, T *out, const T *in,      \
+                           size_t dim, size_t B, int par);                                                             \
+    int fp_sop_apply_weighted_##SFX(int n, size_t S, const uint8_t *codes, size_t K, const T *coeffs, T *out,          \
+                                    const T *in, const void *data, int data_is_f64, size_t dim, size_t B, int par);    \
+    int fp_sop_expval_##SFX(int n, size_t S, const uint8_t *codes, size_t K, const T *coeffs, T *out, const T *in,     \
+                            size_t dim, size_t B, int par);
+    FP_DECLARE_ONESHOT(c128, double)
+    FP_DECLARE_ONESHOT(c64, float)
+#undef FP_DECLARE_ONESHOT
+    /* The default context used by the one-shot entry points (created on first use). */
+    int fp_default_ctx(fp_ctx **ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTPAULI_B200_H */

@@ -1,0 +1,93 @@
+"""CPU tests (no GPU): the C-ABI library builds, loads and exports every symbol include/*.h declares,
+and the product path fails loudly -- not silently on a CPU fallback -- when no CUDA device is present."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+LIB = os.path.join(ROOT, "fast-pauli_b200", "lib", "libfastpauli_b200.so")
+HDR = os.path.join(ROOT, "include", "fastpauli_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(LIB):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "fast-pauli_b200")], check=True, capture_output=True)
+    return C.CDLL(LIB)
+
+
+def declared_symbols() -> list[str]:
+    text = open(HDR).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = set(re.findall(r"\b(fp_[a-z0-9_]+)\s*\(", text))
+    # one-shot entry points are stamped out by a macro for both dtypes
+    macro = re.search(r"#define FP_DECLARE_ONESHOT\(SFX, T\)(.*?)FP_DECLARE_ONESHOT\(c128", text, flags=re.S).group(1)
+    for stem in re.findall(r"\b(fp_[a-z0-9_]+_)##SFX", macro):
+        names.add(stem + "c128")
+        names.add(stem + "c64")
+    return sorted(n for n in names if not n.endswith("_"))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 50
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, f"declared in include/fastpauli_b200.h but not exported: {missing}"
+
+
+def test_sass_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_gpu_fails_loudly(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the failure path is for GPU-less hosts")
+    lib.fp_last_error.restype = C.c_char_p
+    ctx = C.c_void_p()
+    rc = lib.fp_ctx_create(C.c_int(0), C.byref(ctx))
+    assert rc == 3, "FP_NO_DEVICE expected without a GPU"  # never a silent CPU path
+    assert b"cuda" in lib.fp_last_error().lower() or b"device" in lib.fp_last_error().lower()
+    # the one-shot entry points fail the same way
+    import numpy as np
+
+    psi = np.zeros(2, dtype=np.complex128)
+    out = np.zeros(2, dtype=np.complex128)
+    codes = np.array([1], dtype=np.uint8)
+    c = np.array([1.0, 0.0])
+    rc = lib.fp_string_apply1d_c128(C.c_int(1), codes.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p),
+                                    out.ctypes.data_as(C.c_void_p), psi.ctypes.data_as(C.c_void_p), C.c_size_t(2),
+                                    C.c_int(0))
+    assert rc == 3
+
+
+def test_python_binding_imports_and_validates_without_gpu():
+    from __graft_entry__ import load_package
+
+    fp = load_package()
+    ps = fp.PauliString("IXYZ")
+    assert (ps.n_qubits, ps.dim, ps.weight) == (4, 16, 3)
+    op = fp.PauliOp([1, 2j], ["XX", "ZI"])
+    assert (op.dim, op.n_qubits, op.n_pauli_strings) == (4, 2, 2)
+    with pytest.raises(ValueError):
+        fp.PauliString("XQZ")  # PS:194
+    with pytest.raises(ValueError):
+        fp.PauliOp([1.0], ["XX", "YY"])  # PO:92-95
+    with pytest.raises(ValueError):
+        fp.PauliOp([1.0, 1.0], ["XX", "YYY"])  # PO:578-591
+    import numpy as np
+
+    with pytest.raises(ValueError):
+        fp.SummedPauliOp(["XX", "YY"], np.ones((3, 2)))  # SPO:60-64
+    sop = fp.SummedPauliOp(["XX", "YY"], np.ones((2, 3)))
+    assert (sop.n_operators, sop.n_pauli_strings, sop.dim) == (3, 2, 4)
+    assert sop.coeffs.shape == (3, 2)  # transposed getter, B_SPO:113-135

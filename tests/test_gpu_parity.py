@@ -1,0 +1,376 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path through the C ABI vs the CPU oracle.
+
+Tolerances are the north star's: 1e-12 relative for complex128, 1e-5 for complex64 (max |gpu - cpu| / |cpu|_inf).
+The oracle is the unmodified reference (oracle/_ref) when its prebuilt library travelled with the repo,
+else the plain-C port.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, TOL, rand_states, rand_strings, rel_err
+from __graft_entry__ import load_package
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+fp = load_package()
+ORC = orc.best()
+DTYPES = [np.complex128, np.complex64]
+
+
+def tol(dtype) -> float:
+    return TOL[np.dtype(dtype)]
+
+
+# ------------------------------------------------------------------ golden vectors from the reference's numpy code
+def test_golden_pauli_string():
+    g = np.load(os.path.join(GOLDEN, "pauli_string.npz"))
+    for idx, s in enumerate(g["strings"]):
+        ps = fp.PauliString(str(s))
+        psi = g[f"{idx}_states"]
+        c = complex(g[f"{idx}_coeff"])
+        assert rel_err(ps.apply(psi, c), g[f"{idx}_apply2d"]) < 1e-14
+        assert rel_err(ps.apply(psi[:, 0].copy()), g[f"{idx}_apply1d"]) < 1e-14
+        assert rel_err(ps.expectation_value(psi), g[f"{idx}_expval"]) < 1e-13
+
+
+def test_golden_pauli_op():
+    g = np.load(os.path.join(GOLDEN, "pauli_op.npz"))
+    for idx in range(int(g["n_cases"])):
+        strings = [str(s) for s in g[f"{idx}_strings"]]
+        op = fp.PauliOp(g[f"{idx}_coeffs"], strings)
+        psi = g[f"{idx}_states"]
+        assert rel_err(op.apply(psi), g[f"{idx}_apply2d"]) < 1e-13
+        assert rel_err(op.apply(psi[:, 0].copy()), g[f"{idx}_apply1d"]) < 1e-13
+        assert rel_err(op.expectation_value(psi), g[f"{idx}_expval"]) < 1e-13
+
+
+def test_golden_summed_pauli_op():
+    g = np.load(os.path.join(GOLDEN, "summed_pauli_op.npz"))
+    for idx in range(int(g["n_cases"])):
+        strings = [str(s) for s in g[f"{idx}_strings"]]
+        sop = fp.SummedPauliOp(strings, g[f"{idx}_coeffs"])
+        psi, data = g[f"{idx}_states"], g[f"{idx}_data"]
+        assert rel_err(sop.apply(psi), g[f"{idx}_apply"]) < 1e-13
+        assert rel_err(sop.apply_weighted(psi, data), g[f"{idx}_apply_weighted"]) < 1e-13
+        assert rel_err(sop.expectation_value(psi), g[f"{idx}_expval"]) < 1e-13
+
+
+# ------------------------------------------------------------------ known-answer tests of the reference
+def test_kats():
+    ones = np.ones(16, dtype=np.complex128)
+    np.testing.assert_array_equal(fp.PauliString("IIII").apply(ones), ones)  # T_PS:217-229
+    st = np.zeros(8, dtype=np.complex128)
+    st[6] = st[7] = 1
+    exp = np.zeros(8, dtype=np.complex128)
+    exp[4] = exp[5] = 1
+    np.testing.assert_array_equal(fp.PauliString("IXI").apply(st), exp)  # T_PS:231-247
+    # PY_PS:184-200 (inputs of other dtypes are converted like nanobind does)
+    np.testing.assert_array_equal(fp.PauliString("III").apply(np.arange(8)), np.arange(8))
+    k, m = orc.np_sparse("ZYX")
+    dense = np.zeros((8, 8), dtype=np.complex128)
+    dense[np.arange(8), k] = m
+    np.testing.assert_allclose(fp.PauliString("ZYX").apply(np.ones(8)), dense.sum(axis=1))
+    np.testing.assert_allclose(fp.PauliString("ZYX").apply(np.eye(8)), dense)
+    assert fp.PauliString("III").expectation_value(np.arange(8))[0] == pytest.approx(140.0)  # PY_PS:285-295
+    assert fp.PauliOp([1, 1], ["III", "III"]).expectation_value(np.arange(8))[0] == pytest.approx(280.0)
+    np.testing.assert_allclose(fp.PauliOp([0.5, 0.5], ["III", "III"]).apply(np.arange(8)), np.arange(8))
+    rng = np.random.default_rng(18)
+    psi = rand_states(rng, 16, 10)
+    np.testing.assert_allclose(fp.PauliOp([1 / 16] * 16, ["IIII"] * 16).apply(psi), psi, atol=1e-15)  # T_PO:228-267
+
+
+# ------------------------------------------------------------------ randomised parity, all nine entry points
+SHAPES = [
+    # (n_qubits, n_strings, n_states, n_operators)
+    (1, 3, 1, 2),
+    (2, 16, 3, 3),
+    (4, 20, 5, 3),     # odd batch: complex64 takes the 8-byte vector path
+    (6, 40, 10, 4),
+    (7, 37, 33, 2),    # non power-of-two batch
+    (10, 64, 16, 5),   # BASELINE config 1 shape
+    (12, 30, 100, 3),
+    (13, 8, 2, 2),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,S,B,K", SHAPES)
+def test_all_entry_points_vs_oracle(dtype, n, S, B, K):
+    rng = np.random.default_rng(1000 * n + S)
+    strings = rand_strings(rng, n, S)
+    strings[-1] = strings[0]  # duplicate string: exercises the merge in the packer
+    if n >= 4:
+        strings[1] = "Z" * n  # diagonal group
+        strings[2] = "I" * n
+    psi = rand_states(rng, 2**n, B, dtype)
+    h = (rand_states(rng, S, None, dtype) * 2 - (1 + 1j)).astype(dtype)
+    hk = (rand_states(rng, S, K, dtype) * 2 - (1 + 1j)).astype(dtype)
+    data = rng.random((K, B)).astype(np.float64 if dtype == np.complex128 else np.float32)
+    c = 0.3 - 1.7j
+    t = tol(dtype)
+    for s0 in (strings[0], strings[1], strings[2]):
+        ps = fp.PauliString(s0)
+        assert rel_err(ps.apply(psi, c), ORC.string_apply(s0, psi, c)) < t
+        assert rel_err(ps.apply(psi[:, 0].copy()), ORC.string_apply(s0, psi[:, 0].copy())) < t
+        assert rel_err(ps.expectation_value(psi, c), ORC.string_expval(s0, psi, c)) < t
+    op = fp.PauliOp(h, strings)
+    assert rel_err(op.apply(psi), ORC.op_apply(strings, h, psi)) < t
+    assert rel_err(op.apply(psi[:, 0].copy()), ORC.op_apply(strings, h, psi[:, 0].copy())) < t
+    assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi)) < t
+    assert rel_err(op.expectation_value(psi[:, 0].copy()), ORC.op_expval(strings, h, psi[:, :1].copy())) < t
+    sop = fp.SummedPauliOp(strings, hk)
+    assert rel_err(sop.apply(psi), ORC.sop_apply(strings, hk, psi)) < t
+    assert rel_err(sop.apply_weighted(psi, data), ORC.sop_apply_weighted(strings, hk, psi, data)) < t
+    assert rel_err(sop.expectation_value(psi), ORC.sop_expval(strings, hk, psi)) < t
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_summed_pauli_op_reference_test_shapes(dtype):
+    # PY_SPO:50-180: all weight<=2 strings on 1/2/6 qubits x {1,10,100} ops x {1,10,1000} states (subset)
+    import itertools as it
+
+    rng = np.random.default_rng(7)
+    for n, K, B in [(1, 1, 1), (2, 10, 10), (6, 100, 10), (6, 10, 1000)]:
+        strings = ["I" * n]
+        for w in (1, 2):
+            if w > n:
+                break
+            for let in it.product("XYZ", repeat=w):
+                for combo in it.combinations(range(n), w):
+                    s = ["I"] * n
+                    for p, ch in zip(combo, let):
+                        s[p] = ch
+                    strings.append("".join(s))
+        S = len(strings)
+        hk = rand_states(rng, S, K, dtype)
+        psi = rand_states(rng, 2**n, B, dtype)
+        data = rng.random((K, B)).astype(np.float64 if dtype == np.complex128 else np.float32)
+        sop = fp.SummedPauliOp(strings, hk)
+        t = tol(dtype)
+        assert rel_err(sop.apply(psi), ORC.sop_apply(strings, hk, psi)) < t
+        assert rel_err(sop.apply_weighted(psi, data), ORC.sop_apply_weighted(strings, hk, psi, data)) < t
+        assert rel_err(sop.expectation_value(psi), ORC.sop_expval(strings, hk, psi)) < t
+
+
+def test_mixed_weight_dtype():
+    # data_dtype is independent of T in the reference signature (SPO:364-366); the port oracle supports both
+    rng = np.random.default_rng(5)
+    strings = rand_strings(rng, 5, 12)
+    P = orc.port()
+    for dtype, ddt in [(np.complex128, np.float32), (np.complex64, np.float64)]:
+        hk = rand_states(rng, 12, 3, dtype)
+        psi = rand_states(rng, 32, 6, dtype)
+        data = rng.random((3, 6)).astype(ddt)
+        got = fp.SummedPauliOp(strings, hk).apply_weighted(psi, data)
+        assert rel_err(got, P.sop_apply_weighted(strings, hk, psi, data)) < tol(dtype)
+
+
+# ------------------------------------------------------------------ raw C ABI (oracle-shaped one-shots): accumulate semantics
+def test_oneshot_abi_accumulates_like_cpp():
+    G = orc.Backend(os.path.join(ROOT, "fast-pauli_b200", "lib", "libfastpauli_b200.so"), "fp_", "gpu")
+    rng = np.random.default_rng(11)
+    n, S, B, K = 6, 9, 4, 3
+    strings = rand_strings(rng, n, S)
+    for dtype in DTYPES:
+        t = tol(dtype)
+        psi = rand_states(rng, 2**n, B, dtype)
+        base = rand_states(rng, 2**n, B, dtype)
+        h = rand_states(rng, S, None, dtype)
+        hk = rand_states(rng, S, K, dtype)
+        data = rng.random((K, B)).astype(np.float64 if dtype == np.complex128 else np.float32)
+        e0 = rand_states(rng, B, None, dtype)
+        ek0 = rand_states(rng, K, B, dtype)
+        # every C++ method does += into the caller's buffer (PS:419,432,523,534; PO:453,465; SPO:331,346,464,498,588,609)
+        assert rel_err(G.string_apply(strings[0], psi, 0.5 - 2j, out=base.copy()),
+                       ORC.string_apply(strings[0], psi, 0.5 - 2j, out=base.copy())) < t
+        v = psi[:, 0].copy()
+        assert rel_err(G.string_apply(strings[0], v, 0.5 - 2j, out=base[:, 0].copy()),
+                       ORC.string_apply(strings[0], v, 0.5 - 2j, out=base[:, 0].copy())) < t
+        assert rel_err(G.string_expval(strings[0], psi, 2j, out=e0.copy()),
+                       ORC.string_expval(strings[0], psi, 2j, out=e0.copy())) < t
+        assert rel_err(G.op_apply(strings, h, psi, out=base.copy()), ORC.op_apply(strings, h, psi, out=base.copy())) < t
+        assert rel_err(G.op_apply(strings, h, v, out=base[:, 0].copy()),
+                       ORC.op_apply(strings, h, v, out=base[:, 0].copy())) < t
+        assert rel_err(G.op_expval(strings, h, psi, out=e0.copy()), ORC.op_expval(strings, h, psi, out=e0.copy())) < t
+        assert rel_err(G.sop_apply(strings, hk, psi, out=base.copy()),
+                       ORC.sop_apply(strings, hk, psi, out=base.copy())) < t
+        assert rel_err(G.sop_apply_weighted(strings, hk, psi, data, out=base.copy()),
+                       ORC.sop_apply_weighted(strings, hk, psi, data, out=base.copy())) < t
+        assert rel_err(G.sop_expval(strings, hk, psi, out=ek0.copy()),
+                       ORC.sop_expval(strings, hk, psi, out=ek0.copy())) < t
+    # error codes map to the reference's std::invalid_argument sites
+    with pytest.raises(ValueError):
+        G.string_apply("XYZ", np.zeros((4, 2), dtype=np.complex128))
+    with pytest.raises(ValueError):
+        G.op_apply(["XYZ", "III"], [1, 1], np.zeros((4, 2), dtype=np.complex128))
+    with pytest.raises(ValueError):
+        G.sop_expval(["XYZ"], np.ones((1, 2)), np.zeros((4, 2), dtype=np.complex128))
+
+
+def test_python_error_paths():
+    # PY_PS:384-406, PY_PO:880-946
+    with pytest.raises(ValueError):
+        fp.PauliString("XYZ").apply(np.zeros(4, dtype=np.complex128))
+    with pytest.raises(ValueError):
+        fp.PauliString("XYZ").apply(np.zeros((8, 2, 2), dtype=np.complex128))
+    with pytest.raises(ValueError):
+        fp.PauliString("XYZ").expectation_value(np.zeros((16, 2), dtype=np.complex128))
+    with pytest.raises(ValueError):
+        fp.PauliOp([1, 1], ["XYZ", "III"]).apply(np.zeros((4, 2), dtype=np.complex128))
+    with pytest.raises(ValueError):
+        fp.PauliOp([1, 1], ["XYZ", "III"]).expectation_value(np.zeros((4, 2), dtype=np.complex128))
+    with pytest.raises(ValueError):
+        fp.PauliString("XYZ").apply(np.zeros((8, 4), dtype=np.complex128)[:, ::2])  # non-contiguous, NB:55-74
+    with pytest.raises(ValueError):
+        fp.SummedPauliOp(["XX"], np.ones((1, 2))).apply_weighted(np.zeros((4, 3), np.complex128), np.ones((3, 3)))
+
+
+# ------------------------------------------------------------------ device-resident batches (no host staging)
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_device_resident_arrays(dtype):
+    ctx = fp.default_context()
+    rng = np.random.default_rng(3)
+    n, S, B = 9, 25, 8
+    strings = rand_strings(rng, n, S)
+    h = rand_states(rng, S, None, dtype)
+    psi = rand_states(rng, 2**n, B, dtype)
+    d_psi = ctx.to_device(psi)
+    op = fp.PauliOp(h, strings)
+    out = op.apply(d_psi)
+    assert isinstance(out, fp.DeviceArray)
+    assert rel_err(out.get(), ORC.op_apply(strings, h, psi)) < tol(dtype)
+    assert rel_err(op.expectation_value(d_psi).get(), ORC.op_expval(strings, h, psi)) < tol(dtype)
+    ps = fp.PauliString(strings[0])
+    assert rel_err(ps.apply(d_psi, 2.0).get(), ORC.string_apply(strings[0], psi, 2.0)) < tol(dtype)
+    assert rel_err(ps.expectation_value(d_psi).get(), ORC.string_expval(strings[0], psi)) < tol(dtype)
+    # a CUDA torch tensor is accepted zero-copy through __cuda_array_interface__
+    import torch
+
+    tdt = torch.complex128 if dtype == np.complex128 else torch.complex64
+    t_psi = torch.as_tensor(psi, dtype=tdt).cuda()
+    torch.cuda.synchronize()
+    out_t = op.apply(t_psi)
+    assert rel_err(out_t.get(), ORC.op_apply(strings, h, psi)) < tol(dtype)
+
+
+def test_uniform_generator_matches_host():
+    ctx = fp.default_context()
+    from fast_pauli_b200.synth import uniform_host
+
+    for dtype in DTYPES:
+        d = ctx.uniform((37, 5), dtype, seed=18, first=1000)
+        np.testing.assert_array_equal(d.get(), uniform_host((37, 5), dtype, seed=18, first=1000))
+
+
+# ------------------------------------------------------------------ L2 tiling must not change results
+def test_batch_tiling_invariance():
+    ctx = fp.Context(0)
+    rng = np.random.default_rng(9)
+    n, S, B = 10, 50, 64
+    strings = rand_strings(rng, n, S)
+    h = rand_states(rng, S, None)
+    psi = rand_states(rng, 2**n, B)
+    ref = ORC.op_apply(strings, h, psi)
+    for budget in (1 << 12, 1 << 16, 1 << 20, 1 << 30):
+        ctx.set_l2_budget(budget)
+        op = fp.PauliOp(h, strings, ctx=ctx)
+        assert rel_err(op.apply(psi), ref) < 1e-12
+        assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi)) < 1e-12
+
+
+# ------------------------------------------------------------------ BASELINE configs
+def test_config1_pauli_op_apply_10q():
+    # "PauliOp.apply, 10 qubits, 64 random Pauli strings, batch 16 states, complex128"
+    rng = np.random.default_rng(18)
+    strings = rand_strings(rng, 10, 64)
+    h = rand_states(rng, 64, None) * 2 - (1 + 1j)
+    psi = rand_states(rng, 1024, 16)
+    assert rel_err(fp.PauliOp(h, strings).apply(psi), ORC.op_apply(strings, h, psi)) < 1e-12
+
+
+def test_config3_reduced_batch_weight4():
+    # "PauliOp.apply_batch, 16 qubits, 2000 random strings of weight <= 4, batch 1024" at batch 8 for the oracle
+    rng = np.random.default_rng(1234)
+    strings = rand_strings(rng, 16, 2000, max_weight=4)
+    h = rand_states(rng, 2000, None) * 2 - (1 + 1j)
+    psi = rand_states(rng, 2**16, 8)
+    op = fp.PauliOp(h, strings)
+    info = op.plan_info()
+    assert info["n_x_groups"] < info["n_packed_strings"] <= 2000
+    assert rel_err(op.apply(psi), ORC.op_apply(strings, h, psi, par=True)) < 1e-12
+    assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi, par=True)) < 1e-12
+
+
+def test_config4_reduced_summed_c64():
+    # "SummedPauliOp.apply_weighted + expectation_value, 12 qubits, 10k strings x 64 operators, batch 4096, complex64"
+    # reduced to 500 strings x 64 operators x batch 32 so the CPU oracle finishes in seconds
+    rng = np.random.default_rng(4)
+    n, S, K, B = 12, 500, 64, 32
+    strings = rand_strings(rng, n, S)
+    hk = (rand_states(rng, S, K, np.complex64) * 2 - (1 + 1j)).astype(np.complex64)
+    psi = rand_states(rng, 2**n, B, np.complex64)
+    data = rng.random((K, B)).astype(np.float32)
+    sop = fp.SummedPauliOp(strings, hk)
+    # compare with the complex128 oracle on the same (float32-representable) inputs: the stricter check
+    exp_w = ORC.sop_apply_weighted(strings, hk.astype(np.complex128), psi.astype(np.complex128), data.astype(np.float64))
+    exp_e = ORC.sop_expval(strings, hk.astype(np.complex128), psi.astype(np.complex128))
+    assert rel_err(sop.apply_weighted(psi, data), exp_w) < 1e-5
+    assert rel_err(sop.expectation_value(psi), exp_e) < 1e-5
+
+
+def test_config2_full_size_sampled_rows():
+    # "PauliString.apply_batch + expectation_value, 20 qubits, batch 256, complex128": 4 GiB in, 4 GiB out on the GPU.
+    # Full-size check through size-independent handles: (a) sampled output rows against the closed form on
+    # regenerated inputs (the generator is counter based), (b) P(P psi) == psi bit-exactly, (c) the paired
+    # expectation kernel against the generic grouped one and against sampled-column host sums.
+    from fast_pauli_b200.synth import uniform_host
+
+    ctx = fp.default_context()
+    free, _ = ctx.mem_info()
+    n, B = 20, 256
+    if free < 3 * (2**n) * B * 16 + (1 << 30):
+        n, B = 18, 256
+    dim = 2**n
+    rng = np.random.default_rng(2)
+    string = "".join(np.array(list("IXYZ"))[rng.integers(0, 4, size=n)])
+    if "X" not in string and "Y" not in string:
+        string = "X" + string[1:]
+    psi = ctx.uniform((dim, B), np.complex128, seed=18)
+    ps = fp.PauliString(string)
+    c = 0.75 - 0.5j
+    out = ps.apply(psi, c)
+    x, z, ny = orc.masks(string)
+    base = np.array([1, -1j, -1, 1j])[ny]
+    rows = rng.integers(0, dim, size=48)
+    for i in rows:
+        i = int(i)
+        src = uniform_host((1, B), np.complex128, seed=18, first=(i ^ x) * B)
+        sign = -1.0 if bin(i & z).count("1") & 1 else 1.0
+        expect = (c * (base * sign)) * src
+        assert rel_err(out.get_rows(i, i + 1), expect) < 1e-14
+    back = ps.apply(out, 1.0 / c)
+    back2 = ps.apply(ps.apply(psi))  # c = 1: every factor is +-1 or +-i, so the round trip is bit exact
+    for i in rows[:16]:
+        i = int(i)
+        src = uniform_host((1, B), np.complex128, seed=18, first=i * B)
+        np.testing.assert_array_equal(back2.get_rows(i, i + 1), src)
+        assert rel_err(back.get_rows(i, i + 1), src) < 1e-14
+    del back, back2, out
+    e_pair = ps.expectation_value(psi, c).get()
+    e_generic = fp.PauliOp([c], [string]).expectation_value(psi).get()
+    assert rel_err(e_pair, e_generic) < 1e-12
+    # identity string: <psi|I|psi> = sum |psi|^2, checked on 2 columns regenerated on the host in row chunks
+    e_id = fp.PauliString("I" * n).expectation_value(psi).get()
+    from fast_pauli_b200.synth import uniform_complex_at
+
+    cols = [0, B - 1]
+    r = np.arange(dim, dtype=np.uint64)
+    acc = np.array([np.sum(np.abs(uniform_complex_at(r * np.uint64(B) + np.uint64(cc), np.complex128, 18)) ** 2)
+                    for cc in cols])
+    assert rel_err(e_id[cols].real, acc) < 1e-12
+    assert np.max(np.abs(e_id.imag)) == 0.0
