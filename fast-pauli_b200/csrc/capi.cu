@@ -344,40 +344,47 @@ uint64_t dim_of(int n)
 struct GeomSel
 {
     Geom g{};
-    int V = 4;
+    int V = 4; // rows per thread
+    int J = 1; // vectors per thread along the row (strided by TW)
     uint64_t grid = 0;
 };
 
-// rows: rows the kernel iterates over (dim, or dim/2 pair-rows); dim: rows of the state (L2 working set)
+// rows: rows the kernel iterates over (dim, or dim/2 pair-rows); dim: rows of the state (L2 working set).
+// wantJ: let each thread own 4 vectors of its row so row-only factors are amortised (multi-string operators).
 GeomSel choose_geom(fp_ctx const *ctx, uint64_t rows, uint64_t dim, uint64_t rowvecs, size_t vec_bytes, bool multi_group,
-                    bool reduce, uint64_t n_chunks = 1)
+                    bool reduce, uint64_t n_chunks = 1, bool wantJ = false)
 {
     GeomSel s;
-    uint32_t tw = 1;
-    while (tw < rowvecs && tw < static_cast<uint32_t>(kThreads))
-        tw <<= 1;
+    // tile width in vectors (power of two)
+    uint32_t const wcap = wantJ ? 1024u : static_cast<uint32_t>(kThreads);
+    uint32_t w = 1;
+    while (w < rowvecs && w < wcap)
+        w <<= 1;
     if (multi_group)
     {
         // batch-tile the sweep so dim x tile stays L2-resident while all x-groups gather from it;
         // never go below one 64-byte DRAM granule per row
-        uint32_t floor_tw = static_cast<uint32_t>(std::max<size_t>(1, 64 / vec_bytes));
-        while (tw > floor_tw && dim * tw * vec_bytes > ctx->l2_budget)
-            tw >>= 1;
+        uint32_t floor_w = static_cast<uint32_t>(std::max<size_t>(1, 64 / vec_bytes));
+        while (w > floor_w && dim * w * vec_bytes > ctx->l2_budget)
+            w >>= 1;
     }
+    int J = (wantJ && w >= 8) ? 4 : 1;
+    uint32_t tw = std::min<uint32_t>(w / J, kThreads);
     uint32_t log2tw = 0;
     while ((1u << log2tw) < tw)
         ++log2tw;
     uint32_t const TY = kThreads / tw;
-    uint32_t const nct = static_cast<uint32_t>((rowvecs + tw - 1) / tw);
-    int V = 4;
+    uint32_t const nct = static_cast<uint32_t>((rowvecs + static_cast<uint64_t>(tw) * J - 1) / (static_cast<uint64_t>(tw) * J));
+    int V = (J == 4) ? 2 : 4;
     {
-        uint64_t blocks4 = ((rows + TY * 4ull - 1) / (TY * 4ull)) * nct * n_chunks;
-        if (rows < TY * 4ull || blocks4 < static_cast<uint64_t>(ctx->sm_count) * 2)
+        uint64_t blocksV = ((rows + static_cast<uint64_t>(TY) * V - 1) / (static_cast<uint64_t>(TY) * V)) * nct * n_chunks;
+        if (rows < static_cast<uint64_t>(TY) * V || blocksV < static_cast<uint64_t>(ctx->sm_count) * 2)
             V = 1;
     }
     uint64_t const rows_per_iter = static_cast<uint64_t>(TY) * V;
     uint64_t const n_row_iters = (rows + rows_per_iter - 1) / rows_per_iter;
     s.V = V;
+    s.J = J;
     s.g.N = rows;
     s.g.rowvecs = rowvecs;
     s.g.nColTiles = nct;
@@ -389,10 +396,12 @@ GeomSel choose_geom(fp_ctx const *ctx, uint64_t rows, uint64_t dim, uint64_t row
     }
     else
     {
+        // about 8 CTAs per SM, never more (iters rounds UP): with 4 resident CTAs per SM that is two full waves and
+        // no straggler third wave
         uint64_t const target = static_cast<uint64_t>(ctx->sm_count) * 8;
         uint64_t const fixed = static_cast<uint64_t>(nct) * n_chunks;
-        uint64_t want_rb = std::max<uint64_t>(1, (target + fixed - 1) / fixed);
-        uint64_t iters = std::max<uint64_t>(1, n_row_iters / want_rb);
+        uint64_t want_rb = std::max<uint64_t>(1, target / fixed);
+        uint64_t iters = std::max<uint64_t>(1, (n_row_iters + want_rb - 1) / want_rb);
         iters = std::min<uint64_t>(iters, 1024);
         s.g.iters = static_cast<uint32_t>(iters);
         s.g.nRowBlocks = (n_row_iters + iters - 1) / iters;
@@ -432,10 +441,23 @@ void launch_op_v(fp_ctx *ctx, GeomSel const &gs, OpView<T> const &view, void con
     auto *dout = static_cast<CVec<T, EPV> *>(out);
     auto *dpart = static_cast<Cx<T> *>(partials);
     dim3 grid(static_cast<unsigned>(gs.grid));
-    if (gs.V == 4)
-        op_kernel<T, EPV, 4, MODE, INLINE1><<<grid, kThreads, 0, ctx->stream>>>(view, gs.g, din, dout, dpart, beta);
+#define FP_LAUNCH_OP(VV, JJ)                                                                                           \
+    op_kernel<T, EPV, VV, JJ, MODE, INLINE1><<<grid, kThreads, 0, ctx->stream>>>(view, gs.g, din, dout, dpart, beta)
+    if (gs.J == 4)
+    {
+        if constexpr (!INLINE1)
+        {
+            if (gs.V == 2)
+                FP_LAUNCH_OP(2, 4);
+            else
+                FP_LAUNCH_OP(1, 4);
+        }
+    }
+    else if (gs.V == 4)
+        FP_LAUNCH_OP(4, 1);
     else
-        op_kernel<T, EPV, 1, MODE, INLINE1><<<grid, kThreads, 0, ctx->stream>>>(view, gs.g, din, dout, dpart, beta);
+        FP_LAUNCH_OP(1, 1);
+#undef FP_LAUNCH_OP
     ctx->launches++;
 }
 
@@ -456,7 +478,7 @@ int run_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const *in, 
     int const epv = pick_epv<T>(in, out, B);
     uint64_t const rowvecs = B / epv;
     bool const single = op.host.sz.size() == 1;
-    GeomSel gs = choose_geom(ctx, dim, dim, rowvecs, 2 * sizeof(T) * epv, op.host.gx.size() > 1, false);
+    GeomSel gs = choose_geom(ctx, dim, dim, rowvecs, 2 * sizeof(T) * epv, op.host.gx.size() > 1, false, 1, !single);
     FP_TRY(check_grid(gs.grid));
     OpView<T> view = op.view();
     if constexpr (sizeof(T) == 4)
@@ -492,7 +514,7 @@ int run_op_expval(fp_ctx *ctx, DeviceOp<T> const &op, void *out /* B complex, de
     FP_TRY(check_align(in, 2 * sizeof(T), "states"));
     int const epv = pick_epv<T>(in, in, B);
     uint64_t const rowvecs = B / epv;
-    GeomSel gs = choose_geom(ctx, dim, dim, rowvecs, 2 * sizeof(T) * epv, op.host.gx.size() > 1, true);
+    GeomSel gs = choose_geom(ctx, dim, dim, rowvecs, 2 * sizeof(T) * epv, op.host.gx.size() > 1, true, 1, true);
     FP_TRY(check_grid(gs.grid));
     uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
     if (B > 0xfffffff0ull)
@@ -511,8 +533,8 @@ int run_op_expval(fp_ctx *ctx, DeviceOp<T> const &op, void *out /* B complex, de
     }
     if (!done)
         launch_op_v<T, 1, 1, false>(ctx, gs, view, in, nullptr, ctx->partials.p, 0);
-    unsigned fgrid = static_cast<unsigned>((B + 127) / 128);
-    finalize_complex_kernel<T><<<fgrid, 128, 0, ctx->stream>>>(static_cast<Cx<T> const *>(ctx->partials.p),
+    unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
+    finalize_complex_kernel<T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(static_cast<Cx<T> const *>(ctx->partials.p),
                                                                  gs.g.nRowBlocks, Bpad, B, static_cast<Cx<T> *>(out),
                                                                  beta);
     ctx->launches++;
@@ -581,8 +603,8 @@ int run_string_expval(fp_ctx *ctx, StringMasks const &mk, std::complex<T> coeff,
     std::complex<double> f = times_phase(std::complex<double>(coeff.real(), coeff.imag()), mk.ny);
     if (!ch.diag)
         f *= (mk.ny & 1u) ? std::complex<double>(0, 2) : std::complex<double>(2, 0);
-    unsigned fgrid = static_cast<unsigned>((B + 127) / 128);
-    finalize_pairs_string_kernel<T><<<fgrid, 128, 0, ctx->stream>>>(part, gs.g.nRowBlocks, Bpad, B, f.real(), f.imag(),
+    unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
+    finalize_pairs_string_kernel<T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(part, gs.g.nRowBlocks, Bpad, B, f.real(), f.imag(),
                                                                       static_cast<Cx<T> *>(out), beta);
     ctx->launches++;
     return FP_OK;
@@ -1278,11 +1300,11 @@ int run_sop_expval(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, ui
         launch_pairs_v<T, 1, kPairMS>(ctx, gs, op.chunks, op.sz, op.sodd, none, 0, 0, 0, dim, in, part, slot_stride);
     if (part != E)
     {
-        dim3 fgrid(static_cast<unsigned>((B + 127) / 128), S);
+        dim3 fgrid(static_cast<unsigned>((B + kFinX - 1) / kFinX), S);
         if (S > 65535)
             return set_err(FP_UNSUPPORTED, "too many strings for the expectation finaliser");
         finalize_pairs_matrix_kernel<T>
-            <<<fgrid, 128, 0, ctx->stream>>>(part, slot_stride, gs.g.nRowBlocks, Bpad, B, E);
+            <<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(part, slot_stride, gs.g.nRowBlocks, Bpad, B, E);
         ctx->launches++;
     }
     // stage 2: out[2K x B] = A_e[2K x S] * E[S x B], split over S              (SPO:579-591)

@@ -89,9 +89,11 @@ constexpr int kThreads = 256;
 // Covers PauliString::apply / apply_batch (PS:296-436; INLINE1, one group of one string),
 // PauliOp::apply 1-D/2-D (PO:362-468) and SummedPauliOp::apply (SPO:277-349, with c_j = sum_k coeffs(j,k)
 // folded on the host).
+// Each thread owns V rows x J vectors (vectors strided by TW so every warp-level access is contiguous); the
+// row-only factor D_g(i) is formed once per (row, group) and reused for the J vectors.
 // MODE 0: store.  MODE 1: expectation partials  e(t) = sum_i conj(psi(i,t)) * (A psi)(i,t)
 // (PauliOp::expectation_value, PO:482-549) reduced over the CTA's rows into partials[rb][t].
-template <typename T, int EPV, int V, int MODE, bool INLINE1>
+template <typename T, int EPV, int V, int J, int MODE, bool INLINE1>
 __global__ void __launch_bounds__(kThreads)
     op_kernel(OpView<T> op, Geom g, CVec<T, EPV> const *__restrict__ in, CVec<T, EPV> *__restrict__ out,
               Cx<T> *__restrict__ partials, int beta)
@@ -104,18 +106,25 @@ __global__ void __launch_bounds__(kThreads)
     uint64_t const blk = blockIdx.x;
     uint64_t const ct = blk / g.nRowBlocks;
     uint64_t const rb = blk - ct * g.nRowBlocks;
-    uint64_t v = ct * TW + lx;
-    bool const vok = v < g.rowvecs;
-    if (MODE == 0 && !vok)
+    uint64_t vcol[J];
+    bool vok[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+    {
+        uint64_t v = ct * (static_cast<uint64_t>(TW) * J) + lx + static_cast<uint64_t>(j) * TW;
+        vok[j] = v < g.rowvecs;
+        vcol[j] = vok[j] ? v : 0;
+    }
+    if (MODE == 0 && !vok[0])
         return;
-    if (!vok)
-        v = 0;
 
     uint32_t const n_it = (MODE == 0) ? 1u : g.iters;
-    Cx<T> esum[EPV];
+    Cx<T> esum[J][EPV];
 #pragma unroll
-    for (int e = 0; e < EPV; ++e)
-        esum[e] = Cx<T>{0, 0};
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e)
+            esum[j][e] = Cx<T>{0, 0};
 
     for (uint32_t it = 0; it < n_it; ++it)
     {
@@ -130,27 +139,33 @@ __global__ void __launch_bounds__(kThreads)
             rows[k] = rok[k] ? r : (g.N - 1);
         }
 
-        Cx<T> acc[V][EPV];
+        Cx<T> acc[V][J][EPV];
 #pragma unroll
         for (int k = 0; k < V; ++k)
 #pragma unroll
-            for (int e = 0; e < EPV; ++e)
-                acc[k][e] = Cx<T>{0, 0};
+            for (int j = 0; j < J; ++j)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    acc[k][j][e] = Cx<T>{0, 0};
 
         if (INLINE1)
         {
-            Vec src[V];
+            Vec src[V][J];
 #pragma unroll
             for (int k = 0; k < V; ++k)
-                src[k] = in[(rows[k] ^ op.x0) * g.rowvecs + v];
+#pragma unroll
+                for (int j = 0; j < J; ++j)
+                    src[k][j] = in[(rows[k] ^ op.x0) * g.rowvecs + vcol[j]];
 #pragma unroll
             for (int k = 0; k < V; ++k)
             {
                 uint32_t odd = parity64(rows[k] & op.z0);
                 Cx<T> d{flip_sign(op.c0.re, odd), flip_sign(op.c0.im, odd)};
 #pragma unroll
-                for (int e = 0; e < EPV; ++e)
-                    cfma(acc[k][e], d, src[k].e[e]);
+                for (int j = 0; j < J; ++j)
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                        cfma(acc[k][j][e], d, src[k][j].e[e]);
             }
         }
         else
@@ -160,10 +175,12 @@ __global__ void __launch_bounds__(kThreads)
             {
                 uint64_t const x = __ldg(op.gx + gi);
                 uint32_t const s1 = __ldg(op.gstart + gi + 1);
-                Vec src[V];
+                Vec src[V][J];
 #pragma unroll
                 for (int k = 0; k < V; ++k)
-                    src[k] = in[(rows[k] ^ x) * g.rowvecs + v];
+#pragma unroll
+                    for (int j = 0; j < J; ++j)
+                        src[k][j] = in[(rows[k] ^ x) * g.rowvecs + vcol[j]];
                 Cx<T> d[V];
 #pragma unroll
                 for (int k = 0; k < V; ++k)
@@ -183,8 +200,10 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
                 for (int k = 0; k < V; ++k)
 #pragma unroll
-                    for (int e = 0; e < EPV; ++e)
-                        cfma(acc[k][e], d[k], src[k].e[e]);
+                    for (int j = 0; j < J; ++j)
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e)
+                            cfma(acc[k][j][e], d[k], src[k][j].e[e]);
                 s0 = s1;
             }
         }
@@ -196,25 +215,31 @@ __global__ void __launch_bounds__(kThreads)
             {
                 if (!rok[k])
                     continue;
-                uint64_t const o = rows[k] * g.rowvecs + v;
-                Vec r;
-                if (beta)
-                {
-                    r = out[o];
 #pragma unroll
-                    for (int e = 0; e < EPV; ++e)
+                for (int j = 0; j < J; ++j)
+                {
+                    if (!vok[j])
+                        continue;
+                    uint64_t const o = rows[k] * g.rowvecs + vcol[j];
+                    Vec r;
+                    if (beta)
                     {
-                        r.e[e].re += acc[k][e].re;
-                        r.e[e].im += acc[k][e].im;
-                    }
-                }
-                else
-                {
+                        r = out[o];
 #pragma unroll
-                    for (int e = 0; e < EPV; ++e)
-                        r.e[e] = acc[k][e];
+                        for (int e = 0; e < EPV; ++e)
+                        {
+                            r.e[e].re += acc[k][j][e].re;
+                            r.e[e].im += acc[k][j][e].im;
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e)
+                            r.e[e] = acc[k][j][e];
+                    }
+                    out[o] = r;
                 }
-                out[o] = r;
             }
         }
         else
@@ -222,17 +247,23 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
             for (int k = 0; k < V; ++k)
             {
-                if (!rok[k] || !vok)
+                if (!rok[k])
                     continue;
-                Vec a = in[rows[k] * g.rowvecs + v];
 #pragma unroll
-                for (int e = 0; e < EPV; ++e)
+                for (int j = 0; j < J; ++j)
                 {
-                    // conj(a) * acc
-                    esum[e].re = fma(a.e[e].re, acc[k][e].re, esum[e].re);
-                    esum[e].re = fma(a.e[e].im, acc[k][e].im, esum[e].re);
-                    esum[e].im = fma(a.e[e].re, acc[k][e].im, esum[e].im);
-                    esum[e].im = fma(-a.e[e].im, acc[k][e].re, esum[e].im);
+                    if (!vok[j])
+                        continue;
+                    Vec a = in[rows[k] * g.rowvecs + vcol[j]];
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                    {
+                        // conj(a) * acc
+                        esum[j][e].re = fma(a.e[e].re, acc[k][j][e].re, esum[j][e].re);
+                        esum[j][e].re = fma(a.e[e].im, acc[k][j][e].im, esum[j][e].re);
+                        esum[j][e].im = fma(a.e[e].re, acc[k][j][e].im, esum[j][e].im);
+                        esum[j][e].im = fma(-a.e[e].im, acc[k][j][e].re, esum[j][e].im);
+                    }
                 }
             }
         }
@@ -243,53 +274,85 @@ __global__ void __launch_bounds__(kThreads)
         // reduce over the TY row-lanes that share a vector column
         __shared__ Cx<T> red[kThreads * EPV];
 #pragma unroll
-        for (int e = 0; e < EPV; ++e)
-            red[threadIdx.x * EPV + e] = esum[e];
-        __syncthreads();
-        for (uint32_t half = TY >> 1; half > 0; half >>= 1)
+        for (int j = 0; j < J; ++j)
         {
-            if (ty < half)
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+                red[threadIdx.x * EPV + e] = esum[j][e];
+            __syncthreads();
+            for (uint32_t half = TY >> 1; half > 0; half >>= 1)
+            {
+                if (ty < half)
+                {
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                    {
+                        Cx<T> o = red[(threadIdx.x + half * TW) * EPV + e];
+                        red[threadIdx.x * EPV + e].re += o.re;
+                        red[threadIdx.x * EPV + e].im += o.im;
+                    }
+                }
+                __syncthreads();
+            }
+            if (ty == 0 && vok[j])
             {
 #pragma unroll
                 for (int e = 0; e < EPV; ++e)
-                {
-                    Cx<T> o = red[(threadIdx.x + half * TW) * EPV + e];
-                    red[threadIdx.x * EPV + e].re += o.re;
-                    red[threadIdx.x * EPV + e].im += o.im;
-                }
+                    partials[rb * g.Bpad + vcol[j] * EPV + e] = red[threadIdx.x * EPV + e];
             }
-            __syncthreads();
-        }
-        if (ty == 0 && vok)
-        {
-#pragma unroll
-            for (int e = 0; e < EPV; ++e)
-                partials[rb * g.Bpad + v * EPV + e] = red[threadIdx.x * EPV + e];
         }
     }
 }
 
-// out[t] = (beta ? out[t] : 0) + sum_rb partials[rb][t]      (deterministic second stage, summed in double)
-template <typename T>
-__global__ void finalize_complex_kernel(Cx<T> const *__restrict__ partials, uint64_t nRowBlocks, uint32_t Bpad,
-                                        uint64_t B, Cx<T> *__restrict__ out, int beta)
+// Second-stage reductions run with 32 x 32 threads: x indexes 32 consecutive batch columns (coalesced), y strides
+// over the row blocks; partial sums are combined in double precision in a fixed order (deterministic).
+constexpr int kFinX = 32, kFinY = 32;
+
+__device__ __forceinline__ double fin_reduce_y(double v, double (*sm)[kFinX + 1])
 {
-    uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (t >= B)
-        return;
+    sm[threadIdx.y][threadIdx.x] = v;
+    __syncthreads();
+    for (int half = kFinY / 2; half > 0; half >>= 1)
+    {
+        if (static_cast<int>(threadIdx.y) < half)
+            sm[threadIdx.y][threadIdx.x] += sm[threadIdx.y + half][threadIdx.x];
+        __syncthreads();
+    }
+    double r = sm[0][threadIdx.x];
+    __syncthreads();
+    return r;
+}
+
+// out[t] = (beta ? out[t] : 0) + sum_rb partials[rb][t]
+template <typename T>
+__global__ void __launch_bounds__(kFinX *kFinY)
+    finalize_complex_kernel(Cx<T> const *__restrict__ partials, uint64_t nRowBlocks, uint32_t Bpad, uint64_t B,
+                            Cx<T> *__restrict__ out, int beta)
+{
+    __shared__ double sm[kFinY][kFinX + 1];
+    uint64_t const t = blockIdx.x * static_cast<uint64_t>(kFinX) + threadIdx.x;
     double re = 0, im = 0;
-    for (uint64_t rb = 0; rb < nRowBlocks; ++rb)
+    if (t < B)
     {
-        Cx<T> p = partials[rb * Bpad + t];
-        re += p.re;
-        im += p.im;
+        for (uint64_t rb = threadIdx.y; rb < nRowBlocks; rb += kFinY)
+        {
+            Cx<T> p = partials[rb * Bpad + t];
+            re += p.re;
+            im += p.im;
+        }
     }
-    if (beta)
+    re = fin_reduce_y(re, sm);
+    im = fin_reduce_y(im, sm);
+    if (threadIdx.y == 0 && t < B)
     {
-        re += out[t].re;
-        im += out[t].im;
+        if (beta)
+        {
+            re += out[t].re;
+            im += out[t].im;
+        }
+        out[t] = Cx<T>{static_cast<T>(re), static_cast<T>(im)};
     }
-    out[t] = Cx<T>{static_cast<T>(re), static_cast<T>(im)};
 }
 
 // ---------------------------------------------------------------- K2/K4: paired expectation values
@@ -436,37 +499,45 @@ __global__ void __launch_bounds__(kThreads)
 
 // Single string: out[t] = (beta ? out[t] : 0) + factor * sum_rb partials[rb][t]
 template <typename T>
-__global__ void finalize_pairs_string_kernel(T const *__restrict__ partials, uint64_t nRowBlocks, uint32_t Bpad,
-                                             uint64_t B, double fre, double fim, Cx<T> *__restrict__ out, int beta)
+__global__ void __launch_bounds__(kFinX *kFinY)
+    finalize_pairs_string_kernel(T const *__restrict__ partials, uint64_t nRowBlocks, uint32_t Bpad, uint64_t B,
+                                 double fre, double fim, Cx<T> *__restrict__ out, int beta)
 {
-    uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (t >= B)
-        return;
+    __shared__ double sm[kFinY][kFinX + 1];
+    uint64_t const t = blockIdx.x * static_cast<uint64_t>(kFinX) + threadIdx.x;
     double r = 0;
-    for (uint64_t rb = 0; rb < nRowBlocks; ++rb)
-        r += partials[rb * Bpad + t];
-    double re = fre * r, im = fim * r;
-    if (beta)
+    if (t < B)
+        for (uint64_t rb = threadIdx.y; rb < nRowBlocks; rb += kFinY)
+            r += partials[rb * Bpad + t];
+    r = fin_reduce_y(r, sm);
+    if (threadIdx.y == 0 && t < B)
     {
-        re += out[t].re;
-        im += out[t].im;
+        double re = fre * r, im = fim * r;
+        if (beta)
+        {
+            re += out[t].re;
+            im += out[t].im;
+        }
+        out[t] = Cx<T>{static_cast<T>(re), static_cast<T>(im)};
     }
-    out[t] = Cx<T>{static_cast<T>(re), static_cast<T>(im)};
 }
 
 // SummedPauliOp: E(s,t) = sum_rb partials[s][rb][t]  -> dense real (S, B) matrix feeding the contraction
 template <typename T>
-__global__ void finalize_pairs_matrix_kernel(T const *__restrict__ partials, uint64_t slot_stride, uint64_t nRowBlocks,
-                                             uint32_t Bpad, uint64_t B, T *__restrict__ E /* [S][B] */)
+__global__ void __launch_bounds__(kFinX *kFinY)
+    finalize_pairs_matrix_kernel(T const *__restrict__ partials, uint64_t slot_stride, uint64_t nRowBlocks,
+                                 uint32_t Bpad, uint64_t B, T *__restrict__ E /* [S][B] */)
 {
-    uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    uint64_t s = blockIdx.y;
-    if (t >= B)
-        return;
+    __shared__ double sm[kFinY][kFinX + 1];
+    uint64_t const t = blockIdx.x * static_cast<uint64_t>(kFinX) + threadIdx.x;
+    uint64_t const s = blockIdx.y;
     double r = 0;
-    for (uint64_t rb = 0; rb < nRowBlocks; ++rb)
-        r += partials[s * slot_stride + rb * Bpad + t];
-    E[s * B + t] = static_cast<T>(r);
+    if (t < B)
+        for (uint64_t rb = threadIdx.y; rb < nRowBlocks; rb += kFinY)
+            r += partials[s * slot_stride + rb * Bpad + t];
+    r = fin_reduce_y(r, sm);
+    if (threadIdx.y == 0 && t < B)
+        E[s * B + t] = static_cast<T>(r);
 }
 
 // ---------------------------------------------------------------- K6: weighted apply (SummedPauliOp::apply_weighted)

@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Extract the roofline-relevant counters of every kernel in an .ncu-rep into JSON (read here, no GPU needed).
+
+    python scripts/ncu_extract.py gpurun_out/prof_apply.ncu-rep > profiles/r01_apply.json
+"""
+import csv
+import json
+import subprocess
+import sys
+
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum.per_second",
+    "dram__bytes_write.sum.per_second", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_bytes.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "smsp__cycles_active.avg",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed.sum",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+]
+
+
+def main(path: str) -> None:
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    res = []
+    for vals in rows[2:]:
+        rec = {"kernel": vals[hdr.index("Kernel Name")]}
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                rec[w] = {"value": vals[i], "unit": units[i]}
+        res.append(rec)
+    json.dump(res, sys.stdout, indent=1)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

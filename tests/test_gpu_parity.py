@@ -26,6 +26,28 @@ def tol(dtype) -> float:
     return TOL[np.dtype(dtype)]
 
 
+def assert_parity(got, ref_fn, dtype, *args):
+    """North-star bar: max|gpu - ref| / |ref|_inf < 1e-12 (complex128) / 1e-5 (complex64).
+
+    One documented exception, complex64 reductions only: the reference accumulates expectation values
+    sequentially in float32 (PS:534, SPO:609), so over >= 2^12 terms ITS OWN rounding error exceeds 1e-5
+    (measured against its complex128 path on the same inputs).  When the direct comparison misses the bar,
+    the GPU result must instead be within 1e-5 of the complex128 reference AND at least as close to it as
+    the complex64 reference is -- i.e. the discrepancy is the reference's, not ours.
+    """
+    ref = ref_fn(*args)
+    err = rel_err(got, ref)
+    if err < tol(dtype):
+        return
+    assert np.dtype(dtype) == np.complex64, f"complex128 parity {err:.3e}"
+    up = [a.astype(np.complex128) if isinstance(a, np.ndarray) and a.dtype == np.complex64 else
+          (a.astype(np.float64) if isinstance(a, np.ndarray) and a.dtype == np.float32 else a) for a in args]
+    exact = ref_fn(*up)
+    e_gpu, e_ref = rel_err(got, exact), rel_err(ref, exact)
+    assert e_gpu < tol(dtype) and e_gpu <= e_ref, (
+        f"complex64 parity: |gpu-ref32| {err:.3e}, |gpu-ref64| {e_gpu:.3e}, |ref32-ref64| {e_ref:.3e}")
+
+
 # ------------------------------------------------------------------ golden vectors from the reference's numpy code
 def test_golden_pauli_string():
     g = np.load(os.path.join(GOLDEN, "pauli_string.npz"))
@@ -117,16 +139,16 @@ def test_all_entry_points_vs_oracle(dtype, n, S, B, K):
         ps = fp.PauliString(s0)
         assert rel_err(ps.apply(psi, c), ORC.string_apply(s0, psi, c)) < t
         assert rel_err(ps.apply(psi[:, 0].copy()), ORC.string_apply(s0, psi[:, 0].copy())) < t
-        assert rel_err(ps.expectation_value(psi, c), ORC.string_expval(s0, psi, c)) < t
+        assert_parity(ps.expectation_value(psi, c), ORC.string_expval, dtype, s0, psi, c)
     op = fp.PauliOp(h, strings)
     assert rel_err(op.apply(psi), ORC.op_apply(strings, h, psi)) < t
     assert rel_err(op.apply(psi[:, 0].copy()), ORC.op_apply(strings, h, psi[:, 0].copy())) < t
-    assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi)) < t
-    assert rel_err(op.expectation_value(psi[:, 0].copy()), ORC.op_expval(strings, h, psi[:, :1].copy())) < t
+    assert_parity(op.expectation_value(psi), ORC.op_expval, dtype, strings, h, psi)
+    assert_parity(op.expectation_value(psi[:, 0].copy()), ORC.op_expval, dtype, strings, h, psi[:, :1].copy())
     sop = fp.SummedPauliOp(strings, hk)
     assert rel_err(sop.apply(psi), ORC.sop_apply(strings, hk, psi)) < t
     assert rel_err(sop.apply_weighted(psi, data), ORC.sop_apply_weighted(strings, hk, psi, data)) < t
-    assert rel_err(sop.expectation_value(psi), ORC.sop_expval(strings, hk, psi)) < t
+    assert_parity(sop.expectation_value(psi), ORC.sop_expval, dtype, strings, hk, psi)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -154,7 +176,7 @@ def test_summed_pauli_op_reference_test_shapes(dtype):
         t = tol(dtype)
         assert rel_err(sop.apply(psi), ORC.sop_apply(strings, hk, psi)) < t
         assert rel_err(sop.apply_weighted(psi, data), ORC.sop_apply_weighted(strings, hk, psi, data)) < t
-        assert rel_err(sop.expectation_value(psi), ORC.sop_expval(strings, hk, psi)) < t
+        assert_parity(sop.expectation_value(psi), ORC.sop_expval, dtype, strings, hk, psi)
 
 
 def test_mixed_weight_dtype():
@@ -244,10 +266,10 @@ def test_device_resident_arrays(dtype):
     out = op.apply(d_psi)
     assert isinstance(out, fp.DeviceArray)
     assert rel_err(out.get(), ORC.op_apply(strings, h, psi)) < tol(dtype)
-    assert rel_err(op.expectation_value(d_psi).get(), ORC.op_expval(strings, h, psi)) < tol(dtype)
+    assert_parity(op.expectation_value(d_psi).get(), ORC.op_expval, dtype, strings, h, psi)
     ps = fp.PauliString(strings[0])
     assert rel_err(ps.apply(d_psi, 2.0).get(), ORC.string_apply(strings[0], psi, 2.0)) < tol(dtype)
-    assert rel_err(ps.expectation_value(d_psi).get(), ORC.string_expval(strings[0], psi)) < tol(dtype)
+    assert_parity(ps.expectation_value(d_psi).get(), ORC.string_expval, dtype, strings[0], psi)
     # a CUDA torch tensor is accepted zero-copy through __cuda_array_interface__
     import torch
 
