@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -17,6 +18,7 @@
 
 #include <cuda_runtime.h>
 
+#include "coset.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "pack.hpp"
@@ -107,6 +109,8 @@ struct fp_ctx
     bool tensor_core = true;
     uint64_t launches = 0;
     size_t l2_budget = 40ull << 20;
+    int coset_mode = 1;       // 0: never use the coset-blocked kernels, 1: heuristic, 2: whenever applicable
+    int coset_log_twc = -1;   // >= 0 forces the tile shape (TWc = 1 << v vectors, rank 12 - v)
     Scratch stage_in, stage_out, stage_data, partials, work_a, work_b, meta;
     std::mutex mu;
 };
@@ -127,6 +131,15 @@ template <typename T> struct DeviceOp
     PairChunk *chunks = nullptr; // strings of each group in chunks of <= kPairMS (paired expectation kernel)
     uint32_t n_chunks = 0;
     bool any_diag = false;
+    int x_rank = 0; // GF(2) rank of the x-masks (capped at kCosetMaxRank + 1)
+
+    // coset-blocked plans, built lazily per tile shape (key: LOG_TWC)
+    struct CosetPassDev
+    {
+        CosetPassView<T> view{};
+        std::vector<void *> allocs;
+    };
+    mutable std::map<int, std::vector<CosetPassDev>> coset_plans;
 
     OpView<T> view() const
     {
@@ -152,6 +165,11 @@ template <typename T> struct DeviceOp
         cudaFree(sc);
         cudaFree(sodd);
         cudaFree(chunks);
+        for (auto &kv : coset_plans)
+            for (auto &pd : kv.second)
+                for (void *a : pd.allocs)
+                    cudaFree(a);
+        coset_plans.clear();
         gx = nullptr;
         gstart = nullptr;
         sz = nullptr;
@@ -240,6 +258,75 @@ template <typename T> int upload_op(DeviceOp<T> &d)
     }
     d.n_chunks = static_cast<uint32_t>(chunks.size());
     FP_TRY(upload_vec(&d.chunks, chunks));
+    {
+        Gf2Basis bb;
+        d.x_rank = 0;
+        for (uint64_t x : d.host.gx)
+            if (!bb.insert(x, kCosetMaxRank))
+            {
+                d.x_rank = kCosetMaxRank + 1;
+                break;
+            }
+        if (d.x_rank == 0)
+            d.x_rank = bb.r;
+    }
+    return FP_OK;
+}
+
+// ---------------------------------------------------------------- coset-blocked path: plan cache + launch
+template <typename T>
+int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int log_twc,
+                   std::vector<typename DeviceOp<T>::CosetPassDev> const **out)
+{
+    auto it = op.coset_plans.find(log_twc);
+    if (it != op.coset_plans.end())
+    {
+        *out = &it->second;
+        return FP_OK;
+    }
+    int const rank = 12 - log_twc;
+    std::vector<CosetPassHost<T>> host = plan_coset<T>(op.host, n_qubits, rank);
+    std::vector<typename DeviceOp<T>::CosetPassDev> dev(host.size());
+    for (size_t p = 0; p < host.size(); ++p)
+    {
+        CosetPassHost<T> const &h = host[p];
+        auto &d = dev[p];
+        for (int k = 0; k < kCosetMaxRank; ++k)
+            d.view.basis[k] = k < h.basis.r ? h.basis.b[k] : 0;
+        d.view.nonpivot_mask = h.nonpivot_mask;
+        d.view.n_chunks = static_cast<uint32_t>(h.chunks.size());
+        CosetChunk *chunks = nullptr;
+        uint32_t *gxl = nullptr, *gstart = nullptr, *szl = nullptr, *sidx = nullptr;
+        uint64_t *sz = nullptr;
+        Cx<T> *sc = nullptr;
+        std::vector<Cx<T>> scv(h.sc.size());
+        for (size_t i = 0; i < scv.size(); ++i)
+            scv[i] = Cx<T>{h.sc[i].real(), h.sc[i].imag()};
+        int rc = upload_vec(&chunks, h.chunks);
+        if (rc == FP_OK) { d.allocs.push_back(chunks); rc = upload_vec(&gxl, h.gxl); }
+        if (rc == FP_OK) { d.allocs.push_back(gxl); rc = upload_vec(&gstart, h.gstart); }
+        if (rc == FP_OK) { d.allocs.push_back(gstart); rc = upload_vec(&szl, h.szl); }
+        if (rc == FP_OK) { d.allocs.push_back(szl); rc = upload_vec(&sz, h.sz); }
+        if (rc == FP_OK) { d.allocs.push_back(sz); rc = upload_vec(&sc, scv); }
+        if (rc == FP_OK) { d.allocs.push_back(sc); rc = upload_vec(&sidx, h.sidx); }
+        if (rc == FP_OK) d.allocs.push_back(sidx);
+        if (rc != FP_OK)
+        {
+            for (auto &dd : dev)
+                for (void *a : dd.allocs)
+                    cudaFree(a);
+            return rc;
+        }
+        d.view.chunks = chunks;
+        d.view.gxl = gxl;
+        d.view.gstart = gstart;
+        d.view.szl = szl;
+        d.view.sz = sz;
+        d.view.scoef = sc;
+        d.view.sidx = sidx;
+    }
+    auto ins = op.coset_plans.emplace(log_twc, std::move(dev));
+    *out = &ins.first->second;
     return FP_OK;
 }
 
@@ -432,6 +519,123 @@ int check_grid(uint64_t grid)
     return FP_OK;
 }
 
+// ---------------------------------------------------------------- coset-blocked path: heuristics + launch
+// Pick the tile shape (LOG_TWC: TWc = 2^v vectors per row, rank 12 - v) or -1 for "use the generic gather kernel".
+template <typename T>
+int choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, uint64_t rowvecs, int epv)
+{
+    if (ctx->coset_mode == 0 || n_qubits < 8 || op.host.gx.size() < 2)
+        return -1;
+    if (sizeof(T) == 4 && epv != 2)
+        return -1;
+    auto valid = [&](int v) { return v >= 0 && v <= 4 && (rowvecs % (1ull << v)) == 0 && (12 - v) <= n_qubits; };
+    int pick = -1;
+    if (ctx->coset_log_twc >= 0)
+        pick = valid(ctx->coset_log_twc) ? ctx->coset_log_twc : -1;
+    else
+    {
+        for (int v = 4; v >= 2 && pick < 0; --v) // widest tile whose rank covers the operator in a single pass
+            if (op.x_rank <= 12 - v && valid(v))
+                pick = v;
+        if (pick < 0 && n_qubits <= 12 && valid(12 - n_qubits))
+            pick = 12 - n_qubits; // the whole state column fits one tile: single pass
+        for (int v : {2, 3, 4, 1, 0})
+            if (pick < 0 && valid(v))
+                pick = v;
+    }
+    if (pick < 0)
+        return -1;
+    uint64_t const ctas = (1ull << (n_qubits - (12 - pick))) * (rowvecs >> pick);
+    if (ctx->coset_mode == 1 && ctas < static_cast<uint64_t>(ctx->sm_count))
+        return -1;
+    return pick;
+}
+
+template <typename T, int EPV, int LOG_TWC, int MODE>
+int launch_coset_pass(fp_ctx *ctx, CosetPassView<T> const &view, int n_qubits, uint64_t rowvecs, void const *in,
+                      void *out, int beta, void *partials, uint32_t Bpad, T const *Wre, T const *Wim, uint64_t B)
+{
+    using Cfg = CosetCfg<LOG_TWC>;
+    size_t const smem = Cfg::TILE_BYTES + coset_meta_bytes<T>();
+    static bool configured = false; // per template instance
+    if (!configured)
+    {
+        FP_CU(cudaFuncSetAttribute(coset_kernel<T, EPV, LOG_TWC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+        configured = true;
+    }
+    uint32_t const nct = static_cast<uint32_t>(rowvecs >> LOG_TWC);
+    uint64_t const grid = (1ull << (n_qubits - Cfg::R)) * nct;
+    FP_TRY(check_grid(grid));
+    coset_kernel<T, EPV, LOG_TWC, MODE><<<static_cast<unsigned>(grid), kThreads, smem, ctx->stream>>>(
+        view, rowvecs, nct, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta,
+        static_cast<Cx<T> *>(partials), Bpad, Wre, Wim, B);
+    ctx->launches++;
+    return FP_OK;
+}
+
+template <typename T, int EPV, int MODE>
+int launch_coset_pass_v(fp_ctx *ctx, int log_twc, CosetPassView<T> const &view, int n_qubits, uint64_t rowvecs,
+                        void const *in, void *out, int beta, void *partials, uint32_t Bpad, T const *Wre, T const *Wim,
+                        uint64_t B)
+{
+    switch (log_twc)
+    {
+    case 0:
+        return launch_coset_pass<T, EPV, 0, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad, Wre, Wim, B);
+    case 1:
+        return launch_coset_pass<T, EPV, 1, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad, Wre, Wim, B);
+    case 2:
+        return launch_coset_pass<T, EPV, 2, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad, Wre, Wim, B);
+    case 3:
+        return launch_coset_pass<T, EPV, 3, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad, Wre, Wim, B);
+    default:
+        return launch_coset_pass<T, EPV, 4, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad, Wre, Wim, B);
+    }
+}
+
+// Runs all passes.  Returns FP_OK with *used = false when the generic kernel should be used instead.
+template <typename T, int MODE>
+int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void const *in, uint64_t dim, uint64_t B,
+              int beta, T const *Wre, T const *Wim, bool *used)
+{
+    *used = false;
+    constexpr int EPV = sizeof(T) == 4 ? 2 : 1;
+    if (dim != (1ull << n_qubits))
+        return FP_OK;
+    int const epv = pick_epv<T>(in, MODE == 1 ? in : out, B);
+    if (epv != EPV)
+        return FP_OK;
+    uint64_t const rowvecs = B / EPV;
+    int const v = choose_coset<T>(ctx, op, n_qubits, rowvecs, epv);
+    if (v < 0)
+        return FP_OK;
+    std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
+    FP_TRY(get_coset_plan<T>(op, n_qubits, v, &passes));
+    // every pass re-streams the batch (read in, read-modify-write out): only worth it while passes << groups
+    if (ctx->coset_mode == 1 && passes->size() * 3 > op.host.gx.size() && passes->size() > 1)
+        return FP_OK;
+    uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
+    uint64_t const n_cosets = 1ull << (n_qubits - (12 - v));
+    if (MODE == 1)
+        FP_TRY(ctx->partials.ensure(n_cosets * Bpad * 2 * sizeof(T)));
+    for (size_t p = 0; p < passes->size(); ++p)
+    {
+        int const b = (p == 0) ? beta : 1;
+        FP_TRY((launch_coset_pass_v<T, EPV, MODE>(ctx, v, (*passes)[p].view, n_qubits, rowvecs, in, out, b,
+                                                   ctx->partials.p, Bpad, Wre, Wim, B)));
+        if (MODE == 1)
+        {
+            unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
+            finalize_complex_kernel<T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
+                static_cast<Cx<T> const *>(ctx->partials.p), n_cosets, Bpad, B, static_cast<Cx<T> *>(out), b);
+            ctx->launches++;
+        }
+    }
+    *used = true;
+    return FP_OK;
+}
+
 // ---------------------------------------------------------------- launchers (all pointers are device pointers here)
 template <typename T, int EPV, int MODE, bool INLINE1>
 void launch_op_v(fp_ctx *ctx, GeomSel const &gs, OpView<T> const &view, void const *in, void *out, void *partials,
@@ -462,7 +666,8 @@ void launch_op_v(fp_ctx *ctx, GeomSel const &gs, OpView<T> const &view, void con
 }
 
 template <typename T>
-int run_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const *in, uint64_t dim, uint64_t B, int beta)
+int run_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const *in, uint64_t dim, uint64_t B, int beta,
+                 int n_qubits = 0)
 {
     if (dim == 0 || B == 0)
         return FP_OK;
@@ -475,6 +680,13 @@ int run_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const *in, 
     }
     FP_TRY(check_align(in, 2 * sizeof(T), "states"));
     FP_TRY(check_align(out, 2 * sizeof(T), "new_states"));
+    if (op.host.gx.size() > 1 && n_qubits > 0)
+    {
+        bool used = false;
+        FP_TRY((try_coset<T, 0>(ctx, op, n_qubits, out, in, dim, B, beta, nullptr, nullptr, &used)));
+        if (used)
+            return FP_OK;
+    }
     int const epv = pick_epv<T>(in, out, B);
     uint64_t const rowvecs = B / epv;
     bool const single = op.host.sz.size() == 1;
@@ -501,7 +713,7 @@ int run_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const *in, 
 
 template <typename T>
 int run_op_expval(fp_ctx *ctx, DeviceOp<T> const &op, void *out /* B complex, device */, void const *in, uint64_t dim,
-                  uint64_t B, int beta)
+                  uint64_t B, int beta, int n_qubits = 0)
 {
     if (B == 0)
         return FP_OK;
@@ -512,6 +724,13 @@ int run_op_expval(fp_ctx *ctx, DeviceOp<T> const &op, void *out /* B complex, de
         return FP_OK;
     }
     FP_TRY(check_align(in, 2 * sizeof(T), "states"));
+    if (op.host.gx.size() > 1 && n_qubits > 0)
+    {
+        bool used = false;
+        FP_TRY((try_coset<T, 1>(ctx, op, n_qubits, out, in, dim, B, beta, nullptr, nullptr, &used)));
+        if (used)
+            return FP_OK;
+    }
     int const epv = pick_epv<T>(in, in, B);
     uint64_t const rowvecs = B / epv;
     GeomSel gs = choose_geom(ctx, dim, dim, rowvecs, 2 * sizeof(T) * epv, op.host.gx.size() > 1, true, 1, true);
@@ -740,6 +959,10 @@ extern "C"
             ctx->l2_budget = static_cast<size_t>(prop.l2CacheSize) / 3; // one die's worth of L2 minus headroom
         if (char const *env = getenv("FASTPAULI_L2_BUDGET"))
             ctx->l2_budget = strtoull(env, nullptr, 10);
+        if (char const *env = getenv("FASTPAULI_COSET"))
+            ctx->coset_mode = atoi(env);
+        if (char const *env = getenv("FASTPAULI_COSET_LOG_TWC"))
+            ctx->coset_log_twc = atoi(env);
         if (char const *env = getenv("FASTPAULI_TENSOR_CORE"))
             ctx->tensor_core = atoi(env) != 0;
         if (prop.major != 10)
@@ -794,6 +1017,15 @@ extern "C"
         if (!ctx)
             return set_err(FP_INVALID_ARGUMENT, "null context");
         ctx->tensor_core = enable != 0;
+        return FP_OK;
+    }
+
+    int fp_ctx_set_coset(fp_ctx *ctx, int mode, int log_twc)
+    {
+        if (!ctx || mode < 0 || mode > 2 || log_twc > 4)
+            return set_err(FP_INVALID_ARGUMENT, "bad coset mode");
+        ctx->coset_mode = mode;
+        ctx->coset_log_twc = log_twc;
         return FP_OK;
     }
 
@@ -1103,9 +1335,9 @@ extern "C"
         FP_TRY(stage_in(ctx, ctx->stage_in, in, bytes, true, sin));
         FP_TRY(stage_in(ctx, ctx->stage_out, out, bytes, accumulate != 0, sout));
         if (op->dtype == FP_C128)
-            FP_TRY(run_op_apply<double>(ctx, op->d, sout.dev, sin.dev, dim, n_states, accumulate));
+            FP_TRY(run_op_apply<double>(ctx, op->d, sout.dev, sin.dev, dim, n_states, accumulate, op->n_qubits));
         else
-            FP_TRY(run_op_apply<float>(ctx, op->f, sout.dev, sin.dev, dim, n_states, accumulate));
+            FP_TRY(run_op_apply<float>(ctx, op->f, sout.dev, sin.dev, dim, n_states, accumulate, op->n_qubits));
         FP_TRY(stage_back(ctx, sout));
         return finish(ctx, sin.staged || sout.staged);
     }
@@ -1125,9 +1357,9 @@ extern "C"
         FP_TRY(stage_in(ctx, ctx->stage_in, in, dim * n_states * csize(op->dtype), true, sin));
         FP_TRY(stage_in(ctx, ctx->stage_out, out, n_states * csize(op->dtype), accumulate != 0, sout));
         if (op->dtype == FP_C128)
-            FP_TRY(run_op_expval<double>(ctx, op->d, sout.dev, sin.dev, dim, n_states, accumulate));
+            FP_TRY(run_op_expval<double>(ctx, op->d, sout.dev, sin.dev, dim, n_states, accumulate, op->n_qubits));
         else
-            FP_TRY(run_op_expval<float>(ctx, op->f, sout.dev, sin.dev, dim, n_states, accumulate));
+            FP_TRY(run_op_expval<float>(ctx, op->f, sout.dev, sin.dev, dim, n_states, accumulate, op->n_qubits));
         FP_TRY(stage_back(ctx, sout));
         return finish(ctx, sin.staged || sout.staged);
     }
@@ -1227,12 +1459,19 @@ int run_sop_weighted(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, 
     FP_TRY((run_gemm<T, DT>(ctx, static_cast<T const *>(sop->A_w), data, W, 2 * S, B, K, 1, K ? K : 1)));
     FP_TRY(check_align(in, 2 * sizeof(T), "states"));
     FP_TRY(check_align(out, 2 * sizeof(T), "new_states"));
+    T const *Wre = W, *Wim = W + static_cast<uint64_t>(S) * B;
+    if (op.host.gx.size() > 1)
+    {
+        bool used = false;
+        FP_TRY((try_coset<T, 2>(ctx, op, sop->n_qubits, out, in, dim, B, beta, Wre, Wim, &used)));
+        if (used)
+            return FP_OK;
+    }
     int const epv = pick_epv<T>(in, out, B);
     uint64_t const rowvecs = B / epv;
     GeomSel gs = choose_geom(ctx, dim, dim, rowvecs, 2 * sizeof(T) * epv, op.host.gx.size() > 1, false);
     FP_TRY(check_grid(gs.grid));
     OpView<T> view = op.view();
-    T const *Wre = W, *Wim = W + static_cast<uint64_t>(S) * B;
     dim3 grid(static_cast<unsigned>(gs.grid));
     bool done = false;
     if constexpr (sizeof(T) == 4)

@@ -76,6 +76,10 @@ extern "C"
     int fp_ctx_sync(fp_ctx *ctx);
     /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
     int fp_ctx_launch_count(const fp_ctx *ctx, uint64_t *count);
+    /* Coset-blocked (state tile in shared memory) kernels for multi-x-mask operators: mode 0 = never, 1 = heuristic
+     * (default), 2 = whenever applicable; log_twc >= 0 forces the tile shape (2^log_twc vectors x 2^(12-log_twc) rows),
+     * -1 = automatic. */
+    int fp_ctx_set_coset(fp_ctx *ctx, int mode, int log_twc);
     /* Override the L2 working-set budget (bytes) used to pick the batch-tile width of multi-group kernels. */
     int fp_ctx_set_l2_budget(fp_ctx *ctx, size_t bytes);
 

@@ -305,6 +305,75 @@ def test_batch_tiling_invariance():
         assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi)) < 1e-12
 
 
+# ------------------------------------------------------------------ coset-blocked (shared-memory tile) kernels
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("log_twc", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("kind", ["random", "weight4"])
+def test_coset_kernels_every_tile_shape(dtype, log_twc, kind):
+    """Force every tile shape (2^log_twc vectors x 2^(12-log_twc) rows) through apply / expectation_value /
+    apply_weighted; n > tile rank and dense random masks give several passes, weight<=4 masks exercise the
+    bit-subset cover of the planner."""
+    ctx = fp.Context(0)
+    ctx.set_coset(2, log_twc)
+    rng = np.random.default_rng(100 + log_twc)
+    n, S, B, K = 13, 90, 32, 3
+    strings = rand_strings(rng, n, S, max_weight=4 if kind == "weight4" else None)
+    strings[5] = "Z" * n
+    strings[6] = strings[7]
+    h = (rand_states(rng, S, None, dtype) * 2 - (1 + 1j)).astype(dtype)
+    hk = (rand_states(rng, S, K, dtype) * 2 - (1 + 1j)).astype(dtype)
+    psi = rand_states(rng, 2**n, B, dtype)
+    data = rng.random((K, B)).astype(np.float64 if dtype == np.complex128 else np.float32)
+    base = rand_states(rng, 2**n, B, dtype)
+    t = tol(dtype)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    l0 = ctx.launch_count
+    assert rel_err(op.apply(psi), ORC.op_apply(strings, h, psi, par=True)) < t
+    n_launch = ctx.launch_count - l0
+    assert_parity(op.expectation_value(psi), lambda *a: ORC.op_expval(*a, par=True), dtype, strings, h, psi)
+    sop = fp.SummedPauliOp(strings, hk, ctx=ctx)
+    assert rel_err(sop.apply_weighted(psi, data), ORC.sop_apply_weighted(strings, hk, psi, data, par=True)) < t
+    assert rel_err(sop.apply(psi), ORC.sop_apply(strings, hk, psi, par=True)) < t
+    # accumulate through the raw ABI on this context
+    import ctypes as C
+
+    out = base.copy()
+    rc = fp.lib.fp_op_apply(ctx._h, op._plan(dtype), C.c_void_p(out.ctypes.data), C.c_void_p(psi.ctypes.data),
+                            C.c_size_t(2**n), C.c_size_t(B), C.c_int(1))
+    assert rc == 0
+    assert rel_err(out, ORC.op_apply(strings, h, psi, out=base.copy(), par=True)) < t
+    # the forced path really is the coset kernel: one launch per pass, far fewer launches than x-groups
+    assert 1 <= n_launch <= max(1, op.plan_info(dtype)["n_x_groups"] // 2)
+    # and it agrees with the generic gather kernel
+    ctx0 = fp.Context(0)
+    ctx0.set_coset(0, -1)
+    assert rel_err(fp.PauliOp(h, strings, ctx=ctx0).apply(psi), op.apply(psi)) < t
+
+
+def test_coset_heuristic_default_path():
+    # default heuristics on a problem large enough to fill the chip: 8 x-masks x 8 z-variants (single pass, rank 8)
+    rng = np.random.default_rng(77)
+    n, B = 16, 64
+    xs = rand_strings(rng, n, 8)
+    strings = []
+    for s in xs:
+        for _ in range(8):
+            tt = list(s)
+            for q in range(n):
+                if rng.random() < 0.5:
+                    tt[q] = {"X": "Y", "Y": "X", "I": "Z", "Z": "I"}[tt[q]]
+            strings.append("".join(tt))
+    h = rand_states(rng, len(strings), None) * 2 - (1 + 1j)
+    psi = rand_states(rng, 2**n, B)
+    ctx = fp.Context(0)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    l0 = ctx.launch_count
+    got = op.apply(psi)
+    assert ctx.launch_count - l0 == 1  # one coset pass
+    assert rel_err(got, ORC.op_apply(strings, h, psi, par=True)) < 1e-12
+    assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi, par=True)) < 1e-12
+
+
 # ------------------------------------------------------------------ BASELINE configs
 def test_config1_pauli_op_apply_10q():
     # "PauliOp.apply, 10 qubits, 64 random Pauli strings, batch 16 states, complex128"
