@@ -1,0 +1,116 @@
+#!/usr/bin/env python
+"""Run ONE device-resident workload a few times (for ncu captures and quick timing).
+
+    python scripts/run_case.py few20|rand20|cfg3|cfg4w|cfg4e|str20 [--iters N] [--coset MODE] [--log-twc V]
+"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+
+fp = load_package()
+from fast_pauli_b200.synth import random_strings  # noqa: E402
+
+
+def vp(p):
+    return C.c_void_p(p)
+
+
+def sz(v):
+    return C.c_size_t(v)
+
+
+def timed(ctx, fn, iters):
+    fn()
+    ctx.sync()
+    e0, e1 = C.c_void_p(), C.c_void_p()
+    fp.lib.fp_event_create(C.byref(e0))
+    fp.lib.fp_event_create(C.byref(e1))
+    fp.lib.fp_event_record(ctx._h, e0)
+    for _ in range(iters):
+        fn()
+    fp.lib.fp_event_record(ctx._h, e1)
+    ms = C.c_float()
+    fp.lib.fp_event_elapsed_ms(e0, e1, C.byref(ms))
+    return ms.value / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("case")
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--coset", type=int, default=1)
+    ap.add_argument("--log-twc", type=int, default=-1)
+    ap.add_argument("--batch", type=int, default=0)
+    a = ap.parse_args()
+    ctx = fp.Context(0)
+    ctx.set_coset(a.coset, a.log_twc)
+    ctx.set_async(True)
+    rng = np.random.default_rng(1234)
+    if a.case in ("few20", "rand20"):
+        n, B = 20, a.batch or 64
+        if a.case == "few20":
+            xs = random_strings(rng, n, 8)
+            strings = []
+            for s in xs:
+                for _ in range(8):
+                    t = list(s)
+                    for q in range(n):
+                        if rng.random() < 0.5:
+                            t[q] = {"X": "Y", "Y": "X", "I": "Z", "Z": "I"}[t[q]]
+                    strings.append("".join(t))
+        else:
+            strings = random_strings(rng, n, 64)
+        h = rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))
+        psi = ctx.uniform((1 << n, B), np.complex128)
+        op = fp.PauliOp(h, strings, ctx=ctx)
+        y = ctx.empty((1 << n, B), np.complex128)
+        plan = op._plan(np.complex128)
+        ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
+        amps = (1 << n) * B
+        print(f"{a.case}: {ms:.3f} ms  {amps*32/ms/1e6:.0f} GB/s algorithmic  groups={op.plan_info()['n_x_groups']}")
+    elif a.case == "cfg3":
+        n, B, S = 16, a.batch or 1024, 2000
+        strings = random_strings(rng, n, S, max_weight=4)
+        h = rng.uniform(-1, 1, S) + 1j * rng.uniform(-1, 1, S)
+        psi = ctx.uniform((1 << n, B), np.complex128)
+        op = fp.PauliOp(h, strings, ctx=ctx)
+        y = ctx.empty((1 << n, B), np.complex128)
+        plan = op._plan(np.complex128)
+        l0 = ctx.launch_count
+        ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
+        print(f"cfg3: {ms:.3f} ms  launches/call={(ctx.launch_count-l0)//(a.iters+1)} groups={op.plan_info()['n_x_groups']}")
+    elif a.case in ("cfg4w", "cfg4e"):
+        n, B, S, K = 12, a.batch or 4096, 10000, 64
+        strings = random_strings(rng, n, S)
+        hk = (rng.uniform(-1, 1, (S, K)) + 1j * rng.uniform(-1, 1, (S, K))).astype(np.complex64)
+        psi = ctx.uniform((1 << n, B), np.complex64)
+        data = ctx.to_device(rng.random((K, B)).astype(np.float32))
+        sop = fp.SummedPauliOp(strings, hk, ctx=ctx)
+        plan = sop._plan(np.complex64)
+        y = ctx.empty((1 << n, B), np.complex64)
+        ev = ctx.empty((K, B), np.complex64)
+        if a.case == "cfg4w":
+            ms = timed(ctx, lambda: fp.lib.fp_sop_apply_weighted(ctx._h, plan, vp(y.ptr), vp(psi.ptr), vp(data.ptr), 0,
+                                                                 sz(1 << n), sz(B), 0), a.iters)
+        else:
+            ms = timed(ctx, lambda: fp.lib.fp_sop_expval(ctx._h, plan, vp(ev.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0),
+                       a.iters)
+        print(f"{a.case}: {ms:.3f} ms")
+    elif a.case == "str20":
+        n, B = 20, a.batch or 256
+        psi = ctx.uniform((1 << n, B), np.complex128)
+        ps = fp.PauliString(random_strings(rng, n, 1)[0], ctx=ctx)
+        ms = timed(ctx, lambda: ps.apply(psi), a.iters)
+        print(f"str20 apply: {ms:.3f} ms")
+    ctx.sync()
+
+
+if __name__ == "__main__":
+    main()
