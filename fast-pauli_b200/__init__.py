@@ -100,9 +100,10 @@ class Context:
     def set_tensor_core(self, flag: bool) -> None:
         _check(lib.fp_ctx_set_tensor_core(self._h, C.c_int(bool(flag))))
 
-    def set_coset(self, mode: int = 1, log_twc: int = -1) -> None:
-        """Coset-blocked kernels: mode 0 never / 1 heuristic / 2 whenever applicable; log_twc forces the tile shape."""
-        _check(lib.fp_ctx_set_coset(self._h, C.c_int(mode), C.c_int(log_twc)))
+    def set_coset(self, mode: int = 1, log_twc: int = -1, log_nt: int = 0) -> None:
+        """Coset-blocked kernels: mode 0 never / 1 heuristic / 2 whenever applicable; log_twc / log_nt force the tile
+        shape (2^log_twc vectors per row segment, 2^log_nt threads per CTA)."""
+        _check(lib.fp_ctx_set_coset(self._h, C.c_int(mode), C.c_int(log_twc), C.c_int(log_nt)))
 
     def set_l2_budget(self, nbytes: int) -> None:
         _check(lib.fp_ctx_set_l2_budget(self._h, C.c_size_t(nbytes)))

@@ -110,7 +110,8 @@ struct fp_ctx
     uint64_t launches = 0;
     size_t l2_budget = 40ull << 20;
     int coset_mode = 1;       // 0: never use the coset-blocked kernels, 1: heuristic, 2: whenever applicable
-    int coset_log_twc = -1;   // >= 0 forces the tile shape (TWc = 1 << v vectors, rank 12 - v)
+    int coset_log_twc = -1;   // >= 0 forces the row-segment width of the tile (TWc = 1 << v vectors)
+    int coset_log_nt = 0;     // 7 or 8 forces the CTA size (128 / 256 threads); 0 = default (256)
     Scratch stage_in, stage_out, stage_data, partials, work_a, work_b, meta;
     std::mutex mu;
 };
@@ -133,7 +134,7 @@ template <typename T> struct DeviceOp
     bool any_diag = false;
     int x_rank = 0; // GF(2) rank of the x-masks (capped at kCosetMaxRank + 1)
 
-    // coset-blocked plans, built lazily per tile shape (key: LOG_TWC)
+    // coset-blocked plans, built lazily per tile rank (key: rank = log2 rows per tile)
     struct CosetPassDev
     {
         CosetPassView<T> view{};
@@ -275,16 +276,15 @@ template <typename T> int upload_op(DeviceOp<T> &d)
 
 // ---------------------------------------------------------------- coset-blocked path: plan cache + launch
 template <typename T>
-int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int log_twc,
+int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank,
                    std::vector<typename DeviceOp<T>::CosetPassDev> const **out)
 {
-    auto it = op.coset_plans.find(log_twc);
+    auto it = op.coset_plans.find(rank);
     if (it != op.coset_plans.end())
     {
         *out = &it->second;
         return FP_OK;
     }
-    int const rank = 12 - log_twc;
     std::vector<CosetPassHost<T>> host = plan_coset<T>(op.host, n_qubits, rank);
     std::vector<typename DeviceOp<T>::CosetPassDev> dev(host.size());
     for (size_t p = 0; p < host.size(); ++p)
@@ -325,7 +325,7 @@ int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int log_twc,
         d.view.scoef = sc;
         d.view.sidx = sidx;
     }
-    auto ins = op.coset_plans.emplace(log_twc, std::move(dev));
+    auto ins = op.coset_plans.emplace(rank, std::move(dev));
     *out = &ins.first->second;
     return FP_OK;
 }
@@ -520,54 +520,90 @@ int check_grid(uint64_t grid)
 }
 
 // ---------------------------------------------------------------- coset-blocked path: heuristics + launch
-// Pick the tile shape (LOG_TWC: TWc = 2^v vectors per row, rank 12 - v) or -1 for "use the generic gather kernel".
-template <typename T>
-int choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, uint64_t rowvecs, int epv)
+struct CosetShape
 {
-    if (ctx->coset_mode == 0 || n_qubits < 8 || op.host.gx.size() < 2)
-        return -1;
+    int log_twc = -1; // TWc = 2^log_twc vectors per row segment
+    int log_nt = 8;   // threads per CTA (tile = 16 * NT vectors)
+    int rank() const
+    {
+        return 4 + log_nt - log_twc;
+    }
+    bool ok() const
+    {
+        return log_twc >= 0;
+    }
+};
+
+// Pick the tile shape, or an invalid shape for "use the generic gather kernel".
+template <typename T>
+CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, uint64_t rowvecs, int epv)
+{
+    CosetShape none;
+    if (ctx->coset_mode == 0 || op.host.gx.size() < 2)
+        return none;
     if (sizeof(T) == 4 && epv != 2)
-        return -1;
-    auto valid = [&](int v) { return v >= 0 && v <= 4 && (rowvecs % (1ull << v)) == 0 && (12 - v) <= n_qubits; };
-    int pick = -1;
+        return none;
+    auto valid = [&](int v, int lnt) {
+        return v >= 0 && v <= 4 && (lnt == 7 || lnt == 8) && (rowvecs % (1ull << v)) == 0 && (4 + lnt - v) <= n_qubits;
+    };
+    CosetShape pick;
     if (ctx->coset_log_twc >= 0)
-        pick = valid(ctx->coset_log_twc) ? ctx->coset_log_twc : -1;
+    {
+        int lnt = ctx->coset_log_nt > 0 ? ctx->coset_log_nt : 8;
+        if (valid(ctx->coset_log_twc, lnt))
+        {
+            pick.log_twc = ctx->coset_log_twc;
+            pick.log_nt = lnt;
+        }
+    }
     else
     {
-        for (int v = 4; v >= 2 && pick < 0; --v) // widest tile whose rank covers the operator in a single pass
-            if (op.x_rank <= 12 - v && valid(v))
-                pick = v;
-        if (pick < 0 && n_qubits <= 12 && valid(12 - n_qubits))
-            pick = 12 - n_qubits; // the whole state column fits one tile: single pass
+        int const lnt_pref = ctx->coset_log_nt > 0 ? ctx->coset_log_nt : 8;
+        // widest row segment whose tile rank covers the whole operator in a single pass
+        for (int v = 4; v >= 2 && !pick.ok(); --v)
+            if (op.x_rank <= 4 + lnt_pref - v && valid(v, lnt_pref))
+            {
+                pick.log_twc = v;
+                pick.log_nt = lnt_pref;
+            }
+        // the whole state column fits one tile: single pass whatever the operator
+        if (!pick.ok() && n_qubits <= 12 && valid(12 - n_qubits, 8))
+        {
+            pick.log_twc = 12 - n_qubits;
+            pick.log_nt = 8;
+        }
         for (int v : {2, 3, 4, 1, 0})
-            if (pick < 0 && valid(v))
-                pick = v;
+            if (!pick.ok() && valid(v, lnt_pref))
+            {
+                pick.log_twc = v;
+                pick.log_nt = lnt_pref;
+            }
     }
-    if (pick < 0)
-        return -1;
-    uint64_t const ctas = (1ull << (n_qubits - (12 - pick))) * (rowvecs >> pick);
+    if (!pick.ok())
+        return none;
+    uint64_t const ctas = (1ull << (n_qubits - pick.rank())) * (rowvecs >> pick.log_twc);
     if (ctx->coset_mode == 1 && ctas < static_cast<uint64_t>(ctx->sm_count))
-        return -1;
+        return none;
     return pick;
 }
 
-template <typename T, int EPV, int LOG_TWC, int MODE>
+template <typename T, int EPV, int LOG_TWC, int LOG_NT, int MODE>
 int launch_coset_pass(fp_ctx *ctx, CosetPassView<T> const &view, int n_qubits, uint64_t rowvecs, void const *in,
                       void *out, int beta, void *partials, uint32_t Bpad, T const *Wre, T const *Wim, uint64_t B)
 {
-    using Cfg = CosetCfg<LOG_TWC>;
-    size_t const smem = Cfg::TILE_BYTES + coset_meta_bytes<T>();
+    using Cfg = CosetCfg<LOG_TWC, LOG_NT>;
+    size_t const smem = coset_smem_bytes<T, LOG_TWC, LOG_NT>();
     static bool configured = false; // per template instance
     if (!configured)
     {
-        FP_CU(cudaFuncSetAttribute(coset_kernel<T, EPV, LOG_TWC, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
+        FP_CU(cudaFuncSetAttribute(coset_kernel<T, EPV, LOG_TWC, LOG_NT, MODE>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured = true;
     }
     uint32_t const nct = static_cast<uint32_t>(rowvecs >> LOG_TWC);
     uint64_t const grid = (1ull << (n_qubits - Cfg::R)) * nct;
     FP_TRY(check_grid(grid));
-    coset_kernel<T, EPV, LOG_TWC, MODE><<<static_cast<unsigned>(grid), kThreads, smem, ctx->stream>>>(
+    coset_kernel<T, EPV, LOG_TWC, LOG_NT, MODE><<<static_cast<unsigned>(grid), Cfg::NT, smem, ctx->stream>>>(
         view, rowvecs, nct, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta,
         static_cast<Cx<T> *>(partials), Bpad, Wre, Wim, B);
     ctx->launches++;
@@ -575,23 +611,26 @@ int launch_coset_pass(fp_ctx *ctx, CosetPassView<T> const &view, int n_qubits, u
 }
 
 template <typename T, int EPV, int MODE>
-int launch_coset_pass_v(fp_ctx *ctx, int log_twc, CosetPassView<T> const &view, int n_qubits, uint64_t rowvecs,
+int launch_coset_pass_v(fp_ctx *ctx, CosetShape shape, CosetPassView<T> const &view, int n_qubits, uint64_t rowvecs,
                         void const *in, void *out, int beta, void *partials, uint32_t Bpad, T const *Wre, T const *Wim,
                         uint64_t B)
 {
-    switch (log_twc)
-    {
-    case 0:
-        return launch_coset_pass<T, EPV, 0, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad, Wre, Wim, B);
-    case 1:
-        return launch_coset_pass<T, EPV, 1, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad, Wre, Wim, B);
-    case 2:
-        return launch_coset_pass<T, EPV, 2, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad, Wre, Wim, B);
-    case 3:
-        return launch_coset_pass<T, EPV, 3, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad, Wre, Wim, B);
-    default:
-        return launch_coset_pass<T, EPV, 4, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad, Wre, Wim, B);
-    }
+#define FP_COSET_CASE(V, LNT)                                                                                          \
+    if (shape.log_twc == V && shape.log_nt == LNT)                                                                     \
+        return launch_coset_pass<T, EPV, V, LNT, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad,    \
+                                                       Wre, Wim, B);
+    FP_COSET_CASE(0, 8)
+    FP_COSET_CASE(1, 8)
+    FP_COSET_CASE(2, 8)
+    FP_COSET_CASE(3, 8)
+    FP_COSET_CASE(4, 8)
+    FP_COSET_CASE(0, 7)
+    FP_COSET_CASE(1, 7)
+    FP_COSET_CASE(2, 7)
+    FP_COSET_CASE(3, 7)
+    FP_COSET_CASE(4, 7)
+#undef FP_COSET_CASE
+    return set_err(FP_UNSUPPORTED, "unsupported coset tile shape");
 }
 
 // Runs all passes.  Returns FP_OK with *used = false when the generic kernel should be used instead.
@@ -601,28 +640,28 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
 {
     *used = false;
     constexpr int EPV = sizeof(T) == 4 ? 2 : 1;
-    if (dim != (1ull << n_qubits))
+    if (n_qubits <= 0 || dim != (1ull << n_qubits))
         return FP_OK;
     int const epv = pick_epv<T>(in, MODE == 1 ? in : out, B);
     if (epv != EPV)
         return FP_OK;
     uint64_t const rowvecs = B / EPV;
-    int const v = choose_coset<T>(ctx, op, n_qubits, rowvecs, epv);
-    if (v < 0)
+    CosetShape const shape = choose_coset<T>(ctx, op, n_qubits, rowvecs, epv);
+    if (!shape.ok())
         return FP_OK;
     std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
-    FP_TRY(get_coset_plan<T>(op, n_qubits, v, &passes));
+    FP_TRY(get_coset_plan<T>(op, n_qubits, shape.rank(), &passes));
     // every pass re-streams the batch (read in, read-modify-write out): only worth it while passes << groups
     if (ctx->coset_mode == 1 && passes->size() * 3 > op.host.gx.size() && passes->size() > 1)
         return FP_OK;
     uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
-    uint64_t const n_cosets = 1ull << (n_qubits - (12 - v));
+    uint64_t const n_cosets = 1ull << (n_qubits - shape.rank());
     if (MODE == 1)
         FP_TRY(ctx->partials.ensure(n_cosets * Bpad * 2 * sizeof(T)));
     for (size_t p = 0; p < passes->size(); ++p)
     {
         int const b = (p == 0) ? beta : 1;
-        FP_TRY((launch_coset_pass_v<T, EPV, MODE>(ctx, v, (*passes)[p].view, n_qubits, rowvecs, in, out, b,
+        FP_TRY((launch_coset_pass_v<T, EPV, MODE>(ctx, shape, (*passes)[p].view, n_qubits, rowvecs, in, out, b,
                                                    ctx->partials.p, Bpad, Wre, Wim, B)));
         if (MODE == 1)
         {
@@ -963,6 +1002,8 @@ extern "C"
             ctx->coset_mode = atoi(env);
         if (char const *env = getenv("FASTPAULI_COSET_LOG_TWC"))
             ctx->coset_log_twc = atoi(env);
+        if (char const *env = getenv("FASTPAULI_COSET_LOG_NT"))
+            ctx->coset_log_nt = atoi(env);
         if (char const *env = getenv("FASTPAULI_TENSOR_CORE"))
             ctx->tensor_core = atoi(env) != 0;
         if (prop.major != 10)
@@ -1020,12 +1061,13 @@ extern "C"
         return FP_OK;
     }
 
-    int fp_ctx_set_coset(fp_ctx *ctx, int mode, int log_twc)
+    int fp_ctx_set_coset(fp_ctx *ctx, int mode, int log_twc, int log_nt)
     {
-        if (!ctx || mode < 0 || mode > 2 || log_twc > 4)
+        if (!ctx || mode < 0 || mode > 2 || log_twc > 4 || !(log_nt == 0 || log_nt == 7 || log_nt == 8))
             return set_err(FP_INVALID_ARGUMENT, "bad coset mode");
         ctx->coset_mode = mode;
         ctx->coset_log_twc = log_twc;
+        ctx->coset_log_nt = log_nt;
         return FP_OK;
     }
 

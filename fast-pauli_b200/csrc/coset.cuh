@@ -74,69 +74,99 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-template <int LOG_TWC> struct CosetCfg
+// Tile shape: NT threads per CTA, every thread owns 16 vectors (RPT rows x TWC vectors), so a tile holds
+// NT * 16 vectors (64 KiB at NT = 256, 32 KiB at NT = 128) and spans rank R = log2(NT * 16 / TWC) row bits.
+template <int LOG_TWC, int LOG_NT> struct CosetCfg
 {
-    static constexpr int TWC = 1 << LOG_TWC;           // vectors per row in the tile
-    static constexpr int RPT = 16 >> LOG_TWC;          // rows per thread
-    static constexpr int R = 12 - LOG_TWC;             // tile rank: 2^R rows
+    static constexpr int NT = 1 << LOG_NT;
+    static constexpr int TWC = 1 << LOG_TWC;              // vectors per row in the tile
+    static constexpr int RPT = 16 >> LOG_TWC;             // rows per thread
+    static constexpr int R = 4 + LOG_NT - LOG_TWC;        // tile rank: 2^R rows
     static constexpr int ROWS = 1 << R;
-    static constexpr int PITCH = TWC + (TWC > 1 ? 1 : 0); // row pitch in vectors (padded)
+    static constexpr int PITCH = TWC + (TWC > 1 ? 1 : 0); // row pitch in vectors (padded against bank conflicts)
     static constexpr size_t TILE_BYTES = static_cast<size_t>(ROWS) * PITCH * 16;
 };
 
-template <typename T> constexpr size_t coset_meta_bytes()
+// staged string metadata (per chunk) + small tables + cross-warp reduction scratch
+template <typename T> struct CosetSmemLayout
 {
-    // s_c[CH_S] + s_zl[CH_S] + s_sidx[CH_S] + s_gxl[CH_G] + s_gstart[CH_G+1] + comb_hi[16]
-    return kCosetChunkStrings * (sizeof(Cx<T>) + 4 + 4) + kCosetChunkGroups * 4 + (kCosetChunkGroups + 1) * 4 + 16 * 8 +
-           64;
+    static constexpr size_t off_c = 0;                                                // Cx<T>  [CH_S]
+    static constexpr size_t off_zl = off_c + kCosetChunkStrings * sizeof(Cx<T>);     // uint32 [CH_S] local z
+    static constexpr size_t off_aux = off_zl + kCosetChunkStrings * 4;               // uint32 [CH_S] row-slot sign mask
+    static constexpr size_t off_sidx = off_aux + kCosetChunkStrings * 4;             // uint32 [CH_S] W row (MODE 2)
+    static constexpr size_t off_gxl = off_sidx + kCosetChunkStrings * 4;             // uint32 [CH_G]
+    static constexpr size_t off_gstart = off_gxl + kCosetChunkGroups * 4;            // uint32 [CH_G + 2]
+    static constexpr size_t off_comb_hi = off_gstart + (kCosetChunkGroups + 2) * 4;  // uint64 [16] load/store steps
+    static constexpr size_t off_red = (off_comb_hi + 16 * 8 + 15) / 16 * 16;         // Cx<T>  [8 warps][32 columns]
+    static constexpr size_t bytes = off_red + 8 * 32 * sizeof(Cx<T>);
+};
+
+template <typename T, int LOG_TWC, int LOG_NT> constexpr size_t coset_smem_bytes()
+{
+    return CosetCfg<LOG_TWC, LOG_NT>::TILE_BYTES + CosetSmemLayout<T>::bytes;
 }
 
-template <typename T, int EPV, int LOG_TWC, int MODE>
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ float sign_mul(float, uint32_t odd)
+{
+    return __int_as_float(0x3f800000 | static_cast<int>(odd << 31));
+}
+__device__ __forceinline__ double sign_mul(double, uint32_t odd)
+{
+    return __hiloint2double(0x3ff00000 | static_cast<int>(odd << 31), 0);
+}
+
+// One CTA per (coset, column tile).  Several CTAs are resident per SM (2 at NT = 256, 4 at NT = 128) so that some
+// are streaming their tile in or out while the others evaluate groups; measured on B200 this beats a persistent
+// single-CTA double-buffered variant (too few warps to cover the LDS -> FMA latency) by 1.3-1.5x.
+template <typename T, int EPV, int LOG_TWC, int LOG_NT, int MODE>
+__global__ void __launch_bounds__(1 << LOG_NT)
     coset_kernel(CosetPassView<T> pass, uint64_t rowvecs, uint32_t nColTiles, CVec<T, EPV> const *__restrict__ in,
                  CVec<T, EPV> *__restrict__ out, int beta, Cx<T> *__restrict__ partials, uint32_t Bpad,
                  T const *__restrict__ Wre, T const *__restrict__ Wim, uint64_t B)
 {
-    using Cfg = CosetCfg<LOG_TWC>;
+    using Cfg = CosetCfg<LOG_TWC, LOG_NT>;
+    using L = CosetSmemLayout<T>;
     using Vec = CVec<T, EPV>;
-    constexpr int TWC = Cfg::TWC, RPT = Cfg::RPT, R = Cfg::R, PITCH = Cfg::PITCH;
-    constexpr int ROWS_PER_STEP = kThreads >> LOG_TWC; // rows covered by one cooperative load/store step
+    constexpr int NT = Cfg::NT, TWC = Cfg::TWC, RPT = Cfg::RPT, R = Cfg::R, PITCH = Cfg::PITCH;
+    constexpr int ROWS_PER_STEP = NT >> LOG_TWC; // rows covered by one cooperative load/store step
+    constexpr int NCOL = TWC * EPV;              // batch columns per tile
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Vec *tile = reinterpret_cast<Vec *>(smem_raw);
     unsigned char *meta = smem_raw + Cfg::TILE_BYTES;
-    Cx<T> *s_c = reinterpret_cast<Cx<T> *>(meta);
-    uint32_t *s_zl = reinterpret_cast<uint32_t *>(s_c + kCosetChunkStrings);
-    uint32_t *s_aux = s_zl + kCosetChunkStrings; // MODE 2: (sidx << 1) | sigma
-    uint32_t *s_gxl = s_aux + kCosetChunkStrings;
-    uint32_t *s_gstart = s_gxl + kCosetChunkGroups;
-    uint64_t *s_comb_hi = reinterpret_cast<uint64_t *>(s_gstart + kCosetChunkGroups + 2);
+    Cx<T> *s_c = reinterpret_cast<Cx<T> *>(meta + L::off_c);
+    uint32_t *s_zl = reinterpret_cast<uint32_t *>(meta + L::off_zl);
+    uint32_t *s_aux = reinterpret_cast<uint32_t *>(meta + L::off_aux);
+    uint32_t *s_sidx = reinterpret_cast<uint32_t *>(meta + L::off_sidx);
+    uint32_t *s_gxl = reinterpret_cast<uint32_t *>(meta + L::off_gxl);
+    uint32_t *s_gstart = reinterpret_cast<uint32_t *>(meta + L::off_gstart);
+    uint64_t *s_comb_hi = reinterpret_cast<uint64_t *>(meta + L::off_comb_hi);
+    Cx<T> *s_red = reinterpret_cast<Cx<T> *>(meta + L::off_red);
 
     uint32_t const tid = threadIdx.x;
     uint64_t const blk = blockIdx.x;
     uint64_t const coset = blk / nColTiles;
     uint32_t const ct = static_cast<uint32_t>(blk - coset * nColTiles);
     uint64_t const base = deposit_bits(coset, pass.nonpivot_mask);
+    uint64_t const t0 = static_cast<uint64_t>(ct) * NCOL; // first batch column of the tile
+    uint64_t const vcol0 = static_cast<uint64_t>(ct) * TWC;
 
-    // ---- cooperative load of the coset tile
+    // ---- cooperative load of the coset tile: vector jv of rows l_lo + k * ROWS_PER_STEP
     if (tid < 16)
         s_comb_hi[tid] = comb_of<R>(pass.basis, tid * ROWS_PER_STEP);
     uint32_t const l_lo = tid >> LOG_TWC;
     uint32_t const jv = tid & (TWC - 1);
     uint64_t const row_lo = base ^ comb_of<R>(pass.basis, l_lo);
-    uint64_t const col = static_cast<uint64_t>(ct) * TWC + jv;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k)
     {
         uint64_t row = row_lo ^ s_comb_hi[k];
         uint32_t l = l_lo + k * ROWS_PER_STEP;
-        cp_async16(&tile[l * PITCH + jv], &in[row * rowvecs + col]);
+        cp_async16(&tile[l * PITCH + jv], &in[row * rowvecs + vcol0 + jv]);
     }
-    cp_async_wait_all();
-    __syncthreads();
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
 
-    // ---- accumulate all groups of the pass out of shared memory
     Cx<T> acc[RPT][TWC][EPV];
 #pragma unroll
     for (int q = 0; q < RPT; ++q)
@@ -145,30 +175,35 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
             for (int e = 0; e < EPV; ++e)
                 acc[q][j][e] = Cx<T>{0, 0};
-    uint64_t const t0 = static_cast<uint64_t>(ct) * TWC * EPV; // first batch column of the tile (MODE 2)
 
     for (uint32_t ci = 0; ci < pass.n_chunks; ++ci)
     {
+        // stage this chunk's metadata; the coset-base sign and the sign of the row bits above the thread index
+        // (rows tid + NT*q, q < 16) are folded into one 16-bit mask per string
         CosetChunk const ch = pass.chunks[ci];
         uint32_t const ns = ch.s_hi - ch.s_lo, ng = ch.g_hi - ch.g_lo;
-        for (uint32_t s = tid; s < ns; s += kThreads)
+        for (uint32_t s = tid; s < ns; s += NT)
         {
-            uint32_t sigma = parity64(base & pass.sz[ch.s_lo + s]);
-            s_zl[s] = pass.szl[ch.s_lo + s];
+            uint32_t const zl = pass.szl[ch.s_lo + s];
+            uint32_t hp = parity64(base & pass.sz[ch.s_lo + s]) ? 0xffffu : 0u;
+#pragma unroll
+            for (uint32_t q = 0; q < RPT; ++q)
+                hp ^= (__popc((q << LOG_NT) & zl) & 1u) << q;
+            s_zl[s] = zl & (NT - 1);
+            s_aux[s] = hp;
             if (MODE == 2)
-                s_aux[s] = (pass.sidx[ch.s_lo + s] << 1) | sigma;
+                s_sidx[s] = pass.sidx[ch.s_lo + s];
             else
-            {
-                Cx<T> c = pass.scoef[ch.s_lo + s];
-                s_c[s] = Cx<T>{flip_sign(c.re, sigma), flip_sign(c.im, sigma)};
-            }
+                s_c[s] = pass.scoef[ch.s_lo + s];
         }
-        for (uint32_t gq = tid; gq <= ng; gq += kThreads)
+        for (uint32_t gq = tid; gq <= ng; gq += NT)
         {
             s_gstart[gq] = pass.gstart[ch.g_lo + gq] - ch.s_lo;
             if (gq < ng)
                 s_gxl[gq] = pass.gxl[ch.g_lo + gq];
         }
+        if (ci == 0)
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory"); // the tile landed while the metadata was staged
         __syncthreads();
 
         for (uint32_t gq = 0; gq < ng; ++gq)
@@ -183,12 +218,12 @@ __global__ void __launch_bounds__(kThreads)
                     d[q] = Cx<T>{0, 0};
                 for (uint32_t s = s0; s < s1; ++s)
                 {
-                    uint32_t const zl = s_zl[s];
                     Cx<T> const c = s_c[s];
+                    uint32_t const par = s_aux[s] ^ ((__popc(tid & s_zl[s]) & 1u) ? 0xffffu : 0u);
 #pragma unroll
                     for (int q = 0; q < RPT; ++q)
                     {
-                        uint32_t odd = __popc((tid + q * kThreads) & zl) & 1u;
+                        uint32_t odd = (par >> q) & 1u;
                         d[q].re += flip_sign(c.re, odd);
                         d[q].im += flip_sign(c.im, odd);
                     }
@@ -196,7 +231,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
                 for (int q = 0; q < RPT; ++q)
                 {
-                    Vec const *src = &tile[((tid + q * kThreads) ^ xl) * PITCH];
+                    Vec const *src = &tile[((tid + q * NT) ^ xl) * PITCH];
 #pragma unroll
                     for (int j = 0; j < TWC; ++j)
                     {
@@ -219,12 +254,11 @@ __global__ void __launch_bounds__(kThreads)
                             d[q][j][e] = Cx<T>{0, 0};
                 for (uint32_t s = s0; s < s1; ++s)
                 {
-                    uint32_t const zl = s_zl[s];
-                    uint32_t const aux = s_aux[s];
-                    uint64_t const wrow = static_cast<uint64_t>(aux >> 1) * B + t0;
-                    T wre[TWC * EPV], wim[TWC * EPV];
+                    uint32_t const par = s_aux[s] ^ ((__popc(tid & s_zl[s]) & 1u) ? 0xffffu : 0u);
+                    uint64_t const wrow = static_cast<uint64_t>(s_sidx[s]) * B + t0;
+                    T wre[NCOL], wim[NCOL];
 #pragma unroll
-                    for (int c = 0; c < TWC * EPV; ++c)
+                    for (int c = 0; c < NCOL; ++c)
                     {
                         wre[c] = __ldg(Wre + wrow + c);
                         wim[c] = __ldg(Wim + wrow + c);
@@ -232,21 +266,21 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
                     for (int q = 0; q < RPT; ++q)
                     {
-                        uint32_t odd = (__popc((tid + q * kThreads) & zl) + aux) & 1u;
+                        T const sf = sign_mul(T(0), (par >> q) & 1u); // +-1: one FMA per component, no sign flips
 #pragma unroll
                         for (int j = 0; j < TWC; ++j)
 #pragma unroll
                             for (int e = 0; e < EPV; ++e)
                             {
-                                d[q][j][e].re += flip_sign(wre[j * EPV + e], odd);
-                                d[q][j][e].im += flip_sign(wim[j * EPV + e], odd);
+                                d[q][j][e].re = fma(sf, wre[j * EPV + e], d[q][j][e].re);
+                                d[q][j][e].im = fma(sf, wim[j * EPV + e], d[q][j][e].im);
                             }
                     }
                 }
 #pragma unroll
                 for (int q = 0; q < RPT; ++q)
                 {
-                    Vec const *src = &tile[((tid + q * kThreads) ^ xl) * PITCH];
+                    Vec const *src = &tile[((tid + q * NT) ^ xl) * PITCH];
 #pragma unroll
                     for (int j = 0; j < TWC; ++j)
                     {
@@ -263,8 +297,7 @@ __global__ void __launch_bounds__(kThreads)
 
     if (MODE == 1)
     {
-        // e(col) = sum over this CTA's rows of conj(psi) * acc ; warp shuffle, then 8 warps through smem
-        Cx<T> e_col[TWC][EPV];
+        // e(col) = sum over this tile's rows of conj(psi) * acc: warp shuffle, then the warps through smem
 #pragma unroll
         for (int j = 0; j < TWC; ++j)
 #pragma unroll
@@ -274,7 +307,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
                 for (int q = 0; q < RPT; ++q)
                 {
-                    Cx<T> a = tile[(tid + q * kThreads) * PITCH + j].e[e];
+                    Cx<T> a = tile[(tid + q * NT) * PITCH + j].e[e];
                     sum.re = fma(a.re, acc[q][j][e].re, sum.re);
                     sum.re = fma(a.im, acc[q][j][e].im, sum.re);
                     sum.im = fma(a.re, acc[q][j][e].im, sum.im);
@@ -286,35 +319,27 @@ __global__ void __launch_bounds__(kThreads)
                     sum.re += __shfl_xor_sync(0xffffffffu, sum.re, off);
                     sum.im += __shfl_xor_sync(0xffffffffu, sum.im, off);
                 }
-                e_col[j][e] = sum;
+                if ((tid & 31) == 0)
+                    s_red[(tid >> 5) * 32 + j * EPV + e] = sum;
             }
-        __syncthreads(); // everyone is done reading the tile: reuse its first bytes for the cross-warp reduction
-        Cx<T> *red = reinterpret_cast<Cx<T> *>(smem_raw);
-        if ((tid & 31) == 0)
-        {
-#pragma unroll
-            for (int j = 0; j < TWC; ++j)
-#pragma unroll
-                for (int e = 0; e < EPV; ++e)
-                    red[(tid >> 5) * (TWC * EPV) + j * EPV + e] = e_col[j][e];
-        }
         __syncthreads();
-        if (tid < TWC * EPV)
+        if (tid < NCOL)
         {
             Cx<T> sum{0, 0};
 #pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w)
+            for (int w = 0; w < NT / 32; ++w)
             {
-                sum.re += red[w * (TWC * EPV) + tid].re;
-                sum.im += red[w * (TWC * EPV) + tid].im;
+                sum.re += s_red[w * 32 + tid].re;
+                sum.im += s_red[w * 32 + tid].im;
             }
             partials[coset * Bpad + t0 + tid] = sum;
         }
-        return;
     }
-
-    // ---- accumulators -> shared memory -> coalesced global stores
-    __syncthreads();
+    else
+    {
+    // ---- accumulators -> the (now dead) tile buffer -> coalesced 16-byte stores: a warp writes whole TWC*16-byte
+    // row segments (direct register stores scatter 32 sixteen-byte pieces per instruction and saturate the LSU
+    // queue: measured 2.7x slower)
 #pragma unroll
     for (int q = 0; q < RPT; ++q)
 #pragma unroll
@@ -324,7 +349,7 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
             for (int e = 0; e < EPV; ++e)
                 v.e[e] = acc[q][j][e];
-            tile[(tid + q * kThreads) * PITCH + j] = v;
+            tile[(tid + q * NT) * PITCH + j] = v;
         }
     __syncthreads();
 #pragma unroll
@@ -333,7 +358,7 @@ __global__ void __launch_bounds__(kThreads)
         uint64_t row = row_lo ^ s_comb_hi[k];
         uint32_t l = l_lo + k * ROWS_PER_STEP;
         Vec v = tile[l * PITCH + jv];
-        Vec *dst = &out[row * rowvecs + col];
+        Vec *dst = &out[row * rowvecs + vcol0 + jv];
         if (beta)
         {
             Vec o = *dst;
@@ -345,6 +370,7 @@ __global__ void __launch_bounds__(kThreads)
             }
         }
         *dst = v;
+    }
     }
 }
 

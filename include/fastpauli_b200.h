@@ -77,9 +77,10 @@ extern "C"
     /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
     int fp_ctx_launch_count(const fp_ctx *ctx, uint64_t *count);
     /* Coset-blocked (state tile in shared memory) kernels for multi-x-mask operators: mode 0 = never, 1 = heuristic
-     * (default), 2 = whenever applicable; log_twc >= 0 forces the tile shape (2^log_twc vectors x 2^(12-log_twc) rows),
-     * -1 = automatic. */
-    int fp_ctx_set_coset(fp_ctx *ctx, int mode, int log_twc);
+     * (default), 2 = whenever applicable.  log_twc >= 0 forces the row-segment width of the tile (2^log_twc 16-byte
+     * vectors, 0..4; -1 = automatic); log_nt = 7 or 8 forces 128- or 256-thread CTAs (0 = default).  A tile holds
+     * 16 * 2^log_nt vectors, i.e. 2^(4 + log_nt - log_twc) rows. */
+    int fp_ctx_set_coset(fp_ctx *ctx, int mode, int log_twc, int log_nt);
     /* Override the L2 working-set budget (bytes) used to pick the batch-tile width of multi-group kernels. */
     int fp_ctx_set_l2_budget(fp_ctx *ctx, size_t bytes);
 

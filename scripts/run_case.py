@@ -47,10 +47,11 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--coset", type=int, default=1)
     ap.add_argument("--log-twc", type=int, default=-1)
+    ap.add_argument("--log-nt", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0)
     a = ap.parse_args()
     ctx = fp.Context(0)
-    ctx.set_coset(a.coset, a.log_twc)
+    ctx.set_coset(a.coset, a.log_twc, a.log_nt)
     ctx.set_async(True)
     rng = np.random.default_rng(1234)
     if a.case in ("few20", "rand20"):

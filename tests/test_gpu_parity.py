@@ -308,13 +308,14 @@ def test_batch_tiling_invariance():
 # ------------------------------------------------------------------ coset-blocked (shared-memory tile) kernels
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("log_twc", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("log_nt", [7, 8])
 @pytest.mark.parametrize("kind", ["random", "weight4"])
-def test_coset_kernels_every_tile_shape(dtype, log_twc, kind):
+def test_coset_kernels_every_tile_shape(dtype, log_twc, log_nt, kind):
     """Force every tile shape (2^log_twc vectors x 2^(12-log_twc) rows) through apply / expectation_value /
     apply_weighted; n > tile rank and dense random masks give several passes, weight<=4 masks exercise the
     bit-subset cover of the planner."""
     ctx = fp.Context(0)
-    ctx.set_coset(2, log_twc)
+    ctx.set_coset(2, log_twc, log_nt)
     rng = np.random.default_rng(100 + log_twc)
     n, S, B, K = 13, 90, 32, 3
     strings = rand_strings(rng, n, S, max_weight=4 if kind == "weight4" else None)
@@ -346,7 +347,7 @@ def test_coset_kernels_every_tile_shape(dtype, log_twc, kind):
     assert 1 <= n_launch <= max(1, op.plan_info(dtype)["n_x_groups"] // 2)
     # and it agrees with the generic gather kernel
     ctx0 = fp.Context(0)
-    ctx0.set_coset(0, -1)
+    ctx0.set_coset(0, -1, 0)
     assert rel_err(fp.PauliOp(h, strings, ctx=ctx0).apply(psi), op.apply(psi)) < t
 
 
