@@ -678,14 +678,15 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
 // ---------------------------------------------------------------- launchers (all pointers are device pointers here)
 template <typename T, int EPV, int MODE, bool INLINE1>
 void launch_op_v(fp_ctx *ctx, GeomSel const &gs, OpView<T> const &view, void const *in, void *out, void *partials,
-                 int beta)
+                 int beta, void const *bra = nullptr)
 {
     auto const *din = static_cast<CVec<T, EPV> const *>(in);
+    auto const *dbra = bra ? static_cast<CVec<T, EPV> const *>(bra) : din;
     auto *dout = static_cast<CVec<T, EPV> *>(out);
     auto *dpart = static_cast<Cx<T> *>(partials);
     dim3 grid(static_cast<unsigned>(gs.grid));
 #define FP_LAUNCH_OP(VV, JJ)                                                                                           \
-    op_kernel<T, EPV, VV, JJ, MODE, INLINE1><<<grid, kThreads, 0, ctx->stream>>>(view, gs.g, din, dout, dpart, beta)
+    op_kernel<T, EPV, VV, JJ, MODE, INLINE1><<<grid, kThreads, 0, ctx->stream>>>(view, gs.g, din, dout, dpart, beta, dbra)
     if (gs.J == 4)
     {
         if constexpr (!INLINE1)
@@ -752,7 +753,7 @@ int run_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const *in, 
 
 template <typename T>
 int run_op_expval(fp_ctx *ctx, DeviceOp<T> const &op, void *out /* B complex, device */, void const *in, uint64_t dim,
-                  uint64_t B, int beta, int n_qubits = 0)
+                  uint64_t B, int beta, int n_qubits = 0, void const *bra = nullptr)
 {
     if (B == 0)
         return FP_OK;
@@ -763,14 +764,16 @@ int run_op_expval(fp_ctx *ctx, DeviceOp<T> const &op, void *out /* B complex, de
         return FP_OK;
     }
     FP_TRY(check_align(in, 2 * sizeof(T), "states"));
-    if (op.host.gx.size() > 1 && n_qubits > 0)
+    if (bra)
+        FP_TRY(check_align(bra, 2 * sizeof(T), "bra states"));
+    if (op.host.gx.size() > 1 && n_qubits > 0 && (!bra || bra == in))
     {
         bool used = false;
         FP_TRY((try_coset<T, 1>(ctx, op, n_qubits, out, in, dim, B, beta, nullptr, nullptr, &used)));
         if (used)
             return FP_OK;
     }
-    int const epv = pick_epv<T>(in, in, B);
+    int const epv = pick_epv<T>(in, bra ? bra : in, B);
     uint64_t const rowvecs = B / epv;
     GeomSel gs = choose_geom(ctx, dim, dim, rowvecs, 2 * sizeof(T) * epv, op.host.gx.size() > 1, true, 1, true);
     FP_TRY(check_grid(gs.grid));
@@ -785,12 +788,12 @@ int run_op_expval(fp_ctx *ctx, DeviceOp<T> const &op, void *out /* B complex, de
     {
         if (epv == 2)
         {
-            launch_op_v<T, 2, 1, false>(ctx, gs, view, in, nullptr, ctx->partials.p, 0);
+            launch_op_v<T, 2, 1, false>(ctx, gs, view, in, nullptr, ctx->partials.p, 0, bra);
             done = true;
         }
     }
     if (!done)
-        launch_op_v<T, 1, 1, false>(ctx, gs, view, in, nullptr, ctx->partials.p, 0);
+        launch_op_v<T, 1, 1, false>(ctx, gs, view, in, nullptr, ctx->partials.p, 0, bra);
     unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
     finalize_complex_kernel<T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(static_cast<Cx<T> const *>(ctx->partials.p),
                                                                  gs.g.nRowBlocks, Bpad, B, static_cast<Cx<T> *>(out),
@@ -1382,6 +1385,26 @@ extern "C"
             FP_TRY(run_op_apply<float>(ctx, op->f, sout.dev, sin.dev, dim, n_states, accumulate, op->n_qubits));
         FP_TRY(stage_back(ctx, sout));
         return finish(ctx, sin.staged || sout.staged);
+    }
+
+    int fp_op_expval_bra(fp_ctx *ctx, const fp_op *op, void *out, const void *bra, const void *in, size_t dim,
+                         size_t n_states, int accumulate)
+    {
+        FP_TRY(op_check(ctx, op));
+        uint64_t const opdim = op->n_strings ? dim_of(op->n_qubits) : 0;
+        if (dim != opdim)
+            return set_err(FP_INVALID_ARGUMENT, "[PauliOp] state size must match the dimension of the operators");
+        if (n_states == 0)
+            return FP_OK;
+        if (!is_device_ptr(bra) || !is_device_ptr(in) || !is_device_ptr(out))
+            return set_err(FP_INVALID_ARGUMENT, "fp_op_expval_bra takes device pointers only");
+        DeviceGuard g(ctx->device);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (op->dtype == FP_C128)
+            FP_TRY(run_op_expval<double>(ctx, op->d, out, in, dim, n_states, accumulate, op->n_qubits, bra));
+        else
+            FP_TRY(run_op_expval<float>(ctx, op->f, out, in, dim, n_states, accumulate, op->n_qubits, bra));
+        return finish(ctx, false);
     }
 
     int fp_op_expval(fp_ctx *ctx, const fp_op *op, void *out, const void *in, size_t dim, size_t n_states,

@@ -91,12 +91,12 @@ constexpr int kThreads = 256;
 // folded on the host).
 // Each thread owns V rows x J vectors (vectors strided by TW so every warp-level access is contiguous); the
 // row-only factor D_g(i) is formed once per (row, group) and reused for the J vectors.
-// MODE 0: store.  MODE 1: expectation partials  e(t) = sum_i conj(psi(i,t)) * (A psi)(i,t)
-// (PauliOp::expectation_value, PO:482-549) reduced over the CTA's rows into partials[rb][t].
+// MODE 0: store.  MODE 1: expectation partials  e(t) = sum_i conj(bra(i,t)) * (A psi)(i,t)
+// (PauliOp::expectation_value, PO:482-549; bra = psi) reduced over the CTA's rows into partials[rb][t].
 template <typename T, int EPV, int V, int J, int MODE, bool INLINE1>
 __global__ void __launch_bounds__(kThreads)
     op_kernel(OpView<T> op, Geom g, CVec<T, EPV> const *__restrict__ in, CVec<T, EPV> *__restrict__ out,
-              Cx<T> *__restrict__ partials, int beta)
+              Cx<T> *__restrict__ partials, int beta, CVec<T, EPV> const *__restrict__ bra)
 {
     using Vec = CVec<T, EPV>;
     uint32_t const TW = 1u << g.log2TW;
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(kThreads)
                 {
                     if (!vok[j])
                         continue;
-                    Vec a = in[rows[k] * g.rowvecs + vcol[j]];
+                    Vec a = bra[rows[k] * g.rowvecs + vcol[j]]; // bra == in except for sharded states
 #pragma unroll
                     for (int e = 0; e < EPV; ++e)
                     {

@@ -127,6 +127,11 @@ extern "C"
     int fp_op_expval(fp_ctx *ctx, const fp_op *op, void *out /* n_states complex */, const void *in, size_t dim,
                      size_t n_states, int accumulate);
 
+    /* Sharded-state building block (no reference counterpart): out[t] (+)= sum_i conj(bra(i,t)) (A in)(i,t) with
+     * bra != in, i.e. the local bra shard against a peer's ket shard.  Device pointers only. */
+    int fp_op_expval_bra(fp_ctx *ctx, const fp_op *op, void *out, const void *bra, const void *in, size_t dim,
+                         size_t n_states, int accumulate);
+
     /* ---- SummedPauliOp (SPO:37-145): K operators over one string set, coeffs (n_strings, n_operators) ---- */
     int fp_sop_create(fp_ctx *ctx, int dtype, int n_qubits, size_t n_strings, const uint8_t *codes,
                       size_t n_operators, const void *coeffs /* row-major (n_strings, n_operators) complex */,
