@@ -299,6 +299,8 @@ def run_ours(args) -> None:
     dist = None
     torch = None
     if world > 1:
+        # NCCL writes its banner / debug lines to stdout by default; keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", f"/tmp/fp_nccl_debug_{os.getpid()}.log")
         import torch
         import torch.distributed as dist
 

@@ -33,6 +33,7 @@ def main():
     a = ap.parse_args()
     rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     os.environ["FASTPAULI_DEVICE"] = str(local_rank)
+    os.environ.setdefault("NCCL_DEBUG_FILE", f"/tmp/fp_nccl_debug_{os.getpid()}.log")  # keep stdout to the JSON line
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     fp = load_package()
