@@ -108,6 +108,7 @@ struct fp_ctx
     bool async = false;
     bool tensor_core = true;
     uint64_t launches = 0;
+    int last_gemm_engine = -1; // 0 = SIMT, 1 = tcgen05 (diagnostics)
     size_t l2_budget = 40ull << 20;
     int coset_mode = 1;       // 0: never use the coset-blocked kernels, 1: heuristic, 2: whenever applicable
     int coset_log_twc = -1;   // >= 0 forces the row-segment width of the tile (TWc = 1 << v vectors)
@@ -886,6 +887,7 @@ int run_gemm(fp_ctx *ctx, T const *A, DT const *Bm, T *C, uint32_t M, uint64_t N
             if (rc == 0)
             {
                 ctx->launches++;
+                ctx->last_gemm_engine = 1;
                 return FP_OK;
             }
         }
@@ -895,6 +897,7 @@ int run_gemm(fp_ctx *ctx, T const *A, DT const *Bm, T *C, uint32_t M, uint64_t N
         return set_err(FP_UNSUPPORTED, "contraction too large");
     gemm_simt_kernel<T, DT><<<grid, 256, 0, ctx->stream>>>(A, Bm, C, M, N, Kd, kchunk);
     ctx->launches++;
+    ctx->last_gemm_engine = 0;
     return FP_OK;
 }
 
@@ -1071,6 +1074,14 @@ extern "C"
         ctx->coset_mode = mode;
         ctx->coset_log_twc = log_twc;
         ctx->coset_log_nt = log_nt;
+        return FP_OK;
+    }
+
+    int fp_ctx_last_gemm_engine(const fp_ctx *ctx, int *engine)
+    {
+        if (!ctx || !engine)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        *engine = ctx->last_gemm_engine;
         return FP_OK;
     }
 
@@ -1726,6 +1737,33 @@ extern "C"
             FP_TRY(run_sop_expval<float>(ctx, sop, sout.dev, sin.dev, dim, n_states, accumulate));
         FP_TRY(stage_back(ctx, sout));
         return finish(ctx, sin.staged || sout.staged);
+    }
+
+    // ------------------------------------------------------------ diagnostics
+    int fp_debug_gemm_f32(fp_ctx *ctx, int engine, const float *A, const float *B, float *C, uint32_t M, uint64_t N,
+                          uint32_t Kd, uint32_t split_k)
+    {
+        if (!ctx || !A || !B || !C || M == 0 || N == 0 || Kd == 0 || split_k == 0)
+            return set_err(FP_INVALID_ARGUMENT, "bad gemm arguments");
+        DeviceGuard g(ctx->device);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        Staged sa, sb, sc;
+        FP_TRY(stage_in(ctx, ctx->stage_in, A, static_cast<size_t>(M) * Kd * 4, true, sa));
+        FP_TRY(stage_in(ctx, ctx->stage_data, B, static_cast<size_t>(Kd) * N * 4, true, sb));
+        FP_TRY(stage_in(ctx, ctx->stage_out, C, static_cast<size_t>(split_k) * M * N * 4, false, sc));
+        uint32_t kchunk = (Kd + split_k - 1) / split_k;
+        if (split_k > 1)
+            kchunk = (kchunk + 31) / 32 * 32;
+        bool const saved = ctx->tensor_core;
+        ctx->tensor_core = engine == 1;
+        uint64_t const before = ctx->launches;
+        int rc = run_gemm<float, float>(ctx, static_cast<float const *>(sa.dev), static_cast<float const *>(sb.dev),
+                                        static_cast<float *>(sc.dev), M, N, Kd, split_k, kchunk);
+        ctx->tensor_core = saved;
+        FP_TRY(rc);
+        (void)before;
+        FP_TRY(stage_back(ctx, sc));
+        return finish(ctx, true);
     }
 
     // ------------------------------------------------------------ one-shot entry points (oracle-shaped)

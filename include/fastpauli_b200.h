@@ -151,6 +151,14 @@ extern "C"
      * 0 = FP32 SIMT, 1 = tcgen05 3xTF32 tensor-core path (default when available). */
     int fp_ctx_set_tensor_core(fp_ctx *ctx, int enable);
 
+    /* ---- diagnostics ----------------------------------------------------------------------------
+     * The contraction engine on its own: C[split_k][M x N] = A[M x Kd] * B[Kd x N] (row-major fp32, split-K planes
+     * left unreduced), engine 0 = FP32 SIMT, 1 = tcgen05 3xTF32 (falls back to SIMT when the shape is unsupported;
+     * fp_ctx_last_gemm_engine tells which one ran). */
+    int fp_debug_gemm_f32(fp_ctx *ctx, int engine, const float *A, const float *B, float *C, uint32_t M, uint64_t N,
+                          uint32_t Kd, uint32_t split_k);
+    int fp_ctx_last_gemm_engine(const fp_ctx *ctx, int *engine);
+
     /* ---- one-shot entry points with the oracle's raw signature ---------------------------------
      * Same argument lists as orc_* (oracle/pauli_oracle.c) and ref_* (oracle/ref_wrapper.cpp) so one
      * harness drives the reference, the port and the GPU.  They run on a process-wide default context

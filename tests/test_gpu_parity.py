@@ -375,6 +375,62 @@ def test_coset_heuristic_default_path():
     assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi, par=True)) < 1e-12
 
 
+# ------------------------------------------------------------------ K5: tcgen05 3xTF32 contraction engine
+@pytest.mark.parametrize("M,N,Kd,split", [(128, 128, 32, 1), (256, 384, 64, 1), (200, 100, 36, 1), (20000 // 8, 512, 64, 1),
+                                          (128, 256, 1000, 4), (130, 4100, 12, 1), (64, 8, 8, 1)])
+def test_tensor_core_gemm_matches_fp64(M, N, Kd, split):
+    import ctypes as C
+
+    ctx = fp.default_context()
+    rng = np.random.default_rng(M + N + Kd)
+    A = (rng.random((M, Kd)) * 2 - 1).astype(np.float32)
+    B = (rng.random((Kd, N)) * 2 - 1).astype(np.float32)
+    exact = A.astype(np.float64) @ B.astype(np.float64)
+    res = {}
+    for engine in (0, 1):
+        Cbuf = np.zeros((split, M, N), dtype=np.float32)
+        rc = fp.lib.fp_debug_gemm_f32(ctx._h, C.c_int(engine), A.ctypes.data_as(C.c_void_p), B.ctypes.data_as(C.c_void_p),
+                                      Cbuf.ctypes.data_as(C.c_void_p), C.c_uint32(M), C.c_uint64(N), C.c_uint32(Kd),
+                                      C.c_uint32(split))
+        assert rc == 0, fp.lib.fp_last_error()
+        used = C.c_int()
+        fp.lib.fp_ctx_last_gemm_engine(ctx._h, C.byref(used))
+        assert used.value == engine  # the tensor-core engine really ran for every shape in this list
+        res[engine] = Cbuf.astype(np.float64).sum(axis=0)
+    scale = np.abs(exact).max()
+    err_simt = np.abs(res[0] - exact).max() / scale
+    err_tc = np.abs(res[1] - exact).max() / scale
+    assert err_simt < 2e-6
+    assert err_tc < 2e-6, f"3xTF32 error {err_tc:.3e} (fp32 SIMT {err_simt:.3e})"  # fp32-class accuracy, not TF32's 1e-3
+
+
+def test_summed_pauli_op_tensor_core_vs_simt():
+    # complex64 plans with n_operators % 4 == 0 take the tcgen05 engine for W = coeffs * data and out = coeffs^T * E
+    import ctypes as C
+
+    rng = np.random.default_rng(21)
+    n, S, K, B = 8, 300, 16, 96
+    strings = rand_strings(rng, n, S)
+    hk = (rand_states(rng, S, K, np.complex64) * 2 - (1 + 1j)).astype(np.complex64)
+    psi = rand_states(rng, 2**n, B, np.complex64)
+    data = rng.random((K, B)).astype(np.float32)
+    exp_w = ORC.sop_apply_weighted(strings, hk.astype(np.complex128), psi.astype(np.complex128), data.astype(np.float64))
+    exp_e = ORC.sop_expval(strings, hk.astype(np.complex128), psi.astype(np.complex128))
+    for tc_on in (True, False):
+        ctx = fp.Context(0)
+        ctx.set_tensor_core(tc_on)
+        sop = fp.SummedPauliOp(strings, hk, ctx=ctx)
+        got_w = sop.apply_weighted(psi, data)
+        used = C.c_int()
+        fp.lib.fp_ctx_last_gemm_engine(ctx._h, C.byref(used))
+        assert used.value == int(tc_on)
+        got_e = sop.expectation_value(psi)
+        fp.lib.fp_ctx_last_gemm_engine(ctx._h, C.byref(used))
+        assert used.value == int(tc_on)
+        assert rel_err(got_w, exp_w) < 1e-5
+        assert rel_err(got_e, exp_e) < 1e-5
+
+
 # ------------------------------------------------------------------ BASELINE configs
 def test_config1_pauli_op_apply_10q():
     # "PauliOp.apply, 10 qubits, 64 random Pauli strings, batch 16 states, complex128"
