@@ -97,6 +97,9 @@ class Context:
     def set_async(self, flag: bool) -> None:
         _check(lib.fp_ctx_set_async(self._h, C.c_int(bool(flag))))
 
+    def set_zero_copy(self, flag: bool) -> None:
+        _check(lib.fp_ctx_set_zero_copy(self._h, C.c_int(bool(flag))))
+
     def set_tensor_core(self, flag: bool) -> None:
         _check(lib.fp_ctx_set_tensor_core(self._h, C.c_int(bool(flag))))
 

@@ -107,6 +107,7 @@ struct fp_ctx
     cudaStream_t stream = nullptr;
     bool async = false;
     bool tensor_core = true;
+    bool zero_copy = true; // single-pass kernels read/write pinned host buffers in place
     uint64_t launches = 0;
     int last_gemm_engine = -1; // 0 = SIMT, 1 = tcgen05 (diagnostics)
     size_t l2_budget = 40ull << 20;
@@ -352,9 +353,27 @@ struct Staged
     void *host = nullptr;
     size_t bytes = 0;
     bool staged = false;
+    bool zero_copy = false; // pinned host memory used in place by the kernel: the call must still synchronise
 };
 
-int stage_in(fp_ctx *ctx, Scratch &scratch, void const *p, size_t bytes, bool copy, Staged &s)
+// Pinned (page-locked / registered) host memory is mapped into the device address space: single-pass streaming
+// kernels can read and write it in place over PCIe, which overlaps the two directions inside one launch instead of
+// H2D copy -> kernel -> D2H copy back to back.
+void *pinned_device_alias(void const *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer)
+        return nullptr;
+    return a.devicePointer;
+}
+
+int stage_in(fp_ctx *ctx, Scratch &scratch, void const *p, size_t bytes, bool copy, Staged &s,
+             bool allow_zero_copy = false)
 {
     s.bytes = bytes;
     if (bytes == 0)
@@ -368,6 +387,16 @@ int stage_in(fp_ctx *ctx, Scratch &scratch, void const *p, size_t bytes, bool co
     {
         s.dev = const_cast<void *>(p);
         return FP_OK;
+    }
+    if (allow_zero_copy && ctx->zero_copy)
+    {
+        if (void *alias = pinned_device_alias(p))
+        {
+            s.dev = alias;
+            s.host = const_cast<void *>(p);
+            s.zero_copy = true;
+            return FP_OK;
+        }
     }
     FP_TRY(scratch.ensure(bytes));
     s.dev = scratch.p;
@@ -1010,6 +1039,8 @@ extern "C"
             ctx->coset_log_twc = atoi(env);
         if (char const *env = getenv("FASTPAULI_COSET_LOG_NT"))
             ctx->coset_log_nt = atoi(env);
+        if (char const *env = getenv("FASTPAULI_ZERO_COPY"))
+            ctx->zero_copy = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_TENSOR_CORE"))
             ctx->tensor_core = atoi(env) != 0;
         if (prop.major != 10)
@@ -1056,6 +1087,14 @@ extern "C"
         if (!ctx)
             return set_err(FP_INVALID_ARGUMENT, "null context");
         ctx->async = async != 0;
+        return FP_OK;
+    }
+
+    int fp_ctx_set_zero_copy(fp_ctx *ctx, int enable)
+    {
+        if (!ctx)
+            return set_err(FP_INVALID_ARGUMENT, "null context");
+        ctx->zero_copy = enable != 0;
         return FP_OK;
     }
 
@@ -1263,8 +1302,8 @@ extern "C"
         std::lock_guard<std::mutex> lk(ctx->mu);
         size_t const bytes = dim * n_states * csize(dtype);
         Staged sin, sout;
-        FP_TRY(stage_in(ctx, ctx->stage_in, in, bytes, true, sin));
-        FP_TRY(stage_in(ctx, ctx->stage_out, out, bytes, accumulate != 0, sout));
+        FP_TRY(stage_in(ctx, ctx->stage_in, in, bytes, true, sin, true));
+        FP_TRY(stage_in(ctx, ctx->stage_out, out, bytes, accumulate != 0, sout, true));
         int rc;
         if (dtype == FP_C128)
         {
@@ -1288,7 +1327,7 @@ extern "C"
         }
         FP_TRY(rc);
         FP_TRY(stage_back(ctx, sout));
-        return finish(ctx, sin.staged || sout.staged);
+        return finish(ctx, sin.staged || sout.staged || sin.zero_copy || sout.zero_copy);
     }
 
     int fp_string_expval(fp_ctx *ctx, int dtype, int n_qubits, const uint8_t *codes, const void *coeff, void *out,
@@ -1317,7 +1356,7 @@ extern "C"
         DeviceGuard g(ctx->device);
         std::lock_guard<std::mutex> lk(ctx->mu);
         Staged sin, sout;
-        FP_TRY(stage_in(ctx, ctx->stage_in, in, dim * n_states * csize(dtype), true, sin));
+        FP_TRY(stage_in(ctx, ctx->stage_in, in, dim * n_states * csize(dtype), true, sin, true));
         FP_TRY(stage_in(ctx, ctx->stage_out, out, n_states * csize(dtype), accumulate != 0, sout));
         int rc;
         if (dtype == FP_C128)
@@ -1328,7 +1367,7 @@ extern "C"
                                           dim, n_states, accumulate);
         FP_TRY(rc);
         FP_TRY(stage_back(ctx, sout));
-        return finish(ctx, sin.staged || sout.staged);
+        return finish(ctx, sin.staged || sout.staged || sin.zero_copy);
     }
 
     // ------------------------------------------------------------ PauliOp

@@ -76,6 +76,9 @@ extern "C"
     int fp_ctx_sync(fp_ctx *ctx);
     /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
     int fp_ctx_launch_count(const fp_ctx *ctx, uint64_t *count);
+    /* Pinned (page-locked) HOST buffers passed to the single-string entry points are read and written in place by
+     * the kernel over PCIe (both directions overlap inside one launch) instead of being staged; 0 disables. */
+    int fp_ctx_set_zero_copy(fp_ctx *ctx, int enable);
     /* Coset-blocked (state tile in shared memory) kernels for multi-x-mask operators: mode 0 = never, 1 = heuristic
      * (default), 2 = whenever applicable.  log_twc >= 0 forces the row-segment width of the tile (2^log_twc 16-byte
      * vectors, 0..4; -1 = automatic); log_nt = 7 or 8 forces 128- or 256-thread CTAs (0 = default).  A tile holds

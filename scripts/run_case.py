@@ -104,6 +104,44 @@ def main():
             ms = timed(ctx, lambda: fp.lib.fp_sop_expval(ctx._h, plan, vp(ev.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0),
                        a.iters)
         print(f"{a.case}: {ms:.3f} ms")
+    elif a.case == "e2e":
+        # host-pointer paths of the single-string entry points: zero-copy vs staged, apply and expval separately
+        import time
+
+        n, B = 20, a.batch or 256
+        dim = 1 << n
+        ctx.set_async(False)
+        string = random_strings(rng, n, 1)[0]
+        codes, _ = fp._encode([string])
+        coeff = np.array([0.75 - 0.5j])
+        psi = ctx.uniform((dim, B), np.complex128)
+        h_in = ctx.pinned_empty((dim, B), np.complex128)
+        h_out = ctx.pinned_empty((dim, B), np.complex128)
+        h_ev = ctx.pinned_empty((B,), np.complex128)
+        fp.lib.fp_memcpy(ctx._h, vp(h_in.ctypes.data), vp(psi.ptr), sz(h_in.nbytes))
+        d_out = ctx.empty((dim, B), np.complex128)
+
+        def t(fn, reps=3):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return (time.perf_counter() - t0) / reps * 1e3
+
+        def apply(i, o):
+            return lambda: fp.lib.fp_string_apply(ctx._h, 1, n, vp(codes.ctypes.data), vp(coeff.ctypes.data), vp(o),
+                                                  vp(i), sz(dim), sz(B), 0)
+
+        def expval(i):
+            return lambda: fp.lib.fp_string_expval(ctx._h, 1, n, vp(codes.ctypes.data), vp(coeff.ctypes.data),
+                                                   vp(h_ev.ctypes.data), vp(i), sz(dim), sz(B), 0)
+
+        for zc in (1, 0):
+            ctx.set_zero_copy(bool(zc))
+            print(f"zero_copy={zc}: apply host->host {t(apply(h_in.ctypes.data, h_out.ctypes.data)):.1f} ms, "
+                  f"apply host->dev {t(apply(h_in.ctypes.data, d_out.ptr)):.1f} ms, "
+                  f"apply dev->host {t(apply(psi.ptr, h_out.ctypes.data)):.1f} ms, "
+                  f"expval host {t(expval(h_in.ctypes.data)):.1f} ms")
     elif a.case == "str20":
         n, B = 20, a.batch or 256
         psi = ctx.uniform((1 << n, B), np.complex128)

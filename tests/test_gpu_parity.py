@@ -280,6 +280,43 @@ def test_device_resident_arrays(dtype):
     assert rel_err(out_t.get(), ORC.op_apply(strings, h, psi)) < tol(dtype)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_pinned_host_buffers_zero_copy(dtype):
+    """Pinned host buffers are read/written in place by the single-string kernels (no staging copies)."""
+    import ctypes as C
+
+    ctx = fp.Context(0)
+    rng = np.random.default_rng(13)
+    n, B = 11, 24
+    s = rand_strings(rng, n, 1)[0]
+    psi = rand_states(rng, 2**n, B, dtype)
+    base = rand_states(rng, 2**n, B, dtype)
+    h_in = ctx.pinned_empty((2**n, B), dtype)
+    h_out = ctx.pinned_empty((2**n, B), dtype)
+    h_ev = ctx.pinned_empty((B,), dtype)
+    h_in[...] = psi
+    codes, _ = fp._encode([s])
+    c = np.array([0.3 - 1.7j], dtype=dtype)
+    for zero_copy in (True, False):
+        ctx.set_zero_copy(zero_copy)
+        for acc in (0, 1):
+            h_out[...] = base
+            rc = fp.lib.fp_string_apply(ctx._h, fp._dtype_code(dtype), n, C.c_void_p(codes.ctypes.data),
+                                        C.c_void_p(c.ctypes.data), C.c_void_p(h_out.ctypes.data),
+                                        C.c_void_p(h_in.ctypes.data), C.c_size_t(2**n), C.c_size_t(B), acc)
+            assert rc == 0, fp.lib.fp_last_error()
+            exp = ORC.string_apply(s, psi, complex(c[0]), out=base.copy() if acc else None)
+            assert rel_err(np.array(h_out), exp) < tol(dtype)
+        h_ev[...] = 0
+        rc = fp.lib.fp_string_expval(ctx._h, fp._dtype_code(dtype), n, C.c_void_p(codes.ctypes.data),
+                                     C.c_void_p(c.ctypes.data), C.c_void_p(h_ev.ctypes.data),
+                                     C.c_void_p(h_in.ctypes.data), C.c_size_t(2**n), C.c_size_t(B), 0)
+        assert rc == 0
+        assert_parity(np.array(h_ev), ORC.string_expval, dtype, s, psi, complex(c[0]))
+    for a in (h_in, h_out, h_ev):
+        ctx.pinned_free(a)
+
+
 def test_uniform_generator_matches_host():
     ctx = fp.default_context()
     from fast_pauli_b200.synth import uniform_host
