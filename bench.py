@@ -41,6 +41,7 @@ SEED = 18
 STRING_SEED = 1234
 METRIC = "PauliOp.apply amplitude*strings/s (PauliString.apply_batch + expectation_value, 20 qubits, batch 256/GPU, complex128)"
 UNIT = "amplitude*strings/s"
+EMIT = print
 
 
 def make_string(n: int, seed: int = STRING_SEED) -> str:
@@ -164,7 +165,7 @@ def run_reference_arm(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    EMIT(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -504,9 +505,22 @@ def run_ours(args) -> None:
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "extras": extras,
         }
-        print(json.dumps(line), flush=True)
+        EMIT(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """Keep the real stdout for the single JSON line: everything else written to fd 1 (NCCL's version banner, library
+    chatter) is sent to stderr.  Returns a writer for the JSON line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(text: str) -> None:
+        os.write(real, (text + "\n").encode())
+
+    return emit
 
 
 def main() -> None:
@@ -518,6 +532,8 @@ def main() -> None:
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global EMIT
+    EMIT = _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

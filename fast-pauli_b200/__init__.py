@@ -92,7 +92,12 @@ class Context:
         _check(lib.fp_ctx_sync(self._h))
 
     def set_stream(self, cuda_stream: int | None) -> None:
-        _check(lib.fp_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Run on a caller-owned ``cudaStream_t`` handle (``0`` = the legacy default stream, which is what
+        ``torch.cuda.current_stream().cuda_stream`` returns by default); ``None`` restores the context's own stream."""
+        if cuda_stream is None:
+            _check(lib.fp_ctx_set_stream(self._h, C.c_void_p(0), C.c_int(0)))
+        else:
+            _check(lib.fp_ctx_set_stream(self._h, C.c_void_p(int(cuda_stream)), C.c_int(1)))
 
     def set_async(self, flag: bool) -> None:
         _check(lib.fp_ctx_set_async(self._h, C.c_int(bool(flag))))

@@ -1074,11 +1074,13 @@ extern "C"
         return FP_OK;
     }
 
-    int fp_ctx_set_stream(fp_ctx *ctx, void *cuda_stream)
+    int fp_ctx_set_stream(fp_ctx *ctx, void *cuda_stream, int external)
     {
         if (!ctx)
             return set_err(FP_INVALID_ARGUMENT, "null context");
-        ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+        // external != 0: run on exactly this cudaStream_t -- including 0, the legacy default stream PyTorch uses
+        // unless told otherwise; external == 0 restores the context's own stream
+        ctx->stream = external ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
         return FP_OK;
     }
 

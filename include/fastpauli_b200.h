@@ -70,8 +70,9 @@ extern "C"
     int fp_ctx_create(int device, fp_ctx **ctx);
     int fp_ctx_destroy(fp_ctx *ctx);
     int fp_ctx_device(const fp_ctx *ctx, int *device);
-    /* Run on a caller-owned cudaStream_t (e.g. PyTorch's current stream); NULL restores the context's own stream. */
-    int fp_ctx_set_stream(fp_ctx *ctx, void *cuda_stream);
+    /* external != 0: run on exactly this caller-owned cudaStream_t (e.g. PyTorch's current stream; 0 / NULL is the
+     * legacy default stream); external == 0 restores the context's own non-blocking stream. */
+    int fp_ctx_set_stream(fp_ctx *ctx, void *cuda_stream, int external);
     int fp_ctx_set_async(fp_ctx *ctx, int async);
     int fp_ctx_sync(fp_ctx *ctx);
     /* Number of kernels this context has launched so far (bench.py's gpu_launches). */

@@ -24,6 +24,19 @@ sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
 
 
+def _claim_stdout():
+    """Keep the real stdout for the single JSON line: everything else written to fd 1 (NCCL's version banner, library
+    chatter) is sent to stderr.  Returns a writer for the JSON line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(text: str) -> None:
+        os.write(real, (text + "\n").encode())
+
+    return emit
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--qubits", type=int, default=28)
@@ -31,6 +44,7 @@ def main():
     ap.add_argument("--iters", type=int, default=2)
     ap.add_argument("--samples", type=int, default=24)
     a = ap.parse_args()
+    emit = _claim_stdout()
     rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     os.environ["FASTPAULI_DEVICE"] = str(local_rank)
     os.environ.setdefault("NCCL_DEBUG_FILE", f"/tmp/fp_nccl_debug_{os.getpid()}.log")  # keep stdout to the JSON line
@@ -95,7 +109,7 @@ def main():
                 "nvlink_bytes_per_gpu_per_apply": n_swaps * shard_bytes,
                 "exchange_GBps_per_gpu_if_exchange_bound": n_swaps * shard_bytes / (ms * 1e-3) / 1e9,
                 "sampled_parity_max_rel_err": float(w.item()), "samples_per_rank": a.samples}
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     assert float(w.item()) < 1e-12, f"sharded parity {float(w.item()):.3e}"
     dist.destroy_process_group()
 

@@ -317,6 +317,31 @@ def test_pinned_host_buffers_zero_copy(dtype):
         ctx.pinned_free(a)
 
 
+def test_runs_on_torch_default_stream_in_order():
+    """set_stream(0) must mean the legacy default stream (torch's default), so kernels order after torch work."""
+    import ctypes as C
+    import torch
+
+    ctx = fp.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)  # 0 unless the caller switched streams
+    ctx.set_async(True)
+    n, B = 18, 32
+    ps = fp.PauliString("X" * n, ctx=ctx)
+    src = torch.zeros((2**n, B), dtype=torch.complex128, device="cuda")
+    for trial in range(3):
+        # a long-running producer on torch's stream, immediately consumed by our kernel with no host sync in between
+        big = torch.randn(1 << 26, device="cuda")
+        for _ in range(20):
+            big = big * 1.0001
+        src.fill_(float(trial + 1))
+        out = ps.apply(src)  # async on the same stream
+        torch.cuda.synchronize()
+        got = out.get_rows(0, 4)
+        assert np.all(got == trial + 1), got[0, :4]
+    ctx.set_stream(None)
+    ctx.set_async(False)
+
+
 def test_uniform_generator_matches_host():
     ctx = fp.default_context()
     from fast_pauli_b200.synth import uniform_host
