@@ -141,6 +141,7 @@ def run_reference_arm(args) -> None:
     from oracle import oracle as orc
 
     be = orc.reference() or orc.port()
+    be.use_all_threads()  # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every host core
     string = make_string(N_QUBITS)
     cols = 16  # bounded sample: 16 of the 256 columns per step (work is exactly linear in the batch)
     threads = be.max_threads()
@@ -470,6 +471,7 @@ def run_ours(args) -> None:
             from oracle import oracle as orc
 
             be = orc.reference() or orc.port()
+            be.use_all_threads()
             cols = 16
             cpu_reference_step(be, string, n, cols)  # warm-up
             best, spent, reps = None, 0.0, 0

@@ -95,6 +95,21 @@ class Backend:
         c = complex(c)
         return np.array([c.real, c.imag], dtype=real)
 
+    def use_all_threads(self) -> int:
+        """Let the OpenMP reference use every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+        if self.prefix == "ref_":
+            self.lib.ref_set_threads(C.c_int(n))
+        else:
+            try:  # the port uses the same libgomp runtime
+                C.CDLL("libgomp.so.1").omp_set_num_threads(C.c_int(n))
+            except OSError:
+                pass
+        return n
+
     def max_threads(self) -> int:
         if self.prefix == "ref_":
             self.lib.ref_max_threads.restype = C.c_int
