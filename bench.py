@@ -217,7 +217,22 @@ def run_extras(fp, ctx, hbm_peak: float) -> dict:
                     if rng.random() < 0.5:
                         t[q] = {"X": "Y", "Y": "X", "I": "Z", "Z": "I"}[t[q]]
                 few.append("".join(t))
-        for tag, strings in (("few_group_64_strings_8_xmasks", few), ("random_64_strings", rand_strings(rng, n, 64))):
+        def variants(xmasks, per_mask):
+            out_s = []
+            for s in xmasks:
+                for _ in range(per_mask):
+                    t = list(s)
+                    for q in range(n):
+                        if rng.random() < 0.5:
+                            t[q] = {"X": "Y", "Y": "X", "I": "Z", "Z": "I"}[t[q]]
+                    out_s.append("".join(t))
+            return out_s
+
+        cases = [("few_group_64_strings_8_xmasks", few), ("random_64_strings", rand_strings(rng, n, 64))]
+        # HBM fraction as a function of the number of distinct x-masks (64 strings each time)
+        for g in (1, 2, 4, 16):
+            cases.append((f"sweep_64_strings_{g}_xmasks", variants(rand_strings(rng, n, g), 64 // g)))
+        for tag, strings in cases:
             h = rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))
             op = fp.PauliOp(h, strings, ctx=ctx)
             info = op.plan_info()

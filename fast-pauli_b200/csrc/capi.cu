@@ -114,6 +114,7 @@ struct fp_ctx
     int coset_mode = 1;       // 0: never use the coset-blocked kernels, 1: heuristic, 2: whenever applicable
     int coset_log_twc = -1;   // >= 0 forces the row-segment width of the tile (TWc = 1 << v vectors)
     int coset_log_nt = 0;     // 7 or 8 forces the CTA size (128 / 256 threads); 0 = default (256)
+    int coset_vpt = 16;       // vectors per thread when the shape is forced (8 or 16)
     Scratch stage_in, stage_out, stage_data, partials, work_a, work_b, meta;
     std::mutex mu;
 };
@@ -553,10 +554,11 @@ int check_grid(uint64_t grid)
 struct CosetShape
 {
     int log_twc = -1; // TWc = 2^log_twc vectors per row segment
-    int log_nt = 8;   // threads per CTA (tile = 16 * NT vectors)
+    int log_nt = 8;   // threads per CTA
+    int vpt = 16;     // vectors per thread (tile = vpt * NT vectors)
     int rank() const
     {
-        return 4 + log_nt - log_twc;
+        return (vpt == 16 ? 4 : 3) + log_nt - log_twc;
     }
     bool ok() const
     {
@@ -580,10 +582,15 @@ CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, 
     if (ctx->coset_log_twc >= 0)
     {
         int lnt = ctx->coset_log_nt > 0 ? ctx->coset_log_nt : 8;
-        if (valid(ctx->coset_log_twc, lnt))
+        int vpt = ctx->coset_vpt == 8 ? 8 : 16;
+        bool ok = vpt == 16 ? valid(ctx->coset_log_twc, lnt)
+                            : (lnt == 8 && ctx->coset_log_twc <= 3 && (rowvecs % (1ull << ctx->coset_log_twc)) == 0 &&
+                               (3 + lnt - ctx->coset_log_twc) <= n_qubits);
+        if (ok)
         {
             pick.log_twc = ctx->coset_log_twc;
             pick.log_nt = lnt;
+            pick.vpt = vpt;
         }
     }
     else
@@ -617,23 +624,23 @@ CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, 
     return pick;
 }
 
-template <typename T, int EPV, int LOG_TWC, int LOG_NT, int MODE>
+template <typename T, int EPV, int LOG_TWC, int LOG_NT, int MODE, int VPT = 16>
 int launch_coset_pass(fp_ctx *ctx, CosetPassView<T> const &view, int n_qubits, uint64_t rowvecs, void const *in,
                       void *out, int beta, void *partials, uint32_t Bpad, T const *Wre, T const *Wim, uint64_t B)
 {
-    using Cfg = CosetCfg<LOG_TWC, LOG_NT>;
-    size_t const smem = coset_smem_bytes<T, LOG_TWC, LOG_NT>();
+    using Cfg = CosetCfg<LOG_TWC, LOG_NT, VPT>;
+    size_t const smem = coset_smem_bytes<T, LOG_TWC, LOG_NT, VPT>();
     static bool configured = false; // per template instance
     if (!configured)
     {
-        FP_CU(cudaFuncSetAttribute(coset_kernel<T, EPV, LOG_TWC, LOG_NT, MODE>,
+        FP_CU(cudaFuncSetAttribute(coset_kernel<T, EPV, LOG_TWC, LOG_NT, MODE, VPT>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured = true;
     }
     uint32_t const nct = static_cast<uint32_t>(rowvecs >> LOG_TWC);
     uint64_t const grid = (1ull << (n_qubits - Cfg::R)) * nct;
     FP_TRY(check_grid(grid));
-    coset_kernel<T, EPV, LOG_TWC, LOG_NT, MODE><<<static_cast<unsigned>(grid), Cfg::NT, smem, ctx->stream>>>(
+    coset_kernel<T, EPV, LOG_TWC, LOG_NT, MODE, VPT><<<static_cast<unsigned>(grid), Cfg::NT, smem, ctx->stream>>>(
         view, rowvecs, nct, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta,
         static_cast<Cx<T> *>(partials), Bpad, Wre, Wim, B);
     ctx->launches++;
@@ -646,9 +653,21 @@ int launch_coset_pass_v(fp_ctx *ctx, CosetShape shape, CosetPassView<T> const &v
                         uint64_t B)
 {
 #define FP_COSET_CASE(V, LNT)                                                                                          \
-    if (shape.log_twc == V && shape.log_nt == LNT)                                                                     \
+    if (shape.vpt == 16 && shape.log_twc == V && shape.log_nt == LNT)                                                  \
         return launch_coset_pass<T, EPV, V, LNT, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad,    \
                                                        Wre, Wim, B);
+#define FP_COSET_CASE8(V)                                                                                              \
+    if (shape.vpt == 8 && shape.log_twc == V && shape.log_nt == 8)                                                     \
+        return launch_coset_pass<T, EPV, V, 8, MODE, 8>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad,   \
+                                                        Wre, Wim, B);
+    if constexpr (MODE != 2)
+    {
+        FP_COSET_CASE8(0)
+        FP_COSET_CASE8(1)
+        FP_COSET_CASE8(2)
+        FP_COSET_CASE8(3)
+    }
+#undef FP_COSET_CASE8
     FP_COSET_CASE(0, 8)
     FP_COSET_CASE(1, 8)
     FP_COSET_CASE(2, 8)
@@ -1039,6 +1058,8 @@ extern "C"
             ctx->coset_log_twc = atoi(env);
         if (char const *env = getenv("FASTPAULI_COSET_LOG_NT"))
             ctx->coset_log_nt = atoi(env);
+        if (char const *env = getenv("FASTPAULI_COSET_VPT"))
+            ctx->coset_vpt = atoi(env);
         if (char const *env = getenv("FASTPAULI_ZERO_COPY"))
             ctx->zero_copy = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_TENSOR_CORE"))

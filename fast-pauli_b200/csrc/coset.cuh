@@ -74,14 +74,18 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
 
-// Tile shape: NT threads per CTA, every thread owns 16 vectors (RPT rows x TWC vectors), so a tile holds
-// NT * 16 vectors (64 KiB at NT = 256, 32 KiB at NT = 128) and spans rank R = log2(NT * 16 / TWC) row bits.
-template <int LOG_TWC, int LOG_NT> struct CosetCfg
+// Tile shape: NT threads per CTA, every thread owns VPT vectors (RPT rows x TWC vectors), so a tile holds
+// NT * VPT vectors (64 KiB at NT = 256, VPT = 16) and spans rank R = log2(NT * VPT / TWC) row bits.  VPT = 8 halves
+// the accumulator registers (twice as many resident warps) at the price of one rank bit.
+template <int LOG_TWC, int LOG_NT, int VPT = 16> struct CosetCfg
 {
+    static_assert(VPT == 8 || VPT == 16, "8 or 16 vectors per thread");
+    static_assert((VPT >> LOG_TWC) >= 1, "a thread owns at least one whole row segment");
     static constexpr int NT = 1 << LOG_NT;
     static constexpr int TWC = 1 << LOG_TWC;              // vectors per row in the tile
-    static constexpr int RPT = 16 >> LOG_TWC;             // rows per thread
-    static constexpr int R = 4 + LOG_NT - LOG_TWC;        // tile rank: 2^R rows
+    static constexpr int RPT = VPT >> LOG_TWC;            // rows per thread
+    static constexpr int LOG_VPT = VPT == 16 ? 4 : 3;
+    static constexpr int R = LOG_VPT + LOG_NT - LOG_TWC;  // tile rank: 2^R rows
     static constexpr int ROWS = 1 << R;
     static constexpr int PITCH = TWC + (TWC > 1 ? 1 : 0); // row pitch in vectors (padded against bank conflicts)
     static constexpr size_t TILE_BYTES = static_cast<size_t>(ROWS) * PITCH * 16;
@@ -98,12 +102,12 @@ template <typename T> struct CosetSmemLayout
     static constexpr size_t off_gstart = off_gxl + kCosetChunkGroups * 4;            // uint32 [CH_G + 2]
     static constexpr size_t off_comb_hi = off_gstart + (kCosetChunkGroups + 2) * 4;  // uint64 [16] load/store steps
     static constexpr size_t off_red = (off_comb_hi + 16 * 8 + 15) / 16 * 16;         // Cx<T>  [8 warps][32 columns]
-    static constexpr size_t bytes = off_red + 8 * 32 * sizeof(Cx<T>);
+    static constexpr size_t bytes = off_red + 8 * 32 * sizeof(Cx<float>); // 8 warps x (16 c128 | 32 c64) columns
 };
 
-template <typename T, int LOG_TWC, int LOG_NT> constexpr size_t coset_smem_bytes()
+template <typename T, int LOG_TWC, int LOG_NT, int VPT = 16> constexpr size_t coset_smem_bytes()
 {
-    return CosetCfg<LOG_TWC, LOG_NT>::TILE_BYTES + CosetSmemLayout<T>::bytes;
+    return CosetCfg<LOG_TWC, LOG_NT, VPT>::TILE_BYTES + CosetSmemLayout<T>::bytes;
 }
 
 __device__ __forceinline__ float sign_mul(float, uint32_t odd)
@@ -118,17 +122,17 @@ __device__ __forceinline__ double sign_mul(double, uint32_t odd)
 // One CTA per (coset, column tile).  Several CTAs are resident per SM (2 at NT = 256, 4 at NT = 128) so that some
 // are streaming their tile in or out while the others evaluate groups; measured on B200 this beats a persistent
 // single-CTA double-buffered variant (too few warps to cover the LDS -> FMA latency) by 1.3-1.5x.
-template <typename T, int EPV, int LOG_TWC, int LOG_NT, int MODE>
+template <typename T, int EPV, int LOG_TWC, int LOG_NT, int MODE, int VPT = 16>
 __global__ void __launch_bounds__(1 << LOG_NT)
     coset_kernel(CosetPassView<T> pass, uint64_t rowvecs, uint32_t nColTiles, CVec<T, EPV> const *__restrict__ in,
                  CVec<T, EPV> *__restrict__ out, int beta, Cx<T> *__restrict__ partials, uint32_t Bpad,
                  T const *__restrict__ Wre, T const *__restrict__ Wim, uint64_t B)
 {
-    using Cfg = CosetCfg<LOG_TWC, LOG_NT>;
+    using Cfg = CosetCfg<LOG_TWC, LOG_NT, VPT>;
     using L = CosetSmemLayout<T>;
     using Vec = CVec<T, EPV>;
     constexpr int NT = Cfg::NT, TWC = Cfg::TWC, RPT = Cfg::RPT, R = Cfg::R, PITCH = Cfg::PITCH;
-    constexpr int ROWS_PER_STEP = NT >> LOG_TWC; // rows covered by one cooperative load/store step
+    constexpr int ROWS_PER_STEP = NT >> LOG_TWC; // rows covered by one cooperative load/store step (VPT steps)
     constexpr int NCOL = TWC * EPV;              // batch columns per tile
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -152,14 +156,14 @@ __global__ void __launch_bounds__(1 << LOG_NT)
     uint64_t const vcol0 = static_cast<uint64_t>(ct) * TWC;
 
     // ---- cooperative load of the coset tile: vector jv of rows l_lo + k * ROWS_PER_STEP
-    if (tid < 16)
+    if (tid < VPT)
         s_comb_hi[tid] = comb_of<R>(pass.basis, tid * ROWS_PER_STEP);
     uint32_t const l_lo = tid >> LOG_TWC;
     uint32_t const jv = tid & (TWC - 1);
     uint64_t const row_lo = base ^ comb_of<R>(pass.basis, l_lo);
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
+    for (int k = 0; k < VPT; ++k)
     {
         uint64_t row = row_lo ^ s_comb_hi[k];
         uint32_t l = l_lo + k * ROWS_PER_STEP;
@@ -320,7 +324,7 @@ __global__ void __launch_bounds__(1 << LOG_NT)
                     sum.im += __shfl_xor_sync(0xffffffffu, sum.im, off);
                 }
                 if ((tid & 31) == 0)
-                    s_red[(tid >> 5) * 32 + j * EPV + e] = sum;
+                    s_red[(tid >> 5) * NCOL + j * EPV + e] = sum;
             }
         __syncthreads();
         if (tid < NCOL)
@@ -329,8 +333,8 @@ __global__ void __launch_bounds__(1 << LOG_NT)
 #pragma unroll
             for (int w = 0; w < NT / 32; ++w)
             {
-                sum.re += s_red[w * 32 + tid].re;
-                sum.im += s_red[w * 32 + tid].im;
+                sum.re += s_red[w * NCOL + tid].re;
+                sum.im += s_red[w * NCOL + tid].im;
             }
             partials[coset * Bpad + t0 + tid] = sum;
         }
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(1 << LOG_NT)
         }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 16; ++k)
+    for (int k = 0; k < VPT; ++k)
     {
         uint64_t row = row_lo ^ s_comb_hi[k];
         uint32_t l = l_lo + k * ROWS_PER_STEP;

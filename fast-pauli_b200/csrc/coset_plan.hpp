@@ -24,8 +24,8 @@ namespace fpk
 {
 
 constexpr int kCosetMaxRank = 12;
-constexpr uint32_t kCosetChunkStrings = 512; // strings staged in shared memory at a time
-constexpr uint32_t kCosetChunkGroups = 512;
+constexpr uint32_t kCosetChunkStrings = 128; // strings staged in shared memory at a time (small: more CTAs per SM)
+constexpr uint32_t kCosetChunkGroups = 128;
 
 struct CosetChunk
 {

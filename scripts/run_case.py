@@ -54,13 +54,15 @@ def main():
     ctx.set_coset(a.coset, a.log_twc, a.log_nt)
     ctx.set_async(True)
     rng = np.random.default_rng(1234)
-    if a.case in ("few20", "rand20"):
+    if a.case in ("few20", "rand20", "few20low", "few20one"):
         n, B = 20, a.batch or 64
-        if a.case == "few20":
+        if a.case in ("few20", "few20low", "few20one"):
             xs = random_strings(rng, n, 8)
+            if a.case == "few20low":  # x-masks confined to the 8 low qubits: cosets are contiguous 256-row blocks
+                xs = ["".join("IZ"[int(rng.integers(0, 2))] for _ in range(n - 8)) + s[n - 8:] for s in xs]
             strings = []
             for s in xs:
-                for _ in range(8):
+                for _ in range(1 if a.case == "few20one" else 8):
                     t = list(s)
                     for q in range(n):
                         if rng.random() < 0.5:
