@@ -533,6 +533,47 @@ def test_config4_reduced_summed_c64():
     assert rel_err(sop.expectation_value(psi), exp_e) < 1e-5
 
 
+def test_config3_full_size_sampled_columns():
+    # "PauliOp.apply_batch, 16 qubits, 2000 random strings of weight <= 4, batch 1024, complex128" at FULL size on
+    # the GPU (1 GiB in, 1 GiB out, device resident).  Batch columns are independent, so the oracle checks a sample
+    # of columns of the full result; apply and expectation_value.
+    ctx = fp.default_context()
+    rng = np.random.default_rng(1234)
+    n, S, B = 16, 2000, 1024
+    strings = rand_strings(rng, n, S, max_weight=4)
+    h = rand_states(rng, S, None) * 2 - (1 + 1j)
+    psi_d = ctx.uniform((2**n, B), np.complex128, seed=18)
+    op = fp.PauliOp(h, strings)
+    out = op.apply(psi_d).get()
+    ev = op.expectation_value(psi_d).get()
+    cols = [0, 317, 1023]
+    psi_cols = np.ascontiguousarray(psi_d.get()[:, cols])
+    assert rel_err(out[:, cols], ORC.op_apply(strings, h, psi_cols, par=True)) < 1e-12
+    assert rel_err(ev[cols], ORC.op_expval(strings, h, psi_cols, par=True)) < 1e-12
+
+
+def test_config4_full_size_sampled_columns():
+    # "SummedPauliOp.apply_weighted + expectation_value, 12 qubits, 10k strings x 64 operators, batch 4096,
+    # complex64" at FULL size on the GPU; the oracle (complex128 on the same float32 inputs) checks sampled columns.
+    ctx = fp.default_context()
+    rng = np.random.default_rng(4)
+    n, S, K, B = 12, 10000, 64, 4096
+    strings = rand_strings(rng, n, S)
+    hk = (rng.uniform(-1, 1, (S, K)) + 1j * rng.uniform(-1, 1, (S, K))).astype(np.complex64)
+    psi_d = ctx.uniform((2**n, B), np.complex64, seed=18)
+    data = rng.random((K, B)).astype(np.float32)
+    sop = fp.SummedPauliOp(strings, hk)
+    got_w = sop.apply_weighted(psi_d, ctx.to_device(data)).get()
+    got_e = sop.expectation_value(psi_d).get()
+    cols = [5, 4090]
+    psi_cols = np.ascontiguousarray(psi_d.get()[:, cols]).astype(np.complex128)
+    exp_w = ORC.sop_apply_weighted(strings, hk.astype(np.complex128), psi_cols,
+                                   np.ascontiguousarray(data[:, cols]).astype(np.float64), par=True)
+    exp_e = ORC.sop_expval(strings, hk.astype(np.complex128), psi_cols, par=True)
+    assert rel_err(got_w[:, cols], exp_w) < 1e-5
+    assert rel_err(got_e[:, cols], exp_e) < 1e-5
+
+
 def test_config2_full_size_sampled_rows():
     # "PauliString.apply_batch + expectation_value, 20 qubits, batch 256, complex128": 4 GiB in, 4 GiB out on the GPU.
     # Full-size check through size-independent handles: (a) sampled output rows against the closed form on
