@@ -279,16 +279,17 @@ template <typename T> int upload_op(DeviceOp<T> &d)
 
 // ---------------------------------------------------------------- coset-blocked path: plan cache + launch
 template <typename T>
-int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank,
+int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank, int reserve_low_bits,
                    std::vector<typename DeviceOp<T>::CosetPassDev> const **out)
 {
-    auto it = op.coset_plans.find(rank);
+    int const key = rank * 8 + reserve_low_bits;
+    auto it = op.coset_plans.find(key);
     if (it != op.coset_plans.end())
     {
         *out = &it->second;
         return FP_OK;
     }
-    std::vector<CosetPassHost<T>> host = plan_coset<T>(op.host, n_qubits, rank);
+    std::vector<CosetPassHost<T>> host = plan_coset<T>(op.host, n_qubits, rank, reserve_low_bits);
     std::vector<typename DeviceOp<T>::CosetPassDev> dev(host.size());
     for (size_t p = 0; p < host.size(); ++p)
     {
@@ -328,7 +329,7 @@ int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank,
         d.view.scoef = sc;
         d.view.sidx = sidx;
     }
-    auto ins = op.coset_plans.emplace(rank, std::move(dev));
+    auto ins = op.coset_plans.emplace(key, std::move(dev));
     *out = &ins.first->second;
     return FP_OK;
 }
@@ -699,7 +700,9 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
     if (!shape.ok())
         return FP_OK;
     std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
-    FP_TRY(get_coset_plan<T>(op, n_qubits, shape.rank(), &passes));
+    // narrow row segments (16 / 32 bytes): force the lowest row bits into the tile so it is made of >= 64-byte runs
+    int const reserve = std::max(0, 2 - shape.log_twc);
+    FP_TRY(get_coset_plan<T>(op, n_qubits, shape.rank(), reserve, &passes));
     // every pass re-streams the batch (read in, read-modify-write out): only worth it while passes << groups
     if (ctx->coset_mode == 1 && passes->size() * 3 > op.host.gx.size() && passes->size() > 1)
         return FP_OK;
@@ -1799,6 +1802,41 @@ extern "C"
             FP_TRY(run_sop_expval<float>(ctx, sop, sout.dev, sin.dev, dim, n_states, accumulate));
         FP_TRY(stage_back(ctx, sout));
         return finish(ctx, sin.staged || sout.staged);
+    }
+
+    // ------------------------------------------------------------ peer memory (one process per GPU, NVLink P2P)
+    int fp_ipc_export(fp_ctx *ctx, const void *dev_ptr, unsigned char *handle)
+    {
+        if (!ctx || !dev_ptr || !handle)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        static_assert(sizeof(cudaIpcMemHandle_t) == FP_IPC_HANDLE_BYTES, "IPC handle size");
+        DeviceGuard g(ctx->device);
+        cudaIpcMemHandle_t h;
+        FP_CU(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+        memcpy(handle, &h, sizeof h);
+        return FP_OK;
+    }
+
+    int fp_ipc_open(fp_ctx *ctx, const unsigned char *handle, void **peer_ptr)
+    {
+        if (!ctx || !handle || !peer_ptr)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        DeviceGuard g(ctx->device);
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, sizeof h);
+        *peer_ptr = nullptr;
+        FP_CU(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        return FP_OK;
+    }
+
+    int fp_ipc_close(fp_ctx *ctx, void *peer_ptr)
+    {
+        if (!ctx)
+            return set_err(FP_INVALID_ARGUMENT, "null context");
+        DeviceGuard g(ctx->device);
+        if (peer_ptr)
+            FP_CU(cudaIpcCloseMemHandle(peer_ptr));
+        return FP_OK;
     }
 
     // ------------------------------------------------------------ diagnostics

@@ -81,6 +81,17 @@ struct Gf2Basis
             c |= static_cast<uint32_t>((x >> pivot[k]) & 1ull) << k;
         return c;
     }
+    // order the basis by pivot position: local row index bit k <-> k-th lowest pivot, so consecutive local rows
+    // (consecutive lanes of a warp) differ in the lowest address bits and neighbouring rows are neighbours in memory
+    void sort_by_pivot()
+    {
+        for (int i = 1; i < r; ++i)
+            for (int j = i; j > 0 && pivot[j - 1] > pivot[j]; --j)
+            {
+                std::swap(pivot[j - 1], pivot[j]);
+                std::swap(b[j - 1], b[j]);
+            }
+    }
     uint32_t zlocal(uint64_t z) const
     {
         uint32_t c = 0;
@@ -108,9 +119,15 @@ template <typename T> struct CosetPassHost
 //      still-uncovered masks (good for low-weight strings: every mask inside T lies in span{e_t});
 //  (b) incremental rank: scan the groups in order and take every mask that keeps the GF(2) rank <= rank
 //      (good for few, dense masks: any `rank` masks fit one pass).
+// reserve_low_bits: number of lowest row-index bits forced into every pass' basis, so that a tile always contains
+// runs of 2^reserve consecutive rows (narrow batches: a row is only 16-32 bytes and coalescing must come from the
+// row index, SURVEY.md hard part 3).
 template <typename T>
-inline std::vector<CosetPassHost<T>> plan_coset(PackedOp<T> const &op, int n_qubits, int rank)
+inline std::vector<CosetPassHost<T>> plan_coset(PackedOp<T> const &op, int n_qubits, int rank, int reserve_low_bits = 0)
 {
+    reserve_low_bits = std::max(0, std::min(reserve_low_bits, std::min(rank - 1, n_qubits)));
+    int const free_rank = rank - reserve_low_bits;
+    uint64_t const low_mask = (1ull << reserve_low_bits) - 1;
     std::vector<CosetPassHost<T>> passes;
     size_t const G = op.gx.size();
     std::vector<char> done(G, 0);
@@ -119,9 +136,9 @@ inline std::vector<CosetPassHost<T>> plan_coset(PackedOp<T> const &op, int n_qub
     while (remaining)
     {
         // ---- candidate (a): bit-subset cover
-        uint64_t Tmask = 0;
+        uint64_t Tmask = low_mask;
         {
-            int used = 0;
+            int used = reserve_low_bits;
             while (used < rank)
             {
                 int best_bit = -1;
@@ -160,10 +177,13 @@ inline std::vector<CosetPassHost<T>> plan_coset(PackedOp<T> const &op, int n_qub
                 ++count_a;
         // ---- candidate (b): incremental rank
         Gf2Basis bb;
+        for (int bit = 0; bit < reserve_low_bits; ++bit)
+            bb.insert(1ull << bit, rank);
         size_t count_b = 0;
         for (size_t g = 0; g < G; ++g)
             if (!done[g] && bb.insert(op.gx[g], rank))
                 ++count_b;
+        (void)free_rank;
 
         CosetPassHost<T> pass;
         if (count_a >= count_b)
@@ -174,6 +194,8 @@ inline std::vector<CosetPassHost<T>> plan_coset(PackedOp<T> const &op, int n_qub
         }
         else
         {
+            for (int bit = 0; bit < reserve_low_bits; ++bit)
+                pass.basis.insert(1ull << bit, rank);
             for (size_t g = 0; g < G; ++g)
                 if (!done[g])
                     pass.basis.insert(op.gx[g], rank); // same scan as above: rebuilds bb
@@ -181,6 +203,7 @@ inline std::vector<CosetPassHost<T>> plan_coset(PackedOp<T> const &op, int n_qub
         // pad to the full tile rank with free low bit positions (the tile then simply holds several cosets)
         for (int bit = 0; bit < n_qubits && pass.basis.r < rank; ++bit)
             pass.basis.insert(1ull << bit, rank);
+        pass.basis.sort_by_pivot();
         pass.nonpivot_mask = full & ~pass.basis.pivot_mask();
 
         // ---- collect every not-yet-done group inside the span

@@ -27,7 +27,7 @@ from typing import Callable, Sequence
 
 import numpy as np
 
-__all__ = ["shard_columns", "HighQubitPlan", "plan_high_qubit", "ShardedStateOp", "gather_columns"]
+__all__ = ["shard_columns", "HighQubitPlan", "plan_high_qubit", "ShardedStateOp", "gather_columns", "PeerShards"]
 
 
 # ------------------------------------------------------------------------------------------------ batch axis
@@ -162,6 +162,25 @@ class ShardedStateOp:
             n_swapped += 1
         return n_swapped
 
+    def apply_peer(self, out_ptr: int, shard_ptrs: Sequence[int], dtype, n_states: int = 1,
+                   accumulate: bool = False) -> int:
+        """Fused exchange + apply over NVLink peer memory: no receive buffers, no NCCL on the data path.
+
+        ``shard_ptrs[r]`` is a device pointer to rank r's input shard as mapped into THIS process (its own shard for
+        r == rank, CUDA-IPC mappings for the others: see :class:`PeerShards`).  Every class reads its source shard
+        ``rank ^ x_hi`` straight through the kernel's gathers, so the transfer is overlapped with the arithmetic
+        element by element and each remote amplitude crosses NVLink exactly once per class.
+        The caller synchronises ranks around the call (all shards complete before, none modified until all done).
+        """
+        first = not accumulate
+        n_remote = 0
+        for cls, op in zip(self.plan.classes, self.local_ops):
+            src = shard_ptrs[self.rank ^ cls.x_hi]
+            op.apply_ptr(out_ptr, src, 1 << self.plan.n_local, n_states, dtype, accumulate=not first)
+            first = False
+            n_remote += cls.x_hi != 0
+        return n_remote
+
     def expectation_value(self, psi, recv_bufs, all_reduce: Callable):
         """<psi|A|psi> per batch column: local partial sums (same swaps as apply) + one all-reduce."""
         classes = self.plan.classes
@@ -212,6 +231,15 @@ class _CudaLocalOp:
         fp._check(fp.lib.fp_op_apply(ctx._h, self.op._plan(dt), C.c_void_p(out.data_ptr()), C.c_void_p(src.data_ptr()),
                                      C.c_size_t(dim), C.c_size_t(B), C.c_int(int(accumulate))))
 
+    def apply_ptr(self, out_ptr: int, src_ptr: int, dim: int, n_states: int, dtype, accumulate: bool):
+        """Same on raw device pointers (``src_ptr`` may be a peer GPU's memory mapped through CUDA IPC)."""
+        import ctypes as C
+
+        fp = self.fp
+        ctx = fp.default_context()
+        fp._check(fp.lib.fp_op_apply(ctx._h, self.op._plan(np.dtype(dtype)), C.c_void_p(out_ptr), C.c_void_p(src_ptr),
+                                     C.c_size_t(dim), C.c_size_t(n_states), C.c_int(int(accumulate))))
+
     def expval(self, bra_side, src):
         """sum_i conj(bra_side[i]) (A src)[i] per column (fp_op_expval_bra), as a torch tensor on the device."""
         import ctypes as C
@@ -243,3 +271,44 @@ def _nccl_exchange(send, recv, peer):
             r.wait()
 
     return wait
+
+
+class PeerShards:
+    """All ranks' input shards mapped into this process (CUDA IPC over NVLink / NVSwitch).
+
+    ``local`` must be a :class:`fast_pauli_b200.DeviceArray` allocated by this library (a plain ``cudaMalloc``
+    allocation, which is what ``cudaIpcGetMemHandle`` needs).  ``ptrs[r]`` is usable as the ``in`` pointer of any
+    entry point; remote ones are read over NVLink by the kernels' ordinary 16-byte loads.
+    """
+
+    def __init__(self, local, dist=None):
+        import ctypes as C
+
+        import fast_pauli_b200 as fp
+
+        if dist is None:
+            import torch.distributed as dist
+        self._fp, self._ctx = fp, local.ctx
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        handle = (C.c_ubyte * 64)()
+        fp._check(fp.lib.fp_ipc_export(self._ctx._h, C.c_void_p(local.ptr), handle))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle))
+        self.ptrs: list[int] = []
+        self._opened: list[int] = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(local.ptr)
+                continue
+            p = C.c_void_p()
+            buf = (C.c_ubyte * 64).from_buffer_copy(h)
+            fp._check(fp.lib.fp_ipc_open(self._ctx._h, buf, C.byref(p)))
+            self.ptrs.append(int(p.value))
+            self._opened.append(int(p.value))
+
+    def close(self) -> None:
+        import ctypes as C
+
+        for p in self._opened:
+            self._fp.lib.fp_ipc_close(self._ctx._h, C.c_void_p(p))
+        self._opened = []

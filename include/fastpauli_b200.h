@@ -155,6 +155,16 @@ extern "C"
      * 0 = FP32 SIMT, 1 = tcgen05 3xTF32 tensor-core path (default when available). */
     int fp_ctx_set_tensor_core(fp_ctx *ctx, int enable);
 
+    /* ---- peer memory: one process per GPU, kernels read a peer GPU's shard directly over NVLink -----------------
+     * fp_ipc_export wraps cudaIpcGetMemHandle for a buffer obtained from fp_device_malloc (the handle is
+     * FP_IPC_HANDLE_BYTES opaque bytes to be shipped to the peer process, e.g. with torch.distributed);
+     * fp_ipc_open maps the peer's buffer into this process (peer access is enabled lazily) and returns a device
+     * pointer that every entry point accepts as `in`; fp_ipc_close unmaps it. */
+#define FP_IPC_HANDLE_BYTES 64
+    int fp_ipc_export(fp_ctx *ctx, const void *dev_ptr, unsigned char *handle);
+    int fp_ipc_open(fp_ctx *ctx, const unsigned char *handle, void **peer_ptr);
+    int fp_ipc_close(fp_ctx *ctx, void *peer_ptr);
+
     /* ---- diagnostics ----------------------------------------------------------------------------
      * The contraction engine on its own: C[split_k][M x N] = A[M x Kd] * B[Kd x N] (row-major fp32, split-K planes
      * left unreduced), engine 0 = FP32 SIMT, 1 = tcgen05 3xTF32 (falls back to SIMT when the shape is unsupported;

@@ -144,6 +144,17 @@ def main():
                   f"apply host->dev {t(apply(h_in.ctypes.data, d_out.ptr)):.1f} ms, "
                   f"apply dev->host {t(apply(psi.ptr, h_out.ctypes.data)):.1f} ms, "
                   f"expval host {t(expval(h_in.ctypes.data)):.1f} ms")
+    elif a.case == "b1":
+        # one big state, batch 1 (the local piece of config 5): coalescing must come from the row index
+        n, S = a.batch or 28, 8
+        strings = random_strings(rng, n, S)
+        h = rng.uniform(-1, 1, S) + 1j * rng.uniform(-1, 1, S)
+        psi = ctx.uniform((1 << n,), np.complex128)
+        y = ctx.empty((1 << n,), np.complex128)
+        op = fp.PauliOp(h, strings, ctx=ctx)
+        plan = op._plan(np.complex128)
+        ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(1), 0), a.iters)
+        print(f"b1 n={n}: {ms:.3f} ms  {(1 << n) * 32 / ms / 1e6:.0f} GB/s algorithmic")
     elif a.case == "str20":
         n, B = 20, a.batch or 256
         psi = ctx.uniform((1 << n, B), np.complex128)
