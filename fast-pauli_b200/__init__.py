@@ -33,7 +33,7 @@ from typing import Iterable, Sequence
 
 import numpy as np
 
-__all__ = ["PauliString", "PauliOp", "SummedPauliOp", "DeviceArray", "Context", "lib", "default_context"]
+__all__ = ["Pauli", "PauliString", "PauliOp", "SummedPauliOp", "DeviceArray", "Context", "lib", "default_context", "helpers"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "lib", "libfastpauli_b200.so")
@@ -294,11 +294,105 @@ def _coef_buf(c, dtype) -> np.ndarray:
     return np.array([complex(c)], dtype=dtype)
 
 
+# --------------------------------------------------------------------------------------------- host-side algebra
+# Everything below the hot path (products, sums, dense exports, generators) is small host code on the (x, z) bit
+# encoding  I=(0,0) X=(1,0) Y=(1,1) Z=(0,1):  sigma(x,z) = i^(x.z) X^x Z^z.
+def _masks(string: str) -> tuple[int, int]:
+    n = len(string)
+    x = z = 0
+    for q, ch in enumerate(string):
+        bit = 1 << (n - 1 - q)
+        if ch in "XY":
+            x |= bit
+        if ch in "YZ":
+            z |= bit
+    return x, z
+
+
+def _string_from_masks(x: int, z: int, n: int) -> str:
+    return "".join("IXZY"[((x >> (n - 1 - q)) & 1) | (((z >> (n - 1 - q)) & 1) << 1)] for q in range(n))
+
+
+def _product(a: str, b: str) -> tuple[complex, str]:
+    """(phase, string) of the matrix product of two Pauli strings (reference: PauliString operator*, PS:228-247)."""
+    if len(a) != len(b):
+        raise ValueError("PauliStrings must have the same size")
+    xa, za = _masks(a)
+    xb, zb = _masks(b)
+    x, z = xa ^ xb, za ^ zb
+    k = (bin(xa & za).count("1") + bin(xb & zb).count("1") + 2 * bin(za & xb).count("1") - bin(x & z).count("1")) & 3
+    return (1, 1j, -1, -1j)[k], _string_from_masks(x, z, len(a))
+
+
+def _dense(string: str) -> np.ndarray:
+    """Dense matrix of a Pauli string from the closed form k[i] = i ^ x, m[i] = (-i)^nY (-1)^popc(i & z)."""
+    n = len(string)
+    dim = 1 << n if n else 0
+    x, z = _masks(string)
+    i = np.arange(dim, dtype=np.int64)
+    par = np.zeros(dim, dtype=np.int64)
+    zz = i & z
+    while np.any(zz):
+        par ^= zz & 1
+        zz >>= 1
+    m = np.array([1, -1j, -1, 1j])[string.count("Y") & 3] * (1 - 2 * par)
+    out = np.zeros((dim, dim), dtype=np.complex128)
+    out[i, i ^ x] = m
+    return out
+
+
+class Pauli:
+    """One 2x2 Pauli matrix (reference binding: __pauli_bindings.hpp:36-106)."""
+
+    __slots__ = ("code",)
+
+    def __init__(self, code: "int | str | Pauli" = 0):
+        if isinstance(code, Pauli):
+            code = code.code
+        if isinstance(code, str):
+            if len(code) != 1 or code not in _CODE:
+                raise ValueError("Invalid Pauli matrix symbol")
+            code = _CODE[code]
+        if not 0 <= int(code) <= 3:
+            raise ValueError("Pauli code must be 0, 1, 2, or 3")
+        self.code = int(code)
+
+    def __matmul__(self, rhs: "Pauli") -> tuple[complex, "Pauli"]:
+        phase, s = _product(_LETTER[self.code], _LETTER[rhs.code])
+        return phase, Pauli(s)
+
+    def to_tensor(self) -> np.ndarray:
+        return _dense(_LETTER[self.code])
+
+    def clone(self) -> "Pauli":
+        return Pauli(self.code)
+
+    def __str__(self) -> str:
+        return _LETTER[self.code]
+
+    def __repr__(self) -> str:
+        return f"Pauli('{self}')"
+
+    def __eq__(self, other) -> bool:
+        return isinstance(other, Pauli) and other.code == self.code
+
+    def __hash__(self) -> int:
+        return hash(self.code)
+
+    def __getstate__(self):
+        return self.code
+
+    def __setstate__(self, code):
+        self.code = int(code)
+
+
 # --------------------------------------------------------------------------------------------- PauliString
 class PauliString:
     """Tensor product of Pauli matrices (reference: ``struct PauliString``, __pauli_string.hpp:126-206)."""
 
-    def __init__(self, string: "str | PauliString" = "", ctx: Context | None = None):
+    def __init__(self, string: "str | PauliString | Sequence[Pauli]" = "", ctx: Context | None = None):
+        if not isinstance(string, (str, PauliString)):
+            string = "".join(str(Pauli(p)) for p in string)  # list of Pauli objects (B_PS: init from paulis)
         string = str(string)
         self._codes, self._n = _encode([string])
         self.string = string
@@ -331,6 +425,32 @@ class PauliString:
 
     def clone(self) -> "PauliString":
         return PauliString(self.string, self._ctx)
+
+    # -- host-side algebra mirrored from the bindings (__pauli_string_bindings.hpp:61-121, 235-260)
+    def __matmul__(self, rhs: "PauliString") -> tuple[complex, "PauliString"]:
+        if not isinstance(rhs, PauliString):
+            return NotImplemented  # PauliString @ PauliOp is PauliOp.__rmatmul__
+        phase, prod = _product(self.string, rhs.string)
+        return phase, PauliString(prod, self._ctx)
+
+    def __add__(self, other: "PauliString") -> "PauliOp":
+        if not isinstance(other, PauliString):
+            return NotImplemented
+        return PauliOp([1, 1], [self, other], self._ctx)
+
+    def __sub__(self, other: "PauliString") -> "PauliOp":
+        if not isinstance(other, PauliString):
+            return NotImplemented
+        return PauliOp([1, -1], [self, other], self._ctx)
+
+    def to_tensor(self) -> np.ndarray:
+        return _dense(self.string)
+
+    def __getstate__(self):
+        return self.string
+
+    def __setstate__(self, string):
+        self.__init__(string)
 
     def _context(self) -> Context:
         return self._ctx or default_context()
@@ -435,6 +555,91 @@ class PauliOp:
     def clone(self) -> "PauliOp":
         return PauliOp(self._coeffs.copy(), list(self._strings), self._ctx)
 
+    # -- host-side operator algebra mirrored from the bindings (__pauli_op_bindings.hpp:113-440, 589-617)
+    def _check_dim(self, other) -> None:
+        if other.dim != self.dim:
+            raise ValueError("Mismatched dimensions for provided PauliOp / PauliString")
+
+    def __matmul__(self, rhs: "PauliOp | PauliString") -> "PauliOp":
+        self._check_dim(rhs)
+        if isinstance(rhs, PauliString):
+            pairs = [_product(s, rhs.string) for s in self._strings]
+            return PauliOp([c * ph for c, (ph, _) in zip(self._coeffs, pairs)], [p for _, p in pairs], self._ctx)
+        merged: dict[str, complex] = {}
+        for ca, sa in zip(self._coeffs, self._strings):  # identical product strings are merged (PO:237-281)
+            for cb, sb in zip(rhs._coeffs, rhs._strings):
+                ph, prod = _product(sa, sb)
+                merged[prod] = merged.get(prod, 0) + ph * ca * cb
+        return PauliOp(list(merged.values()), list(merged.keys()), self._ctx)
+
+    def __rmatmul__(self, lhs: PauliString) -> "PauliOp":
+        self._check_dim(lhs)
+        pairs = [_product(lhs.string, s) for s in self._strings]
+        return PauliOp([c * ph for c, (ph, _) in zip(self._coeffs, pairs)], [p for _, p in pairs], self._ctx)
+
+    def __mul__(self, factor: complex) -> "PauliOp":
+        return PauliOp(self._coeffs * complex(factor), list(self._strings), self._ctx)
+
+    __rmul__ = __mul__
+
+    def __imul__(self, factor: complex) -> "PauliOp":
+        self.scale(complex(factor))
+        return self
+
+    def extend(self, other: "PauliOp | PauliString", multiplier: complex = 1.0, dedupe: bool = True) -> None:
+        """Append terms (PO:291-338): a PauliOp is appended as is, a PauliString is merged when ``dedupe``."""
+        self._check_dim(other) if self._strings else None
+        if isinstance(other, PauliString):
+            if dedupe and other.string in self._strings:
+                self._coeffs[self._strings.index(other.string)] += complex(multiplier)
+            else:
+                self._strings.append(other.string)
+                self._coeffs = np.append(self._coeffs, complex(multiplier))
+        else:
+            self._strings.extend(other._strings)
+            self._coeffs = np.append(self._coeffs, other._coeffs * complex(multiplier))
+        self._codes, self._n = _encode(self._strings)
+        self._drop_plans()
+
+    def _plus(self, other, sign: float) -> "PauliOp":
+        out = self.clone()
+        out.extend(other, sign, dedupe=True) if isinstance(other, PauliString) else out.extend(other, sign)
+        return out
+
+    def __add__(self, other):
+        return self._plus(other, 1.0)
+
+    def __radd__(self, other: PauliString):
+        return self._plus(other, 1.0)
+
+    def __iadd__(self, other):
+        self.extend(other, 1.0)
+        return self
+
+    def __sub__(self, other):
+        return self._plus(other, -1.0)
+
+    def __rsub__(self, other: PauliString):
+        out = self * -1.0
+        out.extend(other, 1.0)
+        return out
+
+    def __isub__(self, other):
+        self.extend(other, -1.0)
+        return self
+
+    def to_tensor(self) -> np.ndarray:
+        out = np.zeros((self.dim, self.dim), dtype=np.complex128)
+        for c, st in zip(self._coeffs, self._strings):
+            out += c * _dense(st)
+        return out
+
+    def __getstate__(self):
+        return (self._coeffs.copy(), list(self._strings))
+
+    def __setstate__(self, state):
+        self.__init__(state[0], state[1])
+
     def _context(self) -> Context:
         return self._ctx or default_context()
 
@@ -534,6 +739,42 @@ class SummedPauliOp:
     def clone(self) -> "SummedPauliOp":
         return SummedPauliOp(list(self._strings), self._coeffs.copy(), self._ctx)
 
+    @property
+    def pauli_strings_as_str(self) -> list[str]:
+        return list(self._strings)
+
+    # -- host-side helpers mirrored from the bindings (__summed_pauli_op_bindings.hpp:291-340)
+    def split(self) -> list[PauliOp]:
+        """The K operators as separate PauliOps (SPO:621-637)."""
+        return [PauliOp(self._coeffs[:, k].copy(), list(self._strings), self._ctx) for k in range(self.n_operators)]
+
+    def to_tensor(self) -> np.ndarray:
+        """Dense (n_operators, dim, dim) tensor (SPO:644-665)."""
+        dense = np.stack([_dense(st) for st in self._strings])  # (S, dim, dim)
+        return np.einsum("sk,sij->kij", self._coeffs, dense)
+
+    def square(self) -> "SummedPauliOp":
+        """A_k -> A_k^2 (SPO:197-268): coefficient of string c in operator k is sum over pairs (a, b) with
+        P_a P_b ~ P_c of phase(a,b) h_ak h_bk; the output string set is every string up to weight
+        min(n, 2 * max weight) in calculate_pauli_strings_max_weight order."""
+        from . import helpers
+
+        max_w = max(sum(ch != "I" for ch in st) for st in self._strings)
+        sq = [str(p) for p in helpers.calculate_pauli_strings_max_weight(self._n, min(self._n, 2 * max_w))]
+        index = {st: i for i, st in enumerate(sq)}
+        out = np.zeros((len(sq), self.n_operators), dtype=np.complex128)
+        for a, sa in enumerate(self._strings):
+            for b, sb in enumerate(self._strings):
+                ph, prod = _product(sa, sb)
+                out[index[prod]] += ph * self._coeffs[a] * self._coeffs[b]
+        return SummedPauliOp(sq, out, self._ctx)
+
+    def __getstate__(self):
+        return (list(self._strings), self._coeffs.copy())
+
+    def __setstate__(self, state):
+        self.__init__(state[0], state[1])
+
     def _context(self) -> Context:
         return self._ctx or default_context()
 
@@ -592,3 +833,6 @@ class SummedPauliOp:
         _check(lib.fp_sop_expval(ctx._h, self._plan(a.dtype), _ptr(out), C.c_void_p(a.ptr), C.c_size_t(a.shape[0]),
                                  C.c_size_t(B), C.c_int(0)))
         return out
+
+
+from . import helpers  # noqa: E402  (the reference exposes these as the `helpers` submodule, fast_pauli.cpp:44-104)
