@@ -80,16 +80,57 @@ class Context:
 
     def __init__(self, device: int = 0):
         self._h = C.c_void_p()
+        self._pool: dict[int, list[int]] = {}
+        self._pooled = 0
         _check(lib.fp_ctx_create(C.c_int(device), C.byref(self._h)))
         self.device = device
 
     def __del__(self):
+        if getattr(self, "_h", None):
+            try:
+                self.trim()
+            except Exception:
+                pass
         h, self._h = getattr(self, "_h", None), None
         if h:
             lib.fp_ctx_destroy(h)
 
     def sync(self) -> None:
         _check(lib.fp_ctx_sync(self._h))
+
+    # -- tiny exact-size free list for result arrays: cudaMalloc / cudaFree per call costs milliseconds and
+    #    synchronises the device, which dominates small device-resident calls
+    _POOL_LIMIT = 8 << 30
+
+    def _take(self, nbytes: int) -> int:
+        pool = self.__dict__.setdefault("_pool", {})
+        lst = pool.get(nbytes)
+        if lst:
+            self._pooled -= nbytes
+            return lst.pop()
+        p = C.c_void_p()
+        rc = lib.fp_device_malloc(self._h, C.c_size_t(nbytes), C.byref(p))
+        if rc == 4 and pool:  # out of memory: drop the cache and retry once
+            self.trim()
+            rc = lib.fp_device_malloc(self._h, C.c_size_t(nbytes), C.byref(p))
+        _check(rc)
+        return int(p.value)
+
+    def _give(self, ptr: int, nbytes: int) -> None:
+        pool = self.__dict__.setdefault("_pool", {})
+        if self.__dict__.get("_pooled", 0) + nbytes > self._POOL_LIMIT:
+            lib.fp_device_free(self._h, C.c_void_p(ptr))
+            return
+        self._pooled = self.__dict__.get("_pooled", 0) + nbytes
+        pool.setdefault(nbytes, []).append(ptr)
+
+    def trim(self) -> None:
+        """Return every cached device buffer to the driver."""
+        for lst in self.__dict__.get("_pool", {}).values():
+            for ptr in lst:
+                lib.fp_device_free(self._h, C.c_void_p(ptr))
+        self._pool = {}
+        self._pooled = 0
 
     def set_stream(self, cuda_stream: int | None) -> None:
         """Run on a caller-owned ``cudaStream_t`` handle (``0`` = the legacy default stream, which is what
@@ -192,9 +233,8 @@ class DeviceArray:
         self.nbytes = self.size * self.dtype.itemsize
         self._owner = owner
         if ptr is None:
-            p = C.c_void_p()
-            _check(lib.fp_device_malloc(ctx._h, C.c_size_t(max(self.nbytes, 16)), C.byref(p)))
-            self.ptr = int(p.value)
+            self._cap = max(self.nbytes, 16)
+            self.ptr = ctx._take(self._cap)
             self._owned = True
         else:
             self.ptr = int(ptr)
@@ -202,7 +242,7 @@ class DeviceArray:
 
     def __del__(self):
         if getattr(self, "_owned", False) and self.ctx._h:
-            lib.fp_device_free(self.ctx._h, C.c_void_p(self.ptr))
+            self.ctx._give(self.ptr, self._cap)
             self._owned = False
 
     @property

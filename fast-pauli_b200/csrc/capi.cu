@@ -572,8 +572,10 @@ template <typename T>
 CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, uint64_t rowvecs, int epv)
 {
     CosetShape none;
-    if (ctx->coset_mode == 0 || op.host.gx.size() < 2)
+    if (ctx->coset_mode == 0 || op.host.sz.size() < 2)
         return none;
+    if (n_qubits > 12 && op.host.gx.size() > 20000)
+        return none; // pass planning is quadratic in the number of x-groups: huge operators use the generic kernel
     if (sizeof(T) == 4 && epv != 2)
         return none;
     auto valid = [&](int v, int lnt) {
@@ -597,25 +599,35 @@ CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, 
     else
     {
         int const lnt_pref = ctx->coset_log_nt > 0 ? ctx->coset_log_nt : 8;
-        // widest row segment whose tile rank covers the whole operator in a single pass
-        for (int v = 4; v >= 2 && !pick.ok(); --v)
-            if (op.x_rank <= 4 + lnt_pref - v && valid(v, lnt_pref))
-            {
-                pick.log_twc = v;
-                pick.log_nt = lnt_pref;
-            }
         // the whole state column fits one tile: single pass whatever the operator
-        if (!pick.ok() && n_qubits <= 12 && valid(12 - n_qubits, 8))
+        if (n_qubits <= 12 && valid(12 - n_qubits, 8))
         {
             pick.log_twc = 12 - n_qubits;
             pick.log_nt = 8;
         }
-        for (int v : {2, 3, 4, 1, 0})
-            if (!pick.ok() && valid(v, lnt_pref))
+        // otherwise: the candidate whose (number of passes) x (relative cost of a pass at that row-segment width)
+        // is smallest; pass counts come from the real planner (plans are cached on the operator)
+        static double const seg_cost[5] = {3.5, 2.0, 1.45, 1.05, 1.0}; // measured, HBM-bound passes, v = 0..4
+        double best = 0;
+        for (int v = 4; v >= 0 && !pick.ok(); --v)
+        {
+            if (!valid(v, lnt_pref))
+                continue;
+            std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
+            int const reserve = std::max(0, 2 - v);
+            if (get_coset_plan<T>(op, n_qubits, 4 + lnt_pref - v, reserve, &passes) != FP_OK)
+                continue;
+            double const cost = static_cast<double>(passes->size()) * seg_cost[v];
+            if (best == 0 || cost < best)
             {
-                pick.log_twc = v;
-                pick.log_nt = lnt_pref;
+                best = cost;
+                none.log_twc = v; // remember the best so far in `none` (returned through `pick` below)
+                none.log_nt = lnt_pref;
             }
+        }
+        if (!pick.ok() && none.ok())
+            pick = none;
+        none = CosetShape{};
     }
     if (!pick.ok())
         return none;
@@ -772,7 +784,7 @@ int run_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const *in, 
     }
     FP_TRY(check_align(in, 2 * sizeof(T), "states"));
     FP_TRY(check_align(out, 2 * sizeof(T), "new_states"));
-    if (op.host.gx.size() > 1 && n_qubits > 0)
+    if (op.host.sz.size() > 1 && n_qubits > 0)
     {
         bool used = false;
         FP_TRY((try_coset<T, 0>(ctx, op, n_qubits, out, in, dim, B, beta, nullptr, nullptr, &used)));
@@ -818,7 +830,7 @@ int run_op_expval(fp_ctx *ctx, DeviceOp<T> const &op, void *out /* B complex, de
     FP_TRY(check_align(in, 2 * sizeof(T), "states"));
     if (bra)
         FP_TRY(check_align(bra, 2 * sizeof(T), "bra states"));
-    if (op.host.gx.size() > 1 && n_qubits > 0 && (!bra || bra == in))
+    if (op.host.sz.size() > 1 && n_qubits > 0 && (!bra || bra == in))
     {
         bool used = false;
         FP_TRY((try_coset<T, 1>(ctx, op, n_qubits, out, in, dim, B, beta, nullptr, nullptr, &used)));

@@ -137,6 +137,7 @@ inline std::vector<CosetPassHost<T>> plan_coset(PackedOp<T> const &op, int n_qub
     {
         // ---- candidate (a): bit-subset cover
         uint64_t Tmask = low_mask;
+        if (G <= 4096) // the cover search is O(rank * n * G) per pass: only worth it for moderately sized operators
         {
             int used = reserve_low_bits;
             while (used < rank)
