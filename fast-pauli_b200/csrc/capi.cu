@@ -1663,16 +1663,45 @@ int run_sop_expval(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, ui
     FP_TRY(check_align(in, 2 * sizeof(T), "states"));
     int const epv = pick_epv<T>(in, in, B);
     uint64_t const rowvecs = B / epv;
+    // stage 1: E(s,t) per packed string                                      (SPO:573-577)
+    FP_TRY(ctx->work_a.ensure(static_cast<uint64_t>(S) * B * sizeof(T)));
+    T *E = static_cast<T *>(ctx->work_a.p);
+    bool stage1_done = false;
+    constexpr int EPV_FULL = sizeof(T) == 4 ? 2 : 1;
+    if (ctx->coset_mode != 0 && sop->n_qubits >= 5 && sop->n_qubits <= 12 && epv == EPV_FULL)
+    {
+        // K4b: the whole state column lives in shared memory and every string is evaluated against it
+        uint32_t splits = 1;
+        while (rowvecs * splits < static_cast<uint64_t>(ctx->sm_count) * 2 && splits * 8 < op.n_chunks)
+            splits *= 2;
+        size_t const smem = (static_cast<size_t>(1) << sop->n_qubits) * 16;
+        static bool configured = false;
+        if (!configured)
+        {
+            FP_CU(cudaFuncSetAttribute(sop_expval_tile_kernel<T, EPV_FULL, kPairMS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            configured = true;
+        }
+        if (rowvecs <= 0x7fffffffull)
+        {
+            dim3 grid(static_cast<unsigned>(rowvecs), splits);
+            sop_expval_tile_kernel<T, EPV_FULL, kPairMS><<<grid, kThreads, smem, ctx->stream>>>(
+                op.chunks, op.n_chunks, op.sz, op.sodd, static_cast<uint32_t>(sop->n_qubits), rowvecs,
+                static_cast<CVec<T, EPV_FULL> const *>(in), E, B);
+            ctx->launches++;
+            stage1_done = true;
+        }
+    }
     uint64_t const rows = op.any_diag ? dim : dim / 2;
     GeomSel gs = choose_geom(ctx, rows, dim, rowvecs, 2 * sizeof(T) * epv, false, true, op.n_chunks);
     FP_TRY(check_grid(gs.grid));
     uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
     gs.g.Bpad = Bpad;
     uint64_t const slot_stride = gs.g.nRowBlocks * Bpad;
-    // stage 1: E(s,t) per packed string                                      (SPO:573-577, paired kernel)
-    FP_TRY(ctx->work_a.ensure(static_cast<uint64_t>(S) * B * sizeof(T)));
-    T *E = static_cast<T *>(ctx->work_a.p);
+    // generic stage 1 (any register size): paired kernel with per-row-block partial sums
     T *part = E;
+    if (!stage1_done)
+    {
     if (gs.g.nRowBlocks > 1 || Bpad != B)
     {
         FP_TRY(ctx->partials.ensure(static_cast<uint64_t>(S) * slot_stride * sizeof(T)));
@@ -1698,6 +1727,7 @@ int run_sop_expval(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, ui
         finalize_pairs_matrix_kernel<T>
             <<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(part, slot_stride, gs.g.nRowBlocks, Bpad, B, E);
         ctx->launches++;
+    }
     }
     // stage 2: out[2K x B] = A_e[2K x S] * E[S x B], split over S              (SPO:579-591)
     uint32_t kchunk = 512;
