@@ -115,6 +115,7 @@ struct fp_ctx
     int coset_log_twc = -1;   // >= 0 forces the row-segment width of the tile (TWc = 1 << v vectors)
     int coset_log_nt = 0;     // 7 or 8 forces the CTA size (128 / 256 threads); 0 = default (256)
     int coset_vpt = 16;       // vectors per thread when the shape is forced (8 or 16)
+    bool coset_wide_cta = true; // 512-thread CTAs for the rank-12 weighted-apply tile
     Scratch stage_in, stage_out, stage_data, partials, work_a, work_b, meta;
     std::mutex mu;
 };
@@ -669,6 +670,14 @@ int launch_coset_pass_v(fp_ctx *ctx, CosetShape shape, CosetPassView<T> const &v
     if (shape.vpt == 16 && shape.log_twc == V && shape.log_nt == LNT)                                                  \
         return launch_coset_pass<T, EPV, V, LNT, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad,    \
                                                        Wre, Wim, B);
+    if constexpr (MODE == 2)
+    {
+        // weighted apply on a whole-column tile (rank 12, one vector per row): 512 threads x 8 rows halve the
+        // per-thread accumulator + D registers, so 16 warps are resident per SM instead of 8
+        if (shape.vpt == 16 && shape.log_twc == 0 && shape.log_nt == 8 && ctx->coset_wide_cta)
+            return launch_coset_pass<T, EPV, 0, 9, MODE, 8>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad,
+                                                           Wre, Wim, B);
+    }
 #define FP_COSET_CASE8(V)                                                                                              \
     if (shape.vpt == 8 && shape.log_twc == V && shape.log_nt == 8)                                                     \
         return launch_coset_pass<T, EPV, V, 8, MODE, 8>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad,   \
@@ -1075,6 +1084,8 @@ extern "C"
             ctx->coset_log_nt = atoi(env);
         if (char const *env = getenv("FASTPAULI_COSET_VPT"))
             ctx->coset_vpt = atoi(env);
+        if (char const *env = getenv("FASTPAULI_COSET_WIDE"))
+            ctx->coset_wide_cta = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_ZERO_COPY"))
             ctx->zero_copy = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_TENSOR_CORE"))
