@@ -337,7 +337,45 @@ def run_extras(fp, ctx, hbm_peak: float) -> dict:
         run("PauliOp.expectation_value_16q_1024strings_1000states", op_expval(16, 1024, 1000), 52500.0)
         return res
 
+    # BASELINE config 1 (the reference's own CPU-runnable case): PauliOp.apply, 10 qubits, 64 random strings, batch 16,
+    # complex128 -- host arrays in, host arrays out, timed beside the compiled reference on this box's cores
+    def cfg1():
+        import time as _t
+
+        prng = np.random.default_rng(18)
+        strings = rand_strings(prng, 10, 64)
+        h = prng.uniform(-1, 1, 64) + 1j * prng.uniform(-1, 1, 64)
+        psi = prng.random((1024, 16)) + 1j * prng.random((1024, 16))
+        op = fp.PauliOp(h, strings, ctx=ctx)
+        op.apply(psi)
+        reps = 200
+        t0 = _t.perf_counter()
+        for _ in range(reps):
+            y = op.apply(psi)
+        ours_us = (_t.perf_counter() - t0) / reps * 1e6
+        res = {"ours_host_arrays_us": ours_us, "amp_strings_per_s": 1024 * 16 * 64 / (ours_us * 1e-6)}
+        try:
+            from oracle import oracle as orc
+
+            be = orc.reference() or orc.port()
+            be.use_all_threads()
+            out = np.zeros_like(psi)
+            for par, tag in ((True, "reference_par_us"), (False, "reference_seq_us")):
+                be.op_apply(strings, h, psi, out=out, par=par)
+                t0 = _t.perf_counter()
+                for _ in range(20):
+                    be.op_apply(strings, h, psi, out=out, par=par)
+                res[tag] = (_t.perf_counter() - t0) / 20 * 1e6
+            res["reference_cores"] = be.max_threads()
+            ref = np.zeros_like(psi)
+            be.op_apply(strings, h, psi, out=ref, par=False)
+            res["max_rel_err_vs_reference"] = float(np.max(np.abs(y - ref)) / np.max(np.abs(ref)))
+        except Exception as e:
+            res["reference_error"] = str(e)
+        return res
+
     ctx.set_async(False)
+    guard("config1_pauli_op_apply_10q_64strings_b16_c128", cfg1)
     guard("reference_published_shapes", published)
     ctx.set_async(True)
     guard("pauli_op_apply_20q_b64_c128", op20)
