@@ -228,7 +228,22 @@ def run_extras(fp, ctx, hbm_peak: float) -> dict:
                     out_s.append("".join(t))
             return out_s
 
-        cases = [("few_group_64_strings_8_xmasks", few), ("random_64_strings", rand_strings(rng, n, 64))]
+        def local_dense(k):  # every Pauli string on k fixed qubits: 4^k strings over 2^k x-masks (GF(2) rank k)
+            pos = sorted(int(p) for p in rng.choice(n, size=k, replace=False))
+            out_s = []
+            for idx in range(4**k):
+                t = ["I"] * n
+                for i, p_ in enumerate(pos):
+                    t[p_] = "IXYZ"[(idx >> (2 * i)) & 3]
+                out_s.append("".join(t))
+            return out_s
+
+        cases = [("few_group_64_strings_8_xmasks", few), ("random_64_strings", rand_strings(rng, n, 64)),
+                 # the same 64 strings / 8 x-masks / 8 z-variants shape when the masks are closed under XOR (all
+                 # Paulis on 3 qubits): rank 3, register-resident coset kernel
+                 ("dense_3local_64_strings_8_xmasks", local_dense(3)),
+                 ("dense_2local_16_strings_4_xmasks", local_dense(2)),
+                 ("dense_4local_256_strings_16_xmasks", local_dense(4))]
         # HBM fraction as a function of the number of distinct x-masks (64 strings each time)
         for g in (1, 2, 4, 16):
             cases.append((f"sweep_64_strings_{g}_xmasks", variants(rand_strings(rng, n, g), 64 // g)))
@@ -243,6 +258,12 @@ def run_extras(fp, ctx, hbm_peak: float) -> dict:
             res[tag] = {"ms": ms, "amp_strings_per_s": amps * len(strings) / (ms * 1e-3),
                         "algorithmic_GBps": amps * 32 / (ms * 1e-3) / 1e9,
                         "hbm_frac": amps * 32 / (ms * 1e-3) / 1e9 / hbm_peak, "x_groups": info["n_x_groups"]}
+            if tag.startswith("dense_") or tag.startswith("few_group"):
+                ev = ctx.empty((B,), DTYPE)
+                ms_e = timed_ms(fp, ctx, lambda: fp.lib.fp_op_expval(ctx._h, op._plan(DTYPE), _vp(ev.ptr), _vp(psi.ptr),
+                                                                      _sz(1 << n), _sz(B), 0), 5)
+                res[tag]["expectation_value_ms"] = ms_e
+                res[tag]["expectation_value_hbm_frac"] = amps * 16 / (ms_e * 1e-3) / 1e9 / hbm_peak
             del op
         return res
 

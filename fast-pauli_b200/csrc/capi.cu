@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include "coset.cuh"
+#include "rcoset.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "pack.hpp"
@@ -116,6 +117,8 @@ struct fp_ctx
     int coset_log_nt = 0;     // 7 or 8 forces the CTA size (128 / 256 threads); 0 = default (256)
     int coset_vpt = 16;       // vectors per thread when the shape is forced (8 or 16)
     bool coset_wide_cta = true; // 512-thread CTAs for the rank-12 weighted-apply tile
+    int rcoset_mode = 1;        // register-resident coset kernel (x-mask rank <= 4): 0 never, 1 auto, 2 whenever applicable
+    int rcoset_log_nt = 7;      // its CTA size (128 / 256 threads)
     Scratch stage_in, stage_out, stage_data, partials, work_a, work_b, meta;
     std::mutex mu;
 };
@@ -146,6 +149,15 @@ template <typename T> struct DeviceOp
     };
     mutable std::map<int, std::vector<CosetPassDev>> coset_plans;
 
+    // register-resident coset plan (x-mask rank <= kRcMaxRank), built lazily
+    struct RcPlanDev
+    {
+        RcPassView<T> view{};
+        int rr = 0;
+        std::vector<void *> allocs;
+    };
+    mutable std::map<int, RcPlanDev> rc_plans;
+
     OpView<T> view() const
     {
         OpView<T> v{};
@@ -175,6 +187,10 @@ template <typename T> struct DeviceOp
                 for (void *a : pd.allocs)
                     cudaFree(a);
         coset_plans.clear();
+        for (auto &kv : rc_plans)
+            for (void *a : kv.second.allocs)
+                cudaFree(a);
+        rc_plans.clear();
         gx = nullptr;
         gstart = nullptr;
         sz = nullptr;
@@ -748,6 +764,169 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
     return FP_OK;
 }
 
+// ---------------------------------------------------------------- register-resident coset path (K3c, rcoset.cuh)
+template <typename T>
+int get_rc_plan(DeviceOp<T> const &op, int n_qubits, int rr, typename DeviceOp<T>::RcPlanDev const **out)
+{
+    auto it = op.rc_plans.find(rr);
+    if (it != op.rc_plans.end())
+    {
+        *out = &it->second;
+        return FP_OK;
+    }
+    std::vector<CosetPassHost<T>> host = plan_coset<T>(op.host, n_qubits, rr, 0);
+    if (host.size() != 1 || host[0].basis.r != rr)
+        return set_err(FP_UNSUPPORTED, "register coset plan: the operator does not fit one pass");
+    CosetPassHost<T> const &h = host[0];
+    uint32_t const rows = 1u << rr;
+    // strings ordered by local gather mask (the planner may have split a large group into several sub-groups)
+    std::vector<uint32_t> xstart(rows + 1, 0), stab;
+    std::vector<uint64_t> sz;
+    std::vector<Cx<T>> sc;
+    uint32_t present = 0;
+    for (uint32_t xl = 0; xl < rows; ++xl)
+    {
+        for (size_t g = 0; g < h.gxl.size(); ++g)
+        {
+            if (h.gxl[g] != xl)
+                continue;
+            for (uint32_t s = h.gstart[g]; s < h.gstart[g + 1]; ++s)
+            {
+                uint32_t tab = 0;
+                for (uint32_t l = 0; l < rows; ++l)
+                    tab |= static_cast<uint32_t>(__builtin_popcount(l & h.szl[s]) & 1) << l;
+                stab.push_back(tab);
+                sz.push_back(h.sz[s]);
+                sc.push_back(Cx<T>{h.sc[s].real(), h.sc[s].imag()});
+            }
+        }
+        xstart[xl + 1] = static_cast<uint32_t>(sz.size());
+        if (xstart[xl + 1] > xstart[xl])
+            present |= 1u << xl;
+    }
+    typename DeviceOp<T>::RcPlanDev d;
+    d.rr = rr;
+    for (int k = 0; k < kRcMaxRank; ++k)
+    {
+        d.view.basis[k] = k < rr ? h.basis.b[k] : 0;
+        d.view.pivot[k] = k < rr ? static_cast<uint32_t>(h.basis.pivot[k]) : 0;
+    }
+    d.view.present = present;
+    uint32_t *d_xstart = nullptr, *d_stab = nullptr;
+    uint64_t *d_sz = nullptr;
+    Cx<T> *d_sc = nullptr;
+    int rc = upload_vec(&d_xstart, xstart);
+    if (rc == FP_OK) { d.allocs.push_back(d_xstart); rc = upload_vec(&d_stab, stab); }
+    if (rc == FP_OK) { d.allocs.push_back(d_stab); rc = upload_vec(&d_sz, sz); }
+    if (rc == FP_OK) { d.allocs.push_back(d_sz); rc = upload_vec(&d_sc, sc); }
+    if (rc == FP_OK) d.allocs.push_back(d_sc);
+    if (rc != FP_OK)
+    {
+        for (void *a : d.allocs)
+            cudaFree(a);
+        return rc;
+    }
+    d.view.xstart = d_xstart;
+    d.view.stab = d_stab;
+    d.view.sz = d_sz;
+    d.view.scoef = d_sc;
+    auto ins = op.rc_plans.emplace(rr, std::move(d));
+    *out = &ins.first->second;
+    return FP_OK;
+}
+
+template <typename T, int EPV, int RR, int LOG_NT, int MODE>
+int launch_rcoset(fp_ctx *ctx, RcPassView<T> const &view, uint64_t n_cosets, uint64_t rowvecs, uint32_t log2tw,
+                  uint32_t log2p, uint32_t nct, uint64_t n_blocks, uint32_t iters, size_t smem, void const *in, void *out, int beta,
+                  void *partials, uint32_t Bpad)
+{
+    static size_t configured = 48 * 1024; // per template instance
+    if (smem > configured)
+    {
+        FP_CU(cudaFuncSetAttribute(rcoset_kernel<T, EPV, RR, LOG_NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+        configured = smem;
+    }
+    rcoset_kernel<T, EPV, RR, LOG_NT, MODE><<<static_cast<unsigned>(n_blocks * nct), 1 << LOG_NT, smem, ctx->stream>>>(
+        view, n_cosets, rowvecs, log2tw, log2p, nct, iters, static_cast<CVec<T, EPV> const *>(in),
+        static_cast<CVec<T, EPV> *>(out), beta, static_cast<Cx<T> *>(partials), Bpad);
+    ctx->launches++;
+    return FP_OK;
+}
+
+// Returns FP_OK with *used = false when the operator / batch shape is left to the other kernels.
+template <typename T, int MODE>
+int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void const *in, uint64_t dim, uint64_t B,
+               int beta, bool *used)
+{
+    *used = false;
+    constexpr int EPV = sizeof(T) == 4 ? 2 : 1;
+    bool const enabled = ctx->rcoset_mode == 2 ||
+                         (ctx->rcoset_mode == 1 && ctx->coset_mode == 1 && ctx->coset_log_twc < 0);
+    if (!enabled || n_qubits <= 0 || dim != (1ull << n_qubits) || op.host.sz.size() < 2 || op.x_rank > kRcMaxRank)
+        return FP_OK;
+    if (pick_epv<T>(in, MODE == 1 ? in : out, B) != EPV)
+        return FP_OK;
+    uint64_t const rowvecs = B / EPV;
+    if (rowvecs < 4 && ctx->rcoset_mode != 2)
+        return FP_OK; // rows shorter than 64 bytes: coalescing must come from the row index (shared-memory tiles)
+    int const rr = std::min(n_qubits, std::max(2, op.x_rank)); // 2-row threads keep too few bytes in flight
+    int const log_nt = ctx->rcoset_log_nt == 8 ? 8 : 7;
+    uint32_t const NT = 1u << log_nt;
+    uint32_t log2tw = 0;
+    while ((1ull << log2tw) < rowvecs && (1u << log2tw) < NT)
+        ++log2tw;
+    uint32_t const TW = 1u << log2tw, TY = NT / TW;
+    size_t smem = static_cast<size_t>(TY) * (1u << (2 * rr)) * 2 * sizeof(T);
+    if (MODE == 1)
+        smem = std::max(smem, static_cast<size_t>(NT) * EPV * 2 * sizeof(T));
+    if (smem > 64 * 1024)
+        return FP_OK;
+    typename DeviceOp<T>::RcPlanDev const *plan = nullptr;
+    FP_TRY(get_rc_plan<T>(op, n_qubits, rr, &plan));
+    uint64_t const n_cosets = 1ull << (n_qubits - rr);
+    uint32_t const nct = static_cast<uint32_t>((rowvecs + TW - 1) / TW);
+    uint64_t const n_sets = (n_cosets + TY - 1) / TY;
+    uint64_t iters = 1;
+    if (MODE == 1)
+    {
+        uint64_t const target = static_cast<uint64_t>(ctx->sm_count) * 16;
+        uint64_t const want_cb = std::max<uint64_t>(1, target / nct);
+        iters = std::min<uint64_t>(std::max<uint64_t>(1, (n_sets + want_cb - 1) / want_cb), 4096);
+    }
+    while ((n_sets + iters - 1) / iters * nct > 0x7fffffffull)
+        iters *= 2;
+    uint64_t const n_blocks = (n_sets + iters - 1) / iters;
+    uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
+    if (MODE == 1)
+        FP_TRY(ctx->partials.ensure(n_blocks * Bpad * 2 * sizeof(T)));
+    // lanes cooperating on one factor-table entry: as many as keep every thread busy, at most a warp
+    uint32_t log2p = 0;
+    while (log2p < 5 && (static_cast<uint64_t>(TY) << (2 * rr + log2p + 1)) <= NT)
+        ++log2p;
+#define FP_RC_CASE(RRV, LNT)                                                                                           \
+    if (rr == RRV && log_nt == LNT)                                                                                    \
+        FP_TRY((launch_rcoset<T, EPV, RRV, LNT, MODE>(ctx, plan->view, n_cosets, rowvecs, log2tw, log2p, nct, n_blocks, \
+                                                      static_cast<uint32_t>(iters), smem, in, out, beta,               \
+                                                      ctx->partials.p, Bpad)));
+    FP_RC_CASE(2, 7)
+    FP_RC_CASE(3, 7)
+    FP_RC_CASE(4, 7)
+    FP_RC_CASE(2, 8)
+    FP_RC_CASE(3, 8)
+    FP_RC_CASE(4, 8)
+#undef FP_RC_CASE
+    if (MODE == 1)
+    {
+        unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
+        finalize_complex_kernel<T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
+            static_cast<Cx<T> const *>(ctx->partials.p), n_blocks, Bpad, B, static_cast<Cx<T> *>(out), beta);
+        ctx->launches++;
+    }
+    *used = true;
+    return FP_OK;
+}
+
 // ---------------------------------------------------------------- launchers (all pointers are device pointers here)
 template <typename T, int EPV, int MODE, bool INLINE1>
 void launch_op_v(fp_ctx *ctx, GeomSel const &gs, OpView<T> const &view, void const *in, void *out, void *partials,
@@ -796,6 +975,9 @@ int run_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const *in, 
     if (op.host.sz.size() > 1 && n_qubits > 0)
     {
         bool used = false;
+        FP_TRY((try_rcoset<T, 0>(ctx, op, n_qubits, out, in, dim, B, beta, &used)));
+        if (used)
+            return FP_OK;
         FP_TRY((try_coset<T, 0>(ctx, op, n_qubits, out, in, dim, B, beta, nullptr, nullptr, &used)));
         if (used)
             return FP_OK;
@@ -842,6 +1024,9 @@ int run_op_expval(fp_ctx *ctx, DeviceOp<T> const &op, void *out /* B complex, de
     if (op.host.sz.size() > 1 && n_qubits > 0 && (!bra || bra == in))
     {
         bool used = false;
+        FP_TRY((try_rcoset<T, 1>(ctx, op, n_qubits, out, in, dim, B, beta, &used)));
+        if (used)
+            return FP_OK;
         FP_TRY((try_coset<T, 1>(ctx, op, n_qubits, out, in, dim, B, beta, nullptr, nullptr, &used)));
         if (used)
             return FP_OK;
@@ -1086,6 +1271,10 @@ extern "C"
             ctx->coset_vpt = atoi(env);
         if (char const *env = getenv("FASTPAULI_COSET_WIDE"))
             ctx->coset_wide_cta = atoi(env) != 0;
+        if (char const *env = getenv("FASTPAULI_RCOSET"))
+            ctx->rcoset_mode = atoi(env);
+        if (char const *env = getenv("FASTPAULI_RCOSET_LOG_NT"))
+            ctx->rcoset_log_nt = atoi(env);
         if (char const *env = getenv("FASTPAULI_ZERO_COPY"))
             ctx->zero_copy = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_TENSOR_CORE"))
@@ -1162,6 +1351,15 @@ extern "C"
         ctx->coset_mode = mode;
         ctx->coset_log_twc = log_twc;
         ctx->coset_log_nt = log_nt;
+        return FP_OK;
+    }
+
+    int fp_ctx_set_rcoset(fp_ctx *ctx, int mode, int log_nt)
+    {
+        if (!ctx || mode < 0 || mode > 2 || !(log_nt == 0 || log_nt == 7 || log_nt == 8))
+            return set_err(FP_INVALID_ARGUMENT, "bad register-coset mode");
+        ctx->rcoset_mode = mode;
+        ctx->rcoset_log_nt = log_nt == 0 ? 7 : log_nt;
         return FP_OK;
     }
 

@@ -85,6 +85,11 @@ extern "C"
      * vectors, 0..4; -1 = automatic); log_nt = 7 or 8 forces 128- or 256-thread CTAs (0 = default).  A tile holds
      * 16 * 2^log_nt vectors, i.e. 2^(4 + log_nt - log_twc) rows. */
     int fp_ctx_set_coset(fp_ctx *ctx, int mode, int log_twc, int log_nt);
+    /* Register-resident coset kernels (operators whose x-masks span a GF(2) subspace of rank <= 4: each thread holds
+     * the <= 16 rows of one coset for one 16-byte vector, no shared-memory staging): mode 0 = never, 1 = automatic
+     * (default; stands aside when fp_ctx_set_coset forces a mode or shape), 2 = whenever applicable.  log_nt = 7 or 8
+     * picks 128- or 256-thread CTAs (0 = default, 128). */
+    int fp_ctx_set_rcoset(fp_ctx *ctx, int mode, int log_nt);
     /* Override the L2 working-set budget (bytes) used to pick the batch-tile width of multi-group kernels. */
     int fp_ctx_set_l2_budget(fp_ctx *ctx, size_t bytes);
 

@@ -78,6 +78,40 @@ def main():
         ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
         amps = (1 << n) * B
         print(f"{a.case}: {ms:.3f} ms  {amps*32/ms/1e6:.0f} GB/s algorithmic  groups={op.plan_info()['n_x_groups']}")
+    elif a.case in ("span1", "span2", "span3", "span4", "local3"):
+        # x-masks confined to a GF(2) span of rank r (register-resident coset kernel): 64 strings over 2^r masks;
+        # local3 = all 64 Pauli strings on 3 fixed qubits (8 x-masks x 8 z-masks)
+        n, B = 20, a.batch or 64
+        if a.case == "local3":
+            pos = sorted(int(p) for p in rng.choice(n, size=3, replace=False))
+            strings = []
+            for k in range(64):
+                t = ["I"] * n
+                for i, p_ in enumerate(pos):
+                    t[p_] = "IXYZ"[(k >> (2 * i)) & 3]
+                strings.append("".join(t))
+        else:
+            r = int(a.case[-1])
+            gens = [int(rng.integers(1, 1 << n)) for _ in range(r)]
+            strings = []
+            for k in range(64):
+                x = 0
+                for j in range(r):
+                    if (k >> j) & 1:
+                        x ^= gens[j]
+                z = int(rng.integers(0, 1 << n))
+                strings.append("".join("IZXY"[2 * ((x >> (n - 1 - q)) & 1) + ((z >> (n - 1 - q)) & 1)] for q in range(n)))
+        h = rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))
+        psi = ctx.uniform((1 << n, B), np.complex128)
+        op = fp.PauliOp(h, strings, ctx=ctx)
+        y = ctx.empty((1 << n, B), np.complex128)
+        ev = ctx.empty((B,), np.complex128)
+        plan = op._plan(np.complex128)
+        ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
+        ms2 = timed(ctx, lambda: fp.lib.fp_op_expval(ctx._h, plan, vp(ev.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
+        amps = (1 << n) * B
+        print(f"{a.case}: apply {ms:.3f} ms  {amps*32/ms/1e6:.0f} GB/s | expval {ms2:.3f} ms {amps*16/ms2/1e6:.0f} GB/s "
+              f"groups={op.plan_info()['n_x_groups']}")
     elif a.case == "cfg3":
         n, B, S = 16, a.batch or 1024, 2000
         strings = random_strings(rng, n, S, max_weight=4)

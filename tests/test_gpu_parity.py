@@ -437,6 +437,102 @@ def test_coset_heuristic_default_path():
     assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi, par=True)) < 1e-12
 
 
+def _span_strings(rng, n, rank, n_strings):
+    """Strings whose x-masks lie in the GF(2) span of `rank` random masks, with random z parts."""
+    gens = []
+    while len(gens) < rank:
+        m = int(rng.integers(1, 2**n))
+        # keep the generators independent
+        basis = []
+        ok = True
+        for g in gens + [m]:
+            v = g
+            for b in basis:
+                v = min(v, v ^ b)
+            if v == 0:
+                ok = False
+                break
+            basis.append(v)
+        if ok:
+            gens.append(m)
+    out = []
+    for k in range(n_strings):
+        sel = int(rng.integers(0, 2**rank)) if k >= rank else (1 << k)  # every generator appears: span rank = rank
+        x = 0
+        for j in range(rank):
+            if (sel >> j) & 1:
+                x ^= gens[j]
+        z = int(rng.integers(0, 2**n))
+        s = []
+        for q in range(n):
+            bit = n - 1 - q
+            xb, zb = (x >> bit) & 1, (z >> bit) & 1
+            s.append("IZXY"[2 * xb + zb])
+        out.append("".join(s))
+    return out
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rank", [1, 2, 3, 4])
+@pytest.mark.parametrize("log_nt", [7, 8])
+@pytest.mark.parametrize("n,B", [(6, 8), (9, 34), (12, 300)])
+def test_register_coset_kernels(dtype, rank, log_nt, n, B):
+    """K3c (rcoset.cuh): operators whose x-masks span rank <= 4 run as ONE register-resident launch; parity for
+    apply / expectation_value / accumulate against the oracle and against the generic gather kernel."""
+    import ctypes as C
+
+    ctx = fp.Context(0)
+    ctx.set_rcoset(2, log_nt)
+    rng = np.random.default_rng(7000 + 10 * rank + n)
+    S = 40
+    strings = _span_strings(rng, n, rank, S)
+    strings[-1] = strings[0]  # duplicate: merged by the packer
+    h = (rand_states(rng, S, None, dtype) * 2 - (1 + 1j)).astype(dtype)
+    psi = rand_states(rng, 2**n, B, dtype)
+    base = rand_states(rng, 2**n, B, dtype)
+    t = tol(dtype)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    l0 = ctx.launch_count
+    got = op.apply(psi)
+    assert ctx.launch_count - l0 == 1
+    assert rel_err(got, ORC.op_apply(strings, h, psi, par=True)) < t
+    l0 = ctx.launch_count
+    ev = op.expectation_value(psi)
+    assert ctx.launch_count - l0 == 2  # kernel + finaliser
+    assert_parity(ev, lambda *a: ORC.op_expval(*a, par=True), dtype, strings, h, psi)
+    out = base.copy()
+    rc = fp.lib.fp_op_apply(ctx._h, op._plan(dtype), C.c_void_p(out.ctypes.data), C.c_void_p(psi.ctypes.data),
+                            C.c_size_t(2**n), C.c_size_t(B), C.c_int(1))
+    assert rc == 0
+    assert rel_err(out, ORC.op_apply(strings, h, psi, out=base.copy(), par=True)) < t
+    ctx0 = fp.Context(0)
+    ctx0.set_rcoset(0, 0)
+    ctx0.set_coset(0, -1, 0)
+    assert rel_err(fp.PauliOp(h, strings, ctx=ctx0).apply(psi), got) < t
+
+
+def test_register_coset_default_path_headline_shape():
+    """The north-star headline shape at reduced batch: 64 strings over 8 x-masks (rank 3) at 16 qubits takes the
+    register-resident kernel by default; a diagonal-only operator (rank 0) does too."""
+    rng = np.random.default_rng(5)
+    n, B = 16, 64
+    strings = _span_strings(rng, n, 3, 64)
+    h = rand_states(rng, 64, None) * 2 - (1 + 1j)
+    psi = rand_states(rng, 2**n, B)
+    ctx = fp.Context(0)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    l0 = ctx.launch_count
+    got = op.apply(psi)
+    assert ctx.launch_count - l0 == 1
+    assert rel_err(got, ORC.op_apply(strings, h, psi, par=True)) < 1e-12
+    assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi, par=True)) < 1e-12
+    diag = ["".join(rng.choice(list("IZ"), size=n)) for _ in range(10)]
+    hd = rand_states(rng, 10, None)
+    opd = fp.PauliOp(hd, diag, ctx=ctx)
+    assert rel_err(opd.apply(psi), ORC.op_apply(diag, hd, psi, par=True)) < 1e-12
+    assert rel_err(opd.expectation_value(psi), ORC.op_expval(diag, hd, psi, par=True)) < 1e-12
+
+
 # ------------------------------------------------------------------ K5: tcgen05 3xTF32 contraction engine
 @pytest.mark.parametrize("M,N,Kd,split", [(128, 128, 32, 1), (256, 384, 64, 1), (200, 100, 36, 1), (20000 // 8, 512, 64, 1),
                                           (128, 256, 1000, 4), (130, 4100, 12, 1), (64, 8, 8, 1)])
