@@ -20,6 +20,7 @@
 
 #include "coset.cuh"
 #include "rcoset.cuh"
+#include "wtile.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "pack.hpp"
@@ -117,6 +118,7 @@ struct fp_ctx
     int coset_log_nt = 0;     // 7 or 8 forces the CTA size (128 / 256 threads); 0 = default (256)
     int coset_vpt = 16;       // vectors per thread when the shape is forced (8 or 16)
     bool coset_wide_cta = true; // 512-thread CTAs for the rank-12 weighted-apply tile
+    bool wtile = true;          // dedicated whole-column weighted-apply kernel (complex64, 11-12 qubits)
     int rcoset_mode = 1;        // register-resident coset kernel (x-mask rank <= 4): 0 never, 1 auto, 2 whenever applicable
     int rcoset_log_nt = 7;      // its CTA size (128 / 256 threads)
     Scratch stage_in, stage_out, stage_data, partials, work_a, work_b, meta;
@@ -1271,6 +1273,8 @@ extern "C"
             ctx->coset_vpt = atoi(env);
         if (char const *env = getenv("FASTPAULI_COSET_WIDE"))
             ctx->coset_wide_cta = atoi(env) != 0;
+        if (char const *env = getenv("FASTPAULI_WTILE"))
+            ctx->wtile = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_RCOSET"))
             ctx->rcoset_mode = atoi(env);
         if (char const *env = getenv("FASTPAULI_RCOSET_LOG_NT"))
@@ -1809,6 +1813,53 @@ int sop_check(fp_ctx *ctx, fp_sop const *sop)
     return FP_OK;
 }
 
+// K6b (wtile.cuh): whole state column pair in shared memory, packed-FP32 arithmetic; complex64, 11 or 12 qubits
+template <int LOG_NT>
+int launch_wtile(fp_ctx *ctx, CosetPassView<float> const &view, uint64_t rowvecs, void const *in, void *out, int beta,
+                 float const *Wre, float const *Wim, uint64_t B)
+{
+    constexpr size_t smem = WtileSmem<LOG_NT>::bytes;
+    static bool configured = false;
+    if (!configured)
+    {
+        FP_CU(cudaFuncSetAttribute(wtile_kernel<LOG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+        configured = true;
+    }
+    FP_TRY(check_grid(rowvecs));
+    wtile_kernel<LOG_NT><<<static_cast<unsigned>(rowvecs), 1 << LOG_NT, smem, ctx->stream>>>(
+        view, rowvecs, static_cast<CVec<float, 2> const *>(in), static_cast<CVec<float, 2> *>(out), beta, Wre, Wim, B);
+    ctx->launches++;
+    return FP_OK;
+}
+
+template <typename T>
+int try_wtile(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void const *in, uint64_t dim, uint64_t B,
+              int beta, T const *Wre, T const *Wim, bool *used)
+{
+    *used = false;
+    if constexpr (sizeof(T) == 4)
+    {
+        if (!ctx->wtile || ctx->coset_mode != 1 || ctx->coset_log_twc >= 0 || (n_qubits != 11 && n_qubits != 12) ||
+            dim != (1ull << n_qubits) || pick_epv<T>(in, out, B) != 2)
+            return FP_OK;
+        std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
+        FP_TRY(get_coset_plan<T>(op, n_qubits, n_qubits, 2, &passes));
+        if (passes->size() != 1)
+            return FP_OK;
+        CosetPassView<T> const &view = (*passes)[0].view;
+        for (int k = 0; k < n_qubits; ++k)
+            if (view.basis[k] != (1ull << k))
+                return FP_OK; // cannot happen for a full-rank reduced basis; the kernel relies on local row == row
+        if (n_qubits == 12)
+            FP_TRY(launch_wtile<9>(ctx, view, B / 2, in, out, beta, Wre, Wim, B));
+        else
+            FP_TRY(launch_wtile<8>(ctx, view, B / 2, in, out, beta, Wre, Wim, B));
+        *used = true;
+    }
+    return FP_OK;
+}
+
 template <typename T, typename DT>
 int run_sop_weighted(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, DT const *data, uint64_t dim, uint64_t B,
                      int beta)
@@ -1825,6 +1876,9 @@ int run_sop_weighted(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, 
     if (op.host.gx.size() > 1)
     {
         bool used = false;
+        FP_TRY((try_wtile<T>(ctx, op, sop->n_qubits, out, in, dim, B, beta, Wre, Wim, &used)));
+        if (used)
+            return FP_OK;
         FP_TRY((try_coset<T, 2>(ctx, op, sop->n_qubits, out, in, dim, B, beta, Wre, Wim, &used)));
         if (used)
             return FP_OK;
