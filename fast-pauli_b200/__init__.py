@@ -154,6 +154,10 @@ class Context:
         shape (2^log_twc vectors per row segment, 2^log_nt threads per CTA)."""
         _check(lib.fp_ctx_set_coset(self._h, C.c_int(mode), C.c_int(log_twc), C.c_int(log_nt)))
 
+    def set_pipeline(self, enable: bool = True, min_bytes: int = 0, chunk_bytes: int = 0) -> None:
+        """Chunked upload / kernel / download pipeline of PauliString.apply on host arrays (0 keeps a size)."""
+        _check(lib.fp_ctx_set_pipeline(self._h, C.c_int(bool(enable)), C.c_size_t(min_bytes), C.c_size_t(chunk_bytes)))
+
     def set_rcoset(self, mode: int = 1, log_nt: int = 0) -> None:
         """Register-resident coset kernels (x-mask rank <= 4): mode 0 never / 1 automatic / 2 whenever applicable."""
         _check(lib.fp_ctx_set_rcoset(self._h, C.c_int(mode), C.c_int(log_nt)))

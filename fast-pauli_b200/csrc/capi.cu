@@ -118,6 +118,10 @@ struct fp_ctx
     int coset_log_nt = 0;     // 7 or 8 forces the CTA size (128 / 256 threads); 0 = default (256)
     int coset_vpt = 16;       // vectors per thread when the shape is forced (8 or 16)
     bool coset_wide_cta = true; // 512-thread CTAs for the rank-12 weighted-apply tile
+    bool pipeline = true;       // chunked H2D / kernel / D2H pipeline for large host-resident single-string applies
+    size_t pipeline_min_bytes = 128ull << 20, pipeline_chunk_bytes = 32ull << 20;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t pipe_in[3] = {}, pipe_k[3] = {}, pipe_out[3] = {}, pipe_start = nullptr;
     bool wtile = true;          // dedicated whole-column weighted-apply kernel (complex64, 11-12 qubits)
     int rcoset_mode = 1;        // register-resident coset kernel (x-mask rank <= 4): 0 never, 1 auto, 2 whenever applicable
     int rcoset_log_nt = 7;      // its CTA size (128 / 256 threads)
@@ -1161,6 +1165,72 @@ int run_gemm(fp_ctx *ctx, T const *A, DT const *Bm, T *C, uint32_t M, uint64_t N
 }
 
 // ---------------------------------------------------------------- typed front-ends over fp_op
+// Host-resident PauliString::apply_batch (PS:377-436) as a three-stage pipeline.  An aligned block of 2^m rows of
+// the output depends on exactly one such block of the input (block index ^ (x >> m), rows permuted by the low bits
+// of x inside it), so the batch streams through the GPU in chunks: copy engine 1 uploads chunk j+1 while the
+// kernel permutes chunk j and copy engine 2 downloads chunk j-1 -- both PCIe directions stay busy for the whole
+// call instead of upload, kernel and download running back to back.  The sign of the block index is folded into
+// the coefficient, so every chunk runs the ordinary single-string kernel K1 on (x_low, z_low).
+template <typename T>
+int pipelined_string_apply(fp_ctx *ctx, StringMasks const &mk, std::complex<T> coeff, void *out, void const *in,
+                           uint64_t dim, uint64_t B)
+{
+    size_t const rowbytes = B * 2 * sizeof(T);
+    int m = 0;
+    while ((2ull << m) * rowbytes <= ctx->pipeline_chunk_bytes && (2ull << m) <= dim)
+        ++m;
+    uint64_t const rows = 1ull << m, n_chunks = dim >> m;
+    size_t const cbytes = rows * rowbytes;
+    if (!ctx->h2d_stream)
+    {
+        FP_CU(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+        FP_CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i)
+        {
+            FP_CU(cudaEventCreateWithFlags(&ctx->pipe_in[i], cudaEventDisableTiming));
+            FP_CU(cudaEventCreateWithFlags(&ctx->pipe_k[i], cudaEventDisableTiming));
+            FP_CU(cudaEventCreateWithFlags(&ctx->pipe_out[i], cudaEventDisableTiming));
+        }
+        FP_CU(cudaEventCreateWithFlags(&ctx->pipe_start, cudaEventDisableTiming));
+    }
+    FP_TRY(ctx->stage_in.ensure(3 * cbytes));
+    FP_TRY(ctx->stage_out.ensure(3 * cbytes));
+    // work already queued on the context's stream may still use the scratch buffers
+    FP_CU(cudaEventRecord(ctx->pipe_start, ctx->stream));
+    FP_CU(cudaStreamWaitEvent(ctx->h2d_stream, ctx->pipe_start, 0));
+    uint64_t const xlo = mk.x & (rows - 1), xhi = mk.x >> m, zlo = mk.z & (rows - 1);
+    std::complex<T> const c0 = times_phase(coeff, mk.ny);
+    for (uint64_t j = 0; j < n_chunks; ++j)
+    {
+        int const b = static_cast<int>(j % 3);
+        auto *d_in = static_cast<unsigned char *>(ctx->stage_in.p) + static_cast<size_t>(b) * cbytes;
+        auto *d_out = static_cast<unsigned char *>(ctx->stage_out.p) + static_cast<size_t>(b) * cbytes;
+        uint64_t const jo = j ^ xhi; // output block fed by input block j
+        if (j >= 3)
+            FP_CU(cudaStreamWaitEvent(ctx->h2d_stream, ctx->pipe_k[b], 0)); // kernel j-3 has consumed this buffer
+        FP_CU(cudaMemcpyAsync(d_in, static_cast<unsigned char const *>(in) + j * cbytes, cbytes,
+                              cudaMemcpyHostToDevice, ctx->h2d_stream));
+        FP_CU(cudaEventRecord(ctx->pipe_in[b], ctx->h2d_stream));
+        FP_CU(cudaStreamWaitEvent(ctx->stream, ctx->pipe_in[b], 0));
+        if (j >= 3)
+            FP_CU(cudaStreamWaitEvent(ctx->stream, ctx->pipe_out[b], 0)); // download j-3 has drained this buffer
+        DeviceOp<T> op;
+        op.host.gx.assign(1, xlo);
+        op.host.gstart.assign({0u, 1u});
+        op.host.sz.assign(1, zlo);
+        op.host.sc.assign(1, (__builtin_popcountll((jo << m) & mk.z) & 1) ? -c0 : c0);
+        FP_TRY(run_op_apply<T>(ctx, op, d_out, d_in, rows, B, 0));
+        FP_CU(cudaEventRecord(ctx->pipe_k[b], ctx->stream));
+        FP_CU(cudaStreamWaitEvent(ctx->d2h_stream, ctx->pipe_k[b], 0));
+        FP_CU(cudaMemcpyAsync(static_cast<unsigned char *>(out) + jo * cbytes, d_out, cbytes, cudaMemcpyDeviceToHost,
+                              ctx->d2h_stream));
+        FP_CU(cudaEventRecord(ctx->pipe_out[b], ctx->d2h_stream));
+    }
+    for (int b = 0; b < 3 && static_cast<uint64_t>(b) < n_chunks; ++b)
+        FP_CU(cudaStreamWaitEvent(ctx->stream, ctx->pipe_out[b], 0)); // the call's stream completes after every download
+    return FP_OK;
+}
+
 template <typename T> DeviceOp<T> &dop(fp_op *op);
 template <> DeviceOp<float> &dop<float>(fp_op *op)
 {
@@ -1273,6 +1343,10 @@ extern "C"
             ctx->coset_vpt = atoi(env);
         if (char const *env = getenv("FASTPAULI_COSET_WIDE"))
             ctx->coset_wide_cta = atoi(env) != 0;
+        if (char const *env = getenv("FASTPAULI_PIPELINE"))
+            ctx->pipeline = atoi(env) != 0;
+        if (char const *env = getenv("FASTPAULI_PIPELINE_CHUNK"))
+            ctx->pipeline_chunk_bytes = std::max<size_t>(1 << 16, strtoull(env, nullptr, 10));
         if (char const *env = getenv("FASTPAULI_WTILE"))
             ctx->wtile = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_RCOSET"))
@@ -1302,6 +1376,16 @@ extern "C"
             s->release();
         if (ctx->own_stream)
             cudaStreamDestroy(ctx->own_stream);
+        if (ctx->h2d_stream)
+            cudaStreamDestroy(ctx->h2d_stream);
+        if (ctx->d2h_stream)
+            cudaStreamDestroy(ctx->d2h_stream);
+        for (int i = 0; i < 3; ++i)
+            for (cudaEvent_t e : {ctx->pipe_in[i], ctx->pipe_k[i], ctx->pipe_out[i]})
+                if (e)
+                    cudaEventDestroy(e);
+        if (ctx->pipe_start)
+            cudaEventDestroy(ctx->pipe_start);
         delete ctx;
         return FP_OK;
     }
@@ -1355,6 +1439,18 @@ extern "C"
         ctx->coset_mode = mode;
         ctx->coset_log_twc = log_twc;
         ctx->coset_log_nt = log_nt;
+        return FP_OK;
+    }
+
+    int fp_ctx_set_pipeline(fp_ctx *ctx, int enable, size_t min_bytes, size_t chunk_bytes)
+    {
+        if (!ctx)
+            return set_err(FP_INVALID_ARGUMENT, "null context");
+        ctx->pipeline = enable != 0;
+        if (min_bytes)
+            ctx->pipeline_min_bytes = min_bytes;
+        if (chunk_bytes)
+            ctx->pipeline_chunk_bytes = chunk_bytes;
         return FP_OK;
     }
 
@@ -1552,6 +1648,21 @@ extern "C"
         DeviceGuard g(ctx->device);
         std::lock_guard<std::mutex> lk(ctx->mu);
         size_t const bytes = dim * n_states * csize(dtype);
+        if (ctx->pipeline && !accumulate && bytes >= ctx->pipeline_min_bytes && in && out && !is_device_ptr(in) &&
+            !is_device_ptr(out))
+        {
+            auto const *ib = static_cast<unsigned char const *>(in);
+            auto const *ob = static_cast<unsigned char const *>(out);
+            if (ib + bytes <= ob || ob + bytes <= ib) // disjoint host buffers
+            {
+                FP_TRY(dtype == FP_C128
+                           ? pipelined_string_apply<double>(ctx, mk, *static_cast<std::complex<double> const *>(coeff),
+                                                            out, in, dim, n_states)
+                           : pipelined_string_apply<float>(ctx, mk, *static_cast<std::complex<float> const *>(coeff),
+                                                           out, in, dim, n_states));
+                return finish(ctx, true);
+            }
+        }
         Staged sin, sout;
         FP_TRY(stage_in(ctx, ctx->stage_in, in, bytes, true, sin, true));
         FP_TRY(stage_in(ctx, ctx->stage_out, out, bytes, accumulate != 0, sout, true));
@@ -1607,7 +1718,10 @@ extern "C"
         DeviceGuard g(ctx->device);
         std::lock_guard<std::mutex> lk(ctx->mu);
         Staged sin, sout;
-        FP_TRY(stage_in(ctx, ctx->stage_in, in, dim * n_states * csize(dtype), true, sin, true));
+        // large pinned batches: the copy engine uploads faster (~55 GB/s) than the kernel's own reads over PCIe
+        // (~51 GB/s), so above the pipeline threshold the batch is staged instead of being read in place
+        bool const in_place = !(ctx->pipeline && dim * n_states * csize(dtype) >= ctx->pipeline_min_bytes);
+        FP_TRY(stage_in(ctx, ctx->stage_in, in, dim * n_states * csize(dtype), true, sin, in_place));
         FP_TRY(stage_in(ctx, ctx->stage_out, out, n_states * csize(dtype), accumulate != 0, sout));
         int rc;
         if (dtype == FP_C128)

@@ -85,6 +85,11 @@ extern "C"
      * vectors, 0..4; -1 = automatic); log_nt = 7 or 8 forces 128- or 256-thread CTAs (0 = default).  A tile holds
      * 16 * 2^log_nt vectors, i.e. 2^(4 + log_nt - log_twc) rows. */
     int fp_ctx_set_coset(fp_ctx *ctx, int mode, int log_twc, int log_nt);
+    /* fp_string_apply with HOST in/out buffers of at least min_bytes (default 128 MiB; accumulate = 0) streams the
+     * batch through the GPU in aligned row blocks of about chunk_bytes (default 32 MiB): upload of block j+1, the
+     * kernel on block j and download of block j-1 overlap, so both PCIe directions are busy for the whole call.
+     * enable = 0 restores the single-shot path; 0 for a size keeps the current value. */
+    int fp_ctx_set_pipeline(fp_ctx *ctx, int enable, size_t min_bytes, size_t chunk_bytes);
     /* Register-resident coset kernels (operators whose x-masks span a GF(2) subspace of rank <= 4: each thread holds
      * the <= 16 rows of one coset for one 16-byte vector, no shared-memory staging): mode 0 = never, 1 = automatic
      * (default; stands aside when fp_ctx_set_coset forces a mode or shape), 2 = whenever applicable.  log_nt = 7 or 8

@@ -317,6 +317,43 @@ def test_pinned_host_buffers_zero_copy(dtype):
         ctx.pinned_free(a)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("pinned", [False, True])
+def test_pipelined_host_string_apply(dtype, pinned):
+    """fp_string_apply on host buffers above the pipeline threshold: chunked upload / kernel / download; the block
+    index sign and the block permutation (x touching the high row bits) must reproduce the one-shot result."""
+    ctx = fp.Context(0)
+    n, B = 12, 24
+    nbytes = 2**n * B * np.dtype(dtype).itemsize
+    ctx.set_pipeline(True, 1, nbytes // 32)  # 32 chunks of 128 rows
+    rng = np.random.default_rng(12)
+    c = 0.3 - 1.7j
+    for s in ("XYZIXYZIXYZI", "IIIIIIZZXYXY", "YZXIIIIIIIII", "ZZZZZZZZZZZZ", "IIIIIIIIIIII"):
+        if pinned:
+            psi = ctx.pinned_empty((2**n, B), dtype)
+            psi[...] = rand_states(rng, 2**n, B, dtype)
+            out = ctx.pinned_empty((2**n, B), dtype)
+            out[...] = -7
+        else:
+            psi = rand_states(rng, 2**n, B, dtype)
+            out = np.full((2**n, B), -7, dtype=dtype)
+        ps = fp.PauliString(s, ctx=ctx)
+        l0 = ctx.launch_count
+        got = ps.apply(np.asarray(psi), c) if not pinned else None
+        if pinned:
+            import ctypes as C
+
+            codes, _ = fp._encode([s])
+            coeff = np.array([c], dtype=dtype)
+            rc = fp.lib.fp_string_apply(ctx._h, 1 if dtype == np.complex128 else 0, n, C.c_void_p(codes.ctypes.data),
+                                        C.c_void_p(coeff.ctypes.data), C.c_void_p(out.ctypes.data),
+                                        C.c_void_p(psi.ctypes.data), C.c_size_t(2**n), C.c_size_t(B), C.c_int(0))
+            assert rc == 0, fp.lib.fp_last_error()
+            got = np.array(out)
+        assert ctx.launch_count - l0 == 32  # one kernel per chunk
+        assert rel_err(got, ORC.string_apply(s, np.asarray(psi), c)) < tol(dtype)
+
+
 def test_runs_on_torch_default_stream_in_order():
     """set_stream(0) must mean the legacy default stream (torch's default), so kernels order after torch work."""
     import ctypes as C
