@@ -21,6 +21,7 @@
 #include "coset.cuh"
 #include "rcoset.cuh"
 #include "wtile.cuh"
+#include "etile.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "pack.hpp"
@@ -122,6 +123,7 @@ struct fp_ctx
     size_t pipeline_min_bytes = 128ull << 20, pipeline_chunk_bytes = 32ull << 20;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t pipe_in[3] = {}, pipe_k[3] = {}, pipe_out[3] = {}, pipe_start = nullptr;
+    bool etile = true;          // packed-FP32 per-string expectation kernel (complex64, 9-12 qubits)
     bool wtile = true;          // dedicated whole-column weighted-apply kernel (complex64, 11-12 qubits)
     int rcoset_mode = 1;        // register-resident coset kernel (x-mask rank <= 4): 0 never, 1 auto, 2 whenever applicable
     int rcoset_log_nt = 7;      // its CTA size (128 / 256 threads)
@@ -1347,6 +1349,8 @@ extern "C"
             ctx->pipeline = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_PIPELINE_CHUNK"))
             ctx->pipeline_chunk_bytes = std::max<size_t>(1 << 16, strtoull(env, nullptr, 10));
+        if (char const *env = getenv("FASTPAULI_ETILE"))
+            ctx->etile = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_WTILE"))
             ctx->wtile = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_RCOSET"))
@@ -2059,7 +2063,28 @@ int run_sop_expval(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, ui
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
             configured = true;
         }
-        if (rowvecs <= 0x7fffffffull)
+        bool launched = false;
+        if constexpr (sizeof(T) == 4)
+        {
+            if (ctx->etile && sop->n_qubits >= 9 && rowvecs <= 0x7fffffffull)
+            {
+                // K4c (etile.cuh): planar pair tile, packed FP32, compile-time sign patterns
+                static bool configured2 = false;
+                if (!configured2)
+                {
+                    FP_CU(cudaFuncSetAttribute(sop_expval_tile2_kernel<kPairMS>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+                    configured2 = true;
+                }
+                dim3 grid(static_cast<unsigned>(rowvecs), splits);
+                sop_expval_tile2_kernel<kPairMS><<<grid, kThreads, smem, ctx->stream>>>(
+                    op.chunks, op.n_chunks, op.sz, op.sodd, static_cast<uint32_t>(sop->n_qubits), rowvecs,
+                    static_cast<CVec<float, 2> const *>(in), E, B);
+                ctx->launches++;
+                stage1_done = launched = true;
+            }
+        }
+        if (!launched && rowvecs <= 0x7fffffffull)
         {
             dim3 grid(static_cast<unsigned>(rowvecs), splits);
             sop_expval_tile_kernel<T, EPV_FULL, kPairMS><<<grid, kThreads, smem, ctx->stream>>>(

@@ -1,0 +1,192 @@
+// K4c: SummedPauliOp::expectation_value first stage (SPO:573-577), E(s, t) = <psi_t| P_s |psi_t> for every string,
+// for complex64 registers of 9..12 qubits.  Same plan as sop_expval_tile_kernel (coset.cuh) -- the whole state
+// column pair lives in shared memory, warps take the x-mask chunks (<= MS strings sharing a gather), rows are
+// visited as unordered pairs {i, i^x} so q = conj(psi_i) psi_{i^x} is formed once per pair -- with the per-element
+// integer work removed:
+//
+//   * the tile is stored planar per pair, (re0, re1, im0, im1): q of both columns is two packed FP32 ops;
+//   * a lane visits pair indices p = lane + 32 j; the sign (-1)^{popc(i & z)} factors into a lane part (applied
+//     once at the very end), a block part (j >> 3, one flip per 8 pairs) and a part that depends on j & 7 only
+//     through three bits of z: q of 8 consecutive j is kept in registers and a warp-uniform 8-way switch adds it
+//     up with compile-time signs -- one FADD2 per (string, pair) instead of popc / xor / flip / add per column.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "coset.cuh"
+
+namespace fpk
+{
+
+__device__ __forceinline__ float2 f2neg(float2 a)
+{
+    return make_float2(-a.x, -a.y);
+}
+__device__ __forceinline__ float2 f2flip(float2 a, uint32_t odd)
+{
+    uint32_t const s = odd << 31;
+    return make_float2(__uint_as_float(__float_as_uint(a.x) ^ s), __uint_as_float(__float_as_uint(a.y) ^ s));
+}
+
+// sum_k (-1)^{popc(k & K)} q[k], k < 8, K compile time
+template <int K> __device__ __forceinline__ float2 signed_sum8(float2 const (&q)[8])
+{
+    float2 p = make_float2(0.f, 0.f), m = make_float2(0.f, 0.f);
+    bool pf = true, mf = true;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+        if (__builtin_popcount(k & K) & 1)
+        {
+            m = mf ? q[k] : __fadd2_rn(m, q[k]);
+            mf = false;
+        }
+        else
+        {
+            p = pf ? q[k] : __fadd2_rn(p, q[k]);
+            pf = false;
+        }
+    }
+    if (K == 0)
+        return p;
+    return make_float2(p.x - m.x, p.y - m.y);
+}
+
+__device__ __forceinline__ float2 signed_sum8_dyn(uint32_t zk, float2 const (&q)[8])
+{
+    switch (zk) // warp-uniform
+    {
+    case 0:
+        return signed_sum8<0>(q);
+    case 1:
+        return signed_sum8<1>(q);
+    case 2:
+        return signed_sum8<2>(q);
+    case 3:
+        return signed_sum8<3>(q);
+    case 4:
+        return signed_sum8<4>(q);
+    case 5:
+        return signed_sum8<5>(q);
+    case 6:
+        return signed_sum8<6>(q);
+    default:
+        return signed_sum8<7>(q);
+    }
+}
+
+template <int MS>
+__global__ void __launch_bounds__(kThreads)
+    sop_expval_tile2_kernel(PairChunk const *__restrict__ chunks, uint32_t n_chunks, uint64_t const *__restrict__ sz,
+                            uint8_t const *__restrict__ sodd, uint32_t n_qubits, uint64_t rowvecs,
+                            CVec<float, 2> const *__restrict__ in, float *__restrict__ E /* [S][B] */, uint64_t B)
+{
+    extern __shared__ __align__(16) unsigned char et_smem[];
+    float4 *tile = reinterpret_cast<float4 *>(et_smem);
+    uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t const rows = 1u << n_qubits;
+    uint64_t const v = blockIdx.x; // column pair of this CTA
+    float4 const *in4 = reinterpret_cast<float4 const *>(in);
+    for (uint32_t r = tid; r < rows; r += kThreads)
+    {
+        float4 const a = in4[static_cast<uint64_t>(r) * rowvecs + v];
+        tile[r] = make_float4(a.x, a.z, a.y, a.w); // planar per pair
+    }
+    __syncthreads();
+
+    uint32_t const n_warps_total = (kThreads / 32) * gridDim.y;
+    for (uint32_t c = blockIdx.y * (kThreads / 32) + warp; c < n_chunks; c += n_warps_total)
+    {
+        PairChunk const ch = chunks[c];
+        uint32_t const x = static_cast<uint32_t>(ch.x);
+        // pair index p = lane + 32 j  ->  row i = lane_part | jpart(j), where the pair's representative has bit hbit
+        // of x cleared: the zero is inserted among the lane bits (hbit < 5) or among the j bits (hbit >= 5)
+        uint32_t lane_part = lane, sh = 5, hp = 20; // hp: position of the inserted zero among the j bits (20: none)
+        if (!ch.diag)
+        {
+            if (ch.hbit < 5)
+            {
+                lane_part = ((lane >> ch.hbit) << (ch.hbit + 1)) | (lane & ((1u << ch.hbit) - 1u));
+                sh = 6;
+            }
+            else
+                hp = ch.hbit - 5;
+        }
+        uint32_t const hp_low = (1u << hp) - 1u;
+        uint32_t const n_blocks = (ch.diag ? rows : (rows >> 1)) >> 8; // 8 pairs per lane per block
+        uint32_t sl[MS], zk[MS], zb[MS], odd_ny[MS];
+        bool any_odd = false;
+#pragma unroll
+        for (int m = 0; m < MS; ++m)
+        {
+            bool const live = static_cast<uint32_t>(m) < ch.count;
+            uint32_t const z = live ? static_cast<uint32_t>(sz[ch.s0 + m]) : 0u;
+            odd_ny[m] = live ? sodd[ch.s0 + m] : 0u;
+            any_odd |= odd_ny[m] != 0;
+            sl[m] = __popc(lane_part & z) & 1u;
+            uint32_t const zz = z >> sh;
+            uint32_t const zj = ((zz >> (hp + 1)) << hp) | (zz & hp_low); // z over the j bits
+            zk[m] = zj & 7u;
+            zb[m] = zj >> 3;
+        }
+        float2 r[MS];
+#pragma unroll
+        for (int m = 0; m < MS; ++m)
+            r[m] = make_float2(0.f, 0.f);
+
+        for (uint32_t blk = 0; blk < n_blocks; ++blk)
+        {
+            float2 qre[8], qim[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+            {
+                uint32_t const j = blk * 8 + k;
+                uint32_t const jp = (((j >> hp) << (hp + 1)) | (j & hp_low)) << sh;
+                uint32_t const i = lane_part | jp;
+                float4 const a = tile[i];
+                float2 const ar = make_float2(a.x, a.y), ai = make_float2(a.z, a.w);
+                if (ch.diag)
+                {
+                    qre[k] = __ffma2_rn(ar, ar, __fmul2_rn(ai, ai));
+                    qim[k] = make_float2(0.f, 0.f);
+                }
+                else
+                {
+                    float4 const b = tile[i ^ x];
+                    float2 const br = make_float2(b.x, b.y), bi = make_float2(b.z, b.w);
+                    qre[k] = __ffma2_rn(ar, br, __fmul2_rn(ai, bi));
+                    if (any_odd)
+                        qim[k] = __ffma2_rn(ar, bi, __fmul2_rn(ai, f2neg(br)));
+                    else
+                        qim[k] = make_float2(0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < MS; ++m)
+            {
+                if (static_cast<uint32_t>(m) < ch.count)
+                {
+                    float2 const rb = odd_ny[m] ? signed_sum8_dyn(zk[m], qim) : signed_sum8_dyn(zk[m], qre);
+                    r[m] = __fadd2_rn(r[m], f2flip(rb, __popc(blk & zb[m]) & 1u));
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MS; ++m)
+        {
+            if (static_cast<uint32_t>(m) >= ch.count)
+                break;
+            float2 val = f2flip(r[m], sl[m]);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1)
+            {
+                val.x += __shfl_xor_sync(0xffffffffu, val.x, off);
+                val.y += __shfl_xor_sync(0xffffffffu, val.y, off);
+            }
+            if (lane == 0)
+                *reinterpret_cast<float2 *>(E + static_cast<uint64_t>(ch.s0 + m) * B + v * 2) = val;
+        }
+    }
+}
+
+} // namespace fpk

@@ -701,6 +701,40 @@ def test_weighted_tile_kernel_c64(n):
     assert rel_err(fp.SummedPauliOp(strings, hk, ctx=ctx0).apply_weighted(psi, data), got) < 1e-5
 
 
+@pytest.mark.parametrize("n", [9, 10, 12])
+def test_expval_tile_kernel_c64(n):
+    """K4c (etile.cuh): complex64 SummedPauliOp.expectation_value on 9..12-qubit registers; x-masks whose top bit
+    lies among the lane bits (hbit < 5), among the block bits, diagonal strings, odd/even Y counts, groups with more
+    strings than one chunk holds; compared with the complex128 oracle and with the generic K4b kernel."""
+    rng = np.random.default_rng(90 + n)
+    S, K, B = 300, 4, 12
+    strings = rand_strings(rng, n, S)
+    for k in range(5):  # top x bit at positions 0..4
+        strings[k] = "I" * (n - 1 - k) + "XY"[k % 2] + "".join(rng.choice(list("IXYZ"), size=k))
+    for k in range(5, 12):  # same x-mask, many z-variants (> kPairMS strings in one group)
+        strings[k] = "".join({"X": rng.choice(["X", "Y"]), "Y": rng.choice(["X", "Y"]), "I": rng.choice(["I", "Z"]),
+                              "Z": rng.choice(["I", "Z"])}[ch] for ch in strings[20])
+    strings[12] = "Z" * n
+    strings[13] = "I" * n
+    strings[14] = "".join(rng.choice(list("IZ"), size=n))
+    hk = (rand_states(rng, S, K, np.complex64) * 2 - (1 + 1j)).astype(np.complex64)
+    psi = (rand_states(rng, 2**n, B, np.complex64) * 2 - (1 + 1j)).astype(np.complex64)
+    exp_e = ORC.sop_expval(strings, hk.astype(np.complex128), psi.astype(np.complex128))
+    ctx = fp.Context(0)
+    got = fp.SummedPauliOp(strings, hk, ctx=ctx).expectation_value(psi)
+    assert rel_err(got, exp_e) < 1e-5
+    import os as _os
+
+    _os.environ["FASTPAULI_ETILE"] = "0"
+    try:
+        ctx_old = fp.Context(0)
+    finally:
+        del _os.environ["FASTPAULI_ETILE"]
+    old = fp.SummedPauliOp(strings, hk, ctx=ctx_old).expectation_value(psi)
+    assert rel_err(old, exp_e) < 1e-5
+    assert rel_err(got, old) < 1e-5
+
+
 def test_config3_full_size_sampled_columns():
     # "PauliOp.apply_batch, 16 qubits, 2000 random strings of weight <= 4, batch 1024, complex128" at FULL size on
     # the GPU (1 GiB in, 1 GiB out, device resident).  Batch columns are independent, so the oracle checks a sample
