@@ -12,8 +12,8 @@
 //     chunk) and read as one broadcast LDS.128 per string;
 //   * a thread owns rows tid + q*NT, q < 8; the sign pattern of a string over q depends only on the string's three
 //     top z bits, so a warp-uniform 8-way switch selects a fully unrolled body whose +-1 factors are compile-time
-//     choices between the string's signed and negated W pair: no per-row integer work at all, one FADD2 per row and
-//     component (the thread's own parity bit costs 8 LOP3 per string).
+//     choices between the string's signed W pair and its negation: no per-row integer work at all, one FFMA2 per row and
+//     component (the thread's own parity bit costs 4 LOP3 per string; FFMA2 negates its operand for free).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -38,8 +38,8 @@ template <int LOG_NT> struct WtileSmem
 #define FP_WT_ROW(K, Q)                                                                                                \
     {                                                                                                                  \
         bool const neg = __builtin_popcount((Q) & (K)) & 1;                                                            \
-        dre[Q] = __fadd2_rn(dre[Q], neg ? nwr : wr);                                                                   \
-        dim[Q] = __fadd2_rn(dim[Q], neg ? nwi : wi);                                                                   \
+        dre[Q] = __ffma2_rn(neg ? make_float2(-wr.x, -wr.y) : wr, one2, dre[Q]);                                       \
+        dim[Q] = __ffma2_rn(neg ? make_float2(-wi.x, -wi.y) : wi, one2, dim[Q]);                                       \
     }
 #define FP_WT_CASE(K)                                                                                                  \
     case K:                                                                                                            \
@@ -68,6 +68,10 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
     float4 const *in4 = reinterpret_cast<float4 const *>(in);
     float4 *out4 = reinterpret_cast<float4 *>(out);
 
+    uint32_t rowoff[RPT]; // byte offset of the thread's rows inside the tile
+#pragma unroll
+    for (int q = 0; q < RPT; ++q)
+        rowoff[q] = (tid + q * NT) * 16u;
     // state column pair -> shared memory, planar per pair: (re0, re1, im0, im1)
 #pragma unroll
     for (int q = 0; q < RPT; ++q)
@@ -105,6 +109,7 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
     for (int q = 0; q < RPT; ++q)
         acc_rp[q] = acc_rm[q] = acc_im[q] = make_float2(0.f, 0.f);
 
+    float2 const one2 = make_float2(1.f, 1.f);
     fetch(0);
     for (uint32_t ci = 0; ci < pass.n_chunks; ++ci)
     {
@@ -140,11 +145,6 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
                                               __uint_as_float(__float_as_uint(w.y) ^ sgn));
                 float2 const wi = make_float2(__uint_as_float(__float_as_uint(w.z) ^ sgn),
                                               __uint_as_float(__float_as_uint(w.w) ^ sgn));
-                uint32_t const nsgn = sgn ^ 0x80000000u; // negated copies: FADD2 has no operand negation
-                float2 const nwr = make_float2(__uint_as_float(__float_as_uint(w.x) ^ nsgn),
-                                               __uint_as_float(__float_as_uint(w.y) ^ nsgn));
-                float2 const nwi = make_float2(__uint_as_float(__float_as_uint(w.z) ^ nsgn),
-                                               __uint_as_float(__float_as_uint(w.w) ^ nsgn));
                 switch ((m >> 16) & 7u) // warp-uniform: the three top z bits of the string
                 {
                     FP_WT_CASE(0)
@@ -157,10 +157,11 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
                     FP_WT_CASE(7)
                 }
             }
+            uint32_t const xl4 = xl << 4;
 #pragma unroll
             for (int q = 0; q < RPT; ++q)
             {
-                float4 const a = tile[(tid + q * NT) ^ xl];
+                float4 const a = *reinterpret_cast<float4 const *>(wt_smem + (rowoff[q] ^ xl4));
                 float2 const vr = make_float2(a.x, a.y), vi = make_float2(a.z, a.w);
                 acc_rp[q] = __ffma2_rn(dre[q], vr, acc_rp[q]);
                 acc_rm[q] = __ffma2_rn(dim[q], vi, acc_rm[q]);
