@@ -28,28 +28,14 @@ __device__ __forceinline__ float2 f2flip(float2 a, uint32_t odd)
     return make_float2(__uint_as_float(__float_as_uint(a.x) ^ s), __uint_as_float(__float_as_uint(a.y) ^ s));
 }
 
-// sum_k (-1)^{popc(k & K)} q[k], k < 8, K compile time
+// sum_k (-1)^{popc(k & K)} q[k], k < 8, K compile time (FADD2 negates an operand for free)
 template <int K> __device__ __forceinline__ float2 signed_sum8(float2 const (&q)[8])
 {
-    float2 p = make_float2(0.f, 0.f), m = make_float2(0.f, 0.f);
-    bool pf = true, mf = true;
+    float2 p = q[0];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-    {
-        if (__builtin_popcount(k & K) & 1)
-        {
-            m = mf ? q[k] : __fadd2_rn(m, q[k]);
-            mf = false;
-        }
-        else
-        {
-            p = pf ? q[k] : __fadd2_rn(p, q[k]);
-            pf = false;
-        }
-    }
-    if (K == 0)
-        return p;
-    return make_float2(p.x - m.x, p.y - m.y);
+    for (int k = 1; k < 8; ++k)
+        p = __fadd2_rn(p, (__builtin_popcount(k & K) & 1) ? f2neg(q[k]) : q[k]);
+    return p;
 }
 
 __device__ __forceinline__ float2 signed_sum8_dyn(uint32_t zk, float2 const (&q)[8])
@@ -72,6 +58,66 @@ __device__ __forceinline__ float2 signed_sum8_dyn(uint32_t zk, float2 const (&q)
         return signed_sum8<6>(q);
     default:
         return signed_sum8<7>(q);
+    }
+}
+
+// All blocks of one chunk.  ADDR: how the 8 pairs of a block are laid out behind the block's first row --
+// 0: rows 32 apart (512-byte immediates; diagonal chunks and x-masks whose top bit is >= 8), 1: rows 64 apart
+// (top bit < 5: the pair bit sits among the lane bits), 2: the pair bit sits among the three in-block bits
+// (top bit 5..7): offsets from a register table.  DIAG: x = 0, q = |psi|^2.  ODD: some string of the chunk has an
+// odd number of Y, so Im q is needed as well.
+template <int MS, int ADDR, bool DIAG, bool ODD>
+__device__ __forceinline__ void etile_chunk(unsigned char const *tile_bytes, uint32_t lane_off, uint32_t x4,
+                                            uint32_t n_blocks, uint32_t hp, uint32_t sh, uint32_t count,
+                                            uint32_t const (&zk)[MS], uint32_t const (&zb)[MS],
+                                            uint32_t const (&odd_ny)[MS], float2 (&r)[MS])
+{
+    uint32_t dk[8]; // ADDR == 2 only: byte offset of pair k inside the block
+    if (ADDR == 2)
+    {
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k)
+            dk[k] = (((k >> hp) << (hp + 1)) | (k & ((1u << hp) - 1u))) << (sh + 4);
+    }
+    // blocks step the j bits above the in-block three; for ADDR == 2 the inserted zero lies below them
+    uint32_t const hp_low = (1u << hp) - 1u;
+    for (uint32_t blk = 0; blk < n_blocks; ++blk)
+    {
+        uint32_t const j0 = blk * 8;
+        uint32_t const jp0 = ADDR == 2 ? (j0 << (sh + 1)) : ((((j0 >> hp) << (hp + 1)) | (j0 & hp_low)) << sh);
+        uint32_t const a0 = lane_off + (jp0 << 4); // byte offset of the block's first row
+        uint32_t const b0 = a0 ^ x4;
+        float2 qre[8], qim[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+        {
+            uint32_t const dko = ADDR == 0 ? (k << 9) : ADDR == 1 ? (k << 10) : dk[k];
+            float4 const a = *reinterpret_cast<float4 const *>(tile_bytes + a0 + dko);
+            float2 const ar = make_float2(a.x, a.y), ai = make_float2(a.z, a.w);
+            if (DIAG)
+                qre[k] = __ffma2_rn(ar, ar, __fmul2_rn(ai, ai));
+            else
+            {
+                float4 const b = *reinterpret_cast<float4 const *>(tile_bytes + (b0 ^ dko));
+                float2 const br = make_float2(b.x, b.y), bi = make_float2(b.z, b.w);
+                qre[k] = __ffma2_rn(ar, br, __fmul2_rn(ai, bi));
+                if (ODD)
+                    qim[k] = __ffma2_rn(ar, bi, __fmul2_rn(ai, f2neg(br)));
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < MS; ++m)
+        {
+            if (static_cast<uint32_t>(m) < count)
+            {
+                float2 rb;
+                if (ODD && odd_ny[m])
+                    rb = signed_sum8_dyn(zk[m], qim);
+                else
+                    rb = signed_sum8_dyn(zk[m], qre);
+                r[m] = __fadd2_rn(r[m], f2flip(rb, __popc(blk & zb[m]) & 1u));
+            }
+        }
     }
 }
 
@@ -134,42 +180,30 @@ __global__ void __launch_bounds__(kThreads)
         for (int m = 0; m < MS; ++m)
             r[m] = make_float2(0.f, 0.f);
 
-        for (uint32_t blk = 0; blk < n_blocks; ++blk)
+        unsigned char const *tb = et_smem;
+        uint32_t const lane_off = lane_part << 4, x4 = x << 4;
+        if (ch.diag)
+            etile_chunk<MS, 0, true, false>(tb, lane_off, 0, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+        else if (ch.hbit < 5)
         {
-            float2 qre[8], qim[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-            {
-                uint32_t const j = blk * 8 + k;
-                uint32_t const jp = (((j >> hp) << (hp + 1)) | (j & hp_low)) << sh;
-                uint32_t const i = lane_part | jp;
-                float4 const a = tile[i];
-                float2 const ar = make_float2(a.x, a.y), ai = make_float2(a.z, a.w);
-                if (ch.diag)
-                {
-                    qre[k] = __ffma2_rn(ar, ar, __fmul2_rn(ai, ai));
-                    qim[k] = make_float2(0.f, 0.f);
-                }
-                else
-                {
-                    float4 const b = tile[i ^ x];
-                    float2 const br = make_float2(b.x, b.y), bi = make_float2(b.z, b.w);
-                    qre[k] = __ffma2_rn(ar, br, __fmul2_rn(ai, bi));
-                    if (any_odd)
-                        qim[k] = __ffma2_rn(ar, bi, __fmul2_rn(ai, f2neg(br)));
-                    else
-                        qim[k] = make_float2(0.f, 0.f);
-                }
-            }
-#pragma unroll
-            for (int m = 0; m < MS; ++m)
-            {
-                if (static_cast<uint32_t>(m) < ch.count)
-                {
-                    float2 const rb = odd_ny[m] ? signed_sum8_dyn(zk[m], qim) : signed_sum8_dyn(zk[m], qre);
-                    r[m] = __fadd2_rn(r[m], f2flip(rb, __popc(blk & zb[m]) & 1u));
-                }
-            }
+            if (any_odd)
+                etile_chunk<MS, 1, false, true>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+            else
+                etile_chunk<MS, 1, false, false>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+        }
+        else if (ch.hbit >= 8)
+        {
+            if (any_odd)
+                etile_chunk<MS, 0, false, true>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+            else
+                etile_chunk<MS, 0, false, false>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+        }
+        else
+        {
+            if (any_odd)
+                etile_chunk<MS, 2, false, true>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+            else
+                etile_chunk<MS, 2, false, false>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
         }
 #pragma unroll
         for (int m = 0; m < MS; ++m)
