@@ -787,31 +787,30 @@ int get_rc_plan(DeviceOp<T> const &op, int n_qubits, int rr, typename DeviceOp<T
         return set_err(FP_UNSUPPORTED, "register coset plan: the operator does not fit one pass");
     CosetPassHost<T> const &h = host[0];
     uint32_t const rows = 1u << rr;
-    // strings ordered by local gather mask (the planner may have split a large group into several sub-groups)
-    std::vector<uint32_t> xstart(rows + 1, 0), stab;
+    // strings ordered by (local gather mask, local z-mask); the planner may have split a large group into
+    // several sub-groups with the same gather mask
+    std::vector<uint32_t> ustart(rows * rows + 1, 0);
     std::vector<uint64_t> sz;
     std::vector<Cx<T>> sc;
     uint32_t present = 0;
     for (uint32_t xl = 0; xl < rows; ++xl)
-    {
-        for (size_t g = 0; g < h.gxl.size(); ++g)
+        for (uint32_t zl = 0; zl < rows; ++zl)
         {
-            if (h.gxl[g] != xl)
-                continue;
-            for (uint32_t s = h.gstart[g]; s < h.gstart[g + 1]; ++s)
+            for (size_t g = 0; g < h.gxl.size(); ++g)
             {
-                uint32_t tab = 0;
-                for (uint32_t l = 0; l < rows; ++l)
-                    tab |= static_cast<uint32_t>(__builtin_popcount(l & h.szl[s]) & 1) << l;
-                stab.push_back(tab);
-                sz.push_back(h.sz[s]);
-                sc.push_back(Cx<T>{h.sc[s].real(), h.sc[s].imag()});
+                if (h.gxl[g] != xl)
+                    continue;
+                for (uint32_t s = h.gstart[g]; s < h.gstart[g + 1]; ++s)
+                {
+                    if (h.szl[s] != zl)
+                        continue;
+                    sz.push_back(h.sz[s]);
+                    sc.push_back(Cx<T>{h.sc[s].real(), h.sc[s].imag()});
+                    present |= 1u << xl;
+                }
             }
+            ustart[xl * rows + zl + 1] = static_cast<uint32_t>(sz.size());
         }
-        xstart[xl + 1] = static_cast<uint32_t>(sz.size());
-        if (xstart[xl + 1] > xstart[xl])
-            present |= 1u << xl;
-    }
     typename DeviceOp<T>::RcPlanDev d;
     d.rr = rr;
     for (int k = 0; k < kRcMaxRank; ++k)
@@ -820,12 +819,11 @@ int get_rc_plan(DeviceOp<T> const &op, int n_qubits, int rr, typename DeviceOp<T
         d.view.pivot[k] = k < rr ? static_cast<uint32_t>(h.basis.pivot[k]) : 0;
     }
     d.view.present = present;
-    uint32_t *d_xstart = nullptr, *d_stab = nullptr;
+    uint32_t *d_ustart = nullptr;
     uint64_t *d_sz = nullptr;
     Cx<T> *d_sc = nullptr;
-    int rc = upload_vec(&d_xstart, xstart);
-    if (rc == FP_OK) { d.allocs.push_back(d_xstart); rc = upload_vec(&d_stab, stab); }
-    if (rc == FP_OK) { d.allocs.push_back(d_stab); rc = upload_vec(&d_sz, sz); }
+    int rc = upload_vec(&d_ustart, ustart);
+    if (rc == FP_OK) { d.allocs.push_back(d_ustart); rc = upload_vec(&d_sz, sz); }
     if (rc == FP_OK) { d.allocs.push_back(d_sz); rc = upload_vec(&d_sc, sc); }
     if (rc == FP_OK) d.allocs.push_back(d_sc);
     if (rc != FP_OK)
@@ -834,8 +832,7 @@ int get_rc_plan(DeviceOp<T> const &op, int n_qubits, int rr, typename DeviceOp<T
             cudaFree(a);
         return rc;
     }
-    d.view.xstart = d_xstart;
-    d.view.stab = d_stab;
+    d.view.ustart = d_ustart;
     d.view.sz = d_sz;
     d.view.scoef = d_sc;
     auto ins = op.rc_plans.emplace(rr, std::move(d));
@@ -885,7 +882,7 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
     while ((1ull << log2tw) < rowvecs && (1u << log2tw) < NT)
         ++log2tw;
     uint32_t const TW = 1u << log2tw, TY = NT / TW;
-    size_t smem = static_cast<size_t>(TY) * (1u << (2 * rr)) * 2 * sizeof(T);
+    size_t smem = 2 * static_cast<size_t>(TY) * (1u << (2 * rr)) * 2 * sizeof(T); // factor table + its z-mask sums
     if (MODE == 1)
         smem = std::max(smem, static_cast<size_t>(NT) * EPV * 2 * sizeof(T));
     if (smem > 64 * 1024)
@@ -908,7 +905,7 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
     uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
     if (MODE == 1)
         FP_TRY(ctx->partials.ensure(n_blocks * Bpad * 2 * sizeof(T)));
-    // lanes cooperating on one factor-table entry: as many as keep every thread busy, at most a warp
+    // lanes cooperating on one entry of the z-mask sums: as many as keep every thread busy, at most a warp
     uint32_t log2p = 0;
     while (log2p < 5 && (static_cast<uint64_t>(TY) << (2 * rr + log2p + 1)) <= NT)
         ++log2p;

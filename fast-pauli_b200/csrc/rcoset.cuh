@@ -8,8 +8,8 @@
 //   load   2^RR vectors, one per coset row; the lanes of a warp run along the batch axis, so every load/store
 //          instruction moves one contiguous row segment (512 B per warp): no shared-memory staging at all
 //   table  the CTA's threads fill D[coset][xl][l] = sum_{s: x_s = xl} c_s (-1)^{par(base & z_s) ^ par(l & zl_s)}
-//          in shared memory (all threads: several lanes split the strings of one entry; the loads above are in
-//          flight meanwhile)
+//          in shared memory while the loads above are in flight: strings are first summed per local z-mask (one
+//          pass over the strings per coset), then a 2^RR-point sign transform gives the 2^RR rows
 //   fma    acc[l] += D[xl][l] * psi[l ^ xl] for every present xl: the gather is a compile-time register
 //          permutation (the loop over xl is fully unrolled, absent masks are skipped by a uniform branch), the
 //          factors are warp-broadcast LDS
@@ -36,9 +36,9 @@ template <typename T> struct RcPassView
     uint64_t basis[kRcMaxRank];
     uint32_t pivot[kRcMaxRank]; // ascending pivot bit positions of the basis
     uint32_t present;           // bit xl set <=> some string gathers with local mask xl
-    uint32_t const *xstart;     // [2^RR + 1] strings with local gather xl: [xstart[xl], xstart[xl+1])
+    uint32_t const *ustart;     // [4^RR + 1] strings sorted by (xl, zl): those with local masks (xl, zl) are
+                                //            [ustart[(xl << RR) + zl], ustart[(xl << RR) + zl + 1])
     uint64_t const *sz;         // [S] full z-mask (coset-base parity)
-    uint32_t const *stab;       // [S] bit l = par(l & zl_s): sign pattern over the coset's local rows
     Cx<T> const *scoef;         // [S] h_s (-i)^nY_s
 };
 
@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(1 << LOG_NT, (RR == 4 ? 512 : RR == 3 ? 640 : 
     constexpr int NT = 1 << LOG_NT, ROWS = 1 << RR;
     extern __shared__ __align__(16) unsigned char rc_smem[];
     Cx<T> *Dt = reinterpret_cast<Cx<T> *>(rc_smem); // [TY][xl][l]
+    Cx<T> *Ut = Dt + ((NT >> log2TW) << (2 * RR));  // [TY][xl][zl]
 
     uint32_t const tid = threadIdx.x;
     uint32_t const TW = 1u << log2TW, TY = NT >> log2TW;
@@ -119,33 +120,56 @@ __global__ void __launch_bounds__(1 << LOG_NT, (RR == 4 ? 512 : RR == 3 ? 640 : 
             }
         }
 
-        // row-only factors of this iteration's cosets (the loads above are still in flight): 2^log2P consecutive
-        // lanes share one table entry, each summing a strided slice of the group's strings
+        // row-only factors of this iteration's cosets (the loads above are still in flight), in two steps:
+        //   U[c][xl][zl] = sum over the strings with local masks (xl, zl) of c_s (-1)^{par(base_c & z_s)}
+        //   D[c][xl][l]  = sum_zl (-1)^{popc(l & zl)} U[c][xl][zl]
+        // every string is touched once per coset (not once per coset row) and the second step is a tiny
+        // fixed-size transform
         {
+            // 2^log2P consecutive lanes share one U entry (small tables: keeps every thread busy)
             uint32_t const P = 1u << log2P, part = tid & (P - 1);
             for (uint32_t ent = tid >> log2P; ent < TY * ROWS * ROWS; ent += NT >> log2P)
             {
-                uint32_t const c = ent >> (2 * RR), xl = (ent >> RR) & (ROWS - 1), l = ent & (ROWS - 1);
-                Cx<T> d{0, 0};
-                if ((pass.present >> xl) & 1u)
+                uint32_t const c = ent >> (2 * RR), xz = ent & (ROWS * ROWS - 1);
+                Cx<T> u{0, 0};
+                uint32_t const s0 = __ldg(pass.ustart + xz), s1 = __ldg(pass.ustart + xz + 1);
+                if (s0 < s1)
                 {
                     uint64_t const b = rc_base<RR>(cs0 + c, pass.pivot);
-                    uint32_t const s0 = __ldg(pass.xstart + xl), s1 = __ldg(pass.xstart + xl + 1);
                     for (uint32_t s = s0 + part; s < s1; s += P)
                     {
                         Cx<T> const cf = pass.scoef[s];
-                        uint32_t const odd = parity64(b & __ldg(pass.sz + s)) ^ ((__ldg(pass.stab + s) >> l) & 1u);
-                        d.re += flip_sign(cf.re, odd);
-                        d.im += flip_sign(cf.im, odd);
+                        uint32_t const odd = parity64(b & __ldg(pass.sz + s));
+                        u.re += flip_sign(cf.re, odd);
+                        u.im += flip_sign(cf.im, odd);
                     }
                 }
                 for (uint32_t off = P >> 1; off > 0; off >>= 1)
                 {
-                    d.re += __shfl_xor_sync(0xffffffffu, d.re, off);
-                    d.im += __shfl_xor_sync(0xffffffffu, d.im, off);
+                    u.re += __shfl_xor_sync(0xffffffffu, u.re, off);
+                    u.im += __shfl_xor_sync(0xffffffffu, u.im, off);
                 }
                 if (part == 0)
-                    Dt[ent] = d;
+                    Ut[ent] = u;
+            }
+        }
+        __syncthreads();
+        for (uint32_t ent = tid; ent < TY * ROWS * ROWS; ent += NT)
+        {
+            uint32_t const xl = (ent >> RR) & (ROWS - 1), l = ent & (ROWS - 1);
+            if ((pass.present >> xl) & 1u)
+            {
+                Cx<T> const *Ux = Ut + (ent & ~static_cast<uint32_t>(ROWS - 1));
+                Cx<T> d{0, 0};
+#pragma unroll
+                for (int zl = 0; zl < ROWS; ++zl)
+                {
+                    Cx<T> const u = Ux[zl];
+                    uint32_t const odd = __popc(l & zl) & 1u;
+                    d.re += flip_sign(u.re, odd);
+                    d.im += flip_sign(u.im, odd);
+                }
+                Dt[ent] = d;
             }
         }
         __syncthreads();

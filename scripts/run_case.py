@@ -78,14 +78,15 @@ def main():
         ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
         amps = (1 << n) * B
         print(f"{a.case}: {ms:.3f} ms  {amps*32/ms/1e6:.0f} GB/s algorithmic  groups={op.plan_info()['n_x_groups']}")
-    elif a.case in ("span1", "span2", "span3", "span4", "local3"):
+    elif a.case in ("span1", "span2", "span3", "span4", "local2", "local3", "local4"):
         # x-masks confined to a GF(2) span of rank r (register-resident coset kernel): 64 strings over 2^r masks;
         # local3 = all 64 Pauli strings on 3 fixed qubits (8 x-masks x 8 z-masks)
         n, B = 20, a.batch or 64
-        if a.case == "local3":
-            pos = sorted(int(p) for p in rng.choice(n, size=3, replace=False))
+        if a.case.startswith("local"):
+            kq = int(a.case[-1])
+            pos = sorted(int(p) for p in rng.choice(n, size=kq, replace=False))
             strings = []
-            for k in range(64):
+            for k in range(4**kq):
                 t = ["I"] * n
                 for i, p_ in enumerate(pos):
                     t[p_] = "IXYZ"[(k >> (2 * i)) & 3]
