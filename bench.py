@@ -545,6 +545,8 @@ def run_ours(args) -> None:
     ctx.set_async(False)
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         h_in = ctx.pinned_empty((dim, B), DTYPE)
         h_out = ctx.pinned_empty((dim, B), DTYPE)
         h_ev = ctx.pinned_empty((B,), DTYPE)
@@ -673,6 +675,7 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (ncu launch lists)")
     args = ap.parse_args()
     global EMIT
     EMIT = _claim_stdout()
