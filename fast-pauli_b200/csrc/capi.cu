@@ -20,6 +20,7 @@
 
 #include "coset.cuh"
 #include "rcoset.cuh"
+#include "dcoset.cuh"
 #include "wtile.cuh"
 #include "etile.cuh"
 #include "gemm_tc.cuh"
@@ -126,6 +127,7 @@ struct fp_ctx
     bool etile = true;          // packed-FP32 per-string expectation kernel (complex64, 9-12 qubits)
     bool wtile = true;          // dedicated whole-column weighted-apply kernel (complex64, 11-12 qubits)
     int rcoset_mode = 1;        // register-resident coset kernel (x-mask rank <= 4): 0 never, 1 auto, 2 whenever applicable
+    bool dcoset = true;         // FP64 tensor-core dense-coset kernel (complex128 apply, x-mask rank 4 or 5)
     int rcoset_log_nt = 7;      // its CTA size (128 / 256 threads)
     Scratch stage_in, stage_out, stage_data, partials, work_a, work_b, meta;
     std::mutex mu;
@@ -859,6 +861,30 @@ int launch_rcoset(fp_ctx *ctx, RcPassView<T> const &view, uint64_t n_cosets, uin
     return FP_OK;
 }
 
+// K3d (dcoset.cuh): FP64 tensor-core dense-coset kernel, complex128 apply, rank 4 (one warp per coset) or 5 (two)
+template <int RR, int WPC>
+int launch_dcoset(fp_ctx *ctx, RcPassView<double> const &view, uint32_t n_strings, uint64_t n_cosets, uint64_t rowvecs,
+                  void const *in, void *out, int beta)
+{
+    using Cfg = DcosetCfg<RR, WPC>;
+    static int resident = 0; // CTAs per SM (per template instance): the kernel is persistent
+    if (!resident)
+    {
+        FP_CU(cudaFuncSetAttribute(dcoset_kernel<RR, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(Cfg::smem)));
+        int nb = 0;
+        FP_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dcoset_kernel<RR, WPC>, Cfg::NT, Cfg::smem));
+        resident = std::max(1, nb);
+    }
+    uint64_t const sets = (n_cosets + Cfg::CPI - 1) / Cfg::CPI;
+    uint64_t const grid = std::min<uint64_t>(sets, static_cast<uint64_t>(ctx->sm_count) * resident);
+    dcoset_kernel<RR, WPC><<<static_cast<unsigned>(grid), Cfg::NT, Cfg::smem, ctx->stream>>>(
+        view, n_strings, n_cosets, rowvecs, static_cast<CVec<double, 1> const *>(in),
+        static_cast<CVec<double, 1> *>(out), beta);
+    ctx->launches++;
+    return FP_OK;
+}
+
 // Returns FP_OK with *used = false when the operator / batch shape is left to the other kernels.
 template <typename T, int MODE>
 int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void const *in, uint64_t dim, uint64_t B,
@@ -876,6 +902,25 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
     if (rowvecs < 4 && ctx->rcoset_mode != 2)
         return FP_OK; // rows shorter than 64 bytes: coalescing must come from the row index (shared-memory tiles)
     int const rr = std::min(n_qubits, std::max(2, op.x_rank)); // 2-row threads keep too few bytes in flight
+    if constexpr (sizeof(T) == 8 && MODE == 0)
+    {
+        // ranks 4 and 5 are GEMM-shaped per coset (16x16 / 32x32 complex): FP64 tensor cores
+        if (ctx->dcoset && (rr == 4 || rr == 5) && rowvecs >= 8)
+        {
+            typename DeviceOp<T>::RcPlanDev const *dplan = nullptr;
+            FP_TRY(get_rc_plan<T>(op, n_qubits, rr, &dplan));
+            uint64_t const nc = 1ull << (n_qubits - rr);
+            uint32_t const ns = static_cast<uint32_t>(op.host.sz.size());
+            if (rr == 4)
+                FP_TRY((launch_dcoset<4, 1>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta)));
+            else
+                FP_TRY((launch_dcoset<5, 2>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta)));
+            *used = true;
+            return FP_OK;
+        }
+    }
+    if (rr > kRcMaxSimtRank)
+        return FP_OK;
     int const log_nt = ctx->rcoset_log_nt == 8 ? 8 : 7;
     uint32_t const NT = 1u << log_nt;
     uint32_t log2tw = 0;
@@ -1352,6 +1397,8 @@ extern "C"
             ctx->wtile = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_RCOSET"))
             ctx->rcoset_mode = atoi(env);
+        if (char const *env = getenv("FASTPAULI_DCOSET"))
+            ctx->dcoset = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_RCOSET_LOG_NT"))
             ctx->rcoset_log_nt = atoi(env);
         if (char const *env = getenv("FASTPAULI_ZERO_COPY"))

@@ -1,0 +1,287 @@
+// K3d: dense-coset tensor-core kernel for complex128 operators whose x-masks span a GF(2) subspace of rank 4 or 5
+// (every k-local dense term with k = 4, 5: up to 1024 strings over 32 masks).
+//
+// On one coset the operator is a dense 2^RR x 2^RR complex matrix M_c (entry (l', l) = D[l ^ l'][l'], the same row
+// factors as rcoset.cuh) applied to 2^RR rows x all batch columns -- GEMM-shaped work, so it runs on the FP64
+// tensor cores (mma.sync.m8n8k4.f64: measured 63.7 FMA/clk/SM on B200, the full FP64 rate) with M_c held in
+// REGISTERS as A fragments.  The SIMT register kernel (K3c) is bound at rank 4 by one broadcast LDS.128 of D per
+// complex FMA on the SM's single load/store unit; here D is read once per coset and warp.
+//
+// Real formulation: [out_re; out_im] = [[Re M, -Im M], [Im M, Re M]] [x_re; x_im], planar ordering (all real parts,
+// then all imaginary parts) on both sides, so that
+//   * a lane's 16-byte global load psi(row 4*kb + lane%4, column n0 + lane/4) feeds two B fragments (k-block kb with
+//     its real part, k-block kb + ROWS/4 with its imaginary part): every LDG.128 instruction moves four contiguous
+//     128-byte row segments;
+//   * the real and imaginary parts of an output element land in the same lane (m-tiles rt and rt + ROWS/8), and one
+//     pair exchange per row tile lets every STG.128 instruction write whole 32-byte sectors.
+// WPC warps share one coset: each owns ROWS/8/WPC row tiles of the output and loads the full input tile.
+//
+// Covers PauliOp::apply (PO:399-468) / SummedPauliOp::apply (SPO:277-349) for std::complex<double>.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "rcoset.cuh"
+
+namespace fpk
+{
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// barrier among the WPC warps that share a coset (named barrier 1 + group index; a single warp needs __syncwarp only)
+template <int WPC> __device__ __forceinline__ void group_sync(uint32_t group)
+{
+    if (WPC == 1)
+        __syncwarp();
+    else
+        asm volatile("bar.sync %0, %1;\n" ::"r"(group + 1), "n"(WPC * 32) : "memory");
+}
+
+template <int RR, int WPC> struct DcosetCfg
+{
+    static constexpr int NT = 128, WARPS = NT / 32;
+    static constexpr int ROWS = 1 << RR;
+    static constexpr int CPI = WARPS / WPC;          // cosets per CTA iteration
+    static constexpr int RT = ROWS / 8;              // row tiles of the output (real part; the same again imaginary)
+    static constexpr int RT_OWN = RT / WPC;          // row tiles per warp
+    static constexpr int KB = ROWS / 4;              // k-blocks per part (real / imaginary)
+    static constexpr int PITCH = ROWS + 1;           // table row pitch (entries): column accesses stay conflict-free
+    static constexpr size_t tables = 2 * static_cast<size_t>(CPI) * ROWS * PITCH * sizeof(Cx<double>); // D and U tables
+    static_assert(WPC * 32 == 2 * ROWS, "the sign transform maps one (local x-mask, re/im) pair to each thread");
+    static constexpr int MAX_STAGED = 1024; // strings whose (coefficient, z-mask) are staged in shared memory
+    static constexpr size_t smem = tables + MAX_STAGED * (sizeof(Cx<double>) + 8) + (ROWS * ROWS + 1) * 4 + 12;
+    static_assert(RT % WPC == 0 && WARPS % WPC == 0, "warps must split the row tiles evenly");
+};
+
+template <int RR, int WPC>
+__global__ void __launch_bounds__(128)
+    dcoset_kernel(RcPassView<double> pass, uint32_t n_strings, uint64_t n_cosets, uint64_t rowvecs,
+                  CVec<double, 1> const *__restrict__ in, CVec<double, 1> *__restrict__ out, int beta)
+{
+    using Cfg = DcosetCfg<RR, WPC>;
+    constexpr int ROWS = Cfg::ROWS, CPI = Cfg::CPI, PITCH = Cfg::PITCH, RT_OWN = Cfg::RT_OWN, KB = Cfg::KB;
+    extern __shared__ __align__(16) unsigned char dc_smem[];
+    Cx<double> *Dt = reinterpret_cast<Cx<double> *>(dc_smem); // [CPI][xl][l], rows PITCH entries apart
+    Cx<double> *Ut = Dt + CPI * ROWS * PITCH;                 // [CPI][xl][zl]
+    // operator metadata staged once per (persistent) CTA: the per-coset table build then never waits on global loads
+    Cx<double> *s_coef = Ut + CPI * ROWS * PITCH;
+    uint64_t *s_z = reinterpret_cast<uint64_t *>(s_coef + Cfg::MAX_STAGED);
+    uint32_t *s_ustart = reinterpret_cast<uint32_t *>(s_z + Cfg::MAX_STAGED);
+    bool const staged = n_strings <= static_cast<uint32_t>(Cfg::MAX_STAGED);
+    Cx<double> const *coefs = pass.scoef;
+    uint64_t const *zs = pass.sz;
+    uint32_t const *ustart = pass.ustart;
+    if (staged)
+    {
+        for (uint32_t i = threadIdx.x; i < n_strings; i += Cfg::NT)
+        {
+            s_coef[i] = pass.scoef[i];
+            s_z[i] = pass.sz[i];
+        }
+        for (uint32_t i = threadIdx.x; i <= ROWS * ROWS; i += Cfg::NT)
+            s_ustart[i] = pass.ustart[i];
+        coefs = s_coef;
+        zs = s_z;
+        ustart = s_ustart;
+        __syncthreads();
+    }
+
+    uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t const cw = warp / WPC, part = warp % WPC; // coset slot of this warp, its share of the row tiles
+    uint32_t const lq = lane >> 2, lr = lane & 3u;
+    double2 const *in2 = reinterpret_cast<double2 const *>(in);
+    double2 *out2 = reinterpret_cast<double2 *>(out);
+
+    constexpr int PF = RR == 4 ? 4 : 2; // input tiles in flight per warp (one 8-column tile of MMAs is ~270 ns, an HBM load ~800 ns)
+    uint64_t const n_tiles = (rowvecs + 7) / 8;
+
+    for (uint64_t cs0 = static_cast<uint64_t>(blockIdx.x) * CPI; cs0 < n_cosets; cs0 += static_cast<uint64_t>(gridDim.x) * CPI)
+    {
+        uint64_t const coset = cs0 + cw;
+        bool const live = coset < n_cosets; // warp-uniform
+        uint64_t const base = rc_base<RR>(live ? coset : 0, pass.pivot);
+        uint64_t rowoff[KB]; // element offset of input row 4*kb + lane%4
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+        {
+            uint64_t comb = 0;
+#pragma unroll
+            for (int k = 0; k < RR; ++k)
+                if (((4 * kb + lr) >> k) & 1u)
+                    comb ^= pass.basis[k];
+            rowoff[kb] = (base ^ comb) * rowvecs;
+        }
+        // ---- the first PF input tiles are requested before the factor tables are built: their latency hides there
+        double2 x[PF][KB];
+#pragma unroll
+        for (int u = 0; u < PF; ++u)
+        {
+            uint64_t const col = static_cast<uint64_t>(u) * 8 + lq;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+                x[u][kb] = (live && col < rowvecs) ? in2[rowoff[kb] + col] : make_double2(0, 0);
+        }
+
+        // ---- row factors of this warp group's coset (same two-step build as rcoset.cuh).  Every group of WPC warps
+        // builds its own table and synchronises only within itself, so the groups of a CTA drift freely through
+        // their table and tensor-core phases instead of meeting at CTA-wide barriers.
+        Cx<double> *Dc = Dt + cw * ROWS * PITCH;
+        Cx<double> *Uc = Ut + cw * ROWS * PITCH;
+        uint32_t const gtid = part * 32 + lane; // thread index inside the group
+        if (live)
+        {
+            for (uint32_t xz = gtid; xz < ROWS * ROWS; xz += WPC * 32)
+            {
+                Cx<double> u{0, 0};
+                uint32_t const s0 = ustart[xz], s1 = ustart[xz + 1];
+                for (uint32_t s = s0; s < s1; ++s)
+                {
+                    Cx<double> const cf = coefs[s];
+                    uint32_t const odd = parity64(base & zs[s]);
+                    u.re += flip_sign(cf.re, odd);
+                    u.im += flip_sign(cf.im, odd);
+                }
+                Uc[(xz >> RR) * PITCH + (xz & (ROWS - 1))] = u;
+            }
+        }
+        group_sync<WPC>(cw);
+        if (live)
+        {
+            // D[xl][.] = Walsh-Hadamard transform of U[xl][.]: one (xl, re/im) pair per thread, in registers
+            uint32_t const xl = gtid >> 1, ri = gtid & 1u;
+            double const *Ud = reinterpret_cast<double const *>(Uc + xl * PITCH) + ri;
+            double v[ROWS];
+#pragma unroll
+            for (int z = 0; z < ROWS; ++z)
+                v[z] = Ud[2 * z];
+#pragma unroll
+            for (int h = 1; h < ROWS; h <<= 1)
+#pragma unroll
+                for (int i = 0; i < ROWS; ++i)
+                    if ((i & h) == 0)
+                    {
+                        double const a = v[i], b = v[i + h];
+                        v[i] = a + b;
+                        v[i + h] = a - b;
+                    }
+            double *Dd = reinterpret_cast<double *>(Dc + xl * PITCH) + ri;
+#pragma unroll
+            for (int l = 0; l < ROWS; ++l)
+                Dd[2 * l] = v[l];
+        }
+        group_sync<WPC>(cw);
+
+        if (live)
+        {
+            // ---- A fragments of M_c for this warp's m-tiles: row kk' = 8*mt + lane/4, column kk = 4*kb + lane%4
+            double A[2 * RT_OWN][2 * KB];
+#pragma unroll
+            for (int r = 0; r < RT_OWN; ++r)
+            {
+                uint32_t const lp = 8 * (part * RT_OWN + r) + lq; // output row l'
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)
+                {
+                    uint32_t const l = 4 * kb + lr; // input row
+                    Cx<double> const m = Dc[(l ^ lp) * PITCH + lp];
+                    A[r][kb] = m.re;               // Re block
+                    A[r][KB + kb] = -m.im;         // -Im block
+                    A[RT_OWN + r][kb] = m.im;      // Im block
+                    A[RT_OWN + r][KB + kb] = m.re; // Re block
+                }
+            }
+            uint64_t orow[RT_OWN]; // element offset of output row 8*rt + lane/4
+#pragma unroll
+            for (int r = 0; r < RT_OWN; ++r)
+            {
+                uint32_t const lp = 8 * (part * RT_OWN + r) + lq;
+                uint64_t comb = 0;
+#pragma unroll
+                for (int k = 0; k < RR; ++k)
+                    if ((lp >> k) & 1u)
+                        comb ^= pass.basis[k];
+                orow[r] = (base ^ comb) * rowvecs;
+            }
+
+            // ---- sweep the batch in tiles of 8 columns through a ring of PF register buffers: the buffer a tile has
+            // just consumed is refilled with the tile PF steps ahead
+            for (uint64_t nt0 = 0; nt0 < n_tiles; nt0 += PF)
+            {
+#pragma unroll
+                for (int u = 0; u < PF; ++u)
+                {
+                    uint64_t const nt = nt0 + u;
+                    if (nt >= n_tiles)
+                        break; // warp-uniform
+                    uint64_t const n0 = nt * 8;
+                    double C[2 * RT_OWN][2];
+#pragma unroll
+                    for (int m = 0; m < 2 * RT_OWN; ++m)
+                        C[m][0] = C[m][1] = 0.0;
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                        for (int m = 0; m < 2 * RT_OWN; ++m)
+                        {
+                            dmma884(C[m][0], C[m][1], A[m][kb], x[u][kb].x);
+                            dmma884(C[m][0], C[m][1], A[m][KB + kb], x[u][kb].y);
+                        }
+                    if (nt + PF < n_tiles)
+                    {
+                        uint64_t const col = n0 + PF * 8 + lq;
+#pragma unroll
+                        for (int kb = 0; kb < KB; ++kb)
+                            x[u][kb] = col < rowvecs ? in2[rowoff[kb] + col] : make_double2(0, 0);
+                    }
+                    // lane holds rows l' (real: C[r], imaginary: C[RT_OWN + r]) x columns n0 + 2*lr + {0, 1}
+#pragma unroll
+                    for (int r = 0; r < RT_OWN; ++r)
+                    {
+                        double2 first = make_double2(C[r][0], C[RT_OWN + r][0]);  // column 2*lr
+                        double2 second = make_double2(C[r][1], C[RT_OWN + r][1]); // column 2*lr + 1
+                        // pair exchange: even lanes end up with columns (4p, 4p+2), odd lanes with (4p+1, 4p+3), so
+                        // each store instruction writes adjacent columns from adjacent lanes = whole 32-byte sectors
+                        bool const oddl = lr & 1u;
+                        double2 const send = oddl ? first : second;
+                        double2 recv;
+                        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                        double2 va = oddl ? recv : first;  // column 2*(lr & ~1) + (lr & 1)
+                        double2 vb = oddl ? second : recv; // that column + 2
+                        uint64_t const ca = n0 + 2 * (lr & ~1u) + (lr & 1u), cb = ca + 2;
+                        if (ca < rowvecs)
+                        {
+                            double2 *dst = &out2[orow[r] + ca];
+                            if (beta)
+                            {
+                                double2 const o = *dst;
+                                va.x += o.x;
+                                va.y += o.y;
+                            }
+                            *dst = va;
+                        }
+                        if (cb < rowvecs)
+                        {
+                            double2 *dst = &out2[orow[r] + cb];
+                            if (beta)
+                            {
+                                double2 const o = *dst;
+                                vb.x += o.x;
+                                vb.y += o.y;
+                            }
+                            *dst = vb;
+                        }
+                    }
+                }
+            }
+        }
+        group_sync<WPC>(cw); // the group's tables are rebuilt by its next iteration
+    }
+}
+
+} // namespace fpk

@@ -29,7 +29,8 @@
 namespace fpk
 {
 
-constexpr int kRcMaxRank = 4;
+constexpr int kRcMaxRank = 5;      // plans up to rank 5 (dcoset.cuh); the SIMT kernels below serve ranks <= 4
+constexpr int kRcMaxSimtRank = 4;
 
 template <typename T> struct RcPassView
 {

@@ -1,5 +1,9 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-for c in span1 span2 span3 span4 local2 local3 local4; do
-  echo -n "rcoset "; python scripts/run_case.py $c --iters 20 2>&1 | tail -1
+for d in 1 0; do
+for c in span4 local4 span5 local5; do
+  echo -n "dcoset=$d "; FASTPAULI_DCOSET=$d python scripts/run_case.py $c --iters 20 2>&1 | tail -1
 done
+done
+echo -n "b256 "; python scripts/run_case.py local4 --iters 10 --batch 256 2>&1 | tail -1
+echo -n "b256 "; python scripts/run_case.py local5 --iters 10 --batch 256 2>&1 | tail -1

@@ -78,7 +78,7 @@ def main():
         ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
         amps = (1 << n) * B
         print(f"{a.case}: {ms:.3f} ms  {amps*32/ms/1e6:.0f} GB/s algorithmic  groups={op.plan_info()['n_x_groups']}")
-    elif a.case in ("span1", "span2", "span3", "span4", "local2", "local3", "local4"):
+    elif a.case in ("span1", "span2", "span3", "span4", "span5", "local2", "local3", "local4", "local5"):
         # x-masks confined to a GF(2) span of rank r (register-resident coset kernel): 64 strings over 2^r masks;
         # local3 = all 64 Pauli strings on 3 fixed qubits (8 x-masks x 8 z-masks)
         n, B = 20, a.batch or 64
@@ -95,7 +95,7 @@ def main():
             r = int(a.case[-1])
             gens = [int(rng.integers(1, 1 << n)) for _ in range(r)]
             strings = []
-            for k in range(64):
+            for k in range(max(64, 4 << r)):
                 x = 0
                 for j in range(r):
                     if (k >> j) & 1:

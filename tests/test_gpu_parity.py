@@ -548,6 +548,43 @@ def test_register_coset_kernels(dtype, rank, log_nt, n, B):
     assert rel_err(fp.PauliOp(h, strings, ctx=ctx0).apply(psi), got) < t
 
 
+@pytest.mark.parametrize("rank", [4, 5])
+@pytest.mark.parametrize("n,B", [(7, 8), (9, 34), (12, 300), (10, 9)])
+def test_dense_coset_tensor_core_kernel(rank, n, B):
+    """K3d (dcoset.cuh): complex128 apply of operators with x-mask rank 4 / 5 runs as ONE FP64 tensor-core launch
+    (dense coset matrix in registers as mma.sync A fragments); parity vs the oracle, accumulate, odd batch widths
+    (partial 8-column tiles), and agreement with the SIMT kernels."""
+    import ctypes as C
+    import os as _os
+
+    ctx = fp.Context(0)
+    rng = np.random.default_rng(8000 + 10 * rank + n)
+    S = 90
+    strings = _span_strings(rng, n, rank, S)
+    strings[-1] = strings[0]
+    strings[-2] = "Z" * n
+    h = rand_states(rng, S, None) * 2 - (1 + 1j)
+    psi = rand_states(rng, 2**n, B)
+    base = rand_states(rng, 2**n, B)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    l0 = ctx.launch_count
+    got = op.apply(psi)
+    assert ctx.launch_count - l0 == 1
+    assert rel_err(got, ORC.op_apply(strings, h, psi, par=True)) < 1e-12
+    out = base.copy()
+    rc = fp.lib.fp_op_apply(ctx._h, op._plan(np.complex128), C.c_void_p(out.ctypes.data), C.c_void_p(psi.ctypes.data),
+                            C.c_size_t(2**n), C.c_size_t(B), C.c_int(1))
+    assert rc == 0
+    assert rel_err(out, ORC.op_apply(strings, h, psi, out=base.copy(), par=True)) < 1e-12
+    assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi, par=True)) < 1e-12
+    _os.environ["FASTPAULI_DCOSET"] = "0"
+    try:
+        ctx0 = fp.Context(0)
+    finally:
+        del _os.environ["FASTPAULI_DCOSET"]
+    assert rel_err(fp.PauliOp(h, strings, ctx=ctx0).apply(psi), got) < 1e-12
+
+
 def test_register_coset_default_path_headline_shape():
     """The north-star headline shape at reduced batch: 64 strings over 8 x-masks (rank 3) at 16 qubits takes the
     register-resident kernel by default; a diagonal-only operator (rank 0) does too."""
