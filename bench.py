@@ -243,7 +243,9 @@ def run_extras(fp, ctx, hbm_peak: float) -> dict:
                  # Paulis on 3 qubits): rank 3, register-resident coset kernel
                  ("dense_3local_64_strings_8_xmasks", local_dense(3)),
                  ("dense_2local_16_strings_4_xmasks", local_dense(2)),
-                 ("dense_4local_256_strings_16_xmasks", local_dense(4))]
+                 ("dense_4local_256_strings_16_xmasks", local_dense(4)),
+                 # rank 4 / 5: FP64 tensor-core dense-coset kernel (apply); expectation_value stays on SIMT / K3b
+                 ("dense_5local_1024_strings_32_xmasks", local_dense(5))]
         # HBM fraction as a function of the number of distinct x-masks (64 strings each time)
         for g in (1, 2, 4, 16):
             cases.append((f"sweep_64_strings_{g}_xmasks", variants(rand_strings(rng, n, g), 64 // g)))

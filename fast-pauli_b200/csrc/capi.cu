@@ -862,7 +862,7 @@ int launch_rcoset(fp_ctx *ctx, RcPassView<T> const &view, uint64_t n_cosets, uin
 }
 
 // K3d (dcoset.cuh): FP64 tensor-core dense-coset kernel, complex128 apply, rank 4 (one warp per coset) or 5 (two)
-template <int RR, int WPC>
+template <int RR, int WPC, int PFD>
 int launch_dcoset(fp_ctx *ctx, RcPassView<double> const &view, uint32_t n_strings, uint64_t n_cosets, uint64_t rowvecs,
                   void const *in, void *out, int beta)
 {
@@ -870,15 +870,15 @@ int launch_dcoset(fp_ctx *ctx, RcPassView<double> const &view, uint32_t n_string
     static int resident = 0; // CTAs per SM (per template instance): the kernel is persistent
     if (!resident)
     {
-        FP_CU(cudaFuncSetAttribute(dcoset_kernel<RR, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        FP_CU(cudaFuncSetAttribute(dcoset_kernel<RR, WPC, PFD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(Cfg::smem)));
         int nb = 0;
-        FP_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dcoset_kernel<RR, WPC>, Cfg::NT, Cfg::smem));
+        FP_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dcoset_kernel<RR, WPC, PFD>, Cfg::NT, Cfg::smem));
         resident = std::max(1, nb);
     }
     uint64_t const sets = (n_cosets + Cfg::CPI - 1) / Cfg::CPI;
     uint64_t const grid = std::min<uint64_t>(sets, static_cast<uint64_t>(ctx->sm_count) * resident);
-    dcoset_kernel<RR, WPC><<<static_cast<unsigned>(grid), Cfg::NT, Cfg::smem, ctx->stream>>>(
+    dcoset_kernel<RR, WPC, PFD><<<static_cast<unsigned>(grid), Cfg::NT, Cfg::smem, ctx->stream>>>(
         view, n_strings, n_cosets, rowvecs, static_cast<CVec<double, 1> const *>(in),
         static_cast<CVec<double, 1> *>(out), beta);
     ctx->launches++;
@@ -912,9 +912,9 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
             uint64_t const nc = 1ull << (n_qubits - rr);
             uint32_t const ns = static_cast<uint32_t>(op.host.sz.size());
             if (rr == 4)
-                FP_TRY((launch_dcoset<4, 1>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta)));
+                FP_TRY((launch_dcoset<4, 1, 4>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta)));
             else
-                FP_TRY((launch_dcoset<5, 2>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta)));
+                FP_TRY((launch_dcoset<5, 2, 2>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta)));
             *used = true;
             return FP_OK;
         }

@@ -28,7 +28,7 @@ namespace fpk
 
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
 {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
@@ -52,13 +52,13 @@ template <int RR, int WPC> struct DcosetCfg
     static constexpr int KB = ROWS / 4;              // k-blocks per part (real / imaginary)
     static constexpr int PITCH = ROWS + 1;           // table row pitch (entries): column accesses stay conflict-free
     static constexpr size_t tables = 2 * static_cast<size_t>(CPI) * ROWS * PITCH * sizeof(Cx<double>); // D and U tables
-    static_assert(WPC * 32 == 2 * ROWS, "the sign transform maps one (local x-mask, re/im) pair to each thread");
+    static_assert(WPC * 32 >= 2 * ROWS, "the sign transform maps one (local x-mask, re/im) pair to a thread");
     static constexpr int MAX_STAGED = 1024; // strings whose (coefficient, z-mask) are staged in shared memory
     static constexpr size_t smem = tables + MAX_STAGED * (sizeof(Cx<double>) + 8) + (ROWS * ROWS + 1) * 4 + 12;
     static_assert(RT % WPC == 0 && WARPS % WPC == 0, "warps must split the row tiles evenly");
 };
 
-template <int RR, int WPC>
+template <int RR, int WPC, int PFD>
 __global__ void __launch_bounds__(128)
     dcoset_kernel(RcPassView<double> pass, uint32_t n_strings, uint64_t n_cosets, uint64_t rowvecs,
                   CVec<double, 1> const *__restrict__ in, CVec<double, 1> *__restrict__ out, int beta)
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128)
     double2 const *in2 = reinterpret_cast<double2 const *>(in);
     double2 *out2 = reinterpret_cast<double2 *>(out);
 
-    constexpr int PF = RR == 4 ? 4 : 2; // input tiles in flight per warp (one 8-column tile of MMAs is ~270 ns, an HBM load ~800 ns)
+    constexpr int PF = PFD; // input tiles in flight per warp (one 8-column tile of MMAs is ~270 ns, an HBM load ~800 ns)
     uint64_t const n_tiles = (rowvecs + 7) / 8;
 
     for (uint64_t cs0 = static_cast<uint64_t>(blockIdx.x) * CPI; cs0 < n_cosets; cs0 += static_cast<uint64_t>(gridDim.x) * CPI)
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128)
             }
         }
         group_sync<WPC>(cw);
-        if (live)
+        if (live && gtid < 2 * ROWS)
         {
             // D[xl][.] = Walsh-Hadamard transform of U[xl][.]: one (xl, re/im) pair per thread, in registers
             uint32_t const xl = gtid >> 1, ri = gtid & 1u;
@@ -223,14 +223,17 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
                     for (int m = 0; m < 2 * RT_OWN; ++m)
                         C[m][0] = C[m][1] = 0.0;
+                    // consecutive MMAs go to different accumulators (the m-tiles), never back to back into one
 #pragma unroll
                     for (int kb = 0; kb < KB; ++kb)
+                    {
 #pragma unroll
                         for (int m = 0; m < 2 * RT_OWN; ++m)
-                        {
                             dmma884(C[m][0], C[m][1], A[m][kb], x[u][kb].x);
+#pragma unroll
+                        for (int m = 0; m < 2 * RT_OWN; ++m)
                             dmma884(C[m][0], C[m][1], A[m][KB + kb], x[u][kb].y);
-                        }
+                    }
                     if (nt + PF < n_tiles)
                     {
                         uint64_t const col = n0 + PF * 8 + lq;
