@@ -1975,22 +1975,37 @@ int sop_check(fp_ctx *ctx, fp_sop const *sop)
     return FP_OK;
 }
 
-// K6b (wtile.cuh): whole state column pair in shared memory, packed-FP32 arithmetic; complex64, 11 or 12 qubits
-template <int LOG_NT>
-int launch_wtile(fp_ctx *ctx, CosetPassView<float> const &view, uint64_t rowvecs, void const *in, void *out, int beta,
-                 float const *Wre, float const *Wim, uint64_t B)
+// K6b (wtile.cuh): whole state column (pair) in shared memory; complex64 (packed FP32) or complex128, 11-12 qubits
+template <typename T, int LOG_NT>
+int launch_wtile(fp_ctx *ctx, CosetPassView<T> const &view, uint64_t rowvecs, void const *in, void *out, int beta,
+                 T const *Wre, T const *Wim, uint64_t B)
 {
     constexpr size_t smem = WtileSmem<LOG_NT>::bytes;
     static bool configured = false;
-    if (!configured)
-    {
-        FP_CU(cudaFuncSetAttribute(wtile_kernel<LOG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
-        configured = true;
-    }
     FP_TRY(check_grid(rowvecs));
-    wtile_kernel<LOG_NT><<<static_cast<unsigned>(rowvecs), 1 << LOG_NT, smem, ctx->stream>>>(
-        view, rowvecs, static_cast<CVec<float, 2> const *>(in), static_cast<CVec<float, 2> *>(out), beta, Wre, Wim, B);
+    if constexpr (sizeof(T) == 4)
+    {
+        if (!configured)
+        {
+            FP_CU(cudaFuncSetAttribute(wtile_kernel<LOG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+            configured = true;
+        }
+        wtile_kernel<LOG_NT><<<static_cast<unsigned>(rowvecs), 1 << LOG_NT, smem, ctx->stream>>>(
+            view, rowvecs, static_cast<CVec<float, 2> const *>(in), static_cast<CVec<float, 2> *>(out), beta, Wre, Wim, B);
+    }
+    else
+    {
+        if (!configured)
+        {
+            FP_CU(cudaFuncSetAttribute(wtile_f64_kernel<LOG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem)));
+            configured = true;
+        }
+        wtile_f64_kernel<LOG_NT><<<static_cast<unsigned>(rowvecs), 1 << LOG_NT, smem, ctx->stream>>>(
+            view, rowvecs, static_cast<CVec<double, 1> const *>(in), static_cast<CVec<double, 1> *>(out), beta, Wre, Wim,
+            B);
+    }
     ctx->launches++;
     return FP_OK;
 }
@@ -2000,25 +2015,23 @@ int try_wtile(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
               int beta, T const *Wre, T const *Wim, bool *used)
 {
     *used = false;
-    if constexpr (sizeof(T) == 4)
-    {
-        if (!ctx->wtile || ctx->coset_mode != 1 || ctx->coset_log_twc >= 0 || (n_qubits != 11 && n_qubits != 12) ||
-            dim != (1ull << n_qubits) || pick_epv<T>(in, out, B) != 2)
-            return FP_OK;
-        std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
-        FP_TRY(get_coset_plan<T>(op, n_qubits, n_qubits, 2, &passes));
-        if (passes->size() != 1)
-            return FP_OK;
-        CosetPassView<T> const &view = (*passes)[0].view;
-        for (int k = 0; k < n_qubits; ++k)
-            if (view.basis[k] != (1ull << k))
-                return FP_OK; // cannot happen for a full-rank reduced basis; the kernel relies on local row == row
-        if (n_qubits == 12)
-            FP_TRY(launch_wtile<9>(ctx, view, B / 2, in, out, beta, Wre, Wim, B));
-        else
-            FP_TRY(launch_wtile<8>(ctx, view, B / 2, in, out, beta, Wre, Wim, B));
-        *used = true;
-    }
+    constexpr int EPV = sizeof(T) == 4 ? 2 : 1;
+    if (!ctx->wtile || ctx->coset_mode != 1 || ctx->coset_log_twc >= 0 || (n_qubits != 11 && n_qubits != 12) ||
+        dim != (1ull << n_qubits) || pick_epv<T>(in, out, B) != EPV)
+        return FP_OK;
+    std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
+    FP_TRY(get_coset_plan<T>(op, n_qubits, n_qubits, 2, &passes));
+    if (passes->size() != 1)
+        return FP_OK;
+    CosetPassView<T> const &view = (*passes)[0].view;
+    for (int k = 0; k < n_qubits; ++k)
+        if (view.basis[k] != (1ull << k))
+            return FP_OK; // cannot happen for a full-rank reduced basis; the kernel relies on local row == row
+    if (n_qubits == 12)
+        FP_TRY((launch_wtile<T, 9>(ctx, view, B / EPV, in, out, beta, Wre, Wim, B)));
+    else
+        FP_TRY((launch_wtile<T, 8>(ctx, view, B / EPV, in, out, beta, Wre, Wim, B)));
+    *used = true;
     return FP_OK;
 }
 

@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--log-twc", type=int, default=-1)
     ap.add_argument("--log-nt", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--c128", action="store_true", help="cfg4w / cfg4e in complex128 instead of complex64")
     a = ap.parse_args()
     ctx = fp.Context(0)
     ctx.set_coset(a.coset, a.log_twc, a.log_nt)
@@ -127,16 +128,17 @@ def main():
     elif a.case in ("cfg4w", "cfg4e"):
         n, B, S, K = 12, a.batch or 4096, 10000, 64
         strings = random_strings(rng, n, S)
-        hk = (rng.uniform(-1, 1, (S, K)) + 1j * rng.uniform(-1, 1, (S, K))).astype(np.complex64)
-        psi = ctx.uniform((1 << n, B), np.complex64)
-        data = ctx.to_device(rng.random((K, B)).astype(np.float32))
+        cdt = np.complex128 if a.c128 else np.complex64
+        hk = (rng.uniform(-1, 1, (S, K)) + 1j * rng.uniform(-1, 1, (S, K))).astype(cdt)
+        psi = ctx.uniform((1 << n, B), cdt)
+        data = ctx.to_device(rng.random((K, B)).astype(np.float64 if a.c128 else np.float32))
         sop = fp.SummedPauliOp(strings, hk, ctx=ctx)
-        plan = sop._plan(np.complex64)
-        y = ctx.empty((1 << n, B), np.complex64)
-        ev = ctx.empty((K, B), np.complex64)
+        plan = sop._plan(cdt)
+        y = ctx.empty((1 << n, B), cdt)
+        ev = ctx.empty((K, B), cdt)
         if a.case == "cfg4w":
-            ms = timed(ctx, lambda: fp.lib.fp_sop_apply_weighted(ctx._h, plan, vp(y.ptr), vp(psi.ptr), vp(data.ptr), 0,
-                                                                 sz(1 << n), sz(B), 0), a.iters)
+            ms = timed(ctx, lambda: fp.lib.fp_sop_apply_weighted(ctx._h, plan, vp(y.ptr), vp(psi.ptr), vp(data.ptr),
+                                                                 1 if a.c128 else 0, sz(1 << n), sz(B), 0), a.iters)
         else:
             ms = timed(ctx, lambda: fp.lib.fp_sop_expval(ctx._h, plan, vp(ev.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0),
                        a.iters)

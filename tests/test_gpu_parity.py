@@ -703,11 +703,12 @@ def test_config4_reduced_summed_c64():
     assert rel_err(sop.expectation_value(psi), exp_e) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", [11, 12])
-def test_weighted_tile_kernel_c64(n):
-    """K6b (wtile.cuh): complex64 apply_weighted on 11/12-qubit registers takes the dedicated whole-column kernel
-    (one launch after the contraction); parity vs the complex128 oracle, accumulate through the ABI, and agreement
-    with the generic weighted-apply path; > 128 strings so several metadata chunks are staged."""
+def test_weighted_tile_kernel(dtype, n):
+    """K6b (wtile.cuh): apply_weighted on 11/12-qubit registers takes the dedicated whole-column kernel (one launch
+    after the contraction), complex64 (packed FP32) and complex128; parity vs the complex128 oracle, accumulate
+    through the ABI, agreement with the generic weighted-apply path; > 128 strings: several metadata chunks."""
     import ctypes as C
 
     rng = np.random.default_rng(40 + n)
@@ -716,26 +717,28 @@ def test_weighted_tile_kernel_c64(n):
     strings[3] = "Z" * n
     strings[4] = "I" * n
     strings[5] = strings[6]
-    hk = (rand_states(rng, S, K, np.complex64) * 2 - (1 + 1j)).astype(np.complex64)
-    psi = rand_states(rng, 2**n, B, np.complex64)
-    base = rand_states(rng, 2**n, B, np.complex64)
-    data = rng.random((K, B)).astype(np.float32)
+    rdt = np.float32 if dtype == np.complex64 else np.float64
+    hk = (rand_states(rng, S, K, dtype) * 2 - (1 + 1j)).astype(dtype)
+    psi = rand_states(rng, 2**n, B, dtype)
+    base = rand_states(rng, 2**n, B, dtype)
+    data = rng.random((K, B)).astype(rdt)
+    t = tol(dtype)
     ctx = fp.Context(0)
     sop = fp.SummedPauliOp(strings, hk, ctx=ctx)
     exp_w = ORC.sop_apply_weighted(strings, hk.astype(np.complex128), psi.astype(np.complex128), data.astype(np.float64))
     l0 = ctx.launch_count
     got = sop.apply_weighted(psi, data)
     assert ctx.launch_count - l0 == 2  # contraction + one whole-column launch
-    assert rel_err(got, exp_w) < 1e-5
+    assert rel_err(got, exp_w) < t
     out = base.copy()
-    rc = fp.lib.fp_sop_apply_weighted(ctx._h, sop._plan(np.complex64), C.c_void_p(out.ctypes.data),
-                                      C.c_void_p(psi.ctypes.data), C.c_void_p(data.ctypes.data), C.c_int(0),
-                                      C.c_size_t(2**n), C.c_size_t(B), C.c_int(1))
+    rc = fp.lib.fp_sop_apply_weighted(ctx._h, sop._plan(dtype), C.c_void_p(out.ctypes.data),
+                                      C.c_void_p(psi.ctypes.data), C.c_void_p(data.ctypes.data),
+                                      C.c_int(1 if rdt == np.float64 else 0), C.c_size_t(2**n), C.c_size_t(B), C.c_int(1))
     assert rc == 0
-    assert rel_err(out, exp_w + base.astype(np.complex128)) < 1e-5
+    assert rel_err(out, exp_w + base.astype(np.complex128)) < t
     ctx0 = fp.Context(0)
     ctx0.set_coset(0, -1, 0)
-    assert rel_err(fp.SummedPauliOp(strings, hk, ctx=ctx0).apply_weighted(psi, data), got) < 1e-5
+    assert rel_err(fp.SummedPauliOp(strings, hk, ctx=ctx0).apply_weighted(psi, data), got) < t
 
 
 @pytest.mark.parametrize("n", [9, 10, 12])
