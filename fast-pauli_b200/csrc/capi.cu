@@ -14,6 +14,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -2121,25 +2122,23 @@ int run_sop_expval(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, ui
             configured = true;
         }
         bool launched = false;
-        if constexpr (sizeof(T) == 4)
+        if (ctx->etile && sop->n_qubits >= 9 && rowvecs <= 0x7fffffffull)
         {
-            if (ctx->etile && sop->n_qubits >= 9 && rowvecs <= 0x7fffffffull)
+            // K4c (etile.cuh): planar pair tile / packed FP32 (complex64) or FP64 (complex128), compile-time sign patterns
+            using P = typename std::conditional<sizeof(T) == 4, EtF32, EtF64>::type;
+            static bool configured2 = false;
+            if (!configured2)
             {
-                // K4c (etile.cuh): planar pair tile, packed FP32, compile-time sign patterns
-                static bool configured2 = false;
-                if (!configured2)
-                {
-                    FP_CU(cudaFuncSetAttribute(sop_expval_tile2_kernel<kPairMS>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-                    configured2 = true;
-                }
-                dim3 grid(static_cast<unsigned>(rowvecs), splits);
-                sop_expval_tile2_kernel<kPairMS><<<grid, kThreads, smem, ctx->stream>>>(
-                    op.chunks, op.n_chunks, op.sz, op.sodd, static_cast<uint32_t>(sop->n_qubits), rowvecs,
-                    static_cast<CVec<float, 2> const *>(in), E, B);
-                ctx->launches++;
-                stage1_done = launched = true;
+                FP_CU(cudaFuncSetAttribute(sop_expval_tile2_kernel<P, kPairMS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+                configured2 = true;
             }
+            dim3 grid(static_cast<unsigned>(rowvecs), splits);
+            sop_expval_tile2_kernel<P, kPairMS><<<grid, kThreads, smem, ctx->stream>>>(
+                op.chunks, op.n_chunks, op.sz, op.sodd, static_cast<uint32_t>(sop->n_qubits), rowvecs,
+                static_cast<CVec<T, EPV_FULL> const *>(in), E, B);
+            ctx->launches++;
+            stage1_done = launched = true;
         }
         if (!launched && rowvecs <= 0x7fffffffull)
         {

@@ -1,5 +1,5 @@
 // K4c: SummedPauliOp::expectation_value first stage (SPO:573-577), E(s, t) = <psi_t| P_s |psi_t> for every string,
-// for complex64 registers of 9..12 qubits.  Same plan as sop_expval_tile_kernel (coset.cuh) -- the whole state
+// for registers of 9..12 qubits (complex64: a column pair per CTA in packed FP32; complex128: one column, FP64).  Same plan as sop_expval_tile_kernel (coset.cuh) -- the whole state
 // column pair lives in shared memory, warps take the x-mask chunks (<= MS strings sharing a gather), rows are
 // visited as unordered pairs {i, i^x} so q = conj(psi_i) psi_{i^x} is formed once per pair -- with the per-element
 // integer work removed:
@@ -28,36 +28,82 @@ __device__ __forceinline__ float2 f2flip(float2 a, uint32_t odd)
     return make_float2(__uint_as_float(__float_as_uint(a.x) ^ s), __uint_as_float(__float_as_uint(a.y) ^ s));
 }
 
-// sum_k (-1)^{popc(k & K)} q[k], k < 8, K compile time (FADD2 negates an operand for free)
-template <int K> __device__ __forceinline__ float2 signed_sum8(float2 const (&q)[8])
+// Arithmetic of one shared-memory row: complex64 = a column PAIR as packed float2 lanes, complex128 = one column.
+struct EtF32
 {
-    float2 p = q[0];
+    using T = float;
+    using V = float2;  // one value per column of the pair
+    using Row = float4; // planar (re0, re1, im0, im1)
+    static constexpr int COLS = 2;
+    static __device__ __forceinline__ Row to_row(float4 a) { return make_float4(a.x, a.z, a.y, a.w); }
+    static __device__ __forceinline__ V re(Row a) { return make_float2(a.x, a.y); }
+    static __device__ __forceinline__ V im(Row a) { return make_float2(a.z, a.w); }
+    static __device__ __forceinline__ V zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ V add(V a, V b) { return __fadd2_rn(a, b); }
+    static __device__ __forceinline__ V mul(V a, V b) { return __fmul2_rn(a, b); }
+    static __device__ __forceinline__ V fma(V a, V b, V c) { return __ffma2_rn(a, b, c); }
+    static __device__ __forceinline__ V neg(V a) { return f2neg(a); }
+    static __device__ __forceinline__ V flip(V a, uint32_t odd) { return f2flip(a, odd); }
+    static __device__ __forceinline__ V shfl_add(V a, int off)
+    {
+        a.x += __shfl_xor_sync(0xffffffffu, a.x, off);
+        a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
+        return a;
+    }
+    static __device__ __forceinline__ void store(T *E, uint64_t s, uint64_t B, uint64_t v, V val)
+    {
+        *reinterpret_cast<float2 *>(E + s * B + v * 2) = val;
+    }
+};
+struct EtF64
+{
+    using T = double;
+    using V = double;
+    using Row = double2; // (re, im)
+    static constexpr int COLS = 1;
+    static __device__ __forceinline__ Row to_row(double2 a) { return a; }
+    static __device__ __forceinline__ V re(Row a) { return a.x; }
+    static __device__ __forceinline__ V im(Row a) { return a.y; }
+    static __device__ __forceinline__ V zero() { return 0.0; }
+    static __device__ __forceinline__ V add(V a, V b) { return a + b; }
+    static __device__ __forceinline__ V mul(V a, V b) { return a * b; }
+    static __device__ __forceinline__ V fma(V a, V b, V c) { return ::fma(a, b, c); }
+    static __device__ __forceinline__ V neg(V a) { return -a; }
+    static __device__ __forceinline__ V flip(V a, uint32_t odd) { return flip_sign(a, odd); }
+    static __device__ __forceinline__ V shfl_add(V a, int off) { return a + __shfl_xor_sync(0xffffffffu, a, off); }
+    static __device__ __forceinline__ void store(T *E, uint64_t s, uint64_t B, uint64_t v, V val) { E[s * B + v] = val; }
+};
+
+// sum_k (-1)^{popc(k & K)} q[k], k < 8, K compile time (FADD2 / DADD negate an operand for free)
+template <typename P, int K> __device__ __forceinline__ typename P::V signed_sum8(typename P::V const (&q)[8])
+{
+    typename P::V p = q[0];
 #pragma unroll
     for (int k = 1; k < 8; ++k)
-        p = __fadd2_rn(p, (__builtin_popcount(k & K) & 1) ? f2neg(q[k]) : q[k]);
+        p = P::add(p, (__builtin_popcount(k & K) & 1) ? P::neg(q[k]) : q[k]);
     return p;
 }
 
-__device__ __forceinline__ float2 signed_sum8_dyn(uint32_t zk, float2 const (&q)[8])
+template <typename P> __device__ __forceinline__ typename P::V signed_sum8_dyn(uint32_t zk, typename P::V const (&q)[8])
 {
     switch (zk) // warp-uniform
     {
     case 0:
-        return signed_sum8<0>(q);
+        return signed_sum8<P, 0>(q);
     case 1:
-        return signed_sum8<1>(q);
+        return signed_sum8<P, 1>(q);
     case 2:
-        return signed_sum8<2>(q);
+        return signed_sum8<P, 2>(q);
     case 3:
-        return signed_sum8<3>(q);
+        return signed_sum8<P, 3>(q);
     case 4:
-        return signed_sum8<4>(q);
+        return signed_sum8<P, 4>(q);
     case 5:
-        return signed_sum8<5>(q);
+        return signed_sum8<P, 5>(q);
     case 6:
-        return signed_sum8<6>(q);
+        return signed_sum8<P, 6>(q);
     default:
-        return signed_sum8<7>(q);
+        return signed_sum8<P, 7>(q);
     }
 }
 
@@ -66,11 +112,11 @@ __device__ __forceinline__ float2 signed_sum8_dyn(uint32_t zk, float2 const (&q)
 // (top bit < 5: the pair bit sits among the lane bits), 2: the pair bit sits among the three in-block bits
 // (top bit 5..7): offsets from a register table.  DIAG: x = 0, q = |psi|^2.  ODD: some string of the chunk has an
 // odd number of Y, so Im q is needed as well.
-template <int MS, int ADDR, bool DIAG, bool ODD>
+template <typename P, int MS, int ADDR, bool DIAG, bool ODD>
 __device__ __forceinline__ void etile_chunk(unsigned char const *tile_bytes, uint32_t lane_off, uint32_t x4,
                                             uint32_t n_blocks, uint32_t hp, uint32_t sh, uint32_t count,
                                             uint32_t const (&zk)[MS], uint32_t const (&zb)[MS],
-                                            uint32_t const (&odd_ny)[MS], float2 (&r)[MS])
+                                            uint32_t const (&odd_ny)[MS], typename P::V (&r)[MS])
 {
     uint32_t dk[8]; // ADDR == 2 only: byte offset of pair k inside the block
     if (ADDR == 2)
@@ -87,22 +133,24 @@ __device__ __forceinline__ void etile_chunk(unsigned char const *tile_bytes, uin
         uint32_t const jp0 = ADDR == 2 ? (j0 << (sh + 1)) : ((((j0 >> hp) << (hp + 1)) | (j0 & hp_low)) << sh);
         uint32_t const a0 = lane_off + (jp0 << 4); // byte offset of the block's first row
         uint32_t const b0 = a0 ^ x4;
-        float2 qre[8], qim[8];
+        using V = typename P::V;
+        using Row = typename P::Row;
+        V qre[8], qim[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k)
         {
             uint32_t const dko = ADDR == 0 ? (k << 9) : ADDR == 1 ? (k << 10) : dk[k];
-            float4 const a = *reinterpret_cast<float4 const *>(tile_bytes + a0 + dko);
-            float2 const ar = make_float2(a.x, a.y), ai = make_float2(a.z, a.w);
+            Row const a = *reinterpret_cast<Row const *>(tile_bytes + a0 + dko);
+            V const ar = P::re(a), ai = P::im(a);
             if (DIAG)
-                qre[k] = __ffma2_rn(ar, ar, __fmul2_rn(ai, ai));
+                qre[k] = P::fma(ar, ar, P::mul(ai, ai));
             else
             {
-                float4 const b = *reinterpret_cast<float4 const *>(tile_bytes + (b0 ^ dko));
-                float2 const br = make_float2(b.x, b.y), bi = make_float2(b.z, b.w);
-                qre[k] = __ffma2_rn(ar, br, __fmul2_rn(ai, bi));
+                Row const b = *reinterpret_cast<Row const *>(tile_bytes + (b0 ^ dko));
+                V const br = P::re(b), bi = P::im(b);
+                qre[k] = P::fma(ar, br, P::mul(ai, bi));
                 if (ODD)
-                    qim[k] = __ffma2_rn(ar, bi, __fmul2_rn(ai, f2neg(br)));
+                    qim[k] = P::fma(ar, bi, P::mul(ai, P::neg(br)));
             }
         }
 #pragma unroll
@@ -110,34 +158,34 @@ __device__ __forceinline__ void etile_chunk(unsigned char const *tile_bytes, uin
         {
             if (static_cast<uint32_t>(m) < count)
             {
-                float2 rb;
+                V rb;
                 if (ODD && odd_ny[m])
-                    rb = signed_sum8_dyn(zk[m], qim);
+                    rb = signed_sum8_dyn<P>(zk[m], qim);
                 else
-                    rb = signed_sum8_dyn(zk[m], qre);
-                r[m] = __fadd2_rn(r[m], f2flip(rb, __popc(blk & zb[m]) & 1u));
+                    rb = signed_sum8_dyn<P>(zk[m], qre);
+                r[m] = P::add(r[m], P::flip(rb, __popc(blk & zb[m]) & 1u));
             }
         }
     }
 }
 
-template <int MS>
+template <typename P, int MS>
 __global__ void __launch_bounds__(kThreads)
     sop_expval_tile2_kernel(PairChunk const *__restrict__ chunks, uint32_t n_chunks, uint64_t const *__restrict__ sz,
                             uint8_t const *__restrict__ sodd, uint32_t n_qubits, uint64_t rowvecs,
-                            CVec<float, 2> const *__restrict__ in, float *__restrict__ E /* [S][B] */, uint64_t B)
+                            CVec<typename P::T, P::COLS> const *__restrict__ in, typename P::T *__restrict__ E /* [S][B] */,
+                            uint64_t B)
 {
+    using V = typename P::V;
+    using Row = typename P::Row;
     extern __shared__ __align__(16) unsigned char et_smem[];
-    float4 *tile = reinterpret_cast<float4 *>(et_smem);
+    Row *tile = reinterpret_cast<Row *>(et_smem);
     uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint32_t const rows = 1u << n_qubits;
-    uint64_t const v = blockIdx.x; // column pair of this CTA
-    float4 const *in4 = reinterpret_cast<float4 const *>(in);
+    uint64_t const v = blockIdx.x; // column (pair) of this CTA: one 16-byte vector per row
+    Row const *in4 = reinterpret_cast<Row const *>(in);
     for (uint32_t r = tid; r < rows; r += kThreads)
-    {
-        float4 const a = in4[static_cast<uint64_t>(r) * rowvecs + v];
-        tile[r] = make_float4(a.x, a.z, a.y, a.w); // planar per pair
-    }
+        tile[r] = P::to_row(in4[static_cast<uint64_t>(r) * rowvecs + v]); // complex64: planar per pair
     __syncthreads();
 
     uint32_t const n_warps_total = (kThreads / 32) * gridDim.y;
@@ -175,50 +223,47 @@ __global__ void __launch_bounds__(kThreads)
             zk[m] = zj & 7u;
             zb[m] = zj >> 3;
         }
-        float2 r[MS];
+        V r[MS];
 #pragma unroll
         for (int m = 0; m < MS; ++m)
-            r[m] = make_float2(0.f, 0.f);
+            r[m] = P::zero();
 
         unsigned char const *tb = et_smem;
         uint32_t const lane_off = lane_part << 4, x4 = x << 4;
         if (ch.diag)
-            etile_chunk<MS, 0, true, false>(tb, lane_off, 0, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+            etile_chunk<P, MS, 0, true, false>(tb, lane_off, 0, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
         else if (ch.hbit < 5)
         {
             if (any_odd)
-                etile_chunk<MS, 1, false, true>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+                etile_chunk<P, MS, 1, false, true>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
             else
-                etile_chunk<MS, 1, false, false>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+                etile_chunk<P, MS, 1, false, false>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
         }
         else if (ch.hbit >= 8)
         {
             if (any_odd)
-                etile_chunk<MS, 0, false, true>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+                etile_chunk<P, MS, 0, false, true>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
             else
-                etile_chunk<MS, 0, false, false>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+                etile_chunk<P, MS, 0, false, false>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
         }
         else
         {
             if (any_odd)
-                etile_chunk<MS, 2, false, true>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+                etile_chunk<P, MS, 2, false, true>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
             else
-                etile_chunk<MS, 2, false, false>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
+                etile_chunk<P, MS, 2, false, false>(tb, lane_off, x4, n_blocks, hp, sh, ch.count, zk, zb, odd_ny, r);
         }
 #pragma unroll
         for (int m = 0; m < MS; ++m)
         {
             if (static_cast<uint32_t>(m) >= ch.count)
                 break;
-            float2 val = f2flip(r[m], sl[m]);
+            V val = P::flip(r[m], sl[m]);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1)
-            {
-                val.x += __shfl_xor_sync(0xffffffffu, val.x, off);
-                val.y += __shfl_xor_sync(0xffffffffu, val.y, off);
-            }
+                val = P::shfl_add(val, off);
             if (lane == 0)
-                *reinterpret_cast<float2 *>(E + static_cast<uint64_t>(ch.s0 + m) * B + v * 2) = val;
+                P::store(E, ch.s0 + m, B, v, val);
         }
     }
 }

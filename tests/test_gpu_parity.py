@@ -741,9 +741,10 @@ def test_weighted_tile_kernel(dtype, n):
     assert rel_err(fp.SummedPauliOp(strings, hk, ctx=ctx0).apply_weighted(psi, data), got) < t
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("n", [9, 10, 12])
-def test_expval_tile_kernel_c64(n):
-    """K4c (etile.cuh): complex64 SummedPauliOp.expectation_value on 9..12-qubit registers; x-masks whose top bit
+def test_expval_tile_kernel(dtype, n):
+    """K4c (etile.cuh): SummedPauliOp.expectation_value on 9..12-qubit registers, complex64 and complex128; x-masks whose top bit
     lies among the lane bits (hbit < 5), among the block bits, diagonal strings, odd/even Y counts, groups with more
     strings than one chunk holds; compared with the complex128 oracle and with the generic K4b kernel."""
     rng = np.random.default_rng(90 + n)
@@ -757,12 +758,12 @@ def test_expval_tile_kernel_c64(n):
     strings[12] = "Z" * n
     strings[13] = "I" * n
     strings[14] = "".join(rng.choice(list("IZ"), size=n))
-    hk = (rand_states(rng, S, K, np.complex64) * 2 - (1 + 1j)).astype(np.complex64)
-    psi = (rand_states(rng, 2**n, B, np.complex64) * 2 - (1 + 1j)).astype(np.complex64)
+    hk = (rand_states(rng, S, K, dtype) * 2 - (1 + 1j)).astype(dtype)
+    psi = (rand_states(rng, 2**n, B, dtype) * 2 - (1 + 1j)).astype(dtype)
     exp_e = ORC.sop_expval(strings, hk.astype(np.complex128), psi.astype(np.complex128))
     ctx = fp.Context(0)
     got = fp.SummedPauliOp(strings, hk, ctx=ctx).expectation_value(psi)
-    assert rel_err(got, exp_e) < 1e-5
+    assert rel_err(got, exp_e) < tol(dtype)
     import os as _os
 
     _os.environ["FASTPAULI_ETILE"] = "0"
@@ -771,8 +772,8 @@ def test_expval_tile_kernel_c64(n):
     finally:
         del _os.environ["FASTPAULI_ETILE"]
     old = fp.SummedPauliOp(strings, hk, ctx=ctx_old).expectation_value(psi)
-    assert rel_err(old, exp_e) < 1e-5
-    assert rel_err(got, old) < 1e-5
+    assert rel_err(old, exp_e) < tol(dtype)
+    assert rel_err(got, old) < tol(dtype)
 
 
 def test_config3_full_size_sampled_columns():
