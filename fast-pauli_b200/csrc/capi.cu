@@ -863,26 +863,38 @@ int launch_rcoset(fp_ctx *ctx, RcPassView<T> const &view, uint64_t n_cosets, uin
 }
 
 // K3d (dcoset.cuh): FP64 tensor-core dense-coset kernel, complex128 apply, rank 4 (one warp per coset) or 5 (two)
-template <int RR, int WPC, int PFD>
+template <int RR, int WPC, int PFD, int MODE>
 int launch_dcoset(fp_ctx *ctx, RcPassView<double> const &view, uint32_t n_strings, uint64_t n_cosets, uint64_t rowvecs,
-                  void const *in, void *out, int beta)
+                  void const *in, void *out, int beta, uint64_t B)
 {
     using Cfg = DcosetCfg<RR, WPC>;
+    constexpr size_t smem = MODE == 1 ? Cfg::smem_expval : Cfg::smem;
     static int resident = 0; // CTAs per SM (per template instance): the kernel is persistent
     if (!resident)
     {
-        FP_CU(cudaFuncSetAttribute(dcoset_kernel<RR, WPC, PFD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(Cfg::smem)));
+        FP_CU(cudaFuncSetAttribute(dcoset_kernel<RR, WPC, PFD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
         int nb = 0;
-        FP_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dcoset_kernel<RR, WPC, PFD>, Cfg::NT, Cfg::smem));
+        FP_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dcoset_kernel<RR, WPC, PFD, MODE>, Cfg::NT, smem));
         resident = std::max(1, nb);
     }
     uint64_t const sets = (n_cosets + Cfg::CPI - 1) / Cfg::CPI;
-    uint64_t const grid = std::min<uint64_t>(sets, static_cast<uint64_t>(ctx->sm_count) * resident);
-    dcoset_kernel<RR, WPC, PFD><<<static_cast<unsigned>(grid), Cfg::NT, Cfg::smem, ctx->stream>>>(
+    unsigned const ny = MODE == 1 ? static_cast<unsigned>((rowvecs + Cfg::ECOLS - 1) / Cfg::ECOLS) : 1u;
+    uint64_t const gx = std::min<uint64_t>(sets, std::max<uint64_t>(1, static_cast<uint64_t>(ctx->sm_count) * resident / ny));
+    uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
+    if (MODE == 1)
+        FP_TRY(ctx->partials.ensure(gx * Bpad * sizeof(Cx<double>)));
+    dcoset_kernel<RR, WPC, PFD, MODE><<<dim3(static_cast<unsigned>(gx), ny), Cfg::NT, smem, ctx->stream>>>(
         view, n_strings, n_cosets, rowvecs, static_cast<CVec<double, 1> const *>(in),
-        static_cast<CVec<double, 1> *>(out), beta);
+        MODE == 1 ? nullptr : static_cast<CVec<double, 1> *>(out), beta, static_cast<Cx<double> *>(ctx->partials.p), Bpad);
     ctx->launches++;
+    if (MODE == 1)
+    {
+        unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
+        finalize_complex_kernel<double><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
+            static_cast<Cx<double> const *>(ctx->partials.p), gx, Bpad, B, static_cast<Cx<double> *>(out), beta);
+        ctx->launches++;
+    }
     return FP_OK;
 }
 
@@ -903,7 +915,7 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
     if (rowvecs < 4 && ctx->rcoset_mode != 2)
         return FP_OK; // rows shorter than 64 bytes: coalescing must come from the row index (shared-memory tiles)
     int const rr = std::min(n_qubits, std::max(2, op.x_rank)); // 2-row threads keep too few bytes in flight
-    if constexpr (sizeof(T) == 8 && MODE == 0)
+    if constexpr (sizeof(T) == 8)
     {
         // ranks 4 and 5 are GEMM-shaped per coset (16x16 / 32x32 complex): FP64 tensor cores
         if (ctx->dcoset && (rr == 4 || rr == 5) && rowvecs >= 8)
@@ -913,9 +925,9 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
             uint64_t const nc = 1ull << (n_qubits - rr);
             uint32_t const ns = static_cast<uint32_t>(op.host.sz.size());
             if (rr == 4)
-                FP_TRY((launch_dcoset<4, 1, 4>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta)));
+                FP_TRY((launch_dcoset<4, 1, 4, MODE>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta, B)));
             else
-                FP_TRY((launch_dcoset<5, 2, 2>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta)));
+                FP_TRY((launch_dcoset<5, 2, 2, MODE>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta, B)));
             *used = true;
             return FP_OK;
         }

@@ -55,13 +55,20 @@ template <int RR, int WPC> struct DcosetCfg
     static_assert(WPC * 32 >= 2 * ROWS, "the sign transform maps one (local x-mask, re/im) pair to a thread");
     static constexpr int MAX_STAGED = 1024; // strings whose (coefficient, z-mask) are staged in shared memory
     static constexpr size_t smem = tables + MAX_STAGED * (sizeof(Cx<double>) + 8) + (ROWS * ROWS + 1) * 4 + 12;
+    static constexpr int ECOLS = 128; // MODE 1: batch columns per CTA (blockIdx.y picks the range)
+    static constexpr size_t smem_expval = (smem + 15) / 16 * 16 + static_cast<size_t>(WARPS) * ECOLS * sizeof(Cx<double>);
     static_assert(RT % WPC == 0 && WARPS % WPC == 0, "warps must split the row tiles evenly");
 };
 
-template <int RR, int WPC, int PFD>
+// MODE 0: apply (store / accumulate).  MODE 1: expectation-value partials (PauliOp::expectation_value, PO:482-549):
+// every warp sums conj(psi) . (M_c psi) per batch column over its cosets into a private shared-memory array, the CTA
+// folds its warps at the end and writes one partial row per CTA: partials[blockIdx.x][column] (fixed order:
+// deterministic); blockIdx.y selects a range of ECOLS columns.
+template <int RR, int WPC, int PFD, int MODE>
 __global__ void __launch_bounds__(128)
-    dcoset_kernel(RcPassView<double> pass, uint32_t n_strings, uint64_t n_cosets, uint64_t rowvecs,
-                  CVec<double, 1> const *__restrict__ in, CVec<double, 1> *__restrict__ out, int beta)
+    dcoset_kernel(RcPassView<double> pass, uint32_t n_strings, uint64_t n_cosets, uint64_t rowvecs_total,
+                  CVec<double, 1> const *__restrict__ in, CVec<double, 1> *__restrict__ out, int beta,
+                  Cx<double> *__restrict__ partials, uint32_t Bpad)
 {
     using Cfg = DcosetCfg<RR, WPC>;
     constexpr int ROWS = Cfg::ROWS, CPI = Cfg::CPI, PITCH = Cfg::PITCH, RT_OWN = Cfg::RT_OWN, KB = Cfg::KB;
@@ -94,8 +101,18 @@ __global__ void __launch_bounds__(128)
     uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint32_t const cw = warp / WPC, part = warp % WPC; // coset slot of this warp, its share of the row tiles
     uint32_t const lq = lane >> 2, lr = lane & 3u;
-    double2 const *in2 = reinterpret_cast<double2 const *>(in);
+    // MODE 1 CTAs work on the column range [col0, col0 + rowvecs); the row pitch is always rowvecs_total
+    uint64_t const col0 = MODE == 1 ? static_cast<uint64_t>(blockIdx.y) * Cfg::ECOLS : 0;
+    uint64_t const rowvecs = MODE == 1 ? (rowvecs_total - col0 < Cfg::ECOLS ? rowvecs_total - col0 : Cfg::ECOLS) : rowvecs_total;
+    double2 const *in2 = reinterpret_cast<double2 const *>(in) + col0;
     double2 *out2 = reinterpret_cast<double2 *>(out);
+    Cx<double> *esm = reinterpret_cast<Cx<double> *>(dc_smem + (Cfg::smem + 15) / 16 * 16) + warp * Cfg::ECOLS;
+    if (MODE == 1)
+    {
+        for (uint32_t i = lane; i < Cfg::ECOLS; i += 32)
+            esm[i] = Cx<double>{0, 0};
+        __syncwarp();
+    }
 
     constexpr int PF = PFD; // input tiles in flight per warp (one 8-column tile of MMAs is ~270 ns, an HBM load ~800 ns)
     uint64_t const n_tiles = (rowvecs + 7) / 8;
@@ -114,7 +131,7 @@ __global__ void __launch_bounds__(128)
             for (int k = 0; k < RR; ++k)
                 if (((4 * kb + lr) >> k) & 1u)
                     comb ^= pass.basis[k];
-            rowoff[kb] = (base ^ comb) * rowvecs;
+            rowoff[kb] = (base ^ comb) * rowvecs_total;
         }
         // ---- the first PF input tiles are requested before the factor tables are built: their latency hides there
         double2 x[PF][KB];
@@ -205,7 +222,7 @@ __global__ void __launch_bounds__(128)
                 for (int k = 0; k < RR; ++k)
                     if ((lp >> k) & 1u)
                         comb ^= pass.basis[k];
-                orow[r] = (base ^ comb) * rowvecs;
+                orow[r] = (base ^ comb) * rowvecs_total;
             }
 
             // ---- sweep the batch in tiles of 8 columns through a ring of PF register buffers: the buffer a tile has
@@ -241,6 +258,48 @@ __global__ void __launch_bounds__(128)
                         for (int kb = 0; kb < KB; ++kb)
                             x[u][kb] = col < rowvecs ? in2[rowoff[kb] + col] : make_double2(0, 0);
                     }
+                    if (MODE == 1)
+                    {
+                        // e(col) += sum over this lane's rows of conj(psi(l', col)) * out(l', col); the psi values are
+                        // re-read (cache hits: the tile was just loaded), then the 8 row lanes are folded by shuffles
+                        double er[2] = {0, 0}, ei[2] = {0, 0};
+#pragma unroll
+                        for (int r = 0; r < RT_OWN; ++r)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                            {
+                                uint64_t const col = n0 + 2 * lr + c;
+                                double2 const a = col < rowvecs ? in2[orow[r] + col] : make_double2(0, 0);
+                                double const o_re = C[r][c], o_im = C[RT_OWN + r][c];
+                                er[c] = fma(a.x, o_re, er[c]);
+                                er[c] = fma(a.y, o_im, er[c]);
+                                ei[c] = fma(a.x, o_im, ei[c]);
+                                ei[c] = fma(-a.y, o_re, ei[c]);
+                            }
+#pragma unroll
+                        for (int off = 4; off < 32; off <<= 1)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                            {
+                                er[c] += __shfl_xor_sync(0xffffffffu, er[c], off);
+                                ei[c] += __shfl_xor_sync(0xffffffffu, ei[c], off);
+                            }
+                        if (lq == 0)
+                        {
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                            {
+                                uint64_t const col = n0 + 2 * lr + c;
+                                if (col < rowvecs)
+                                {
+                                    esm[col].re += er[c];
+                                    esm[col].im += ei[c];
+                                }
+                            }
+                        }
+                    }
+                    else
+                    {
                     // lane holds rows l' (real: C[r], imaginary: C[RT_OWN + r]) x columns n0 + 2*lr + {0, 1}
 #pragma unroll
                     for (int r = 0; r < RT_OWN; ++r)
@@ -280,10 +339,27 @@ __global__ void __launch_bounds__(128)
                             *dst = vb;
                         }
                     }
+                    }
                 }
             }
         }
         group_sync<WPC>(cw); // the group's tables are rebuilt by its next iteration
+    }
+    if (MODE == 1)
+    {
+        __syncthreads();
+        Cx<double> const *all = reinterpret_cast<Cx<double> const *>(dc_smem + (Cfg::smem + 15) / 16 * 16);
+        for (uint32_t i = tid; i < rowvecs; i += Cfg::NT)
+        {
+            Cx<double> sum{0, 0};
+#pragma unroll
+            for (int w = 0; w < Cfg::WARPS; ++w)
+            {
+                sum.re += all[w * Cfg::ECOLS + i].re;
+                sum.im += all[w * Cfg::ECOLS + i].im;
+            }
+            partials[static_cast<uint64_t>(blockIdx.x) * Bpad + col0 + i] = sum;
+        }
     }
 }
 

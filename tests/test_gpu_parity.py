@@ -549,7 +549,7 @@ def test_register_coset_kernels(dtype, rank, log_nt, n, B):
 
 
 @pytest.mark.parametrize("rank", [4, 5])
-@pytest.mark.parametrize("n,B", [(7, 8), (9, 34), (12, 300), (10, 9)])
+@pytest.mark.parametrize("n,B", [(7, 8), (9, 34), (12, 300), (10, 9), (8, 1100)])
 def test_dense_coset_tensor_core_kernel(rank, n, B):
     """K3d (dcoset.cuh): complex128 apply of operators with x-mask rank 4 / 5 runs as ONE FP64 tensor-core launch
     (dense coset matrix in registers as mma.sync A fragments); parity vs the oracle, accumulate, odd batch widths
@@ -576,7 +576,15 @@ def test_dense_coset_tensor_core_kernel(rank, n, B):
                             C.c_size_t(2**n), C.c_size_t(B), C.c_int(1))
     assert rc == 0
     assert rel_err(out, ORC.op_apply(strings, h, psi, out=base.copy(), par=True)) < 1e-12
-    assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi, par=True)) < 1e-12
+    l0 = ctx.launch_count
+    ev = op.expectation_value(psi)
+    assert ctx.launch_count - l0 == 2  # tensor-core kernel (MODE 1) + finaliser
+    assert rel_err(ev, ORC.op_expval(strings, h, psi, par=True)) < 1e-12
+    ev_acc = np.full(B, 1.5 - 2j)
+    rc = fp.lib.fp_op_expval(ctx._h, op._plan(np.complex128), C.c_void_p(ev_acc.ctypes.data), C.c_void_p(psi.ctypes.data),
+                             C.c_size_t(2**n), C.c_size_t(B), C.c_int(1))
+    assert rc == 0
+    assert rel_err(ev_acc - (1.5 - 2j), ev) < 1e-12
     _os.environ["FASTPAULI_DCOSET"] = "0"
     try:
         ctx0 = fp.Context(0)
