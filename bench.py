@@ -238,7 +238,22 @@ def run_extras(fp, ctx, hbm_peak: float) -> dict:
                 out_s.append("".join(t))
             return out_s
 
+        def chain(kind):  # nearest-neighbour chain Hamiltonians: low-weight x-masks of full rank (multi-pass plans)
+            out_s = []
+            for i in range(n - 1):
+                for pp in (("XX", "YY", "ZZ") if kind == "heisenberg" else ("ZZ",)):
+                    t = ["I"] * n
+                    t[i], t[i + 1] = pp[0], pp[1]
+                    out_s.append("".join(t))
+            if kind == "tfim":
+                for i in range(n):
+                    t = ["I"] * n
+                    t[i] = "X"
+                    out_s.append("".join(t))
+            return out_s
+
         cases = [("few_group_64_strings_8_xmasks", few), ("random_64_strings", rand_strings(rng, n, 64)),
+                 ("heisenberg_chain_57_strings", chain("heisenberg")), ("tfim_chain_39_strings", chain("tfim")),
                  # the same 64 strings / 8 x-masks / 8 z-variants shape when the masks are closed under XOR (all
                  # Paulis on 3 qubits): rank 3, register-resident coset kernel
                  ("dense_3local_64_strings_8_xmasks", local_dense(3)),
@@ -260,7 +275,7 @@ def run_extras(fp, ctx, hbm_peak: float) -> dict:
             res[tag] = {"ms": ms, "amp_strings_per_s": amps * len(strings) / (ms * 1e-3),
                         "algorithmic_GBps": amps * 32 / (ms * 1e-3) / 1e9,
                         "hbm_frac": amps * 32 / (ms * 1e-3) / 1e9 / hbm_peak, "x_groups": info["n_x_groups"]}
-            if tag.startswith("dense_") or tag.startswith("few_group"):
+            if tag.startswith("dense_") or tag.startswith("few_group") or "chain" in tag:
                 ev = ctx.empty((B,), DTYPE)
                 ms_e = timed_ms(fp, ctx, lambda: fp.lib.fp_op_expval(ctx._h, op._plan(DTYPE), _vp(ev.ptr), _vp(psi.ptr),
                                                                       _sz(1 << n), _sz(B), 0), 5)

@@ -356,24 +356,37 @@ __global__ void __launch_bounds__(1 << LOG_NT)
             tile[(tid + q * NT) * PITCH + j] = v;
         }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < VPT; ++k)
+    if (beta)
     {
-        uint64_t row = row_lo ^ s_comb_hi[k];
-        uint32_t l = l_lo + k * ROWS_PER_STEP;
-        Vec v = tile[l * PITCH + jv];
-        Vec *dst = &out[row * rowvecs + vcol0 + jv];
-        if (beta)
+        // accumulating pass: all VPT read-modify-write loads are issued before the first add (one round trip to
+        // memory per thread instead of VPT dependent ones)
+        Vec o[VPT];
+#pragma unroll
+        for (int k = 0; k < VPT; ++k)
+            o[k] = out[(row_lo ^ s_comb_hi[k]) * rowvecs + vcol0 + jv];
+#pragma unroll
+        for (int k = 0; k < VPT; ++k)
         {
-            Vec o = *dst;
+            uint32_t l = l_lo + k * ROWS_PER_STEP;
+            Vec v = tile[l * PITCH + jv];
 #pragma unroll
             for (int e = 0; e < EPV; ++e)
             {
-                v.e[e].re += o.e[e].re;
-                v.e[e].im += o.e[e].im;
+                v.e[e].re += o[k].e[e].re;
+                v.e[e].im += o[k].e[e].im;
             }
+            out[(row_lo ^ s_comb_hi[k]) * rowvecs + vcol0 + jv] = v;
         }
-        *dst = v;
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < VPT; ++k)
+        {
+            uint64_t row = row_lo ^ s_comb_hi[k];
+            uint32_t l = l_lo + k * ROWS_PER_STEP;
+            out[row * rowvecs + vcol0 + jv] = tile[l * PITCH + jv];
+        }
     }
     }
 }

@@ -114,6 +114,35 @@ def main():
         amps = (1 << n) * B
         print(f"{a.case}: apply {ms:.3f} ms  {amps*32/ms/1e6:.0f} GB/s | expval {ms2:.3f} ms {amps*16/ms2/1e6:.0f} GB/s "
               f"groups={op.plan_info()['n_x_groups']}")
+    elif a.case in ("heis20", "tfim20"):
+        # nearest-neighbour chain Hamiltonians on 20 qubits: x-masks of rank ~20 but weight <= 2
+        n, B = 20, a.batch or 64
+        strings, h = [], []
+        for i in range(n - 1):
+            for pp in (("XX", "YY", "ZZ") if a.case == "heis20" else ("ZZ",)):
+                t = ["I"] * n
+                t[i], t[i + 1] = pp[0], pp[1]
+                strings.append("".join(t))
+                h.append(1.0)
+        if a.case == "tfim20":
+            for i in range(n):
+                t = ["I"] * n
+                t[i] = "X"
+                strings.append("".join(t))
+                h.append(0.7)
+        h = np.array(h, dtype=np.complex128)
+        psi = ctx.uniform((1 << n, B), np.complex128)
+        op = fp.PauliOp(h, strings, ctx=ctx)
+        y = ctx.empty((1 << n, B), np.complex128)
+        ev = ctx.empty((B,), np.complex128)
+        plan = op._plan(np.complex128)
+        l0 = ctx.launch_count
+        ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
+        nl = (ctx.launch_count - l0) // (a.iters + 1)
+        ms2 = timed(ctx, lambda: fp.lib.fp_op_expval(ctx._h, plan, vp(ev.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
+        amps = (1 << n) * B
+        print(f"{a.case}: apply {ms:.3f} ms ({nl} launches) {amps*32/ms/1e6:.0f} GB/s | expval {ms2:.3f} ms "
+              f"groups={op.plan_info()['n_x_groups']} strings={len(strings)}")
     elif a.case == "cfg3":
         n, B, S = 16, a.batch or 1024, 2000
         strings = random_strings(rng, n, S, max_weight=4)
