@@ -634,7 +634,7 @@ def run_ours(args) -> None:
             cols = 16
             cpu_reference_step(be, string, n, cols)  # warm-up
             best, spent, reps = None, 0.0, 0
-            while spent < 10.0 and reps < 20:
+            while spent < 10.0 and reps < 2000:
                 dt, w = cpu_reference_step(be, string, n, cols)
                 spent += dt
                 reps += 1
