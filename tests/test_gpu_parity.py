@@ -876,3 +876,55 @@ def test_config2_full_size_sampled_rows():
                     for cc in cols])
     assert rel_err(e_id[cols].real, acc) < 1e-12
     assert np.max(np.abs(e_id.imag)) == 0.0
+
+
+@pytest.mark.parametrize("k_local", [3, 4, 5])
+def test_headline_size_dense_local_operator_sampled_rows(k_local):
+    """The headline shape at full size -- PauliOp.apply / expectation_value on 20 qubits x 64 complex128 states -- for
+    the dense k-local operators that take the register-resident (k = 3) and FP64 tensor-core (k = 4, 5) kernels:
+    sampled output rows against the closed form on regenerated inputs (counter-based generator), and the expectation
+    values of two columns against host sums of conj(psi) . (A psi) over all 2^20 rows."""
+    from fast_pauli_b200.synth import uniform_host, uniform_complex_at
+
+    ctx = fp.default_context()
+    n, B = 20, 64
+    dim = 2**n
+    rng = np.random.default_rng(50 + k_local)
+    pos = sorted(int(p) for p in rng.choice(n, size=k_local, replace=False))
+    strings = []
+    for idx in range(4**k_local):
+        t = ["I"] * n
+        for i, p_ in enumerate(pos):
+            t[p_] = "IXYZ"[(idx >> (2 * i)) & 3]
+        strings.append("".join(t))
+    h = rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))
+    psi = ctx.uniform((dim, B), np.complex128, seed=18)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    l0 = ctx.launch_count
+    out = op.apply(psi)
+    assert ctx.launch_count - l0 == 1
+    masks = [orc.masks(s) for s in strings]
+    phase = np.array([1, -1j, -1, 1j])
+    rows = [int(r) for r in rng.integers(0, dim, size=12)]
+    for i in rows:
+        expect = np.zeros((1, B), dtype=np.complex128)
+        cache = {}
+        for (x, z, ny), hs in zip(masks, h):
+            j = i ^ x
+            if j not in cache:
+                cache[j] = uniform_host((1, B), np.complex128, seed=18, first=j * B)
+            sign = -1.0 if bin(i & z).count("1") & 1 else 1.0
+            expect += (hs * phase[ny] * sign) * cache[j]
+        assert rel_err(out.get_rows(i, i + 1), expect) < 1e-12
+    ev = op.expectation_value(psi).get()
+    # expectation value of two sampled columns on the host: sum_i conj(psi_i) (A psi)_i with A psi taken from the GPU
+    # apply (already verified row-wise above) -- checks the reduction path at full size
+    cols = [0, B - 1]
+    acc = np.zeros(2, dtype=np.complex128)
+    chunk = 1 << 16
+    for r0 in range(0, dim, chunk):
+        o = out.get_rows(r0, r0 + chunk)[:, cols]
+        r = np.arange(r0, r0 + chunk, dtype=np.uint64)
+        p = np.stack([uniform_complex_at(r * np.uint64(B) + np.uint64(cc), np.complex128, 18) for cc in cols], axis=1)
+        acc += np.sum(np.conj(p) * o, axis=0)
+    assert rel_err(ev[cols], acc) < 1e-12
