@@ -323,6 +323,67 @@ def run_extras(fp, ctx, hbm_peak: float) -> dict:
     # the shapes the reference itself publishes (docs/benchmark_results/qiskit_adv.csv, measured
     # through its Python bindings on an i9-13950HX, complex128).  Here: the same calls through this repo's Python
     # classes with HOST numpy arrays (staging included) and device-resident.  Different hardware: context only.
+    # SummedPauliOp.square() at the size of the reference's examples/05_summed_pauli_op_sq.cpp: 12 qubits, all strings
+    # of weight <= 2 (631), 1000 operators, complex64 -> 46666 output strings
+    def square():
+        import itertools as it
+        import time as _t
+
+        n, K = 12, 1000
+        strings = ["I" * n]
+        for w in (1, 2):
+            combos = list(it.combinations(range(n), w))
+            for word in it.product("XYZ", repeat=w):
+                for combo in combos:
+                    t = ["I"] * n
+                    for p_, ch in zip(combo, word):
+                        t[p_] = ch
+                    strings.append("".join(t))
+        sq_strings = list(strings)
+        for w in (3, 4):
+            combos = list(it.combinations(range(n), w))
+            for word in it.product("XYZ", repeat=w):
+                for combo in combos:
+                    t = ["I"] * n
+                    for p_, ch in zip(combo, word):
+                        t[p_] = ch
+                    sq_strings.append("".join(t))
+        coeffs = (rng.uniform(-1, 1, (len(strings), K)) + 1j * rng.uniform(-1, 1, (len(strings), K))).astype(np.complex64)
+        codes, _ = fp._encode(strings)
+        sq_codes, _ = fp._encode(sq_strings)
+        out = ctx.pinned_empty((len(sq_strings), K), np.complex64)
+
+        def call():
+            rc = fp.lib.fp_sop_square(ctx._h, fp.FP_C64, n, _sz(len(strings)), _vp(codes.ctypes.data), _sz(K),
+                                      _vp(coeffs.ctypes.data), _sz(len(sq_strings)), _vp(sq_codes.ctypes.data),
+                                      _vp(out.ctypes.data))
+            if rc:
+                raise RuntimeError(fp.lib.fp_last_error().decode())
+
+        call()
+        t0 = _t.perf_counter()
+        for _ in range(3):
+            call()
+        ours = (_t.perf_counter() - t0) / 3
+        res = {"n_strings": len(strings), "n_output_strings": len(sq_strings), "n_operators": K,
+               "ours_host_to_host_ms": 1e3 * ours}
+        try:
+            from oracle import oracle as orc
+
+            be = orc.reference()
+            if be is not None:
+                be.use_all_threads()
+                t0 = _t.perf_counter()
+                ref = orc.ref_sop_square(strings, coeffs)
+                res["reference_ms"] = 1e3 * (_t.perf_counter() - t0)
+                res["reference_cores"] = be.max_threads()
+                scale = float(np.max(np.abs(ref[1])))
+                res["max_rel_err_vs_reference"] = float(np.max(np.abs(np.asarray(out) - ref[1]))) / scale
+        except Exception as e:  # the CPU comparison is optional
+            res["reference_error"] = f"{type(e).__name__}: {e}"
+        ctx.pinned_free(out)
+        return res
+
     def published():
         import time as _t
 
@@ -415,6 +476,7 @@ def run_extras(fp, ctx, hbm_peak: float) -> dict:
     ctx.set_async(False)
     guard("config1_pauli_op_apply_10q_64strings_b16_c128", cfg1)
     guard("reference_published_shapes", published)
+    guard("summed_pauli_op_square_12q_weight2_1000ops_c64", square)
     ctx.set_async(True)
     guard("pauli_op_apply_20q_b64_c128", op20)
     guard("config3_pauli_op_apply_16q_2000strings_b1024_c128", cfg3)

@@ -804,17 +804,20 @@ class SummedPauliOp:
     def square(self) -> "SummedPauliOp":
         """A_k -> A_k^2 (SPO:197-268): coefficient of string c in operator k is sum over pairs (a, b) with
         P_a P_b ~ P_c of phase(a,b) h_ak h_bk; the output string set is every string up to weight
-        min(n, 2 * max weight) in calculate_pauli_strings_max_weight order."""
+        min(n, 2 * max weight) in calculate_pauli_strings_max_weight order.  The contraction runs on the GPU
+        (fp_sop_square)."""
         from . import helpers
 
         max_w = max(sum(ch != "I" for ch in st) for st in self._strings)
         sq = [str(p) for p in helpers.calculate_pauli_strings_max_weight(self._n, min(self._n, 2 * max_w))]
-        index = {st: i for i, st in enumerate(sq)}
+        sq_codes, _ = _encode(sq)
+        ctx = self._ctx or default_context()
+        coeffs = np.ascontiguousarray(self._coeffs, dtype=np.complex128)
         out = np.zeros((len(sq), self.n_operators), dtype=np.complex128)
-        for a, sa in enumerate(self._strings):
-            for b, sb in enumerate(self._strings):
-                ph, prod = _product(sa, sb)
-                out[index[prod]] += ph * self._coeffs[a] * self._coeffs[b]
+        _check(lib.fp_sop_square(ctx._h, C.c_int(_dtype_code(np.complex128)), C.c_int(self._n),
+                                 C.c_size_t(len(self._strings)), self._codes.ctypes.data_as(C.c_void_p),
+                                 C.c_size_t(self.n_operators), coeffs.ctypes.data_as(C.c_void_p), C.c_size_t(len(sq)),
+                                 sq_codes.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
         return SummedPauliOp(sq, out, self._ctx)
 
     def __getstate__(self):

@@ -1,6 +1,6 @@
 // fast_pauli::SummedPauliOp<T> -- K operators A_k = sum_i h_ik P_i over one string set.
 // Reference API being mirrored: __summed_pauli_op.hpp:37-666 (same members, overloads and exceptions).
-// apply / apply_weighted / expectation_value run on the GPU; square / split / to_tensor are small host code.
+// apply / apply_weighted / expectation_value / square run on the GPU; split / to_tensor are small host code.
 // Unlike the reference (whose implicit copy leaves `coeffs` pointing into the source object, SPO:43-45) copies
 // re-point the mdspan at their own buffer.
 #pragma once
@@ -145,24 +145,22 @@ template <std::floating_point T> struct SummedPauliOp
     // in calculate_pauli_strings_max_weight order.
     SummedPauliOp<T> square() const
     {
+        // output string set as in the reference (SPO:205-214); the T_aij contraction (SPO:216-265) runs on the GPU
         size_t max_w = 0;
         for (auto const &ps : pauli_strings)
             max_w = std::max<size_t>(max_w, ps.weight);
         std::vector<PauliString> sq = calculate_pauli_strings_max_weight(n_qubits(), std::min(n_qubits(), 2 * max_w));
-        std::unordered_map<PauliString, size_t> index;
-        for (size_t i = 0; i < sq.size(); ++i)
-            index.emplace(sq[i], i);
-        size_t const K = n_operators(), S = n_pauli_strings();
+        size_t const K = n_operators(), S = n_pauli_strings(), n = n_qubits();
+        std::vector<uint8_t> codes(S * n), sq_codes(sq.size() * n);
+        for (size_t s = 0; s < S; ++s)
+            for (size_t q = 0; q < n; ++q)
+                codes[s * n + q] = pauli_strings[s].paulis[q].code;
+        for (size_t c = 0; c < sq.size(); ++c)
+            for (size_t q = 0; q < n; ++q)
+                sq_codes[c * n + q] = sq[c].paulis[q].code;
         std::vector<std::complex<T>> out(sq.size() * K);
-        for (size_t a = 0; a < S; ++a)
-            for (size_t b = 0; b < S; ++b)
-            {
-                auto [phase, prod] = pauli_strings[a] * pauli_strings[b];
-                size_t const c = index.at(prod);
-                std::complex<T> const ph(static_cast<T>(phase.real()), static_cast<T>(phase.imag()));
-                for (size_t k = 0; k < K; ++k)
-                    out[c * K + k] += ph * coeffs(a, k) * coeffs(b, k);
-            }
+        gpu::check(fp_sop_square(gpu::context(), gpu::dtype_of<T>(), static_cast<int>(n), S, codes.data(), K,
+                                 coeffs.data_handle(), sq.size(), sq_codes.data(), out.data()));
         return SummedPauliOp<T>(sq, out);
     }
     std::vector<PauliOp<T>> split() const

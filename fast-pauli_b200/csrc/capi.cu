@@ -24,6 +24,7 @@
 #include "dcoset.cuh"
 #include "wtile.cuh"
 #include "etile.cuh"
+#include "square.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "pack.hpp"
@@ -2480,3 +2481,153 @@ extern "C"
     FP_DEFINE_ONESHOT(c64, float, FP_C64)
 
 } // extern "C"
+
+namespace
+{
+// SummedPauliOp::square() on the device (square.cuh): host side = duplicate merge, partner table, staging
+template <typename T>
+int run_sop_square(fp_ctx *ctx, int n, size_t S, uint8_t const *codes, size_t K, std::complex<T> const *coeffs,
+                   size_t n_sq, uint8_t const *sq_codes, std::complex<T> *coeffs_sq)
+{
+    // ---- merge duplicate input strings (sum of their coefficient rows: the same operators A_k)
+    std::map<std::pair<uint64_t, uint64_t>, uint32_t> uniq;
+    std::vector<uint64_t> xs, zs;
+    std::vector<std::complex<T>> h;
+    for (size_t s = 0; s < S; ++s)
+    {
+        StringMasks mk = make_masks(n, codes + s * static_cast<size_t>(n));
+        auto key = std::make_pair(mk.x, mk.z);
+        auto it = uniq.find(key);
+        uint32_t u;
+        if (it == uniq.end())
+        {
+            u = static_cast<uint32_t>(xs.size());
+            uniq.emplace(key, u);
+            xs.push_back(mk.x);
+            zs.push_back(mk.z);
+            h.resize(h.size() + K, std::complex<T>(0));
+        }
+        else
+            u = it->second;
+        for (size_t k = 0; k < K; ++k)
+            h[static_cast<size_t>(u) * K + k] += coeffs[s * K + k];
+    }
+    uint32_t const Su = static_cast<uint32_t>(xs.size());
+    uint32_t tsize = 16;
+    while (tsize < 2 * Su)
+        tsize <<= 1;
+    std::vector<SqEntry> table(tsize, SqEntry{0, 0, 0xffffffffu, 0, 0});
+    auto host_hash = [](uint64_t x, uint64_t z) {
+        uint64_t v = (x * 0x9E3779B97F4A7C15ull) ^ (z * 0xC2B2AE3D27D4EB4Full);
+        v ^= v >> 29;
+        v *= 0xBF58476D1CE4E5B9ull;
+        v ^= v >> 32;
+        return static_cast<uint32_t>(v);
+    };
+    for (uint32_t u = 0; u < Su; ++u)
+    {
+        uint32_t slot = host_hash(xs[u], zs[u]) & (tsize - 1);
+        while (table[slot].idx != 0xffffffffu)
+            slot = (slot + 1) & (tsize - 1);
+        table[slot] = SqEntry{xs[u], zs[u], u, static_cast<uint32_t>(__builtin_popcountll(xs[u] & zs[u])) & 3u, 0};
+    }
+    std::vector<uint64_t> xq(n_sq), zq(n_sq);
+    for (size_t c = 0; c < n_sq; ++c)
+    {
+        StringMasks mk = make_masks(n, sq_codes + c * static_cast<size_t>(n));
+        xq[c] = mk.x;
+        zq[c] = mk.z;
+    }
+    uint64_t *d_xs = nullptr, *d_zs = nullptr, *d_xq = nullptr, *d_zq = nullptr;
+    SqEntry *d_table = nullptr;
+    Cx<T> *d_h = nullptr, *d_out = nullptr;
+    std::vector<void *> allocs;
+    auto cleanup = [&]() {
+        for (void *a : allocs)
+            cudaFree(a);
+    };
+    int rc = upload_vec(&d_xs, xs);
+    if (rc == FP_OK) { allocs.push_back(d_xs); rc = upload_vec(&d_zs, zs); }
+    if (rc == FP_OK) { allocs.push_back(d_zs); rc = upload_vec(&d_xq, xq); }
+    if (rc == FP_OK) { allocs.push_back(d_xq); rc = upload_vec(&d_zq, zq); }
+    if (rc == FP_OK) { allocs.push_back(d_zq); rc = upload_vec(&d_table, table); }
+    if (rc == FP_OK)
+    {
+        allocs.push_back(d_table);
+        std::vector<Cx<T>> hc(h.size());
+        for (size_t i = 0; i < h.size(); ++i)
+            hc[i] = Cx<T>{h[i].real(), h[i].imag()};
+        rc = upload_vec(&d_h, hc);
+    }
+    if (rc == FP_OK)
+    {
+        allocs.push_back(d_h);
+        // the (large) result lives in the context's grow-only scratch: no cudaMalloc / cudaFree of hundreds of MB per call
+        rc = ctx->work_b.ensure(std::max<size_t>(16, n_sq * K * sizeof(Cx<T>)));
+        if (rc == FP_OK)
+            d_out = static_cast<Cx<T> *>(ctx->work_b.p);
+    }
+    if (rc != FP_OK)
+    {
+        cleanup();
+        return rc;
+    }
+    uint32_t const kmax = kSqMaxKChunks * kSqThreads;
+    for (size_t k0 = 0; k0 < K; k0 += kmax)
+    {
+        uint32_t const kn = static_cast<uint32_t>(std::min<size_t>(kmax, K - k0));
+        sop_square_kernel<T><<<static_cast<unsigned>(n_sq), kSqThreads, 0, ctx->stream>>>(
+            Su, d_xs, d_zs, d_table, tsize - 1, d_h + k0, static_cast<uint32_t>(K), kn, d_xq, d_zq, d_out + k0);
+        ctx->launches++;
+    }
+    cudaError_t e = cudaMemcpyAsync(coeffs_sq, d_out, n_sq * K * sizeof(Cx<T>), cudaMemcpyDefault, ctx->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess)
+    {
+        (void)cudaGetLastError();
+        return set_err(FP_CUDA_ERROR, std::string("square: ") + cudaGetErrorString(e));
+    }
+    return FP_OK;
+}
+} // namespace
+
+extern "C"
+{
+    int fp_sop_square(fp_ctx *ctx, int dtype, int n_qubits, size_t n_strings, const uint8_t *codes, size_t n_operators,
+                      const void *coeffs, size_t n_sq, const uint8_t *sq_codes, void *coeffs_sq)
+    {
+        if (!ctx || !codes || !coeffs || !sq_codes || !coeffs_sq)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        FP_TRY(check_dtype(dtype));
+        if (n_qubits < 1 || n_qubits > 62)
+            return set_err(FP_INVALID_ARGUMENT, "n_qubits must be in [1, 62]");
+        if (n_strings == 0 || n_operators == 0 || n_sq == 0)
+            return FP_OK;
+        if (n_sq > 0x7fffffffull || n_strings > 0x7ffffffeull)
+            return set_err(FP_UNSUPPORTED, "too many strings");
+        if (is_device_ptr(coeffs))
+            return set_err(FP_INVALID_ARGUMENT, "square: coefficients are host data (operator metadata)");
+        DeviceGuard g(ctx->device);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        try
+        {
+            if (dtype == FP_C128)
+                return run_sop_square<double>(ctx, n_qubits, n_strings, codes, n_operators,
+                                              static_cast<std::complex<double> const *>(coeffs), n_sq, sq_codes,
+                                              static_cast<std::complex<double> *>(coeffs_sq));
+            return run_sop_square<float>(ctx, n_qubits, n_strings, codes, n_operators,
+                                         static_cast<std::complex<float> const *>(coeffs), n_sq, sq_codes,
+                                         static_cast<std::complex<float> *>(coeffs_sq));
+        }
+        catch (std::invalid_argument const &e)
+        {
+            return set_err(FP_INVALID_ARGUMENT, e.what());
+        }
+        catch (std::bad_alloc const &)
+        {
+            return set_err(FP_OUT_OF_MEMORY, "host allocation failed");
+        }
+    }
+}

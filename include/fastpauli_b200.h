@@ -161,6 +161,14 @@ extern "C"
     /* SummedPauliOp::expectation_value (SPO:520-614): out is (n_operators, n_states) complex. Errors: SPO:539-558. */
     int fp_sop_expval(fp_ctx *ctx, const fp_sop *sop, void *out, const void *in, size_t dim, size_t n_states,
                       int accumulate);
+    /* SummedPauliOp::square() (SPO:197-268), the coefficient contraction of A_k -> A_k^2 on the device:
+     * coeffs_sq(c, k) = sum over ordered pairs (a, b) with P_a P_b = phase P_c of phase * coeffs(a, k) * coeffs(b, k)
+     * for every output string c of sq_codes (n_sq x n_qubits codes; the caller enumerates the reference's output set,
+     * calculate_pauli_strings_max_weight(n, min(n, 2 * max weight)), in its own language).  coeffs is host memory
+     * (n_strings, n_operators) row-major; coeffs_sq (n_sq, n_operators) may be host or device memory and is
+     * overwritten.  Duplicate input strings are merged first (same operators). */
+    int fp_sop_square(fp_ctx *ctx, int dtype, int n_qubits, size_t n_strings, const uint8_t *codes, size_t n_operators,
+                      const void *coeffs, size_t n_sq, const uint8_t *sq_codes, void *coeffs_sq);
     /* Select the coefficient-contraction engine of apply_weighted / expectation_value for FP_C64 plans:
      * 0 = FP32 SIMT, 1 = tcgen05 3xTF32 tensor-core path (default when available). */
     int fp_ctx_set_tensor_core(fp_ctx *ctx, int enable);

@@ -220,6 +220,30 @@ _port: Backend | None = None
 _ref: Backend | None | bool = False
 
 
+def ref_sop_square(strings: Sequence[str], coeffs: np.ndarray) -> tuple[list[str], np.ndarray] | None:
+    """SummedPauliOp::square() of the compiled reference (SPO:197-268): (output strings, coeffs (n_sq, K)); None when
+    the reference library is not available (the plain-C port has no square)."""
+    be = reference()
+    if be is None or not hasattr(be.lib, "ref_sop_square_c128"):
+        return None
+    coeffs = np.ascontiguousarray(coeffs)
+    sfx, real = Backend._sfx(coeffs.dtype)
+    codes, n = encode_strings(strings)
+    S, K = coeffs.shape
+    max_w = max(sum(ch != "I" for ch in s) for s in strings)
+    from math import comb
+
+    cap = sum(comb(n, w) * 3**w for w in range(min(n, 2 * max_w) + 1))
+    sq_codes = np.zeros((cap, n), dtype=np.uint8)
+    out = np.zeros((cap, K), dtype=coeffs.dtype)
+    n_sq = C.c_size_t(0)
+    be._call("sop_square_" + sfx, C.c_int(n), C.c_size_t(S), Backend._p(codes), C.c_size_t(K), Backend._p(coeffs),
+             C.c_size_t(cap), C.byref(n_sq), Backend._p(sq_codes), Backend._p(out))
+    letters = np.array(list("IXYZ"))
+    strs = ["".join(letters[row]) for row in sq_codes[: n_sq.value]]
+    return strs, out[: n_sq.value]
+
+
 def port() -> Backend:
     """The plain-C restatement (always available; compiled on demand)."""
     global _port

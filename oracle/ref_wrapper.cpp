@@ -249,6 +249,29 @@ int sop_expval(int n, size_t S, uint8_t const *codes, size_t K, T const *coeffs,
             op.expectation_value(std::execution::seq, o, i);
     });
 }
+// SummedPauliOp::square() of the reference (SPO:197-268): output strings as codes + coefficients (n_sq, K) row-major
+template <typename T>
+int sop_square(int n, size_t S, uint8_t const *codes, size_t K, T const *coeffs, size_t cap, size_t *n_sq,
+               uint8_t *sq_codes, T *coeffs_sq)
+{
+    return guarded([&] {
+        auto op = make_sop<T>(n, S, codes, K, coeffs);
+        auto sq = op.square();
+        *n_sq = sq.n_pauli_strings();
+        if (sq.n_pauli_strings() > cap)
+            throw std::invalid_argument("square: output capacity too small");
+        for (size_t c = 0; c < sq.n_pauli_strings(); ++c)
+        {
+            for (int q = 0; q < n; ++q)
+                sq_codes[c * static_cast<size_t>(n) + q] = sq.pauli_strings[c].paulis[q].code;
+            for (size_t k = 0; k < K; ++k)
+            {
+                coeffs_sq[2 * (c * K + k)] = sq.coeffs(c, k).real();
+                coeffs_sq[2 * (c * K + k) + 1] = sq.coeffs(c, k).imag();
+            }
+        }
+    });
+}
 } // namespace
 
 extern "C"
@@ -318,4 +341,15 @@ extern "C"
 
     FP_REF_STAMP(c128, double)
     FP_REF_STAMP(c64, float)
+
+    int ref_sop_square_c128(int n, size_t S, uint8_t const *codes, size_t K, double const *coeffs, size_t cap,
+                            size_t *n_sq, uint8_t *sq_codes, double *coeffs_sq)
+    {
+        return sop_square<double>(n, S, codes, K, coeffs, cap, n_sq, sq_codes, coeffs_sq);
+    }
+    int ref_sop_square_c64(int n, size_t S, uint8_t const *codes, size_t K, float const *coeffs, size_t cap,
+                           size_t *n_sq, uint8_t *sq_codes, float *coeffs_sq)
+    {
+        return sop_square<float>(n, S, codes, K, coeffs, cap, n_sq, sq_codes, coeffs_sq);
+    }
 }

@@ -615,6 +615,61 @@ def test_register_coset_default_path_headline_shape():
     assert rel_err(opd.expectation_value(psi), ORC.op_expval(diag, hd, psi, par=True)) < 1e-12
 
 
+# ------------------------------------------------------------------ K8: SummedPauliOp::square on the device
+def _square_host(strings, coeffs, sq_strings):
+    """Host restatement of SPO:216-265: T_aij by pairwise string products, then the contraction."""
+    index = {s: i for i, s in enumerate(sq_strings)}
+    out = np.zeros((len(sq_strings), coeffs.shape[1]), dtype=np.complex128)
+    for a, sa in enumerate(strings):
+        for b, sb in enumerate(strings):
+            ph, prod = fp._product(sa, sb)
+            out[index[prod]] += ph * coeffs[a].astype(np.complex128) * coeffs[b].astype(np.complex128)
+    return out
+
+
+@pytest.mark.parametrize("K", [1, 5, 150])
+def test_summed_pauli_op_square(K):
+    """square(): the dense definition A_k^2 on a small register (T_SPO:411-470), and the reference's pairwise
+    algorithm restated on the host for weight <= 2 strings on 5 qubits with duplicates, through the Python class
+    (complex128) and the raw ABI (complex64)."""
+    import ctypes as C
+
+    rng = np.random.default_rng(70 + K)
+    strings = [str(p) for p in fp.helpers.calculate_pauli_strings_max_weight(3, 2)]
+    coeffs = rng.uniform(-1, 1, (len(strings), K)) + 1j * rng.uniform(-1, 1, (len(strings), K))
+    sop = fp.SummedPauliOp(strings, coeffs)
+    dense = sop.to_tensor()
+    sq = sop.square()
+    np.testing.assert_allclose(sq.to_tensor(), np.einsum("kij,kjl->kil", dense, dense), atol=1e-11)
+
+    n = 5
+    strings = [str(p) for p in fp.helpers.calculate_pauli_strings_max_weight(n, 2)]
+    strings = [strings[i] for i in rng.permutation(len(strings))[:60]] + [strings[3], strings[3]]  # duplicates
+    coeffs = rng.uniform(-1, 1, (len(strings), K)) + 1j * rng.uniform(-1, 1, (len(strings), K))
+    sop = fp.SummedPauliOp(strings, coeffs)
+    sq = sop.square()
+    sq_strings = sq.pauli_strings_as_str
+    assert sq_strings == [str(p) for p in fp.helpers.calculate_pauli_strings_max_weight(n, 4)]
+    ref = _square_host(strings, coeffs, sq_strings)
+    got = np.asarray(sq.coeffs).T  # the getter returns (n_operators, n_strings) like the reference (B_SPO:113-135)
+    assert rel_err(got, ref) < 1e-12
+    ref_lib = orc.ref_sop_square(strings, coeffs)  # the unmodified reference, when its compiled library travelled
+    if ref_lib is not None:
+        assert ref_lib[0] == sq_strings
+        assert rel_err(got, ref_lib[1]) < 1e-12
+    # complex64 through the raw ABI
+    ctx = fp.default_context()
+    codes, _ = fp._encode(strings)
+    sq_codes, _ = fp._encode(sq_strings)
+    c32 = np.ascontiguousarray(coeffs.astype(np.complex64))
+    out32 = np.zeros((len(sq_strings), K), dtype=np.complex64)
+    rc = fp.lib.fp_sop_square(ctx._h, C.c_int(0), C.c_int(n), C.c_size_t(len(strings)), C.c_void_p(codes.ctypes.data),
+                              C.c_size_t(K), C.c_void_p(c32.ctypes.data), C.c_size_t(len(sq_strings)),
+                              C.c_void_p(sq_codes.ctypes.data), C.c_void_p(out32.ctypes.data))
+    assert rc == 0, fp.lib.fp_last_error()
+    assert rel_err(out32, _square_host(strings, c32, sq_strings)) < 1e-5
+
+
 # ------------------------------------------------------------------ K5: tcgen05 3xTF32 contraction engine
 @pytest.mark.parametrize("M,N,Kd,split", [(128, 128, 32, 1), (256, 384, 64, 1), (200, 100, 36, 1), (20000 // 8, 512, 64, 1),
                                           (128, 256, 1000, 4), (130, 4100, 12, 1), (64, 8, 8, 1)])
