@@ -63,6 +63,21 @@ int set_err(int code, std::string msg)
             return rc_;                                                                                                \
     } while (0)
 
+// cudaFuncSetAttribute is per device: remember per template instance (one static PerDevice each) which devices of
+// this process have been configured (a host may hold one context per GPU)
+struct PerDevice
+{
+    uint64_t mask = 0;
+    bool done(int device) const
+    {
+        return (mask >> (device & 63)) & 1ull;
+    }
+    void set(int device)
+    {
+        mask |= 1ull << (device & 63);
+    }
+};
+
 struct Scratch
 {
     void *p = nullptr;
@@ -672,12 +687,12 @@ int launch_coset_pass(fp_ctx *ctx, CosetPassView<T> const &view, int n_qubits, u
 {
     using Cfg = CosetCfg<LOG_TWC, LOG_NT, VPT>;
     size_t const smem = coset_smem_bytes<T, LOG_TWC, LOG_NT, VPT>();
-    static bool configured = false; // per template instance
-    if (!configured)
+    static PerDevice configured; // per template instance
+    if (!configured.done(ctx->device))
     {
         FP_CU(cudaFuncSetAttribute(coset_kernel<T, EPV, LOG_TWC, LOG_NT, MODE, VPT>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        configured = true;
+        configured.set(ctx->device);
     }
     uint32_t const nct = static_cast<uint32_t>(rowvecs >> LOG_TWC);
     uint64_t const grid = (1ull << (n_qubits - Cfg::R)) * nct;
@@ -849,12 +864,12 @@ int launch_rcoset(fp_ctx *ctx, RcPassView<T> const &view, uint64_t n_cosets, uin
                   uint32_t log2p, uint32_t nct, uint64_t n_blocks, uint32_t iters, size_t smem, void const *in, void *out, int beta,
                   void *partials, uint32_t Bpad)
 {
-    static size_t configured = 48 * 1024; // per template instance
-    if (smem > configured)
+    static PerDevice configured; // per template instance; try_rcoset never asks for more than 64 KiB
+    if (!configured.done(ctx->device))
     {
         FP_CU(cudaFuncSetAttribute(rcoset_kernel<T, EPV, RR, LOG_NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
-        configured = smem;
+                                   64 * 1024));
+        configured.set(ctx->device);
     }
     rcoset_kernel<T, EPV, RR, LOG_NT, MODE><<<static_cast<unsigned>(n_blocks * nct), 1 << LOG_NT, smem, ctx->stream>>>(
         view, n_cosets, rowvecs, log2tw, log2p, nct, iters, static_cast<CVec<T, EPV> const *>(in),
@@ -871,13 +886,15 @@ int launch_dcoset(fp_ctx *ctx, RcPassView<double> const &view, uint32_t n_string
     using Cfg = DcosetCfg<RR, WPC>;
     constexpr size_t smem = MODE == 1 ? Cfg::smem_expval : Cfg::smem;
     static int resident = 0; // CTAs per SM (per template instance): the kernel is persistent
-    if (!resident)
+    static PerDevice configured;
+    if (!configured.done(ctx->device))
     {
         FP_CU(cudaFuncSetAttribute(dcoset_kernel<RR, WPC, PFD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
         int nb = 0;
         FP_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dcoset_kernel<RR, WPC, PFD, MODE>, Cfg::NT, smem));
         resident = std::max(1, nb);
+        configured.set(ctx->device);
     }
     uint64_t const sets = (n_cosets + Cfg::CPI - 1) / Cfg::CPI;
     unsigned const ny = MODE == 1 ? static_cast<unsigned>((rowvecs + Cfg::ECOLS - 1) / Cfg::ECOLS) : 1u;
@@ -1995,26 +2012,26 @@ int launch_wtile(fp_ctx *ctx, CosetPassView<T> const &view, uint64_t rowvecs, vo
                  T const *Wre, T const *Wim, uint64_t B)
 {
     constexpr size_t smem = WtileSmem<LOG_NT>::bytes;
-    static bool configured = false;
+    static PerDevice configured;
     FP_TRY(check_grid(rowvecs));
     if constexpr (sizeof(T) == 4)
     {
-        if (!configured)
+        if (!configured.done(ctx->device))
         {
             FP_CU(cudaFuncSetAttribute(wtile_kernel<LOG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-            configured = true;
+            configured.set(ctx->device);
         }
         wtile_kernel<LOG_NT><<<static_cast<unsigned>(rowvecs), 1 << LOG_NT, smem, ctx->stream>>>(
             view, rowvecs, static_cast<CVec<float, 2> const *>(in), static_cast<CVec<float, 2> *>(out), beta, Wre, Wim, B);
     }
     else
     {
-        if (!configured)
+        if (!configured.done(ctx->device))
         {
             FP_CU(cudaFuncSetAttribute(wtile_f64_kernel<LOG_NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem)));
-            configured = true;
+            configured.set(ctx->device);
         }
         wtile_f64_kernel<LOG_NT><<<static_cast<unsigned>(rowvecs), 1 << LOG_NT, smem, ctx->stream>>>(
             view, rowvecs, static_cast<CVec<double, 1> const *>(in), static_cast<CVec<double, 1> *>(out), beta, Wre, Wim,
@@ -2127,24 +2144,24 @@ int run_sop_expval(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, ui
         while (rowvecs * splits < static_cast<uint64_t>(ctx->sm_count) * 2 && splits * 8 < op.n_chunks)
             splits *= 2;
         size_t const smem = (static_cast<size_t>(1) << sop->n_qubits) * 16;
-        static bool configured = false;
-        if (!configured)
+        static PerDevice configured;
+        if (!configured.done(ctx->device))
         {
             FP_CU(cudaFuncSetAttribute(sop_expval_tile_kernel<T, EPV_FULL, kPairMS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-            configured = true;
+            configured.set(ctx->device);
         }
         bool launched = false;
         if (ctx->etile && sop->n_qubits >= 9 && rowvecs <= 0x7fffffffull)
         {
             // K4c (etile.cuh): planar pair tile / packed FP32 (complex64) or FP64 (complex128), compile-time sign patterns
             using P = typename std::conditional<sizeof(T) == 4, EtF32, EtF64>::type;
-            static bool configured2 = false;
-            if (!configured2)
+            static PerDevice configured2;
+            if (!configured2.done(ctx->device))
             {
                 FP_CU(cudaFuncSetAttribute(sop_expval_tile2_kernel<P, kPairMS>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-                configured2 = true;
+                configured2.set(ctx->device);
             }
             dim3 grid(static_cast<unsigned>(rowvecs), splits);
             sop_expval_tile2_kernel<P, kPairMS><<<grid, kThreads, smem, ctx->stream>>>(

@@ -245,15 +245,22 @@ inline bool gemm_tc_supported(uint32_t M, uint64_t N, uint32_t Kd, uint32_t spli
 inline int gemm_tc_3xtf32(cudaStream_t stream, float const *A, float const *B, float *C, uint32_t M, uint64_t N,
                           uint32_t Kd, uint32_t splitK, uint32_t kchunk)
 {
-    static bool configured = false, ok = true;
-    if (!configured)
+    // the attribute is per device: one bit per device of this process
+    static uint64_t configured = 0, failed = 0;
+    int dev = 0;
+    (void)cudaGetDevice(&dev);
+    uint64_t const bit = 1ull << (dev & 63);
+    if (!(configured & bit))
     {
-        ok = cudaFuncSetAttribute(tc::gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(tc::kSmemBytes)) == cudaSuccess;
-        if (!ok)
+        if (cudaFuncSetAttribute(tc::gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(tc::kSmemBytes)) != cudaSuccess)
+        {
             (void)cudaGetLastError();
-        configured = true;
+            failed |= bit;
+        }
+        configured |= bit;
     }
+    bool const ok = !(failed & bit);
     if (!ok || (reinterpret_cast<uintptr_t>(A) % 16) != 0 || (splitK > 1 && kchunk % tc::BK != 0))
         return 1;
     dim3 grid(static_cast<unsigned>((N + tc::BN - 1) / tc::BN), (M + tc::BM - 1) / tc::BM, splitK);

@@ -983,3 +983,34 @@ def test_headline_size_dense_local_operator_sampled_rows(k_local):
         p = np.stack([uniform_complex_at(r * np.uint64(B) + np.uint64(cc), np.complex128, 18) for cc in cols], axis=1)
         acc += np.sum(np.conj(p) * o, axis=0)
     assert rel_err(ev[cols], acc) < 1e-12
+
+
+def test_two_devices_in_one_process():
+    """One context per GPU in a single process: every kernel family that needs opt-in shared memory must be configured
+    on each device it runs on (cudaFuncSetAttribute is per device).  Skipped on single-GPU boxes."""
+    import ctypes as C
+
+    cnt = C.c_int(0)
+    assert fp.lib.fp_device_count(C.byref(cnt)) == 0
+    if cnt.value < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(5)
+    n, B = 12, 16
+    for dev in (1, 0, 1):
+        ctx = fp.Context(dev)
+        for rank, S in ((3, 20), (4, 40), (5, 80), (9, 60)):
+            strings = _span_strings(rng, n, rank, S)
+            h = rand_states(rng, S, None) * 2 - (1 + 1j)
+            psi = rand_states(rng, 2**n, B)
+            op = fp.PauliOp(h, strings, ctx=ctx)
+            assert rel_err(op.apply(psi), ORC.op_apply(strings, h, psi, par=True)) < 1e-12
+            assert rel_err(op.expectation_value(psi), ORC.op_expval(strings, h, psi, par=True)) < 1e-12
+        strings = rand_strings(rng, n, 200)
+        for dtype in DTYPES:
+            hk = (rand_states(rng, 200, 3, dtype) * 2 - (1 + 1j)).astype(dtype)
+            psi = rand_states(rng, 2**n, B, dtype)
+            data = rng.random((3, B)).astype(np.float64 if dtype == np.complex128 else np.float32)
+            sop = fp.SummedPauliOp(strings, hk, ctx=ctx)
+            up = (hk.astype(np.complex128), psi.astype(np.complex128))
+            assert rel_err(sop.apply_weighted(psi, data), ORC.sop_apply_weighted(strings, up[0], up[1], data.astype(np.float64))) < tol(dtype)
+            assert rel_err(sop.expectation_value(psi), ORC.sop_expval(strings, up[0], up[1])) < tol(dtype)
