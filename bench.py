@@ -523,6 +523,8 @@ def run_ours(args) -> None:
 
     fp = load_package()  # raises ImportError if the CUDA extension is missing: no fallback
     ctx = fp.Context(local_rank)
+    # one process per GPU: keep the process and its pinned buffers on the GPU's NUMA node (e2e leg)
+    numa_node = ctx.bind_host_to_gpu_numa() if world > 1 else None
     pk = peaks()
 
     n, B = N_QUBITS, BATCH
@@ -653,6 +655,7 @@ def run_ours(args) -> None:
             dt = float(t.item())
         e2e = {"value": world * 2.0 * dim * B * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * h_in.nbytes,
                "d2h_bytes_per_step": h_out.nbytes + h_ev.nbytes, "steps": Ke, "ms_per_step": 1e3 * dt / Ke,
+               "host_numa_node_rank0": numa_node,
                "path": "fp_string_apply + fp_string_expval with pinned host pointers: apply streams the batch through "
                        "the GPU in 32 MiB row blocks (upload j+1 | kernel j | download j-1 on two copy engines), "
                        "expectation_value uploads with the copy engine and reduces on the device"}

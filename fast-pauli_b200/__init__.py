@@ -154,6 +154,31 @@ class Context:
         shape (2^log_twc vectors per row segment, 2^log_nt threads per CTA)."""
         _check(lib.fp_ctx_set_coset(self._h, C.c_int(mode), C.c_int(log_twc), C.c_int(log_nt)))
 
+    def bind_host_to_gpu_numa(self) -> int | None:
+        """Pin this process (and therefore the pinned host buffers it allocates from now on) to the NUMA node of the
+        context's GPU; returns the node, or None when the topology is unknown.  With one process per GPU this keeps
+        host<->device copies off the inter-socket link."""
+        buf = C.create_string_buffer(32)
+        _check(lib.fp_ctx_pci_bus_id(self._h, buf, C.c_int(32)))
+        bus = buf.value.decode().lower()
+        try:
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node = int(f.read().strip())
+            if node < 0:
+                return None
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus: set[int] = set()
+                for part in f.read().strip().split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+            allowed = cpus & set(os.sched_getaffinity(0))
+            if not allowed:
+                return None
+            os.sched_setaffinity(0, allowed)
+            return node
+        except (OSError, ValueError):
+            return None
+
     def set_pipeline(self, enable: bool = True, min_bytes: int = 0, chunk_bytes: int = 0) -> None:
         """Chunked upload / kernel / download pipeline of PauliString.apply on host arrays (0 keeps a size)."""
         _check(lib.fp_ctx_set_pipeline(self._h, C.c_int(bool(enable)), C.c_size_t(min_bytes), C.c_size_t(chunk_bytes)))

@@ -1477,6 +1477,14 @@ extern "C"
         return FP_OK;
     }
 
+    int fp_ctx_pci_bus_id(const fp_ctx *ctx, char *buf, int len)
+    {
+        if (!ctx || !buf || len < 16)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer or buffer shorter than 16 bytes");
+        FP_CU(cudaDeviceGetPCIBusId(buf, len, ctx->device));
+        return FP_OK;
+    }
+
     int fp_ctx_set_stream(fp_ctx *ctx, void *cuda_stream, int external)
     {
         if (!ctx)

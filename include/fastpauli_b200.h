@@ -72,6 +72,9 @@ extern "C"
     int fp_ctx_device(const fp_ctx *ctx, int *device);
     /* external != 0: run on exactly this caller-owned cudaStream_t (e.g. PyTorch's current stream; 0 / NULL is the
      * legacy default stream); external == 0 restores the context's own non-blocking stream. */
+    /* PCI bus id of the context's GPU ("0000:1b:00.0"; buf >= 16 bytes): lets a multi-GPU host place each process and
+     * its pinned buffers on the NUMA node its GPU hangs off (/sys/bus/pci/devices/<id>/numa_node). */
+    int fp_ctx_pci_bus_id(const fp_ctx *ctx, char *buf, int len);
     int fp_ctx_set_stream(fp_ctx *ctx, void *cuda_stream, int external);
     int fp_ctx_set_async(fp_ctx *ctx, int async);
     int fp_ctx_sync(fp_ctx *ctx);
