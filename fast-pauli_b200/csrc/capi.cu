@@ -2016,12 +2016,11 @@ int sop_check(fp_ctx *ctx, fp_sop const *sop)
 
 // K6b (wtile.cuh): whole state column (pair) in shared memory; complex64 (packed FP32) or complex128, 11-12 qubits
 template <typename T, int LOG_NT>
-int launch_wtile(fp_ctx *ctx, CosetPassView<T> const &view, uint64_t rowvecs, void const *in, void *out, int beta,
-                 T const *Wre, T const *Wim, uint64_t B)
+int launch_wtile(fp_ctx *ctx, CosetPassView<T> const &view, uint64_t rowvecs, uint64_t grid, void const *in, void *out,
+                 int beta, T const *Wre, T const *Wim, uint64_t B)
 {
     constexpr size_t smem = WtileSmem<LOG_NT>::bytes;
     static PerDevice configured;
-    FP_TRY(check_grid(rowvecs));
     if constexpr (sizeof(T) == 4)
     {
         if (!configured.done(ctx->device))
@@ -2030,7 +2029,7 @@ int launch_wtile(fp_ctx *ctx, CosetPassView<T> const &view, uint64_t rowvecs, vo
                                        static_cast<int>(smem)));
             configured.set(ctx->device);
         }
-        wtile_kernel<LOG_NT><<<static_cast<unsigned>(rowvecs), 1 << LOG_NT, smem, ctx->stream>>>(
+        wtile_kernel<LOG_NT><<<static_cast<unsigned>(grid), 1 << LOG_NT, smem, ctx->stream>>>(
             view, rowvecs, static_cast<CVec<float, 2> const *>(in), static_cast<CVec<float, 2> *>(out), beta, Wre, Wim, B);
     }
     else
@@ -2041,7 +2040,7 @@ int launch_wtile(fp_ctx *ctx, CosetPassView<T> const &view, uint64_t rowvecs, vo
                                        static_cast<int>(smem)));
             configured.set(ctx->device);
         }
-        wtile_f64_kernel<LOG_NT><<<static_cast<unsigned>(rowvecs), 1 << LOG_NT, smem, ctx->stream>>>(
+        wtile_f64_kernel<LOG_NT><<<static_cast<unsigned>(grid), 1 << LOG_NT, smem, ctx->stream>>>(
             view, rowvecs, static_cast<CVec<double, 1> const *>(in), static_cast<CVec<double, 1> *>(out), beta, Wre, Wim,
             B);
     }
@@ -2055,21 +2054,29 @@ int try_wtile(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
 {
     *used = false;
     constexpr int EPV = sizeof(T) == 4 ? 2 : 1;
-    if (!ctx->wtile || ctx->coset_mode != 1 || ctx->coset_log_twc >= 0 || (n_qubits != 11 && n_qubits != 12) ||
+    if (!ctx->wtile || ctx->coset_mode != 1 || ctx->coset_log_twc >= 0 || n_qubits < 11 ||
         dim != (1ull << n_qubits) || pick_epv<T>(in, out, B) != EPV)
         return FP_OK;
+    if (n_qubits > 12 && op.host.gx.size() > 20000)
+        return FP_OK; // pass planning is quadratic in the number of x-groups
+    int const rank = std::min(n_qubits, 12);
     std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
-    FP_TRY(get_coset_plan<T>(op, n_qubits, n_qubits, 2, &passes));
-    if (passes->size() != 1)
+    FP_TRY(get_coset_plan<T>(op, n_qubits, rank, 2, &passes));
+    // every pass re-streams the batch: only worth it while passes << groups
+    if (passes->size() > 1 && passes->size() * 3 > op.host.gx.size())
         return FP_OK;
-    CosetPassView<T> const &view = (*passes)[0].view;
-    for (int k = 0; k < n_qubits; ++k)
-        if (view.basis[k] != (1ull << k))
-            return FP_OK; // cannot happen for a full-rank reduced basis; the kernel relies on local row == row
-    if (n_qubits == 12)
-        FP_TRY((launch_wtile<T, 9>(ctx, view, B / EPV, in, out, beta, Wre, Wim, B)));
-    else
-        FP_TRY((launch_wtile<T, 8>(ctx, view, B / EPV, in, out, beta, Wre, Wim, B)));
+    uint64_t const rowvecs = B / EPV;
+    uint64_t const grid = (1ull << (n_qubits - rank)) * rowvecs;
+    FP_TRY(check_grid(grid));
+    for (size_t p = 0; p < passes->size(); ++p)
+    {
+        CosetPassView<T> const &view = (*passes)[p].view;
+        int const b = p == 0 ? beta : 1;
+        if (rank == 12)
+            FP_TRY((launch_wtile<T, 9>(ctx, view, rowvecs, grid, in, out, b, Wre, Wim, B)));
+        else
+            FP_TRY((launch_wtile<T, 8>(ctx, view, rowvecs, grid, in, out, b, Wre, Wim, B)));
+    }
     *used = true;
     return FP_OK;
 }

@@ -1,10 +1,11 @@
-// K6b: SummedPauliOp::apply_weighted second stage (SPO:441-455) for registers of 11..12 qubits (complex64 below,
+// K6b: SummedPauliOp::apply_weighted second stage (SPO:441-455) for registers of 11 qubits and more (complex64 below,
 // complex128 at the end of the file):
 //
 //     out(l, t) (+)= sum_g [ sum_{s in g} (-1)^{popc(l & z_s)} W(s, t) ] * psi(l ^ x_g, t)
 //
 // One CTA owns a whole state column pair (2^n rows x 2 complex64 columns = one 16-byte vector per row, <= 64 KiB) in
-// shared memory and evaluates every string against it -- a single pass whatever the operator.  Against the generic
+// shared memory and evaluates every string against it -- a single pass whatever the operator (n <= 12); beyond 12
+// qubits the tile is one rank-12 coset of a pass of the coset plan instead of the whole column.  Against the generic
 // MODE 2 coset kernel this one removes the instruction overhead that bounded it (half its issue slots were sign
 // generation and W address arithmetic):
 //
@@ -47,7 +48,9 @@ template <int LOG_NT> struct WtileSmem
         FP_WT_ROW(K, 0) FP_WT_ROW(K, 1) FP_WT_ROW(K, 2) FP_WT_ROW(K, 3) FP_WT_ROW(K, 4) FP_WT_ROW(K, 5)               \
         FP_WT_ROW(K, 6) FP_WT_ROW(K, 7) break;
 
-// grid.x = B / 2 column pairs; the pass must be the whole-register plan (rank n, unit-vector basis: local row = row)
+// grid.x = (cosets of the pass) x (B / 2 column pairs), column pairs fastest.  For registers of at most 12 qubits the
+// tile is the whole state column and the plan has one pass; larger registers are covered coset by coset (rank-12
+// cosets of the pass' x-mask span, rows base ^ comb(basis, l)), one pass per launch, later passes accumulating.
 template <int LOG_NT>
 __global__ void __launch_bounds__(1 << LOG_NT, 1)
     wtile_kernel(CosetPassView<float> pass, uint64_t rowvecs, CVec<float, 2> const *__restrict__ in,
@@ -64,10 +67,16 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
     uint32_t *s_gstart = reinterpret_cast<uint32_t *>(wt_smem + S::off_gstart);
 
     uint32_t const tid = threadIdx.x;
-    uint64_t const v = blockIdx.x;
+    uint64_t const coset = blockIdx.x / rowvecs;
+    uint64_t const v = blockIdx.x - coset * rowvecs;
     uint64_t const t0 = v * 2;
+    uint64_t const base = deposit_bits(coset, pass.nonpivot_mask);
     float4 const *in4 = reinterpret_cast<float4 const *>(in);
     float4 *out4 = reinterpret_cast<float4 *>(out);
+    uint64_t grow[RPT]; // global row of the thread's local rows tid + q * NT
+#pragma unroll
+    for (int q = 0; q < RPT; ++q)
+        grow[q] = base ^ comb_of<LOG_NT + 3>(pass.basis, tid + q * NT);
 
     uint32_t rowoff[RPT]; // byte offset of the thread's rows inside the tile
 #pragma unroll
@@ -78,7 +87,7 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
     for (int q = 0; q < RPT; ++q)
     {
         uint32_t const l = tid + q * NT;
-        float4 const a = in4[static_cast<uint64_t>(l) * rowvecs + v];
+        float4 const a = in4[grow[q] * rowvecs + v];
         tile[l] = make_float4(a.x, a.z, a.y, a.w);
     }
 
@@ -95,7 +104,9 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
             uint64_t const wrow = static_cast<uint64_t>(pass.sidx[ch.s_lo + tid]) * B + t0;
             float2 const re = *reinterpret_cast<float2 const *>(Wre + wrow);
             float2 const im = *reinterpret_cast<float2 const *>(Wim + wrow);
-            r_w = make_float4(re.x, re.y, im.x, im.y);
+            // the sign of the coset base, (-1)^{par(base & z)}, is folded into the staged weights
+            float const hs = parity64(base & pass.sz[ch.s_lo + tid]) ? -1.f : 1.f;
+            r_w = make_float4(hs * re.x, hs * re.y, hs * im.x, hs * im.y);
         }
         if (tid <= ng)
         {
@@ -175,9 +186,8 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
 #pragma unroll
     for (int q = 0; q < RPT; ++q)
     {
-        uint32_t const l = tid + q * NT;
         float4 r = make_float4(acc_rp[q].x - acc_rm[q].x, acc_im[q].x, acc_rp[q].y - acc_rm[q].y, acc_im[q].y);
-        float4 *dst = &out4[static_cast<uint64_t>(l) * rowvecs + v];
+        float4 *dst = &out4[grow[q] * rowvecs + v];
         if (beta)
         {
             float4 const o = *dst;
@@ -221,9 +231,15 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
     uint32_t *s_gstart = reinterpret_cast<uint32_t *>(wtd_smem + S::off_gstart);
 
     uint32_t const tid = threadIdx.x;
-    uint64_t const v = blockIdx.x; // batch column
+    uint64_t const coset = blockIdx.x / rowvecs;
+    uint64_t const v = blockIdx.x - coset * rowvecs; // batch column
+    uint64_t const base = deposit_bits(coset, pass.nonpivot_mask);
     double2 const *in2 = reinterpret_cast<double2 const *>(in);
     double2 *out2 = reinterpret_cast<double2 *>(out);
+    uint64_t grow[RPT]; // global row of the thread's local rows tid + q * NT
+#pragma unroll
+    for (int q = 0; q < RPT; ++q)
+        grow[q] = base ^ comb_of<LOG_NT + 3>(pass.basis, tid + q * NT);
 
     uint32_t rowoff[RPT];
 #pragma unroll
@@ -233,7 +249,7 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
     for (int q = 0; q < RPT; ++q)
     {
         uint32_t const l = tid + q * NT;
-        tile[l] = in2[static_cast<uint64_t>(l) * rowvecs + v];
+        tile[l] = in2[grow[q] * rowvecs + v];
     }
 
     uint32_t r_meta = 0, r_gxl = 0, r_gstart = 0;
@@ -246,7 +262,8 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
             uint32_t const zl = pass.szl[ch.s_lo + tid];
             r_meta = (zl & (NT - 1)) | ((zl >> LOG_NT) << 16);
             uint64_t const wrow = static_cast<uint64_t>(pass.sidx[ch.s_lo + tid]) * B + v;
-            r_w = make_double2(Wre[wrow], Wim[wrow]);
+            double const hs = parity64(base & pass.sz[ch.s_lo + tid]) ? -1.0 : 1.0; // coset-base sign
+            r_w = make_double2(hs * Wre[wrow], hs * Wim[wrow]);
         }
         if (tid <= ng)
         {
@@ -321,9 +338,8 @@ __global__ void __launch_bounds__(1 << LOG_NT, 1)
 #pragma unroll
     for (int q = 0; q < RPT; ++q)
     {
-        uint32_t const l = tid + q * NT;
         double2 r = make_double2(acc_re[q], acc_im[q]);
-        double2 *dst = &out2[static_cast<uint64_t>(l) * rowvecs + v];
+        double2 *dst = &out2[grow[q] * rowvecs + v];
         if (beta)
         {
             double2 const o = *dst;
