@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """One small call of every kernel family added in the second session, for compute-sanitizer runs:
 
-    compute-sanitizer --tool memcheck  python scripts/sanitize_case.py
-    compute-sanitizer --tool racecheck python scripts/sanitize_case.py
+    compute-sanitizer --tool memcheck  python tests/sanitize_case.py
+    compute-sanitizer --tool racecheck python tests/sanitize_case.py
 """
 import os
 import sys
@@ -11,7 +11,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # conftest helpers
 from __graft_entry__ import load_package  # noqa: E402
 
 fp = load_package()
