@@ -41,13 +41,18 @@ def sampled_parity(out, rank, rows, strings, h, samples) -> float:
     """max relative error of sampled output rows against out[i] = sum_s h_s m_s[i] psi[i ^ x_s] (GLOBAL row index),
     evaluated on inputs regenerated from the counter-based generator; max over ranks."""
     from fast_pauli_b200.synth import uniform_complex_at
-    from oracle import oracle as orc  # checker only
+
+    def masks_of(string):  # closed form of get_sparse_repr (PS:49-118): x, z masks and the number of Y
+        nq = len(string)
+        x = sum(1 << (nq - 1 - q) for q, ch in enumerate(string) if ch in "XY")
+        z = sum(1 << (nq - 1 - q) for q, ch in enumerate(string) if ch in "YZ")
+        return x, z, string.count("Y") & 3
 
     srng = np.random.default_rng(99 + rank)
     idx = srng.integers(0, rows, size=samples)
     got = out[torch.from_numpy(idx).cuda()].cpu().numpy()
     worst = 0.0
-    masks = [orc.masks(s) for s in strings]
+    masks = [masks_of(s) for s in strings]
     base = np.array([1, -1j, -1, 1j])
     for k, il in enumerate(idx):
         i = rank * rows + int(il)
