@@ -172,6 +172,10 @@ template <typename T> struct DeviceOp
     struct CosetPassDev
     {
         CosetPassView<T> view{};
+        // the pass' strings as pair chunks in pass-local coordinates (coset-tiled expectation values, etile.cuh)
+        PairChunk const *echunks = nullptr;
+        uint32_t n_echunks = 0;
+        uint8_t const *esodd = nullptr;
         std::vector<void *> allocs;
     };
     mutable std::map<int, std::vector<CosetPassDev>> coset_plans;
@@ -358,6 +362,35 @@ int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank, int reserve_lo
         if (rc == FP_OK) { d.allocs.push_back(sz); rc = upload_vec(&sc, scv); }
         if (rc == FP_OK) { d.allocs.push_back(sc); rc = upload_vec(&sidx, h.sidx); }
         if (rc == FP_OK) d.allocs.push_back(sidx);
+        if (rc == FP_OK)
+        {
+            std::vector<PairChunk> ech;
+            std::vector<uint8_t> esodd(h.sidx.size());
+            for (size_t i = 0; i < h.sidx.size(); ++i)
+                esodd[i] = op.host.sodd[h.sidx[i]];
+            for (size_t g = 0; g + 1 < h.gstart.size(); ++g)
+            {
+                uint32_t const xl = h.gxl[g];
+                for (uint32_t s0 = h.gstart[g]; s0 < h.gstart[g + 1]; s0 += kPairMS)
+                {
+                    PairChunk c;
+                    c.x = xl;
+                    c.s0 = s0;
+                    c.count = std::min<uint32_t>(kPairMS, h.gstart[g + 1] - s0);
+                    c.hbit = xl ? 31u - static_cast<uint32_t>(__builtin_clz(xl)) : 0u;
+                    c.diag = xl == 0;
+                    ech.push_back(c);
+                }
+            }
+            PairChunk *d_ech = nullptr;
+            uint8_t *d_esodd = nullptr;
+            rc = upload_vec(&d_ech, ech);
+            if (rc == FP_OK) { d.allocs.push_back(d_ech); rc = upload_vec(&d_esodd, esodd); }
+            if (rc == FP_OK) d.allocs.push_back(d_esodd);
+            d.echunks = d_ech;
+            d.n_echunks = static_cast<uint32_t>(ech.size());
+            d.esodd = d_esodd;
+        }
         if (rc != FP_OK)
         {
             for (auto &dd : dev)
@@ -2174,14 +2207,19 @@ int run_sop_expval(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, ui
             static PerDevice configured2;
             if (!configured2.done(ctx->device))
             {
-                FP_CU(cudaFuncSetAttribute(sop_expval_tile2_kernel<P, kPairMS>,
+                FP_CU(cudaFuncSetAttribute(sop_expval_tile2_kernel<P, kPairMS, false>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
                 configured2.set(ctx->device);
             }
+            EtStrings st{};
+            st.chunks = op.chunks;
+            st.n_chunks = op.n_chunks;
+            st.sz = op.sz;
+            st.sodd = op.sodd;
+            st.n_cosets = 1;
             dim3 grid(static_cast<unsigned>(rowvecs), splits);
-            sop_expval_tile2_kernel<P, kPairMS><<<grid, kThreads, smem, ctx->stream>>>(
-                op.chunks, op.n_chunks, op.sz, op.sodd, static_cast<uint32_t>(sop->n_qubits), rowvecs,
-                static_cast<CVec<T, EPV_FULL> const *>(in), E, B);
+            sop_expval_tile2_kernel<P, kPairMS, false><<<grid, kThreads, smem, ctx->stream>>>(
+                st, static_cast<uint32_t>(sop->n_qubits), rowvecs, static_cast<CVec<T, EPV_FULL> const *>(in), E, B);
             ctx->launches++;
             stage1_done = launched = true;
         }
@@ -2192,6 +2230,46 @@ int run_sop_expval(fp_ctx *ctx, fp_sop const *sop, void *out, void const *in, ui
                 op.chunks, op.n_chunks, op.sz, op.sodd, static_cast<uint32_t>(sop->n_qubits), rowvecs,
                 static_cast<CVec<T, EPV_FULL> const *>(in), E, B);
             ctx->launches++;
+            stage1_done = true;
+        }
+    }
+    if (!stage1_done && ctx->etile && ctx->coset_mode == 1 && sop->n_qubits > 12 && epv == EPV_FULL &&
+        dim == (1ull << sop->n_qubits) && rowvecs <= 0x7fffffffull && op.host.gx.size() <= 20000)
+    {
+        // K4c over rank-12 coset tiles: every CTA walks all cosets of a pass for its column (pair)
+        using P = typename std::conditional<sizeof(T) == 4, EtF32, EtF64>::type;
+        std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
+        FP_TRY(get_coset_plan<T>(op, sop->n_qubits, 12, 2, &passes));
+        if (passes->size() == 1 || passes->size() * 3 <= op.host.gx.size())
+        {
+            static PerDevice configured3;
+            if (!configured3.done(ctx->device))
+            {
+                FP_CU(cudaFuncSetAttribute(sop_expval_tile2_kernel<P, kPairMS, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+                configured3.set(ctx->device);
+            }
+            for (auto const &pd : *passes)
+            {
+                EtStrings st{};
+                st.chunks = pd.echunks;
+                st.n_chunks = pd.n_echunks;
+                st.sz = pd.view.sz;
+                st.szl = pd.view.szl;
+                st.sodd = pd.esodd;
+                st.sidx = pd.view.sidx;
+                for (int k = 0; k < 12; ++k)
+                    st.basis[k] = pd.view.basis[k];
+                st.nonpivot_mask = pd.view.nonpivot_mask;
+                st.n_cosets = 1ull << (sop->n_qubits - 12);
+                uint32_t splits = 1;
+                while (rowvecs * splits < static_cast<uint64_t>(ctx->sm_count) * 2 && splits * 8 < st.n_chunks)
+                    splits *= 2;
+                dim3 grid(static_cast<unsigned>(rowvecs), splits);
+                sop_expval_tile2_kernel<P, kPairMS, true><<<grid, kThreads, 65536, ctx->stream>>>(
+                    st, static_cast<uint32_t>(sop->n_qubits), rowvecs, static_cast<CVec<T, EPV_FULL> const *>(in), E, B);
+                ctx->launches++;
+            }
             stage1_done = true;
         }
     }

@@ -50,9 +50,16 @@ struct EtF32
         a.y += __shfl_xor_sync(0xffffffffu, a.y, off);
         return a;
     }
-    static __device__ __forceinline__ void store(T *E, uint64_t s, uint64_t B, uint64_t v, V val)
+    static __device__ __forceinline__ void store(T *E, uint64_t s, uint64_t B, uint64_t v, V val, bool accumulate)
     {
-        *reinterpret_cast<float2 *>(E + s * B + v * 2) = val;
+        float2 *p = reinterpret_cast<float2 *>(E + s * B + v * 2);
+        if (accumulate)
+        {
+            float2 const o = *p;
+            val.x += o.x;
+            val.y += o.y;
+        }
+        *p = val;
     }
 };
 struct EtF64
@@ -71,7 +78,10 @@ struct EtF64
     static __device__ __forceinline__ V neg(V a) { return -a; }
     static __device__ __forceinline__ V flip(V a, uint32_t odd) { return flip_sign(a, odd); }
     static __device__ __forceinline__ V shfl_add(V a, int off) { return a + __shfl_xor_sync(0xffffffffu, a, off); }
-    static __device__ __forceinline__ void store(T *E, uint64_t s, uint64_t B, uint64_t v, V val) { E[s * B + v] = val; }
+    static __device__ __forceinline__ void store(T *E, uint64_t s, uint64_t B, uint64_t v, V val, bool accumulate)
+    {
+        E[s * B + v] = accumulate ? E[s * B + v] + val : val;
+    }
 };
 
 // sum_k (-1)^{popc(k & K)} q[k], k < 8, K compile time (FADD2 / DADD negate an operand for free)
@@ -169,10 +179,27 @@ __device__ __forceinline__ void etile_chunk(unsigned char const *tile_bytes, uin
     }
 }
 
-template <typename P, int MS>
+// Strings of one launch.  Whole-column launches (registers of <= 12 qubits): the masks are the global ones, one
+// coset.  Coset launches (COSET = true, larger registers): the tile is one rank-12 coset of a pass of the coset plan
+// (rows base ^ comb(basis, l)); x / z are the pass-local masks, the coset-base sign (-1)^{par(base & z)} is applied per
+// string and coset, and the CTA walks all cosets for its column (pair), accumulating into E from the second coset on
+// (the chunk -> warp assignment is fixed, so every E entry is updated by one thread in a fixed order).
+struct EtStrings
+{
+    PairChunk const *chunks;
+    uint32_t n_chunks;
+    uint64_t const *sz;   // full z-mask per string
+    uint32_t const *szl;  // pass-local z-mask (COSET only)
+    uint8_t const *sodd;  // odd number of Y
+    uint32_t const *sidx; // row of E (COSET only; identity otherwise)
+    uint64_t basis[12];   // COSET only
+    uint64_t nonpivot_mask;
+    uint64_t n_cosets;
+};
+
+template <typename P, int MS, bool COSET>
 __global__ void __launch_bounds__(kThreads)
-    sop_expval_tile2_kernel(PairChunk const *__restrict__ chunks, uint32_t n_chunks, uint64_t const *__restrict__ sz,
-                            uint8_t const *__restrict__ sodd, uint32_t n_qubits, uint64_t rowvecs,
+    sop_expval_tile2_kernel(EtStrings st, uint32_t n_qubits, uint64_t rowvecs,
                             CVec<typename P::T, P::COLS> const *__restrict__ in, typename P::T *__restrict__ E /* [S][B] */,
                             uint64_t B)
 {
@@ -181,11 +208,21 @@ __global__ void __launch_bounds__(kThreads)
     extern __shared__ __align__(16) unsigned char et_smem[];
     Row *tile = reinterpret_cast<Row *>(et_smem);
     uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    uint32_t const rows = 1u << n_qubits;
+    uint32_t const rows = COSET ? 4096u : (1u << n_qubits);
     uint64_t const v = blockIdx.x; // column (pair) of this CTA: one 16-byte vector per row
     Row const *in4 = reinterpret_cast<Row const *>(in);
+    PairChunk const *chunks = st.chunks;
+    uint32_t const n_chunks = st.n_chunks;
+    for (uint64_t coset = 0; coset < (COSET ? st.n_cosets : 1); ++coset)
+    {
+    uint64_t const base = COSET ? deposit_bits(coset, st.nonpivot_mask) : 0;
+    if (COSET)
+        __syncthreads(); // the previous coset's readers are done
     for (uint32_t r = tid; r < rows; r += kThreads)
-        tile[r] = P::to_row(in4[static_cast<uint64_t>(r) * rowvecs + v]); // complex64: planar per pair
+    {
+        uint64_t const grow = COSET ? (base ^ comb_of<12>(st.basis, r)) : r;
+        tile[r] = P::to_row(in4[grow * rowvecs + v]); // complex64: planar per pair
+    }
     __syncthreads();
 
     uint32_t const n_warps_total = (kThreads / 32) * gridDim.y;
@@ -214,10 +251,12 @@ __global__ void __launch_bounds__(kThreads)
         for (int m = 0; m < MS; ++m)
         {
             bool const live = static_cast<uint32_t>(m) < ch.count;
-            uint32_t const z = live ? static_cast<uint32_t>(sz[ch.s0 + m]) : 0u;
-            odd_ny[m] = live ? sodd[ch.s0 + m] : 0u;
+            uint32_t const z = !live ? 0u : COSET ? st.szl[ch.s0 + m] : static_cast<uint32_t>(st.sz[ch.s0 + m]);
+            odd_ny[m] = live ? st.sodd[ch.s0 + m] : 0u;
             any_odd |= odd_ny[m] != 0;
             sl[m] = __popc(lane_part & z) & 1u;
+            if (COSET && live)
+                sl[m] ^= parity64(base & st.sz[ch.s0 + m]);
             uint32_t const zz = z >> sh;
             uint32_t const zj = ((zz >> (hp + 1)) << hp) | (zz & hp_low); // z over the j bits
             zk[m] = zj & 7u;
@@ -263,8 +302,9 @@ __global__ void __launch_bounds__(kThreads)
             for (int off = 16; off > 0; off >>= 1)
                 val = P::shfl_add(val, off);
             if (lane == 0)
-                P::store(E, ch.s0 + m, B, v, val);
+                P::store(E, COSET ? st.sidx[ch.s0 + m] : ch.s0 + m, B, v, val, COSET && coset > 0);
         }
+    }
     }
 }
 

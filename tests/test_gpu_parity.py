@@ -808,9 +808,10 @@ def test_weighted_tile_kernel(dtype, n):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("n", [9, 10, 12])
+@pytest.mark.parametrize("n", [9, 10, 12, 13, 15])
 def test_expval_tile_kernel(dtype, n):
-    """K4c (etile.cuh): SummedPauliOp.expectation_value on 9..12-qubit registers, complex64 and complex128; x-masks whose top bit
+    """K4c (etile.cuh): SummedPauliOp.expectation_value on 9..12-qubit registers (whole-column tile) and beyond
+    (rank-12 coset tiles, one launch per pass of the coset plan), complex64 and complex128; x-masks whose top bit
     lies among the lane bits (hbit < 5), among the block bits, diagonal strings, odd/even Y counts, groups with more
     strings than one chunk holds; compared with the complex128 oracle and with the generic K4b kernel."""
     rng = np.random.default_rng(90 + n)
