@@ -359,6 +359,19 @@ def _alloc_like(arg: _Arg, shape, dtype):
     return np.empty(shape, dtype=dtype)
 
 
+def _state_arg(op, states, what: str):
+    """Normalise the states argument and run the reference's shape checks (PS:271-283, PO:343-350, SPO:290-293,
+    B_PS:155, B_PO:512) BEFORE a device context is needed: a wrong shape is a ValueError on any machine."""
+    a = _Arg(states, None)
+    if a.ndim not in (1, 2):
+        raise ValueError(f"{what}: expected 1 or 2 dimensions, got {a.ndim}")
+    if a.shape[0] != op.dim:
+        raise ValueError(f"[{type(op).__name__}] states shape ({a.shape[0]}) must match the dimension of the "
+                         f"operators ({op.dim})")
+    a.ctx = ctx = op._context()
+    return ctx, a
+
+
 def _ptr(o) -> C.c_void_p:
     return C.c_void_p(o.ptr if isinstance(o, DeviceArray) else o.ctypes.data)
 
@@ -419,11 +432,16 @@ class Pauli:
 
     __slots__ = ("code",)
 
-    def __init__(self, code: "int | str | Pauli" = 0):
+    def __init__(self, code: "int | str | Pauli" = 0, *, symbol: "str | None" = None):
+        # the reference binds three overloads: Pauli(), Pauli(code: int), Pauli(symbol: str) (B_P:41-58)
+        if symbol is not None:
+            code = symbol
         if isinstance(code, Pauli):
             code = code.code
         if isinstance(code, str):
-            if len(code) != 1 or code not in _CODE:
+            if len(code) != 1:
+                raise TypeError("Pauli(symbol): expected a single character")  # no overload matches (PY_P:68-69)
+            if code not in _CODE:
                 raise ValueError("Invalid Pauli matrix symbol")
             code = _CODE[code]
         if not 0 <= int(code) <= 3:
@@ -534,10 +552,7 @@ class PauliString:
         Mirrors a quirk of the reference binding: for a 1-D state the ``coeff`` argument is NOT applied
         (``__pauli_string_bindings.hpp:142`` calls ``apply`` without ``c``); 2-D honours it.
         """
-        ctx = self._context()
-        a = _Arg(states, ctx)
-        if a.ndim not in (1, 2):
-            raise ValueError(f"apply: expected 1 or 2 dimensions, got {a.ndim}")
+        ctx, a = _state_arg(self, states, "apply")
         if a.ndim == 1:
             coeff = 1.0
         B = 1 if a.ndim == 1 else a.shape[1]
@@ -550,10 +565,7 @@ class PauliString:
 
     def expectation_value(self, states, coeff: complex = 1.0):
         """``<psi_t| coeff P |psi_t>``: 1-D state -> shape (1,), batch -> (n_states,) (B_PS:182-211)."""
-        ctx = self._context()
-        a = _Arg(states, ctx)
-        if a.ndim not in (1, 2):
-            raise ValueError(f"expectation_value: expected 1 or 2 dimensions, got {a.ndim}")
+        ctx, a = _state_arg(self, states, "expectation_value")
         B = 1 if a.ndim == 1 else a.shape[1]
         out = _alloc_like(a, (B,), a.dtype)
         c = _coef_buf(coeff, a.dtype)
@@ -574,7 +586,7 @@ class PauliOp:
                  strings: Sequence["str | PauliString"] | None = None, ctx: Context | None = None):
         if strings is None and coeffs is not None and len(coeffs) and isinstance(coeffs[0], (str, PauliString)):
             strings, coeffs = coeffs, None  # PauliOp(strings): coefficients default to one (PO:59-80)
-        strings = [str(s) for s in (strings or [])]
+        strings = [str(s) for s in ([] if strings is None else strings)]
         self._coeffs = np.ones(len(strings), np.complex128) if coeffs is None else \
             np.array(coeffs, dtype=np.complex128).reshape(-1)
         if len(self._coeffs) != len(strings):
@@ -734,10 +746,7 @@ class PauliOp:
 
     def apply(self, states):
         """``(sum_i h_i P_i) |psi_t>`` for a 1-D state or (dim, n_states) batch (B_PO:489-516)."""
-        ctx = self._context()
-        a = _Arg(states, ctx)
-        if a.ndim not in (1, 2):
-            raise ValueError(f"apply: expected 1 or 2 dimensions, got {a.ndim}")
+        ctx, a = _state_arg(self, states, "apply")
         B = 1 if a.ndim == 1 else a.shape[1]
         out = _alloc_like(a, a.shape, a.dtype)
         _check(lib.fp_op_apply(ctx._h, self._plan(a.dtype), _ptr(out), C.c_void_p(a.ptr), C.c_size_t(a.shape[0]),
@@ -746,10 +755,7 @@ class PauliOp:
 
     def expectation_value(self, states):
         """``<psi_t| sum_i h_i P_i |psi_t>`` (B_PO:537-567)."""
-        ctx = self._context()
-        a = _Arg(states, ctx)
-        if a.ndim not in (1, 2):
-            raise ValueError(f"expectation_value: expected 1 or 2 dimensions, got {a.ndim}")
+        ctx, a = _state_arg(self, states, "expectation_value")
         B = 1 if a.ndim == 1 else a.shape[1]
         out = _alloc_like(a, (B,), a.dtype)
         _check(lib.fp_op_expval(ctx._h, self._plan(a.dtype), _ptr(out), C.c_void_p(a.ptr), C.c_size_t(a.shape[0]),
@@ -780,9 +786,7 @@ class SummedPauliOp:
         self._plans: dict[int, C.c_void_p] = {}
 
     def __del__(self):
-        for h in getattr(self, "_plans", {}).values():
-            lib.fp_sop_destroy(h)
-        self._plans = {}
+        self._drop_plans()
 
     @property
     def dim(self) -> int:
@@ -804,6 +808,20 @@ class SummedPauliOp:
     def coeffs(self) -> np.ndarray:
         """(n_operators, n_pauli_strings): the reference getter returns the transpose (B_SPO:113-135)."""
         return self._coeffs.T.copy()
+
+    @coeffs.setter
+    def coeffs(self, coeffs_new) -> None:
+        """Takes the getter's (n_operators, n_pauli_strings) orientation (B_SPO:125-135); drops the device plans."""
+        c = np.asarray(coeffs_new, dtype=np.complex128)
+        if c.ndim != 2 or c.shape != (self.n_operators, self.n_pauli_strings):
+            raise ValueError("The shape of provided coeffs must match the number of operators and PauliStrings")
+        self._coeffs = np.ascontiguousarray(c.T)
+        self._drop_plans()
+
+    def _drop_plans(self) -> None:
+        for h in getattr(self, "_plans", {}).values():
+            lib.fp_sop_destroy(h)
+        self._plans = {}
 
     @property
     def pauli_strings(self) -> list[PauliString]:
@@ -867,10 +885,7 @@ class SummedPauliOp:
 
     def apply(self, states):
         """``sum_k A_k |psi_t>`` (B_SPO:156-182)."""
-        ctx = self._context()
-        a = _Arg(states, ctx)
-        if a.ndim not in (1, 2):
-            raise ValueError(f"apply: expected 1 or 2 dimensions, got {a.ndim}")
+        ctx, a = _state_arg(self, states, "apply")
         B = 1 if a.ndim == 1 else a.shape[1]
         out = _alloc_like(a, a.shape, a.dtype)
         _check(lib.fp_sop_apply(ctx._h, self._plan(a.dtype), _ptr(out), C.c_void_p(a.ptr), C.c_size_t(a.shape[0]),
@@ -879,11 +894,8 @@ class SummedPauliOp:
 
     def apply_weighted(self, states, data):
         """``sum_k x_kt A_k |psi_t>`` with real weights ``data`` of shape (n_operators, n_states) (B_SPO:199-228)."""
-        ctx = self._context()
-        a = _Arg(states, ctx)
+        ctx, a = _state_arg(self, states, "apply_weighted")
         d = _Arg(data, ctx, want_real=True)
-        if a.ndim not in (1, 2):
-            raise ValueError(f"apply_weighted: expected 1 or 2 dimensions, got {a.ndim}")
         B = 1 if a.ndim == 1 else a.shape[1]
         dshape = d.shape if d.ndim == 2 else (d.shape[0], 1)
         if d.ndim not in (1, 2) or d.ndim != a.ndim or dshape != (self.n_operators, B):  # SPO:389-394
@@ -899,10 +911,7 @@ class SummedPauliOp:
 
     def expectation_value(self, states):
         """``<psi_t| A_k |psi_t>``: 1-D state -> (n_operators,), batch -> (n_operators, n_states) (B_SPO:246-274)."""
-        ctx = self._context()
-        a = _Arg(states, ctx)
-        if a.ndim not in (1, 2):
-            raise ValueError(f"expectation_value: expected 1 or 2 dimensions, got {a.ndim}")
+        ctx, a = _state_arg(self, states, "expectation_value")
         B = 1 if a.ndim == 1 else a.shape[1]
         shape = (self.n_operators,) if a.ndim == 1 else (self.n_operators, B)
         out = _alloc_like(a, shape, a.dtype)

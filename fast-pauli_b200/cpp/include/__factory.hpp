@@ -1,0 +1,4 @@
+// Forwarding header: user code written against the reference includes "__factory.hpp" by name
+// (e.g. its examples/01, 03, 05); here the declarations live in fast_pauli_b200/factory.hpp.
+#pragma once
+#include "fast_pauli_b200/factory.hpp"

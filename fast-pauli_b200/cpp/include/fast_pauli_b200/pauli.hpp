@@ -1,11 +1,22 @@
 // fast_pauli::Pauli -- one 2x2 Pauli matrix as a small value type (reference API: __pauli.hpp:39-212).
 #pragma once
 #include <array>
+#include <chrono>
 #include <compare>
 #include <ostream>
+#include <random>
+#include <ranges>
+#include <span>
+#include <unordered_map>
 #include <utility>
 
 #include "detail.hpp"
+
+// Source compatibility: the reference's headers make these names visible at global scope (__pauli.hpp:29,
+// __pauli_op.hpp:26) and pull in <ranges>, <random>, <chrono>, <unordered_map>; code written against them (its own
+// tests use `1i` literals and std::views without including anything else) must keep compiling.
+using namespace std::literals;
+using namespace std::experimental;
 
 namespace fast_pauli
 {
