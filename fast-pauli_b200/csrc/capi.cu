@@ -983,8 +983,8 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
             return FP_OK;
         }
     }
-    if (rr > kRcMaxSimtRank)
-        return FP_OK;
+    if (rr > kRcMaxSimtRank || rr < 2)
+        return FP_OK; // a 1-qubit register has no rank-2 coset: the generic kernel takes it
     int const log_nt = ctx->rcoset_log_nt == 8 ? 8 : 7;
     uint32_t const NT = 1u << log_nt;
     uint32_t log2tw = 0;
@@ -1018,11 +1018,15 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
     uint32_t log2p = 0;
     while (log2p < 5 && (static_cast<uint64_t>(TY) << (2 * rr + log2p + 1)) <= NT)
         ++log2p;
+    bool launched = false;
 #define FP_RC_CASE(RRV, LNT)                                                                                           \
     if (rr == RRV && log_nt == LNT)                                                                                    \
+    {                                                                                                                  \
         FP_TRY((launch_rcoset<T, EPV, RRV, LNT, MODE>(ctx, plan->view, n_cosets, rowvecs, log2tw, log2p, nct, n_blocks, \
                                                       static_cast<uint32_t>(iters), smem, in, out, beta,               \
-                                                      ctx->partials.p, Bpad)));
+                                                      ctx->partials.p, Bpad)));                                        \
+        launched = true;                                                                                               \
+    }
     FP_RC_CASE(2, 7)
     FP_RC_CASE(3, 7)
     FP_RC_CASE(4, 7)
@@ -1030,6 +1034,8 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
     FP_RC_CASE(3, 8)
     FP_RC_CASE(4, 8)
 #undef FP_RC_CASE
+    if (!launched)
+        return FP_OK; // no instantiation for this shape: never claim a result that was not computed
     if (MODE == 1)
     {
         unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);

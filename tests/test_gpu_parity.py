@@ -110,7 +110,11 @@ def test_kats():
 SHAPES = [
     # (n_qubits, n_strings, n_states, n_operators)
     (1, 3, 1, 2),
+    (1, 4, 10, 2),     # T_PO:316-320 "1 qubit x 10 states": wide batch on a 2-row register (found by the reference's
+    (1, 4, 64, 3),     # own C++ test: the register-coset dispatcher used to claim this shape without a kernel for it)
     (2, 16, 3, 3),
+    (2, 9, 64, 2),
+    (3, 30, 40, 2),
     (4, 20, 5, 3),     # odd batch: complex64 takes the 8-byte vector path
     (6, 40, 10, 4),
     (7, 37, 33, 2),    # non power-of-two batch
@@ -149,6 +153,36 @@ def test_all_entry_points_vs_oracle(dtype, n, S, B, K):
     assert rel_err(sop.apply(psi), ORC.sop_apply(strings, hk, psi)) < t
     assert rel_err(sop.apply_weighted(psi, data), ORC.sop_apply_weighted(strings, hk, psi, data)) < t
     assert_parity(sop.expectation_value(psi), ORC.sop_expval, dtype, strings, hk, psi)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5])
+def test_small_registers_every_batch_width(dtype, n):
+    """Dispatch sweep: registers of 1..5 qubits x batch widths around every vector / tile / warp boundary, operators
+    from a single string up to the full Pauli basis, all entry points.  Every kernel-selection branch keyed on the
+    register size or the row width is crossed here with shapes small enough for a dense check."""
+    rng = np.random.default_rng(50 + n)
+    t = tol(dtype)
+    all_strings = ["".join(s) for s in __import__("itertools").product("IXYZ", repeat=n)]
+    for B in (1, 2, 3, 4, 5, 7, 8, 10, 16, 31, 32, 33, 64, 100, 257):
+        for S in sorted({1, 2, min(4, len(all_strings)), len(all_strings) if len(all_strings) <= 256 else 64}):
+            strings = [all_strings[i] for i in rng.choice(len(all_strings), size=S, replace=False)]
+            K = 1 + int(rng.integers(0, 3))
+            psi = rand_states(rng, 2**n, B, dtype)
+            h = (rand_states(rng, S, None, dtype) * 2 - (1 + 1j)).astype(dtype)
+            hk = (rand_states(rng, S, K, dtype) * 2 - (1 + 1j)).astype(dtype)
+            data = rng.random((K, B)).astype(np.float64 if dtype == np.complex128 else np.float32)
+            tag = f"n={n} B={B} S={S} K={K}"
+            ps = fp.PauliString(strings[0])
+            assert rel_err(ps.apply(psi, 0.5 - 1j), ORC.string_apply(strings[0], psi, 0.5 - 1j)) < t, tag
+            assert_parity(ps.expectation_value(psi, 0.5 - 1j), ORC.string_expval, dtype, strings[0], psi, 0.5 - 1j)
+            op = fp.PauliOp(h, strings)
+            assert rel_err(op.apply(psi), ORC.op_apply(strings, h, psi)) < t, tag
+            assert_parity(op.expectation_value(psi), ORC.op_expval, dtype, strings, h, psi)
+            sop = fp.SummedPauliOp(strings, hk)
+            assert rel_err(sop.apply(psi), ORC.sop_apply(strings, hk, psi)) < t, tag
+            assert rel_err(sop.apply_weighted(psi, data), ORC.sop_apply_weighted(strings, hk, psi, data)) < t, tag
+            assert_parity(sop.expectation_value(psi), ORC.sop_expval, dtype, strings, hk, psi)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
