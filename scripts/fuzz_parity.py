@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""Randomised dispatch fuzzer (GPU): random register sizes, batch widths, operator structures, dtypes and array
+residency through every hot-path entry point of the Python front-end, each result checked against the CPU oracle.
+
+    python scripts/fuzz_parity.py --seconds 120 --seed 1        # prints one line per failure + a summary
+
+The operator families are chosen to land on every kernel-selection branch (single mask, few masks x many z, k-local
+dense = register / tensor-core cosets, low weight = shared-memory cosets, i.i.d. = generic gather, chains, diagonal
+only, duplicates).  tests/test_gpu_parity.py::test_fuzz_fixed_seeds replays a bounded slice of it.
+"""
+from __future__ import annotations
+
+import argparse
+import itertools as it
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LETTERS = np.array(list("IXYZ"))
+
+
+def make_strings(rng: np.random.Generator, n: int) -> tuple[str, list[str]]:
+    fam = rng.choice(["iid", "lowweight", "klocal", "fewmasks", "onemask", "diag", "chain", "dups", "single"])
+    if fam == "iid":
+        S = int(rng.integers(1, 80))
+        s = ["".join(LETTERS[rng.integers(0, 4, size=n)]) for _ in range(S)]
+    elif fam == "lowweight":
+        S = int(rng.integers(1, 200))
+        s = []
+        for _ in range(S):
+            w = int(rng.integers(1, min(4, n) + 1))
+            pos = rng.choice(n, size=w, replace=False)
+            st = ["I"] * n
+            for p in pos:
+                st[p] = "XYZ"[int(rng.integers(0, 3))]
+            s.append("".join(st))
+    elif fam == "klocal":
+        k = int(rng.integers(1, min(5, n) + 1))
+        pos = sorted(rng.choice(n, size=k, replace=False))
+        s = []
+        for combo in it.product("IXYZ", repeat=k):
+            st = ["I"] * n
+            for p, ch in zip(pos, combo):
+                st[p] = ch
+            s.append("".join(st))
+        if rng.random() < 0.5:  # a random subset of the dense term
+            keep = rng.random(len(s)) < 0.6
+            s = [x for x, kf in zip(s, keep) if kf] or s[:1]
+    elif fam in ("fewmasks", "onemask"):
+        G = 1 if fam == "onemask" else int(rng.integers(2, 10))
+        s = []
+        for _ in range(G):
+            x = rng.integers(0, 2, size=n)
+            for _ in range(int(rng.integers(1, 9))):
+                z = rng.integers(0, 2, size=n)
+                s.append("".join("IXZY"[a + 2 * b] for a, b in zip(x, z)))
+    elif fam == "diag":
+        S = int(rng.integers(1, 40))
+        s = ["".join("IZ"[b] for b in rng.integers(0, 2, size=n)) for _ in range(S)]
+    elif fam == "chain":
+        s = []
+        for q in range(n - 1):
+            for ch in "XYZ":
+                st = ["I"] * n
+                st[q] = st[q + 1] = ch
+                s.append("".join(st))
+        s = s or ["Z" * n]
+    elif fam == "dups":
+        base = "".join(LETTERS[rng.integers(0, 4, size=n)])
+        s = [base] * int(rng.integers(2, 20)) + ["I" * n] * int(rng.integers(0, 3))
+    else:
+        s = ["".join(LETTERS[rng.integers(0, 4, size=n)])]
+    return str(fam), s
+
+
+def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool = False) -> tuple[int, list[str]]:
+    from __graft_entry__ import load_package
+    from oracle import oracle as orc
+
+    fp = load_package()
+    ORC = orc.port()
+    ctx = fp.default_context()
+    rng = np.random.default_rng(seed)
+    t_end = time.time() + seconds
+    failures: list[str] = []
+    cases = 0
+
+    def rel(a, b):
+        a = a.get() if hasattr(a, "get") else np.asarray(a)
+        scale = max(float(np.max(np.abs(b))) if b.size else 0.0, 1e-300)
+        return float(np.max(np.abs(a - b))) / scale if b.size else 0.0
+
+    while time.time() < t_end and (max_cases is None or cases < max_cases):
+        cases += 1
+        n = int(rng.integers(1, 15))
+        dtype = np.complex128 if rng.random() < 0.5 else np.complex64
+        bmax = max(1, min(300, (1 << 21) >> n))
+        B = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 12, 16, 31, 33, 64, 100, 128, 257]))
+        B = min(B, bmax)
+        fam, strings = make_strings(rng, n)
+        S = len(strings)
+        K = int(rng.integers(1, 6))
+        on_dev = rng.random() < 0.4
+        tol = 1e-12 if dtype == np.complex128 else 2e-5
+        rdt = np.float64 if dtype == np.complex128 else np.float32
+        psi = (rng.random((1 << n, B)) + 1j * rng.random((1 << n, B))).astype(dtype)
+        h = (rng.uniform(-1, 1, S) + 1j * rng.uniform(-1, 1, S)).astype(dtype)
+        hk = (rng.uniform(-1, 1, (S, K)) + 1j * rng.uniform(-1, 1, (S, K))).astype(dtype)
+        data = rng.random((K, B)).astype(rdt)
+        arg = ctx.to_device(psi) if on_dev else psi
+        darg = ctx.to_device(data) if on_dev else data
+        tag = f"seed={seed} case={cases} fam={fam} n={n} S={S} B={B} K={K} dtype={np.dtype(dtype).name} dev={on_dev}"
+        # complex64 expectation values: compare with the complex128 oracle (the reference's own float32 running sums
+        # lose more than the tolerance over long reductions, see tests/test_gpu_parity.assert_parity)
+        psi_hi, h_hi, hk_hi = psi.astype(np.complex128), h.astype(np.complex128), hk.astype(np.complex128)
+        try:
+            checks = {
+                "string.apply": (fp.PauliString(strings[0]).apply(arg, 0.5 - 2j),
+                                 ORC.string_apply(strings[0], psi, 0.5 - 2j)),
+                "string.expval": (fp.PauliString(strings[0]).expectation_value(arg, 0.5 - 2j),
+                                  ORC.string_expval(strings[0], psi_hi, 0.5 - 2j)),
+                "op.apply": (fp.PauliOp(h, strings).apply(arg), ORC.op_apply(strings, h, psi)),
+                "op.expval": (fp.PauliOp(h, strings).expectation_value(arg), ORC.op_expval(strings, h_hi, psi_hi)),
+                "sop.apply": (fp.SummedPauliOp(strings, hk).apply(arg), ORC.sop_apply(strings, hk, psi)),
+                "sop.apply_weighted": (fp.SummedPauliOp(strings, hk).apply_weighted(arg, darg),
+                                       ORC.sop_apply_weighted(strings, hk, psi, data)),
+                "sop.expval": (fp.SummedPauliOp(strings, hk).expectation_value(arg),
+                               ORC.sop_expval(strings, hk_hi, psi_hi)),
+            }
+            for name, (got, want) in checks.items():
+                e = rel(got, want)
+                if not e < tol:
+                    failures.append(f"{name}: rel err {e:.3e} | {tag}")
+        except Exception as exc:  # noqa: BLE001 - report and keep fuzzing
+            failures.append(f"EXC {type(exc).__name__}: {exc} | {tag}")
+        if verbose:
+            print(tag, "FAIL" if failures and tag in failures[-1] else "ok", flush=True)
+    return cases, failures
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=60)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    n_cases, fails = run(a.seconds, a.seed, verbose=a.verbose)
+    for f in fails:
+        print("FAIL", f)
+    print(f"fuzz: {n_cases} cases, {len(fails)} failures (seed {a.seed})")
+    sys.exit(1 if fails else 0)

@@ -7,6 +7,7 @@ else the plain-C port.
 from __future__ import annotations
 
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -183,6 +184,17 @@ def test_small_registers_every_batch_width(dtype, n):
             assert rel_err(sop.apply(psi), ORC.sop_apply(strings, hk, psi)) < t, tag
             assert rel_err(sop.apply_weighted(psi, data), ORC.sop_apply_weighted(strings, hk, psi, data)) < t, tag
             assert_parity(sop.expectation_value(psi), ORC.sop_expval, dtype, strings, hk, psi)
+
+
+@pytest.mark.parametrize("seed", [7, 8])
+def test_fuzz_fixed_seeds(seed):
+    """A bounded replay of scripts/fuzz_parity.py: random registers (1..14 qubits), batch widths, operator families,
+    dtypes and host / device residency through all seven Python entry points against the oracle."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import fuzz_parity
+
+    cases, failures = fuzz_parity.run(seconds=25, seed=seed, max_cases=200)
+    assert cases >= 20 and not failures, "\n".join(failures[:20])
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
