@@ -79,16 +79,67 @@ def make_strings(rng: np.random.Generator, n: int) -> tuple[str, list[str]]:
     return str(fam), s
 
 
-def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool = False) -> tuple[int, list[str]]:
+def exact_string_expvals(strings: list[str], psi: np.ndarray) -> np.ndarray:
+    """E(s, t) = <psi_t| P_s |psi_t> in 80-bit extended precision (numpy clongdouble), the arbiter when the GPU and
+    the oracle disagree on a long, cancelling reduction: the reference sums sequentially (PS:534), so over 2^21 terms
+    its OWN rounding error can exceed 1e-12 of the result."""
+    n = len(strings[0])
+    i = np.arange(1 << n, dtype=np.int64)
+    ph = psi.astype(np.clongdouble)
+    out = np.zeros((len(strings), psi.shape[1]), dtype=np.clongdouble)
+    for k, st in enumerate(strings):
+        x = z = 0
+        for q, ch in enumerate(st):
+            bit = 1 << (n - 1 - q)
+            x |= bit if ch in "XY" else 0
+            z |= bit if ch in "YZ" else 0
+        par = np.zeros(1 << n, dtype=np.int64)
+        zz = i & z
+        while zz.any():
+            par ^= zz & 1
+            zz >>= 1
+        m = (np.array([1, -1j, -1, 1j])[st.count("Y") & 3] * (1 - 2 * par)).astype(np.clongdouble)
+        out[k] = (np.conj(ph) * (m[:, None] * ph[i ^ x])).sum(0)
+    return out
+
+
+def gen_cases(seed: int, n_max: int = 14, log2_elems: int = 21, s_cap: int = 10**9):
+    """The deterministic case stream of one seed (no GPU needed: failures can be replayed anywhere)."""
+    rng = np.random.default_rng(seed)
+    case = 0
+    while True:
+        case += 1
+        n = int(rng.integers(1, n_max + 1))
+        dtype = np.complex128 if rng.random() < 0.5 else np.complex64
+        bmax = max(1, min(300, (1 << log2_elems) >> n))
+        B = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 12, 16, 31, 33, 64, 100, 128, 257]))
+        B = min(B, bmax)
+        fam, strings = make_strings(rng, n)
+        strings = strings[:s_cap]  # large registers: bound the single-threaded oracle's work
+        S = len(strings)
+        K = int(rng.integers(1, 6))
+        on_dev = rng.random() < 0.4
+        rdt = np.float64 if dtype == np.complex128 else np.float32
+        psi = (rng.random((1 << n, B)) + 1j * rng.random((1 << n, B))).astype(dtype)
+        h = (rng.uniform(-1, 1, S) + 1j * rng.uniform(-1, 1, S)).astype(dtype)
+        hk = (rng.uniform(-1, 1, (S, K)) + 1j * rng.uniform(-1, 1, (S, K))).astype(dtype)
+        data = rng.random((K, B)).astype(rdt)
+        tag = f"seed={seed} case={case} fam={fam} n={n} S={S} B={B} K={K} dtype={np.dtype(dtype).name} dev={on_dev}"
+        yield dict(n=n, dtype=dtype, B=B, fam=fam, strings=strings, S=S, K=K, on_dev=on_dev, psi=psi, h=h, hk=hk,
+                   data=data, tag=tag)
+
+
+def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool = False, n_max: int = 14,
+        log2_elems: int = 21, s_cap: int = 10**9) -> tuple[int, list[str]]:
     from __graft_entry__ import load_package
     from oracle import oracle as orc
 
     fp = load_package()
     ORC = orc.port()
     ctx = fp.default_context()
-    rng = np.random.default_rng(seed)
     t_end = time.time() + seconds
     failures: list[str] = []
+    notes: list[str] = []  # disagreements settled in the GPU's favour by the extended-precision arbiter
     cases = 0
 
     def rel(a, b):
@@ -96,26 +147,15 @@ def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool =
         scale = max(float(np.max(np.abs(b))) if b.size else 0.0, 1e-300)
         return float(np.max(np.abs(a - b))) / scale if b.size else 0.0
 
-    while time.time() < t_end and (max_cases is None or cases < max_cases):
+    for case in gen_cases(seed, n_max, log2_elems, s_cap):
+        if time.time() >= t_end or (max_cases is not None and cases >= max_cases):
+            break
         cases += 1
-        n = int(rng.integers(1, 15))
-        dtype = np.complex128 if rng.random() < 0.5 else np.complex64
-        bmax = max(1, min(300, (1 << 21) >> n))
-        B = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 12, 16, 31, 33, 64, 100, 128, 257]))
-        B = min(B, bmax)
-        fam, strings = make_strings(rng, n)
-        S = len(strings)
-        K = int(rng.integers(1, 6))
-        on_dev = rng.random() < 0.4
+        n, dtype, B, fam, strings, S, K, on_dev = (case[k] for k in ("n", "dtype", "B", "fam", "strings", "S", "K", "on_dev"))
+        psi, h, hk, data, tag = case["psi"], case["h"], case["hk"], case["data"], case["tag"]
         tol = 1e-12 if dtype == np.complex128 else 2e-5
-        rdt = np.float64 if dtype == np.complex128 else np.float32
-        psi = (rng.random((1 << n, B)) + 1j * rng.random((1 << n, B))).astype(dtype)
-        h = (rng.uniform(-1, 1, S) + 1j * rng.uniform(-1, 1, S)).astype(dtype)
-        hk = (rng.uniform(-1, 1, (S, K)) + 1j * rng.uniform(-1, 1, (S, K))).astype(dtype)
-        data = rng.random((K, B)).astype(rdt)
         arg = ctx.to_device(psi) if on_dev else psi
         darg = ctx.to_device(data) if on_dev else data
-        tag = f"seed={seed} case={cases} fam={fam} n={n} S={S} B={B} K={K} dtype={np.dtype(dtype).name} dev={on_dev}"
         # complex64 expectation values: compare with the complex128 oracle (the reference's own float32 running sums
         # lose more than the tolerance over long reductions, see tests/test_gpu_parity.assert_parity)
         psi_hi, h_hi, hk_hi = psi.astype(np.complex128), h.astype(np.complex128), hk.astype(np.complex128)
@@ -135,12 +175,28 @@ def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool =
             }
             for name, (got, want) in checks.items():
                 e = rel(got, want)
-                if not e < tol:
-                    failures.append(f"{name}: rel err {e:.3e} | {tag}")
+                if e < tol:
+                    continue
+                if name.endswith("expval"):
+                    # arbitrate in extended precision: the GPU must be within tolerance of the exact value and at
+                    # least as close to it as the reference-order sum is
+                    used = strings[:1] if name.startswith("string") else strings
+                    E = exact_string_expvals(used, psi_hi)
+                    exact = {"string.expval": lambda: E[0] * np.clongdouble(0.5 - 2j),
+                             "op.expval": lambda: h_hi.astype(np.clongdouble) @ E,
+                             "sop.expval": lambda: hk_hi.astype(np.clongdouble).T @ E}[name]()
+                    e_gpu, e_ref = rel(got, exact.reshape(want.shape)), rel(want, exact.reshape(want.shape))
+                    if e_gpu < tol and e_gpu <= e_ref:
+                        notes.append(f"{name}: reference-order rounding {e_ref:.2e} > tol, gpu {e_gpu:.2e} | {tag}")
+                        continue
+                    e = e_gpu
+                failures.append(f"{name}: rel err {e:.3e} | {tag}")
         except Exception as exc:  # noqa: BLE001 - report and keep fuzzing
             failures.append(f"EXC {type(exc).__name__}: {exc} | {tag}")
         if verbose:
             print(tag, "FAIL" if failures and tag in failures[-1] else "ok", flush=True)
+    for nt in notes:
+        print("NOTE", nt)
     return cases, failures
 
 
@@ -149,8 +205,11 @@ if __name__ == "__main__":
     ap.add_argument("--seconds", type=float, default=60)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--n-max", type=int, default=14, help="largest register (qubits)")
+    ap.add_argument("--log2-elems", type=int, default=21, help="cap on dim * n_states")
+    ap.add_argument("--s-cap", type=int, default=10**9, help="cap on the number of strings per operator")
     a = ap.parse_args()
-    n_cases, fails = run(a.seconds, a.seed, verbose=a.verbose)
+    n_cases, fails = run(a.seconds, a.seed, verbose=a.verbose, n_max=a.n_max, log2_elems=a.log2_elems, s_cap=a.s_cap)
     for f in fails:
         print("FAIL", f)
     print(f"fuzz: {n_cases} cases, {len(fails)} failures (seed {a.seed})")
