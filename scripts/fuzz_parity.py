@@ -126,7 +126,7 @@ def gen_cases(seed: int, n_max: int = 14, log2_elems: int = 21, s_cap: int = 10*
         data = rng.random((K, B)).astype(rdt)
         tag = f"seed={seed} case={case} fam={fam} n={n} S={S} B={B} K={K} dtype={np.dtype(dtype).name} dev={on_dev}"
         yield dict(n=n, dtype=dtype, B=B, fam=fam, strings=strings, S=S, K=K, on_dev=on_dev, psi=psi, h=h, hk=hk,
-                   data=data, tag=tag)
+                   data=data, tag=tag, case=case, accumulate=(case % 2 == 0))
 
 
 def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool = False, n_max: int = 14,
@@ -136,6 +136,8 @@ def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool =
 
     fp = load_package()
     ORC = orc.port()
+    # the oracle-shaped one-shot entry points of the GPU library: `out=` is accumulated into, like the C++ methods
+    G = orc.Backend(os.path.join(ROOT, "fast-pauli_b200", "lib", "libfastpauli_b200.so"), "fp_", "gpu")
     ctx = fp.default_context()
     t_end = time.time() + seconds
     failures: list[str] = []
@@ -173,11 +175,32 @@ def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool =
                 "sop.expval": (fp.SummedPauliOp(strings, hk).expectation_value(arg),
                                ORC.sop_expval(strings, hk_hi, psi_hi)),
             }
+            if case["accumulate"] and dtype == np.complex128:
+                # C++ semantics (+= into the caller's buffer, PS:419,432,523,534; PO:453,465; SPO:331,346,464,498,
+                # 588,609) through the raw C ABI; complex128 only so the bases do not mask float32 rounding
+                r2 = np.random.default_rng(case["case"])
+                base = (r2.random(psi.shape) + 1j * r2.random(psi.shape)).astype(dtype)
+                e0 = (r2.random(B) + 1j * r2.random(B)).astype(dtype)
+                ek0 = (r2.random((K, B)) + 1j * r2.random((K, B))).astype(dtype)
+                checks.update({
+                    "acc string.apply": (G.string_apply(strings[0], psi, 0.5 - 2j, out=base.copy()),
+                                         ORC.string_apply(strings[0], psi, 0.5 - 2j, out=base.copy())),
+                    "acc op.apply": (G.op_apply(strings, h, psi, out=base.copy()),
+                                     ORC.op_apply(strings, h, psi, out=base.copy())),
+                    "acc op.expval": (G.op_expval(strings, h, psi, out=e0.copy()),
+                                      ORC.op_expval(strings, h, psi, out=e0.copy())),
+                    "acc sop.apply": (G.sop_apply(strings, hk, psi, out=base.copy()),
+                                      ORC.sop_apply(strings, hk, psi, out=base.copy())),
+                    "acc sop.apply_weighted": (G.sop_apply_weighted(strings, hk, psi, data, out=base.copy()),
+                                               ORC.sop_apply_weighted(strings, hk, psi, data, out=base.copy())),
+                    "acc sop.expval": (G.sop_expval(strings, hk, psi, out=ek0.copy()),
+                                       ORC.sop_expval(strings, hk, psi, out=ek0.copy())),
+                })
             for name, (got, want) in checks.items():
                 e = rel(got, want)
                 if e < tol:
                     continue
-                if name.endswith("expval"):
+                if name.endswith("expval") and not name.startswith("acc"):
                     # arbitrate in extended precision: the GPU must be within tolerance of the exact value and at
                     # least as close to it as the reference-order sum is
                     used = strings[:1] if name.startswith("string") else strings
