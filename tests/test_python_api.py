@@ -128,3 +128,23 @@ def test_summed_pauli_op_host_helpers():
     cl = pickle.loads(pickle.dumps(sop))
     np.testing.assert_allclose(cl.to_tensor(), dense)
     assert sop.clone().coeffs.shape == (4, len(strings))
+
+
+def test_import_fast_pauli_alias_package():
+    """`import fast_pauli` keeps working for code written against the reference package (fast_pauli/__init__.py:18-25)
+    once fast-pauli_b200/compat is on the path."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import fast_pauli as fp, pickle\n"
+        "from fast_pauli.helpers import calculate_pauli_strings_max_weight\n"
+        "assert fp.PauliString('XYZ').dim == 8 and len(calculate_pauli_strings_max_weight(3, 2)) == 37\n"
+        "assert fp.PauliOp([1, 2], ['XI', 'IZ']).n_pauli_strings == 2\n"
+        "assert pickle.loads(pickle.dumps(fp.PauliString('XY'))) == fp.PauliString('XY')\n"
+        "try:\n    fp.from_qiskit(None)\nexcept NotImplementedError:\n    print('ok')\n"
+    )
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, "fast-pauli_b200", "compat"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]
