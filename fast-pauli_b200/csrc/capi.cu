@@ -144,7 +144,8 @@ struct fp_ctx
     bool etile = true;          // packed-FP32 per-string expectation kernel (complex64, 9-12 qubits)
     bool wtile = true;          // dedicated whole-column weighted-apply kernel (complex64, 11-12 qubits)
     int rcoset_mode = 1;        // register-resident coset kernel (x-mask rank <= 4): 0 never, 1 auto, 2 whenever applicable
-    bool dcoset = true;         // FP64 tensor-core dense-coset kernel (complex128 apply, x-mask rank 4 or 5)
+    int dcoset = 1;             // FP64 tensor-core dense-coset kernel (complex128, x-mask rank 4 or 5): 0 never,
+                                // 1 when the cost model below prefers it, 2 whenever applicable
     int rcoset_log_nt = 7;      // its CTA size (128 / 256 threads)
     Scratch stage_in, stage_out, stage_data, partials, work_a, work_b, meta;
     std::mutex mu;
@@ -969,7 +970,15 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
     if constexpr (sizeof(T) == 8)
     {
         // ranks 4 and 5 are GEMM-shaped per coset (16x16 / 32x32 complex): FP64 tensor cores
-        if (ctx->dcoset && (rr == 4 || rr == 5) && rowvecs >= 8)
+        // The tensor-core form costs 2^rr complex FMAs per amplitude however few of the 2^rr coset masks occur; the
+        // SIMT forms cost one per occurring mask.  Measured at 20 qubits x 64 columns (scripts/dispatch_sweep.py,
+        // profiles/r01s3_dispatch_sweep.txt): rank 4 -- DMMA 0.45 ms apply / 0.53 ms expectation value against
+        // 0.37 / 0.43 / 0.49 / 0.57 ms (apply) and 0.34 / 0.42 / 0.50 / 0.58 ms (expectation value) for the register
+        // kernel at 4 / 8 / 12 / 16 masks; rank 5 -- DMMA 0.82-0.94 ms against 0.49 / 0.58 / 0.68 / 0.81 / 1.09 ms for
+        // the shared-memory coset kernel at 5 / 8 / 12 / 16 / 24 masks.
+        size_t const n_masks = op.host.gx.size();
+        bool const dense_enough = rr == 4 ? n_masks > (MODE == 1 ? 12u : 8u) : n_masks > 16u;
+        if ((ctx->dcoset == 2 || (ctx->dcoset == 1 && dense_enough)) && (rr == 4 || rr == 5) && rowvecs >= 8)
         {
             typename DeviceOp<T>::RcPlanDev const *dplan = nullptr;
             FP_TRY(get_rc_plan<T>(op, n_qubits, rr, &dplan));
@@ -1468,7 +1477,7 @@ extern "C"
         if (char const *env = getenv("FASTPAULI_RCOSET"))
             ctx->rcoset_mode = atoi(env);
         if (char const *env = getenv("FASTPAULI_DCOSET"))
-            ctx->dcoset = atoi(env) != 0;
+            ctx->dcoset = atoi(env);
         if (char const *env = getenv("FASTPAULI_RCOSET_LOG_NT"))
             ctx->rcoset_log_nt = atoi(env);
         if (char const *env = getenv("FASTPAULI_ZERO_COPY"))

@@ -603,7 +603,11 @@ def test_dense_coset_tensor_core_kernel(rank, n, B):
     import ctypes as C
     import os as _os
 
-    ctx = fp.Context(0)
+    _os.environ["FASTPAULI_DCOSET"] = "2"  # whenever applicable (the default cost model only picks it for dense spans)
+    try:
+        ctx = fp.Context(0)
+    finally:
+        del _os.environ["FASTPAULI_DCOSET"]
     rng = np.random.default_rng(8000 + 10 * rank + n)
     S = 90
     strings = _span_strings(rng, n, rank, S)
@@ -637,6 +641,15 @@ def test_dense_coset_tensor_core_kernel(rank, n, B):
     finally:
         del _os.environ["FASTPAULI_DCOSET"]
     assert rel_err(fp.PauliOp(h, strings, ctx=ctx0).apply(psi), got) < 1e-12
+    # sparse use of the span (few of the 2^rank masks occur): the default cost model hands these to the SIMT coset
+    # kernels; same numbers whichever family runs
+    few = sorted(set(strings[:6]))
+    hf = h[: len(few)]
+    want = ORC.op_apply(few, hf, psi, par=True)
+    for c in (fp.Context(0), ctx, ctx0):
+        opf = fp.PauliOp(hf, few, ctx=c)
+        assert rel_err(opf.apply(psi), want) < 1e-12
+        assert rel_err(opf.expectation_value(psi), ORC.op_expval(few, hf, psi, par=True)) < 1e-12
 
 
 def test_register_coset_default_path_headline_shape():
