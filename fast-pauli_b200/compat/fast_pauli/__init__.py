@@ -5,7 +5,9 @@ Put ``<repo>/fast-pauli_b200/compat`` on ``sys.path`` / ``PYTHONPATH`` and exist
     import fast_pauli as fp
     op = fp.PauliOp(coeffs, strings); new_states = op.apply(states)      # runs on the B200
 
-The names are the GPU-backed classes of ``fast_pauli_b200`` (same signatures).  The qiskit
+The names are the GPU-backed classes of ``fast_pauli_b200`` (ctypes front-end; same signatures)
+or, with ``FASTPAULI_FRONTEND=native`` in the environment, of the pybind11 module ``_fast_pauli`` over the C++ classes
+(complex128 host arrays only, exactly the reference's binding surface).  The qiskit
 converters of the reference are outside the hot path and are not rebuilt: calling them raises
 ``NotImplementedError`` instead of failing at import time.
 """
@@ -29,7 +31,20 @@ if "fast_pauli_b200" not in sys.modules:
         sys.modules.pop("fast_pauli_b200", None)
         raise
 
-from fast_pauli_b200 import Pauli, PauliOp, PauliString, SummedPauliOp, helpers  # noqa: E402,F401
+if os.environ.get("FASTPAULI_FRONTEND", "ctypes") == "native":
+    import glob
+
+    _hits = glob.glob(os.path.join(_PKG, "_fast_pauli*.so"))
+    if not _hits:
+        raise ImportError("FASTPAULI_FRONTEND=native but fast-pauli_b200/_fast_pauli*.so is not built "
+                          "(make -C fast-pauli_b200)")
+    _nspec = importlib.util.spec_from_file_location("_fast_pauli", _hits[0])
+    _fast_pauli = importlib.util.module_from_spec(_nspec)
+    _nspec.loader.exec_module(_fast_pauli)
+    sys.modules[__name__ + "._fast_pauli"] = sys.modules["_fast_pauli"] = _fast_pauli  # pickle looks the classes up
+    from ._fast_pauli import Pauli, PauliOp, PauliString, SummedPauliOp, helpers  # noqa: E402,F401
+else:
+    from fast_pauli_b200 import Pauli, PauliOp, PauliString, SummedPauliOp, helpers  # noqa: E402,F401
 
 sys.modules.setdefault(__name__ + ".helpers", helpers)
 
