@@ -144,6 +144,7 @@ struct fp_ctx
     bool etile = true;          // packed-FP32 per-string expectation kernel (complex64, 9-12 qubits)
     bool wtile = true;          // dedicated whole-column weighted-apply kernel (complex64, 11-12 qubits)
     int rcoset_mode = 1;        // register-resident coset kernel (x-mask rank <= 4): 0 never, 1 auto, 2 whenever applicable
+    int rc_expval_ctas_per_sm = 16; // MODE 1 grid target: CTAs per SM (each walks n_sets / grid coset sets in turn)
     int dcoset = 1;             // FP64 tensor-core dense-coset kernel (complex128, x-mask rank 4 or 5): 0 never,
                                 // 1 when the cost model below prefers it, 2 whenever applicable
     int rcoset_log_nt = 7;      // its CTA size (128 / 256 threads)
@@ -1013,7 +1014,7 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
     uint64_t iters = 1;
     if (MODE == 1)
     {
-        uint64_t const target = static_cast<uint64_t>(ctx->sm_count) * 16;
+        uint64_t const target = static_cast<uint64_t>(ctx->sm_count) * ctx->rc_expval_ctas_per_sm;
         uint64_t const want_cb = std::max<uint64_t>(1, target / nct);
         iters = std::min<uint64_t>(std::max<uint64_t>(1, (n_sets + want_cb - 1) / want_cb), 4096);
     }
@@ -1478,6 +1479,8 @@ extern "C"
             ctx->rcoset_mode = atoi(env);
         if (char const *env = getenv("FASTPAULI_DCOSET"))
             ctx->dcoset = atoi(env);
+        if (char const *env = getenv("FASTPAULI_RC_EXPVAL_CTAS_PER_SM"))
+            ctx->rc_expval_ctas_per_sm = std::max(1, atoi(env));
         if (char const *env = getenv("FASTPAULI_RCOSET_LOG_NT"))
             ctx->rcoset_log_nt = atoi(env);
         if (char const *env = getenv("FASTPAULI_ZERO_COPY"))
