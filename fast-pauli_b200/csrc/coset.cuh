@@ -95,8 +95,8 @@ template <int LOG_TWC, int LOG_NT, int VPT = 16> struct CosetCfg
 template <typename T> struct CosetSmemLayout
 {
     static constexpr size_t off_c = 0;                                                // Cx<T>  [CH_S]
-    static constexpr size_t off_zl = off_c + kCosetChunkStrings * sizeof(Cx<T>);     // uint32 [CH_S] local z
-    static constexpr size_t off_aux = off_zl + kCosetChunkStrings * 4;               // uint32 [CH_S] row-slot sign mask
+    static constexpr size_t off_zl = off_c + kCosetChunkStrings * sizeof(Cx<T>);     // uint32 [CH_S] local z (low 16 bits) | row-slot sign mask (high 16)
+    static constexpr size_t off_aux = off_zl + kCosetChunkStrings * 4;               // (spare)
     static constexpr size_t off_sidx = off_aux + kCosetChunkStrings * 4;             // uint32 [CH_S] W row (MODE 2)
     static constexpr size_t off_gxl = off_sidx + kCosetChunkStrings * 4;             // uint32 [CH_G]
     static constexpr size_t off_gstart = off_gxl + kCosetChunkGroups * 4;            // uint32 [CH_G + 2]
@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(1 << LOG_NT)
     unsigned char *meta = smem_raw + Cfg::TILE_BYTES;
     Cx<T> *s_c = reinterpret_cast<Cx<T> *>(meta + L::off_c);
     uint32_t *s_zl = reinterpret_cast<uint32_t *>(meta + L::off_zl);
-    uint32_t *s_aux = reinterpret_cast<uint32_t *>(meta + L::off_aux);
     uint32_t *s_sidx = reinterpret_cast<uint32_t *>(meta + L::off_sidx);
     uint32_t *s_gxl = reinterpret_cast<uint32_t *>(meta + L::off_gxl);
     uint32_t *s_gstart = reinterpret_cast<uint32_t *>(meta + L::off_gstart);
@@ -193,8 +192,7 @@ __global__ void __launch_bounds__(1 << LOG_NT)
 #pragma unroll
             for (uint32_t q = 0; q < RPT; ++q)
                 hp ^= (__popc((q << LOG_NT) & zl) & 1u) << q;
-            s_zl[s] = zl & (NT - 1);
-            s_aux[s] = hp;
+            s_zl[s] = (zl & (NT - 1)) | (hp << 16); // one broadcast LDS per string: thread-index z bits | row-slot signs
             if (MODE == 2)
                 s_sidx[s] = pass.sidx[ch.s_lo + s];
             else
@@ -223,7 +221,8 @@ __global__ void __launch_bounds__(1 << LOG_NT)
                 for (uint32_t s = s0; s < s1; ++s)
                 {
                     Cx<T> const c = s_c[s];
-                    uint32_t const par = s_aux[s] ^ ((__popc(tid & s_zl[s]) & 1u) ? 0xffffu : 0u);
+                    uint32_t const zm = s_zl[s];
+                    uint32_t const par = (zm >> 16) ^ ((__popc(tid & zm & 0xffffu) & 1u) ? 0xffffu : 0u);
 #pragma unroll
                     for (int q = 0; q < RPT; ++q)
                     {
@@ -258,7 +257,8 @@ __global__ void __launch_bounds__(1 << LOG_NT)
                             d[q][j][e] = Cx<T>{0, 0};
                 for (uint32_t s = s0; s < s1; ++s)
                 {
-                    uint32_t const par = s_aux[s] ^ ((__popc(tid & s_zl[s]) & 1u) ? 0xffffu : 0u);
+                    uint32_t const zm = s_zl[s];
+                    uint32_t const par = (zm >> 16) ^ ((__popc(tid & zm & 0xffffu) & 1u) ? 0xffffu : 0u);
                     uint64_t const wrow = static_cast<uint64_t>(s_sidx[s]) * B + t0;
                     T wre[NCOL], wim[NCOL];
 #pragma unroll
