@@ -129,8 +129,25 @@ def gen_cases(seed: int, n_max: int = 14, log2_elems: int = 21, s_cap: int = 10*
                    data=data, tag=tag, case=case, accumulate=(case % 2 == 0))
 
 
+def load_native():
+    """The pybind11 front-end (fast-pauli_b200/_fast_pauli*.so), or None when it is not built."""
+    import glob
+    import importlib.util
+
+    if "_fast_pauli" in sys.modules:
+        return sys.modules["_fast_pauli"]
+    hits = glob.glob(os.path.join(ROOT, "fast-pauli_b200", "_fast_pauli*.so"))
+    if not hits:
+        return None
+    spec = importlib.util.spec_from_file_location("_fast_pauli", hits[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sys.modules["_fast_pauli"] = mod
+    return mod
+
+
 def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool = False, n_max: int = 14,
-        log2_elems: int = 21, s_cap: int = 10**9) -> tuple[int, list[str]]:
+        log2_elems: int = 21, s_cap: int = 10**9, native: bool = False) -> tuple[int, list[str]]:
     from __graft_entry__ import load_package
     from oracle import oracle as orc
 
@@ -139,6 +156,7 @@ def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool =
     # the oracle-shaped one-shot entry points of the GPU library: `out=` is accumulated into, like the C++ methods
     G = orc.Backend(os.path.join(ROOT, "fast-pauli_b200", "lib", "libfastpauli_b200.so"), "fp_", "gpu")
     ctx = fp.default_context()
+    nf = load_native() if native else None
     t_end = time.time() + seconds
     failures: list[str] = []
     notes: list[str] = []  # disagreements settled in the GPU's favour by the extended-precision arbiter
@@ -175,6 +193,18 @@ def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool =
                 "sop.expval": (fp.SummedPauliOp(strings, hk).expectation_value(arg),
                                ORC.sop_expval(strings, hk_hi, psi_hi)),
             }
+            if nf is not None and dtype == np.complex128:
+                # the same seven calls through the pybind11 module over the C++ classes (host complex128 arrays)
+                nop, nsop, nps = nf.PauliOp(h, strings), nf.SummedPauliOp(strings, hk), nf.PauliString(strings[0])
+                checks.update({
+                    "native string.apply": (nps.apply(psi, 0.5 - 2j), checks["string.apply"][1]),
+                    "native string.expval": (nps.expectation_value(psi, 0.5 - 2j), checks["string.expval"][1]),
+                    "native op.apply": (nop.apply(psi), checks["op.apply"][1]),
+                    "native op.expval": (nop.expectation_value(psi), checks["op.expval"][1]),
+                    "native sop.apply": (nsop.apply(psi), checks["sop.apply"][1]),
+                    "native sop.apply_weighted": (nsop.apply_weighted(psi, data), checks["sop.apply_weighted"][1]),
+                    "native sop.expval": (nsop.expectation_value(psi), checks["sop.expval"][1]),
+                })
             if case["accumulate"] and dtype == np.complex128:
                 # C++ semantics (+= into the caller's buffer, PS:419,432,523,534; PO:453,465; SPO:331,346,464,498,
                 # 588,609) through the raw C ABI; complex128 only so the bases do not mask float32 rounding
@@ -201,13 +231,14 @@ def run(seconds: float, seed: int, max_cases: int | None = None, verbose: bool =
                 if e < tol:
                     continue
                 if name.endswith("expval") and not name.startswith("acc"):
+                    name_key = name.replace("native ", "")
                     # arbitrate in extended precision: the GPU must be within tolerance of the exact value and at
                     # least as close to it as the reference-order sum is
-                    used = strings[:1] if name.startswith("string") else strings
+                    used = strings[:1] if name_key.startswith("string") else strings
                     E = exact_string_expvals(used, psi_hi)
                     exact = {"string.expval": lambda: E[0] * np.clongdouble(0.5 - 2j),
                              "op.expval": lambda: h_hi.astype(np.clongdouble) @ E,
-                             "sop.expval": lambda: hk_hi.astype(np.clongdouble).T @ E}[name]()
+                             "sop.expval": lambda: hk_hi.astype(np.clongdouble).T @ E}[name_key]()
                     e_gpu, e_ref = rel(got, exact.reshape(want.shape)), rel(want, exact.reshape(want.shape))
                     if e_gpu < tol and e_gpu <= e_ref:
                         notes.append(f"{name}: reference-order rounding {e_ref:.2e} > tol, gpu {e_gpu:.2e} | {tag}")
@@ -231,8 +262,10 @@ if __name__ == "__main__":
     ap.add_argument("--n-max", type=int, default=14, help="largest register (qubits)")
     ap.add_argument("--log2-elems", type=int, default=21, help="cap on dim * n_states")
     ap.add_argument("--s-cap", type=int, default=10**9, help="cap on the number of strings per operator")
+    ap.add_argument("--native", action="store_true", help="also drive the pybind11 front-end (complex128 host cases)")
     a = ap.parse_args()
-    n_cases, fails = run(a.seconds, a.seed, verbose=a.verbose, n_max=a.n_max, log2_elems=a.log2_elems, s_cap=a.s_cap)
+    n_cases, fails = run(a.seconds, a.seed, verbose=a.verbose, n_max=a.n_max, log2_elems=a.log2_elems, s_cap=a.s_cap,
+                         native=a.native)
     for f in fails:
         print("FAIL", f)
     print(f"fuzz: {n_cases} cases, {len(fails)} failures (seed {a.seed})")

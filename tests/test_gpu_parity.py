@@ -193,7 +193,7 @@ def test_fuzz_fixed_seeds(seed):
     sys.path.insert(0, os.path.join(ROOT, "scripts"))
     import fuzz_parity
 
-    cases, failures = fuzz_parity.run(seconds=25, seed=seed, max_cases=200)
+    cases, failures = fuzz_parity.run(seconds=25, seed=seed, max_cases=200, native=(seed == 8))  # 8: both front-ends
     assert cases >= 20 and not failures, "\n".join(failures[:20])
 
 
