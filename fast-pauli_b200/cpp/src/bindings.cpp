@@ -71,18 +71,24 @@ void need_1d_or_2d(CArray const &a, char const *what)
         throw std::invalid_argument(std::string(what) + ": expected 1 or 2 dimensions, got " + std::to_string(a.ndim()));
 }
 
+// The C++ methods take non-const mdspans for their inputs as well (like the reference's); inputs are never written,
+// so read-only numpy arrays (e.g. views of constants, np.broadcast_to results made contiguous) are accepted.
+cd *ptr(CArray &a)
+{
+    return const_cast<cd *>(a.data());
+}
 Span<1> span1(CArray &a)
 {
-    return Span<1>(a.mutable_data(), static_cast<size_t>(a.shape(0)));
+    return Span<1>(ptr(a), static_cast<size_t>(a.shape(0)));
 }
 Span<2> span2(CArray &a)
 {
-    return Span<2>(a.mutable_data(), static_cast<size_t>(a.shape(0)), static_cast<size_t>(a.shape(1)));
+    return Span<2>(ptr(a), static_cast<size_t>(a.shape(0)), static_cast<size_t>(a.shape(1)));
 }
 // a 1-D state viewed as a (dim, 1) batch
 Span<2> column(CArray &a)
 {
-    return Span<2>(a.mutable_data(), static_cast<size_t>(a.shape(0)), 1);
+    return Span<2>(ptr(a), static_cast<size_t>(a.shape(0)), 1);
 }
 
 std::vector<std::string> as_strings(std::vector<fp::PauliString> const &ps)
@@ -426,7 +432,8 @@ PYBIND11_MODULE(_fast_pauli, m)
                 std::vector<py::ssize_t> shape(states.shape(), states.shape() + states.ndim());
                 CArray out = zeros(shape);
                 bool const one = states.ndim() == 1;
-                std::mdspan<double, std::dextents<size_t, 2>> w(data.mutable_data(), static_cast<size_t>(data.shape(0)),
+                std::mdspan<double, std::dextents<size_t, 2>> w(const_cast<double *>(data.data()),
+                                                                static_cast<size_t>(data.shape(0)),
                                                                 one ? 1 : static_cast<size_t>(data.shape(1)));
                 self.apply_weighted(std::execution::par, one ? column(out) : span2(out),
                                     one ? column(states) : span2(states), w);
@@ -441,7 +448,7 @@ PYBIND11_MODULE(_fast_pauli, m)
                 bool const one = states.ndim() == 1;
                 auto const K = static_cast<py::ssize_t>(self.n_operators());
                 CArray out = one ? zeros({K}) : zeros({K, states.shape(1)});
-                Span<2> o(out.mutable_data(), static_cast<size_t>(K), one ? 1 : static_cast<size_t>(states.shape(1)));
+                Span<2> o(ptr(out), static_cast<size_t>(K), one ? 1 : static_cast<size_t>(states.shape(1)));
                 self.expectation_value(std::execution::par, o, one ? column(states) : span2(states));
                 return out;
             },
@@ -450,7 +457,7 @@ PYBIND11_MODULE(_fast_pauli, m)
              [](Sop const &self) {
                  auto const d = static_cast<py::ssize_t>(self.dim());
                  CArray out = zeros({static_cast<py::ssize_t>(self.n_operators()), d, d});
-                 self.to_tensor(Span<3>(out.mutable_data(), self.n_operators(), self.dim(), self.dim()));
+                 self.to_tensor(Span<3>(ptr(out), self.n_operators(), self.dim(), self.dim()));
                  return out;
              })
         .def("clone", [](Sop const &self) { return Sop(self); })
