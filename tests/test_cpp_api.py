@@ -28,6 +28,14 @@ def test_cpp_api_host_only():
     assert "0 failures" in r.stdout
 
 
+def test_host_planners_evaluate_to_the_definition():
+    """pack.hpp + coset_plan.hpp (host code, no GPU): the packed / planned operator, evaluated on the host with the
+    kernels' indexing, equals the definition for 165 random operators x every tile rank x reserved low bits."""
+    build()
+    r = subprocess.run([os.path.join(ROOT, "tests", "cpp", "test_host_plan")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "failed: 0" in r.stdout, r.stdout[-3000:]
+
+
 @pytest.mark.gpu
 def test_cpp_api_gpu():
     if not os.path.exists(EXE):
