@@ -2,7 +2,7 @@
 """Randomised dispatch fuzzer (GPU): random register sizes, batch widths, operator structures, dtypes and array
 residency through every hot-path entry point of the Python front-end, each result checked against the CPU oracle.
 
-    python scripts/fuzz_parity.py --seconds 120 --seed 1        # prints one line per failure + a summary
+    python tests/fuzz_parity.py --seconds 120 --seed 1        # prints one line per failure + a summary
 
 The operator families are chosen to land on every kernel-selection branch (single mask, few masks x many z, k-local
 dense = register / tensor-core cosets, low weight = shared-memory cosets, i.i.d. = generic gather, chains, diagonal

@@ -4,7 +4,7 @@ exercised by ``-m "not gpu"`` tests on a machine without a CUDA device.
 
 ``MockABI`` answers the same entry points as ``include/fastpauli_b200.h`` for HOST pointers, computing with the CPU
 oracle (``oracle/``: the checker, never the product).  It is installed only by the ``mock_abi`` fixture of
-``tests/test_reference_python_cases.py`` (and by ``scripts/run_reference_pytests.py --mock``); nothing under
+``tests/test_reference_python_cases.py`` (and by ``tests/run_reference_pytests.py --mock``); nothing under
 ``fast-pauli_b200/`` knows it exists, and the product still fails with ``RuntimeError`` without a GPU.
 """
 from __future__ import annotations

@@ -188,10 +188,9 @@ def test_small_registers_every_batch_width(dtype, n):
 
 @pytest.mark.parametrize("seed", [7, 8])
 def test_fuzz_fixed_seeds(seed):
-    """A bounded replay of scripts/fuzz_parity.py: random registers (1..14 qubits), batch widths, operator families,
+    """A bounded replay of tests/fuzz_parity.py: random registers (1..14 qubits), batch widths, operator families,
     dtypes and host / device residency through all seven Python entry points against the oracle."""
-    sys.path.insert(0, os.path.join(ROOT, "scripts"))
-    import fuzz_parity
+    import fuzz_parity  # tests/fuzz_parity.py
 
     cases, failures = fuzz_parity.run(seconds=25, seed=seed, max_cases=200, native=(seed == 8))  # 8: both front-ends
     assert cases >= 20 and not failures, "\n".join(failures[:20])

@@ -12,7 +12,7 @@ Every case runs three times:
   by the CPU oracle), which checks the HOST logic only -- dispatch on 1-D / 2-D input, implicit dtype conversion,
   output shapes, shape errors raised before a device is needed, coefficient orientation, plan invalidation.
 
-``scripts/run_reference_pytests.py`` runs the reference's own, unmodified pytest files against this package where
+``tests/run_reference_pytests.py`` runs the reference's own, unmodified pytest files against this package where
 ``/root/reference`` exists (202 passed, 6 skipped over the mock; see README.md).
 """
 from __future__ import annotations
