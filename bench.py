@@ -3,24 +3,28 @@
 
 Metric (BASELINE.json): PauliOp.apply amplitude*strings/s and HBM GB/s (% of roofline).
 
-Workload at every N (weak scaling, one rank per GPU, no data-path collective): BASELINE config 2,
-    PauliString.apply_batch + PauliString.expectation_value, 20 qubits, batch 256 per GPU, complex128
-(4 GiB in + 4 GiB out per GPU; a PauliString is the one-string PauliOp, and both calls run the same
-kernels PauliOp.apply / expectation_value use).  One "step" = one apply_batch + one expectation_value
-over the whole resident batch = 2 * dim * n_states amplitude*strings per GPU.
+Workload at every N (weak scaling, one rank per GPU, no data-path collective): the north-star shape
+    PauliOp.apply (2-D overload, reference __pauli_op.hpp:399-468), 20 qubits, complex128, batch 64 per GPU,
+on the SURVEY.md 8(d) operator pair:
+    (i)  "few_group": 64 strings over 8 x-masks (8 z-variants each)  -> HBM-bound
+    (ii) "random":    64 i.i.d. uniform IXYZ strings (64 x-masks)     -> FP64-bound (8*64 flops per amplitude)
+One "step" = one apply of (i) + one apply of (ii) over the resident batch = 2 * 64 * dim * B amplitude*strings/GPU.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extras] [--no-cpu-baseline]
 
 For N > 1 launch with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ...
-Rank 0 prints exactly one JSON line on stdout.
+Rank 0 prints exactly one JSON line on stdout.  At N > 1 the line also carries `config3_strong` (BASELINE config 3:
+one global batch of 1024 columns split over the ranks) and `config5` (one state sharded by its high index bits,
+pairwise exchange through the C ABI's fp_comm_* entry points).
 
 --impl reference times the reference's own OpenMP CPU implementation (oracle/_ref, compiled from the unmodified
-reference headers; falls back to the plain-C port) on the host cores for the same metric/config, each step a
-bounded column sample of the workload.
+reference headers; falls back to the plain-C port) on the host cores on the SAME config: every step is the full
+20-qubit x 64-column step.
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -35,22 +39,91 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_QUBITS = 20
-BATCH = 256
+BATCH = 64
+N_STRINGS = 64
 DTYPE = np.complex128
 SEED = 18
 STRING_SEED = 1234
-METRIC = "PauliOp.apply amplitude*strings/s (PauliString.apply_batch + expectation_value, 20 qubits, batch 256/GPU, complex128)"
+METRIC = "PauliOp.apply amplitude*strings/s (20 qubits, complex128, batch 64/GPU; 64 strings over 8 x-masks + 64 random strings)"
 UNIT = "amplitude*strings/s"
 EMIT = print
 
 
-def make_string(n: int, seed: int = STRING_SEED) -> str:
-    """One i.i.d. uniform IXYZ string (tests/benchmarks/test_qiskit_adv.py:122-125 style), fixed seed."""
-    rng = np.random.default_rng(seed)
-    s = "".join(np.array(list("IXYZ"))[rng.integers(0, 4, size=n)])
-    if "X" not in s and "Y" not in s:  # keep the gather non-trivial
-        s = "X" + s[1:]
-    return s
+def synth():
+    """fast-pauli_b200/synth.py (numpy only) loaded WITHOUT importing the product package: the reference arm must not
+    map the product library."""
+    mod = sys.modules.get("_fp_synth_standalone")
+    if mod is None:
+        spec = importlib.util.spec_from_file_location("_fp_synth_standalone",
+                                                      os.path.join(ROOT, "fast-pauli_b200", "synth.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["_fp_synth_standalone"] = mod
+        spec.loader.exec_module(mod)
+    return mod
+
+
+def headline_operators(n: int = N_QUBITS) -> dict:
+    """The SURVEY 8(d) operator pair, deterministic: name -> (strings, coefficients)."""
+    rng = np.random.default_rng(STRING_SEED)
+    rs = synth().random_strings
+    few = []
+    for s in rs(rng, n, 8):  # 8 z-variants per x-mask: swapping X<->Y and I<->Z keeps the x-mask
+        for _ in range(8):
+            t = list(s)
+            for q in range(n):
+                if rng.random() < 0.5:
+                    t[q] = {"X": "Y", "Y": "X", "I": "Z", "Z": "I"}[t[q]]
+            few.append("".join(t))
+    rand = rs(rng, n, N_STRINGS)
+    ops = {}
+    for name, strings in (("few_group", few), ("random", rand)):
+        h = rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))
+        ops[name] = (strings, h.astype(DTYPE))
+    return ops
+
+
+def config_dict(world: int) -> dict:
+    dim = 1 << N_QUBITS
+    return {"workload": "PauliOp.apply (2-D), 20 qubits, complex128, batch 64 per GPU: step = apply(64 strings over 8 "
+                        "x-masks) + apply(64 random strings); batch-axis sharded (no collective)",
+            "n_qubits": N_QUBITS, "batch_per_gpu": BATCH, "global_batch": BATCH * world, "n_strings": N_STRINGS,
+            "operators": ["few_group: 64 strings / 8 x-masks", "random: 64 i.i.d. IXYZ strings"],
+            "state_bytes_per_gpu": dim * BATCH * 16,
+            "l2": "inputs (1 GiB in + 1 GiB out per GPU and operator) are 8x larger than L2; no flush needed",
+            "input_generator": f"counter-based splitmix64 U[0,1)+iU[0,1), seed {SEED}+rank; strings seed {STRING_SEED}"}
+
+
+def masks_of(string: str) -> tuple[int, int, int]:
+    """(x, z, nY) with string[q] <-> bit n-1-q (reference __pauli_string.hpp:52-54, 94-98)."""
+    n = len(string)
+    x = z = ny = 0
+    for q, ch in enumerate(string):
+        bit = 1 << (n - 1 - q)
+        if ch in "XY":
+            x |= bit
+        if ch in "YZ":
+            z |= bit
+        ny += ch == "Y"
+    return x, z, ny
+
+
+def closed_form_rows(strings, coeffs, rows: np.ndarray, B: int, seed: int, first: int = 0,
+                     cols: np.ndarray | None = None, ld: int | None = None) -> np.ndarray:
+    """out[rows, cols] of PauliOp.apply on the counter-generated batch, from the closed form
+    out(i,t) = sum_s h_s (-i)^nY_s (-1)^popc(i & z_s) psi(i ^ x_s, t); numpy only (no oracle, no product code)."""
+    sy = synth()
+    ld = B if ld is None else ld
+    cols = np.arange(B, dtype=np.uint64) if cols is None else np.asarray(cols, dtype=np.uint64)
+    rows = np.asarray(rows, dtype=np.uint64)
+    out = np.zeros((len(rows), len(cols)), dtype=np.complex128)
+    for s, h in zip(strings, coeffs):
+        x, z, ny = masks_of(s)
+        src = rows ^ np.uint64(x)
+        par = np.array([bin(int(r) & z).count("1") & 1 for r in rows])
+        m = (1 - 2 * par) * ((-1j) ** ny)
+        idx = src[:, None] * np.uint64(ld) + cols[None, :] + np.uint64(first)
+        out += (h * m)[:, None] * sy.uniform_complex_at(idx, np.complex128, seed)
+    return out
 
 
 def peaks() -> dict:
@@ -111,27 +184,32 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_step(backend, string: str, n: int, cols: int, par: bool = True) -> tuple[float, float]:
-    """One bounded step of the reference CPU path: apply_batch + expectation_value on `cols` columns.
-    Returns (seconds, amplitude*strings processed)."""
-    from __graft_entry__ import load_package
+class CpuStep:
+    """The full benchmark step on the reference CPU path: PauliOp::apply (std::execution::par overload,
+    __pauli_op.hpp:413-468) of both headline operators on the same (dim, 64) host batch the GPU arm uses."""
 
-    load_package()  # only for the host twin of the input generator; no GPU work on this arm
-    from fast_pauli_b200.synth import uniform_host
+    def __init__(self, backend):
+        self.be = backend
+        self.ops = headline_operators()
+        dim = 1 << N_QUBITS
+        self.psi = synth().uniform_host((dim, BATCH), DTYPE, seed=SEED)
+        self.out = np.zeros_like(self.psi)
+        self.work = 2.0 * N_STRINGS * dim * BATCH
 
-    dim = 1 << n
-    psi = getattr(cpu_reference_step, "_psi", None)
-    if psi is None or psi.shape != (dim, cols):
-        psi = uniform_host((dim, cols), DTYPE, seed=SEED)
-        cpu_reference_step._psi = psi
-        cpu_reference_step._out = np.zeros_like(psi)
-        cpu_reference_step._ev = np.zeros(cols, dtype=DTYPE)
-    out, ev = cpu_reference_step._out, cpu_reference_step._ev
-    t0 = time.perf_counter()
-    backend.string_apply(string, psi, 0.75 - 0.5j, out=out, par=par)
-    backend.string_expval(string, psi, 0.75 - 0.5j, out=ev, par=par)
-    dt = time.perf_counter() - t0
-    return dt, 2.0 * dim * cols
+    def run(self, which=("few_group", "random")) -> float:
+        t0 = time.perf_counter()
+        for name in which:
+            strings, h = self.ops[name]
+            self.out[...] = 0
+            self.be.op_apply(strings, h, self.psi, out=self.out, par=True)
+        return time.perf_counter() - t0
+
+
+def cpu_sample_text(be) -> str:
+    impl = ("unmodified reference headers compiled by oracle/Makefile (x86-64-v3: AVX2+FMA, no AVX-512, so the "
+            "prebuilt .so runs on any host), std::execution::par") if be.kind == "reference" else "plain-C port, OpenMP"
+    return (f"the full step: both operators on all {BATCH} columns of one rank's 20-qubit batch (the host has one "
+            f"memory system whatever N is); {impl}")
 
 
 def run_reference_arm(args) -> None:
@@ -142,27 +220,19 @@ def run_reference_arm(args) -> None:
 
     be = orc.reference() or orc.port()
     be.use_all_threads()  # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every host core
-    string = make_string(N_QUBITS)
-    cols = 16  # bounded sample: 16 of the 256 columns per step (work is exactly linear in the batch)
     threads = be.max_threads()
-    for _ in range(max(1, min(args.warmup, 2))):
-        cpu_reference_step(be, string, N_QUBITS, cols)
-    times, work = [], 0.0
-    for _ in range(args.steps):
-        dt, w = cpu_reference_step(be, string, N_QUBITS, cols)
-        times.append(dt)
-        work += w
+    step = CpuStep(be)
+    for _ in range(args.warmup):
+        step.run()
+    times = [step.run() for _ in range(args.steps)]
     total = sum(times)
-    value = work / total
-    sample = (f"{cols} of {BATCH} batch columns per step (work is linear in the batch); "
-              f"{'unmodified reference headers, std::execution::par' if be.kind == 'reference' else 'plain-C port, OpenMP'}")
+    value = step.work * args.steps / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
-        "config": {"workload": "BASELINE config 2: PauliString.apply_batch + expectation_value, 20 qubits, complex128",
-                   "n_qubits": N_QUBITS, "batch_per_step": cols, "string": string},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": be.kind, "sample": sample},
+        "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic", "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": be.kind,
+                         "sample": cpu_sample_text(be), "statistic": "mean over the timed steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -190,7 +260,7 @@ def timed_ms(fp, ctx, fn, iters: int, warmup: int = 1) -> float:
     return ms.value / iters
 
 
-def run_extras(fp, ctx, hbm_peak: float) -> dict:
+def run_extras(fp, ctx, hbm_peak: float, fp64_tflops: float = 37.2) -> dict:
     """Device-resident timings of the other BASELINE configs (reported beside the headline, never as `value`)."""
     from fast_pauli_b200.synth import random_strings as rand_strings
 
@@ -529,25 +599,20 @@ def run_ours(args) -> None:
 
     n, B = N_QUBITS, BATCH
     dim = 1 << n
-    string = make_string(n)
-    coeff = np.array([0.75 - 0.5j], dtype=DTYPE)
-    codes, _ = fp._encode([string])
+    ops = headline_operators(n)
+    names = ("few_group", "random")
+    pauli_ops = {k: fp.PauliOp(ops[k][1], ops[k][0], ctx=ctx) for k in names}
+    plans = {k: pauli_ops[k]._plan(DTYPE) for k in names}
+    infos = {k: pauli_ops[k].plan_info() for k in names}
     # batch shard of this rank: columns [rank*B, (rank+1)*B) of the global (dim, B*world) batch -- the generator is
-    # counter based, so give every rank a distinct stream offset
+    # counter based, so give every rank a distinct stream
     psi = ctx.uniform((dim, B), DTYPE, seed=SEED + rank)
-    out = ctx.empty((dim, B), DTYPE)
-    ev = ctx.empty((B,), DTYPE)
+    outs = {k: ctx.empty((dim, B), DTYPE) for k in names}
     ctx.set_async(True)
 
-    def apply_call():
-        rc = fp.lib.fp_string_apply(ctx._h, fp.FP_C128, n, _vp(codes.ctypes.data), _vp(coeff.ctypes.data), _vp(out.ptr),
-                                    _vp(psi.ptr), _sz(dim), _sz(B), 0)
-        if rc:
-            raise RuntimeError(fp.lib.fp_last_error().decode())
-
-    def expval_call():
-        rc = fp.lib.fp_string_expval(ctx._h, fp.FP_C128, n, _vp(codes.ctypes.data), _vp(coeff.ctypes.data), _vp(ev.ptr),
-                                     _vp(psi.ptr), _sz(dim), _sz(B), 0)
+    def apply_call(k, dst_ptr=None, src_ptr=None):
+        rc = fp.lib.fp_op_apply(ctx._h, plans[k], _vp(outs[k].ptr if dst_ptr is None else dst_ptr),
+                                _vp(psi.ptr if src_ptr is None else src_ptr), _sz(dim), _sz(B), 0)
         if rc:
             raise RuntimeError(fp.lib.fp_last_error().decode())
 
@@ -558,14 +623,31 @@ def run_ours(args) -> None:
         if torch is not None:
             torch.cuda.synchronize()
 
+    # ---- parity gate before anything is timed: sampled rows of both results against the closed form on regenerated
+    # inputs (numpy, no oracle).  A number from a wrong result is not reported.
+    parity = {}
+    prng = np.random.default_rng(99 + rank)
+    rows = np.unique(np.concatenate([prng.integers(0, dim, size=24), [0, dim - 1]])).astype(np.uint64)
+    for k in names:
+        l0 = ctx.launch_count
+        apply_call(k)
+        ctx.sync()
+        launches_call = ctx.launch_count - l0
+        got = np.stack([outs[k].get_rows(int(r), int(r) + 1)[0] for r in rows])
+        exp = closed_form_rows(ops[k][0], ops[k][1], rows, B, SEED + rank)
+        err = float(np.max(np.abs(got - exp)) / np.max(np.abs(exp)))
+        parity[k] = {"max_rel_err": err, "rows_checked": int(len(rows)), "tol": 1e-12, "launches_per_call": int(launches_call)}
+        if not err < 1e-12:
+            raise SystemExit(f"parity gate failed for operator {k}: {err:.3e}")
+
     for _ in range(max(args.warmup, 3)):
-        apply_call()
-        expval_call()
+        for k in names:
+            apply_call(k)
     barrier()
 
     K = args.steps
     evs = []
-    for _ in range(3 * K + 1):
+    for _ in range(2 * K + 1):
         e = C.c_void_p()
         fp.lib.fp_event_create(C.byref(e))
         evs.append(e)
@@ -576,12 +658,11 @@ def run_ours(args) -> None:
     barrier()
     l0 = ctx.launch_count
     fp.lib.fp_event_record(ctx._h, evs[0])
-    for k in range(K):
-        apply_call()
-        fp.lib.fp_event_record(ctx._h, evs[3 * k + 1])
-        expval_call()
-        fp.lib.fp_event_record(ctx._h, evs[3 * k + 2])
-    fp.lib.fp_event_record(ctx._h, evs[3 * K])
+    for k_ in range(K):
+        apply_call("few_group")
+        fp.lib.fp_event_record(ctx._h, evs[2 * k_ + 1])
+        apply_call("random")
+        fp.lib.fp_event_record(ctx._h, evs[2 * k_ + 2])
     barrier()
     launches = ctx.launch_count - l0
     clocks = sampler.stop() if rank == 0 else {}
@@ -591,58 +672,71 @@ def run_ours(args) -> None:
         fp.lib.fp_event_elapsed_ms(evs[a], evs[b], C.byref(ms))
         return float(ms.value)
 
-    total_ms = el(0, 3 * K)
-    apply_ms = [el(3 * k if k == 0 else 3 * k - 1, 3 * k + 1) for k in range(K)]
-    expval_ms = [el(3 * k + 1, 3 * k + 2) for k in range(K)]
+    total_ms = el(0, 2 * K)
+    call_ms = {"few_group": sum(el(2 * k_, 2 * k_ + 1) for k_ in range(K)) / K,
+               "random": sum(el(2 * k_ + 1, 2 * k_ + 2) for k_ in range(K)) / K}
     if dist is not None:
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / K
-    value = world * 2.0 * dim * B / (ms_per_step * 1e-3)
+    value = world * 2.0 * N_STRINGS * dim * B / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (the streaming apply): algorithmic bytes = dim*B*16 B read + 16 B written
-    apply_avg = sum(apply_ms) / K
-    expval_avg = sum(expval_ms) / K
+    # ---- roofline per operator call: algorithmic bytes = dim*B*(16 B read + 16 B written) whatever the number of
+    # strings; companion compute figure 8 flops per amplitude per distinct x-mask; the bound of a call
+    # is the slower of the two and frac is quoted against it.
+    fp64 = fp64_peak(fp, ctx, clocks)
     alg_bytes = dim * B * 32.0
-    achieved = alg_bytes / (apply_avg * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_dram_traffic.json")
+    traffic_db = {}
+    tpath = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("string_apply_c128_20q_b256_bytes")
+            traffic_db = json.load(open(tpath))
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "op_kernel<double,EPV=1,V=4,MODE=0,INLINE1> (PauliString.apply_batch)",
-                "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                "traffic": traffic, "peak_source": pk["source"], "algorithmic_bytes_per_launch": alg_bytes,
-                "avg_launch_ms": apply_avg,
-                "note": "peak is the driver-measured torch copy bandwidth (b.copy_(a)); frac > 1 means this kernel moves "
-                        "its compulsory bytes faster than that copy (nominal HBM3e: 8000 GB/s -> frac_nominal below)",
-                "frac_nominal_8TBps": alg_bytes / (apply_avg * 1e-3) / 1e9 / 8000.0,
-                "second_kernel": {"kernel": "expval_pairs_kernel<double,1,4,1> (PauliString.expectation_value)",
-                                  "algorithmic_bytes_per_launch": dim * B * 16.0, "avg_launch_ms": expval_avg,
-                                  "achieved": dim * B * 16.0 / (expval_avg * 1e-3) / 1e9,
-                                  "frac": dim * B * 16.0 / (expval_avg * 1e-3) / 1e9 / pk["hbm_gbs"]}}
+            traffic_db = {}
 
-    # ---- end to end through the public C ABI with pinned HOST buffers (H2D + kernel + D2H inside the call)
+    def roof(k):
+        G = infos[k]["n_x_groups"]
+        t = call_ms[k] * 1e-3
+        t_hbm = alg_bytes / (pk["hbm_gbs"] * 1e9)
+        flops = 8.0 * G * dim * B
+        t_fp = flops / (fp64["tflops"] * 1e12)
+        tr = traffic_db.get(k, {})
+        r = {"operator": k, "x_groups": G, "strings": N_STRINGS, "avg_call_ms": call_ms[k],
+             "launches_per_call": parity[k]["launches_per_call"],
+             "algorithmic_bytes_per_call": alg_bytes, "hbm_GBps": alg_bytes / t / 1e9,
+             "hbm_frac": t_hbm / t, "fp64_TFLOPs": flops / t / 1e12, "fp64_frac": t_fp / t,
+             "t_hbm_ms": 1e3 * t_hbm, "t_fp64_ms": 1e3 * t_fp,
+             "amp_strings_per_s": N_STRINGS * dim * B / t,
+             "traffic": tr.get("dram_bytes_per_call"), "traffic_source": tr.get("source"),
+             "kernel": tr.get("kernel", "coset_few_kernel<double,1,4,8> (K3e, csrc/coset2.cuh)")}
+        if t_hbm >= t_fp:
+            r.update(bound="hbm", achieved=alg_bytes / t / 1e9, peak=pk["hbm_gbs"], unit="GB/s", frac=t_hbm / t)
+        else:
+            r.update(bound="fp64", achieved=flops / t / 1e12, peak=fp64["tflops"], unit="TFLOP/s", frac=t_fp / t)
+        return r
+
+    per_op = {k: roof(k) for k in names}
+    dominant = max(names, key=lambda k: call_ms[k])
+    roofline = dict(per_op[dominant])
+    roofline.update({"peak_source": pk["source"] + "; fp64: " + fp64["source"],
+                     "note": "dominant = the operator call with the largest share of the step; frac is quoted against "
+                             "max(t_HBM, t_FP64) of that call (SURVEY 8d); `by_operator` has both calls",
+                     "by_operator": per_op})
+
+    # ---- end to end through the public C ABI with pinned HOST buffers (H2D + kernels + D2H inside the call)
     ctx.set_async(False)
     e2e = None
     try:
         if args.no_e2e:
             raise RuntimeError("skipped (--no-e2e)")
         h_in = ctx.pinned_empty((dim, B), DTYPE)
-        h_out = ctx.pinned_empty((dim, B), DTYPE)
-        h_ev = ctx.pinned_empty((B,), DTYPE)
+        h_out = {k: ctx.pinned_empty((dim, B), DTYPE) for k in names}
         fp.lib.fp_memcpy(ctx._h, _vp(h_in.ctypes.data), _vp(psi.ptr), _sz(h_in.nbytes))
 
         def e2e_step():
-            rc = fp.lib.fp_string_apply(ctx._h, fp.FP_C128, n, _vp(codes.ctypes.data), _vp(coeff.ctypes.data),
-                                        _vp(h_out.ctypes.data), _vp(h_in.ctypes.data), _sz(dim), _sz(B), 0)
-            rc |= fp.lib.fp_string_expval(ctx._h, fp.FP_C128, n, _vp(codes.ctypes.data), _vp(coeff.ctypes.data),
-                                          _vp(h_ev.ctypes.data), _vp(h_in.ctypes.data), _sz(dim), _sz(B), 0)
-            if rc:
-                raise RuntimeError(fp.lib.fp_last_error().decode())
+            for k in names:
+                apply_call(k, h_out[k].ctypes.data, h_in.ctypes.data)
 
         Ke = max(2, min(K, 5))
         e2e_step()
@@ -656,42 +750,24 @@ def run_ours(args) -> None:
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": world * 2.0 * dim * B * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * h_in.nbytes,
-               "d2h_bytes_per_step": h_out.nbytes + h_ev.nbytes, "steps": Ke, "ms_per_step": 1e3 * dt / Ke,
-               "host_numa_node_rank0": numa_node,
-               "path": "fp_string_apply + fp_string_expval with pinned host pointers: apply streams the batch through "
-                       "the GPU in 32 MiB row blocks (upload j+1 | kernel j | download j-1 on two copy engines), "
-                       "expectation_value uploads with the copy engine and reduces on the device"}
-
-        def timed_variant() -> float:
-            e2e_step()
-            barrier()
-            t1 = time.perf_counter()
-            for _ in range(2):
-                e2e_step()
-            barrier()
-            return 1e3 * (time.perf_counter() - t1) / 2
-
-        # the same calls without the chunk pipeline, for reference: (a) kernels reading / writing the pinned buffers in
-        # place over PCIe, (b) one-shot staging (cudaMemcpyAsync H2D -> kernel -> D2H)
-        ctx.set_pipeline(False)
-        e2e["zero_copy_ms_per_step"] = timed_variant()
-        ctx.set_zero_copy(False)
-        e2e["staged_copy_ms_per_step"] = timed_variant()
-        ctx.set_zero_copy(True)
-        ctx.set_pipeline(True)
+        e2e = {"value": world * 2.0 * N_STRINGS * dim * B * Ke / dt, "unit": UNIT,
+               "h2d_bytes_per_step": 2 * h_in.nbytes, "d2h_bytes_per_step": sum(h.nbytes for h in h_out.values()),
+               "steps": Ke, "ms_per_step": 1e3 * dt / Ke, "host_numa_node_rank0": numa_node,
+               "path": "fp_op_apply with pinned host pointers for input and output, once per operator: upload, "
+                       "kernels, download inside the call"}
         # keep the device result honest: the host copy of the output must equal the device-resident one
-        chk = out.get_rows(12345, 12346)
-        if not np.array_equal(chk, h_out[12345:12346]):
-            e2e["warning"] = "host-staged result differs from device-resident result"
+        for k in names:
+            chk = outs[k].get_rows(12345, 12346)
+            if not np.array_equal(chk, h_out[k][12345:12346]):
+                e2e["warning"] = "host-staged result differs from device-resident result"
         ctx.pinned_free(h_in)
-        ctx.pinned_free(h_out)
-        ctx.pinned_free(h_ev)
+        for h in h_out.values():
+            ctx.pinned_free(h)
     except Exception as ex:
         e2e = {"value": None, "unit": UNIT, "error": f"{type(ex).__name__}: {ex}", "h2d_bytes_per_step": None,
                "d2h_bytes_per_step": None}
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample)
+    # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's own par path on the same full step
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -699,24 +775,33 @@ def run_ours(args) -> None:
 
             be = orc.reference() or orc.port()
             be.use_all_threads()
-            cols = 16
-            cpu_reference_step(be, string, n, cols)  # warm-up
-            best, spent, reps = None, 0.0, 0
-            while spent < 10.0 and reps < 2000:
-                dt, w = cpu_reference_step(be, string, n, cols)
-                spent += dt
-                reps += 1
-                best = dt if best is None else min(best, dt)
-            cpu_baseline = {"value": 2.0 * dim * cols / best, "unit": UNIT, "cores": be.max_threads(), "kind": be.kind,
-                            "sample": f"{cols} of {B} batch columns, best of {spent:.1f} s of repeats; "
-                                      f"{'unmodified reference headers (std::execution::par)' if be.kind == 'reference' else 'plain-C port + OpenMP'}"}
+            step = CpuStep(be)
+            step.run(("few_group",))  # warm-up: first touch of the n_threads x dim x B private copies (PO:427)
+            dt = step.run()
+            cpu_baseline = {"value": step.work / dt, "unit": UNIT, "cores": be.max_threads(), "kind": be.kind,
+                            "sample": cpu_sample_text(be) + f"; one timed step ({dt:.1f} s) after one warm-up apply",
+                            "statistic": "one step (the --impl reference arm reports the mean over its steps)"}
+            del step
         except Exception as ex:
             cpu_baseline = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {ex}"}
 
+    config3_strong = None
+    if not args.no_extras:
+        try:
+            config3_strong = run_config3_strong(fp, ctx, dist, torch, rank, world, fp64)
+        except Exception as ex:
+            config3_strong = {"error": f"{type(ex).__name__}: {ex}"}
+    config5 = None
+    if world > 1 and not args.no_extras:
+        try:
+            config5 = run_config5(fp, ctx, dist, torch, rank, world, local_rank)
+        except Exception as ex:
+            config5 = {"error": f"{type(ex).__name__}: {ex}"}
+
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
-        del out
-        extras = run_extras(fp, ctx, pk["hbm_gbs"])
+        outs.clear()
+        extras = run_extras(fp, ctx, pk["hbm_gbs"], fp64["tflops"])
 
     if dist is not None:
         dist.barrier()
@@ -724,19 +809,119 @@ def run_ours(args) -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 (complex128)", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: PauliString.apply_batch + PauliString.expectation_value, "
-                                   "20 qubits, batch 256 per GPU, complex128, batch-axis sharded (no collective)",
-                       "n_qubits": n, "batch_per_gpu": B, "global_batch": B * world, "string": string,
-                       "state_bytes_per_gpu": dim * B * 16,
-                       "l2": "inputs (4 GiB per GPU) are 32x larger than L2; no flush needed",
-                       "input_generator": f"counter-based splitmix64 U[0,1)+iU[0,1), seed {SEED}+rank"},
+            "dtype": "f64 (complex128)", "data": "synthetic", "config": config_dict(world),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "extras": extras,
+            "clocks": clocks, "parity": parity, "config3_strong": config3_strong, "config5": config5, "extras": extras,
         }
         EMIT(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def fp64_peak(fp, ctx, clocks: dict) -> dict:
+    """FP64 FMA peak of this GPU: measured in this run by the library's DFMA microkernel when available, else
+    148 SMs x 64 FMA/clk x the maximum SM clock (round 1 measured 63.7 FMA/clk/SM, scripts/micro/dmma_rate.cu)."""
+    import ctypes as C
+
+    try:
+        val = C.c_double()
+        if hasattr(fp.lib, "fp_measure_fp64_tflops") and fp.lib.fp_measure_fp64_tflops(ctx._h, C.byref(val)) == 0 \
+                and val.value > 1.0:
+            return {"tflops": float(val.value), "source": "measured in this run (fp_measure_fp64_tflops: dependent DFMA chains, all SMs)"}
+    except Exception:
+        pass
+    mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    return {"tflops": 148 * 64 * 2 * mhz * 1e6 / 1e12, "source": f"nominal 148 SM x 64 FMA/clk x {mhz:.0f} MHz"}
+
+
+def run_config3_strong(fp, ctx, dist, torch, rank: int, world: int, fp64: dict) -> dict:
+    """BASELINE config 3 as STRONG scaling: PauliOp.apply, 16 qubits, 2000 strings of weight <= 4, ONE global batch
+    of 1024 complex128 columns split over the ranks by column blocks (no collective on the data path).  Every rank
+    regenerates its block of the global counter-based batch, applies the operator, and checks one sampled column of
+    its block against the closed form; rank 0 also times the undivided problem in the same run."""
+    import ctypes as C
+
+    n, Bg, S = 16, 1024, 2000
+    dim = 1 << n
+    rng = np.random.default_rng(STRING_SEED + 3)
+    strings = synth().random_strings(rng, n, S, max_weight=4)
+    h = rng.uniform(-1, 1, S) + 1j * rng.uniform(-1, 1, S)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    plan = op._plan(DTYPE)
+    info = op.plan_info()
+    Bl = Bg // world
+    c0 = rank * Bl
+    # this rank's column block of the global (dim, Bg) batch: element (i, t) has flat index i*Bg + t
+    idx = (np.arange(dim, dtype=np.uint64)[:, None] * np.uint64(Bg) + np.arange(c0, c0 + Bl, dtype=np.uint64)[None, :])
+    host = synth().uniform_complex_at(idx, DTYPE, SEED)
+    psi = ctx.to_device(np.ascontiguousarray(host))
+    out = ctx.empty((dim, Bl), DTYPE)
+    del idx
+
+    def call(o, p, b):
+        rc = fp.lib.fp_op_apply(ctx._h, plan, _vp(o.ptr), _vp(p.ptr), _sz(dim), _sz(b), 0)
+        if rc:
+            raise RuntimeError(fp.lib.fp_last_error().decode())
+
+    ctx.set_async(True)
+    call(out, psi, Bl)
+    ctx.sync()
+    # parity: one sampled column of the block, all rows, closed form in numpy
+    tcol = int(np.random.default_rng(5 + rank).integers(0, Bl))
+    got = out.get()[:, tcol]
+    exp = np.zeros(dim, dtype=np.complex128)
+    i = np.arange(dim, dtype=np.uint64)
+    col = host[:, tcol]
+    for s_, h_ in zip(strings, h):
+        x, z, ny = masks_of(s_)
+        zz = i & np.uint64(z)
+        par = np.zeros(dim, dtype=np.int64)
+        while zz.any():
+            par ^= (zz & np.uint64(1)).astype(np.int64)
+            zz >>= np.uint64(1)
+        exp += (h_ * (-1j) ** ny) * (1 - 2 * par) * col[(i ^ np.uint64(x)).astype(np.int64)]
+    err = float(np.max(np.abs(got - exp)) / np.max(np.abs(exp)))
+    del host
+    iters = 5
+    ms = timed_ms(fp, ctx, lambda: call(out, psi, Bl), iters, warmup=2)
+    ms_all = ms
+    err_all = err
+    if dist is not None:
+        t = torch.tensor([ms, err], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_all, err_all = float(t[0].item()), float(t[1].item())
+    res = {"workload": "PauliOp.apply, 16 qubits, 2000 strings weight<=4, global batch 1024 complex128, column blocks",
+           "n_gpus": world, "batch_per_gpu": Bl, "ms": ms_all, "x_groups": info["n_x_groups"],
+           "amp_strings_per_s": dim * Bg * S / (ms_all * 1e-3), "parity_max_rel_err": err_all, "parity_tol": 1e-12,
+           "parity_check": "one sampled column per rank, all rows, closed form",
+           "fp64_TFLOPs_per_gpu": 8.0 * info["n_x_groups"] * dim * Bl / (ms_all * 1e-3) / 1e12,
+           "fp64_frac_per_gpu": 8.0 * info["n_x_groups"] * dim * Bl / (ms_all * 1e-3) / 1e12 / fp64["tflops"],
+           "scaling": "strong", "timing": "CUDA events per rank, max over ranks"}
+    if not err_all < 1e-12:
+        res["error"] = "parity gate failed"
+    del psi, out
+    if rank == 0 and world > 1:
+        # the undivided problem on one GPU in the same run: the denominator of the speed-up
+        psi1 = ctx.uniform((dim, Bg), DTYPE, seed=SEED)
+        out1 = ctx.empty((dim, Bg), DTYPE)
+        ms1 = timed_ms(fp, ctx, lambda: call(out1, psi1, Bg), 3, warmup=2)
+        res["ms_1gpu_same_run"] = ms1
+        res["speedup_vs_1gpu"] = ms1 / ms_all
+        del psi1, out1
+    ctx.sync()
+    ctx.set_async(False)
+    if dist is not None:
+        dist.barrier()
+    return res
+
+
+def run_config5(fp, ctx, dist, torch, rank: int, world: int, local_rank: int) -> dict:
+    """BASELINE config 5 (scaled to the number of ranks): one complex128 state sharded by its high index bits,
+    PauliOp.apply with pairwise amplitude exchange through the C ABI (fp_comm_* / fp_sharded_op_apply, NCCL linked by
+    the library; torch only hands out the ncclUniqueId bytes)."""
+    from fast_pauli_b200 import sharded
+
+    return sharded.bench_config5(fp, ctx, dist, torch, rank, world, local_rank, seed=SEED, string_seed=STRING_SEED)
 
 
 def _claim_stdout():

@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "coset.cuh"
+#include "coset2.cuh"
 #include "rcoset.cuh"
 #include "dcoset.cuh"
 #include "wtile.cuh"
@@ -137,6 +138,8 @@ struct fp_ctx
     int coset_log_nt = 0;     // 7 or 8 forces the CTA size (128 / 256 threads); 0 = default (256)
     int coset_vpt = 16;       // vectors per thread when the shape is forced (8 or 16)
     bool coset_wide_cta = true; // 512-thread CTAs for the rank-12 weighted-apply tile
+    int coset_few = 1;          // K3e (coset2.cuh): passes with <= 8 x-masks keep their row factors in registers (0 = off)
+    int coset_few_ct = 0;       // column tiles per CTA of K3e (0 = all of them while the grid still fills the chip)
     bool pipeline = true;       // chunked H2D / kernel / D2H pipeline for large host-resident single-string applies
     size_t pipeline_min_bytes = 128ull << 20, pipeline_chunk_bytes = 32ull << 20;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
@@ -349,6 +352,7 @@ int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank, int reserve_lo
             d.view.basis[k] = k < h.basis.r ? h.basis.b[k] : 0;
         d.view.nonpivot_mask = h.nonpivot_mask;
         d.view.n_chunks = static_cast<uint32_t>(h.chunks.size());
+        d.view.n_groups = static_cast<uint32_t>(h.gxl.size());
         CosetChunk *chunks = nullptr;
         uint32_t *gxl = nullptr, *gstart = nullptr, *szl = nullptr, *sidx = nullptr;
         uint64_t *sz = nullptr;
@@ -782,6 +786,38 @@ int launch_coset_pass_v(fp_ctx *ctx, CosetShape shape, CosetPassView<T> const &v
     return set_err(FP_UNSUPPORTED, "unsupported coset tile shape");
 }
 
+// K3e (coset2.cuh): one pass with <= 8 (sub)groups, MODE 0, rank-8 tile (256 rows x 2^LOG_TWC vectors)
+template <typename T, int EPV, int LOG_TWC>
+int launch_coset_few(fp_ctx *ctx, CosetPassView<T> const &view, int n_qubits, uint64_t rowvecs, void const *in, void *out,
+                     int beta)
+{
+    using Cfg = FewCfg<LOG_TWC>;
+    constexpr int GMAX = 8;
+    static PerDevice configured; // per template instance
+    if (!configured.done(ctx->device))
+    {
+        FP_CU(cudaFuncSetAttribute(coset_few_kernel<T, EPV, LOG_TWC, GMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(Cfg::TILE_BYTES)));
+        configured.set(ctx->device);
+    }
+    uint32_t const nct = static_cast<uint32_t>(rowvecs >> LOG_TWC);
+    uint64_t const n_cosets = 1ull << (n_qubits - Cfg::R);
+    // column tiles per CTA: as many as possible (the row factors are formed once per CTA) while >= 4 waves remain
+    uint32_t per = nct;
+    if (ctx->coset_few_ct > 0)
+        per = std::min<uint32_t>(nct, static_cast<uint32_t>(ctx->coset_few_ct));
+    else
+        while (per > 1 && n_cosets * ((nct + per - 1) / per) < 8ull * static_cast<uint64_t>(ctx->sm_count))
+            per = (per + 1) / 2;
+    uint32_t const groups = (nct + per - 1) / per;
+    uint64_t const grid = n_cosets * groups;
+    FP_TRY(check_grid(grid));
+    coset_few_kernel<T, EPV, LOG_TWC, GMAX><<<static_cast<unsigned>(grid), Cfg::NT, Cfg::TILE_BYTES, ctx->stream>>>(
+        view, rowvecs, nct, per, groups, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta);
+    ctx->launches++;
+    return FP_OK;
+}
+
 // Runs all passes.  Returns FP_OK with *used = false when the generic kernel should be used instead.
 template <typename T, int MODE>
 int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void const *in, uint64_t dim, uint64_t B,
@@ -812,6 +848,19 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
     for (size_t p = 0; p < passes->size(); ++p)
     {
         int const b = (p == 0) ? beta : 1;
+        if constexpr (MODE == 0)
+        {
+            auto const &view = (*passes)[p].view;
+            if (ctx->coset_few && view.n_groups <= 8 && shape.rank() == 8 && shape.log_nt == 8 &&
+                ((shape.vpt == 16 && shape.log_twc == 4) || (shape.vpt == 8 && shape.log_twc == 3)))
+            {
+                if (shape.log_twc == 4)
+                    FP_TRY((launch_coset_few<T, EPV, 4>(ctx, view, n_qubits, rowvecs, in, out, b)));
+                else
+                    FP_TRY((launch_coset_few<T, EPV, 3>(ctx, view, n_qubits, rowvecs, in, out, b)));
+                continue;
+            }
+        }
         FP_TRY((launch_coset_pass_v<T, EPV, MODE>(ctx, shape, (*passes)[p].view, n_qubits, rowvecs, in, out, b,
                                                    ctx->partials.p, Bpad, Wre, Wim, B)));
         if (MODE == 1)
@@ -1467,6 +1516,10 @@ extern "C"
             ctx->coset_vpt = atoi(env);
         if (char const *env = getenv("FASTPAULI_COSET_WIDE"))
             ctx->coset_wide_cta = atoi(env) != 0;
+        if (char const *env = getenv("FASTPAULI_COSET_FEW"))
+            ctx->coset_few = atoi(env);
+        if (char const *env = getenv("FASTPAULI_COSET_FEW_CT"))
+            ctx->coset_few_ct = atoi(env);
         if (char const *env = getenv("FASTPAULI_PIPELINE"))
             ctx->pipeline = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_PIPELINE_CHUNK"))

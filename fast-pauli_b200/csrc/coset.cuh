@@ -39,6 +39,7 @@ template <typename T> struct CosetPassView
     Cx<T> const *scoef;
     uint32_t const *sidx;
     uint32_t n_chunks;
+    uint32_t n_groups; // (sub)groups of the pass = entries of gxl
 };
 
 __device__ __forceinline__ uint64_t deposit_bits(uint64_t src, uint64_t mask)
