@@ -138,7 +138,8 @@ struct fp_ctx
     int coset_log_nt = 0;     // 7 or 8 forces the CTA size (128 / 256 threads); 0 = default (256)
     int coset_vpt = 16;       // vectors per thread when the shape is forced (8 or 16)
     bool coset_wide_cta = true; // 512-thread CTAs for the rank-12 weighted-apply tile
-    int coset_few = 1;          // K3e (coset2.cuh): passes with <= 8 x-masks keep their row factors in registers (0 = off)
+    int coset_few = 1;          // K3e / K3f (coset2.cuh) for passes with <= 8 x-masks: 0 off, 1 auto, 2 never the TMA
+                                // kernel (K3f)
     int coset_few_ct = 0;       // column tiles per CTA of K3e (0 = all of them while the grid still fills the chip)
     bool pipeline = true;       // chunked H2D / kernel / D2H pipeline for large host-resident single-string applies
     size_t pipeline_min_bytes = 128ull << 20, pipeline_chunk_bytes = 32ull << 20;
@@ -181,6 +182,8 @@ template <typename T> struct DeviceOp
         PairChunk const *echunks = nullptr;
         uint32_t n_echunks = 0;
         uint8_t const *esodd = nullptr;
+        // the pass' strings as a kernel-parameter block (K3e / K3f): passes with <= 8 groups and <= 128 strings
+        std::shared_ptr<FewStrings<T>> few;
         std::vector<void *> allocs;
     };
     mutable std::map<int, std::vector<CosetPassDev>> coset_plans;
@@ -353,6 +356,20 @@ int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank, int reserve_lo
         d.view.nonpivot_mask = h.nonpivot_mask;
         d.view.n_chunks = static_cast<uint32_t>(h.chunks.size());
         d.view.n_groups = static_cast<uint32_t>(h.gxl.size());
+        if (h.gxl.size() <= 8 && h.sz.size() <= kFewParamStrings && !h.gxl.empty())
+        {
+            d.few = std::make_shared<FewStrings<T>>();
+            std::memset(d.few.get(), 0, sizeof(FewStrings<T>));
+            for (size_t i = 0; i < h.sz.size(); ++i)
+            {
+                d.few->c[i] = Cx<T>{h.sc[i].real(), h.sc[i].imag()};
+                d.few->z[i] = h.sz[i];
+            }
+            for (size_t g = 0; g <= h.gxl.size(); ++g)
+                d.few->gs[g] = h.gstart[g];
+            for (size_t g = 0; g < h.gxl.size(); ++g)
+                d.few->gxl[g] = h.gxl[g];
+        }
         CosetChunk *chunks = nullptr;
         uint32_t *gxl = nullptr, *gstart = nullptr, *szl = nullptr, *sidx = nullptr;
         uint64_t *sz = nullptr;
@@ -786,18 +803,56 @@ int launch_coset_pass_v(fp_ctx *ctx, CosetShape shape, CosetPassView<T> const &v
     return set_err(FP_UNSUPPORTED, "unsupported coset tile shape");
 }
 
-// K3e (coset2.cuh): one pass with <= 8 (sub)groups, MODE 0, rank-8 tile (256 rows x 2^LOG_TWC vectors)
-template <typename T, int EPV, int LOG_TWC>
-int launch_coset_few(fp_ctx *ctx, CosetPassView<T> const &view, int n_qubits, uint64_t rowvecs, void const *in, void *out,
-                     int beta)
+// ---------------------------------------------------------------- K3e / K3f (coset2.cuh): passes with <= 8 x-masks
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, cuuint64_t const *,
+                                      cuuint64_t const *, cuuint32_t const *, cuuint32_t const *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda); nullptr when unavailable
+TensorMapEncodeFn tensor_map_encoder()
+{
+    static TensorMapEncodeFn fn = []() -> TensorMapEncodeFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+        {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<TensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+
+// The batch as a 2-D tensor (rows = dim, inner = real scalars of one row) with a box of one 256-byte row segment:
+// the shape TMA tile::gather4 wants (four arbitrary rows per operation).
+template <typename T> bool make_row_tensor_map(CUtensorMap *tm, void const *base, uint64_t dim, uint64_t rowvecs)
+{
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc)
+        return false;
+    cuuint64_t dims[2] = {rowvecs * (16 / sizeof(T)), dim};
+    cuuint64_t strides[1] = {rowvecs * 16};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(256 / sizeof(T)), 1};
+    cuuint32_t es[2] = {1, 1};
+    return enc(tm, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+               const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename T, int EPV, int LOG_TWC, int NBUF, bool PSTR>
+int launch_coset_few_v(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T> const &strs, int n_qubits,
+                       uint64_t rowvecs, void const *in, void *out, int beta)
 {
     using Cfg = FewCfg<LOG_TWC>;
     constexpr int GMAX = 8;
+    constexpr size_t smem = NBUF * Cfg::TILE_BYTES;
     static PerDevice configured; // per template instance
     if (!configured.done(ctx->device))
     {
-        FP_CU(cudaFuncSetAttribute(coset_few_kernel<T, EPV, LOG_TWC, GMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(Cfg::TILE_BYTES)));
+        FP_CU(cudaFuncSetAttribute(coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured.set(ctx->device);
     }
     uint32_t const nct = static_cast<uint32_t>(rowvecs >> LOG_TWC);
@@ -812,9 +867,67 @@ int launch_coset_few(fp_ctx *ctx, CosetPassView<T> const &view, int n_qubits, ui
     uint32_t const groups = (nct + per - 1) / per;
     uint64_t const grid = n_cosets * groups;
     FP_TRY(check_grid(grid));
-    coset_few_kernel<T, EPV, LOG_TWC, GMAX><<<static_cast<unsigned>(grid), Cfg::NT, Cfg::TILE_BYTES, ctx->stream>>>(
-        view, rowvecs, nct, per, groups, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta);
+    coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR><<<static_cast<unsigned>(grid), Cfg::NT, smem, ctx->stream>>>(
+        view, rowvecs, nct, per, groups, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta,
+        strs);
     ctx->launches++;
+    return FP_OK;
+}
+
+// K3f: persistent TMA-fed kernel, overwrite or accumulate, 12..30 qubits, rows of >= 256 bytes
+template <typename T, int EPV>
+int launch_coset_few_tma(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T> const &strs, int n_qubits,
+                         uint64_t rowvecs, void const *in, void *out, int beta, bool *launched)
+{
+    *launched = false;
+    CUtensorMap tm;
+    if (!make_row_tensor_map<T>(&tm, in, 1ull << n_qubits, rowvecs))
+        return FP_OK;
+    constexpr size_t smem = kFewTmaBufs * kFewTmaTile;
+    static PerDevice configured;
+    if (!configured.done(ctx->device))
+    {
+        FP_CU(cudaFuncSetAttribute(coset_few_tma_kernel<T, EPV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+        configured.set(ctx->device);
+    }
+    uint64_t const n_pairs = 1ull << (n_qubits - 9);
+    unsigned const grid = static_cast<unsigned>(std::min<uint64_t>(n_pairs, static_cast<uint64_t>(ctx->sm_count)));
+    coset_few_tma_kernel<T, EPV, 8><<<grid, kFewTmaThreads, smem, ctx->stream>>>(
+        view, rowvecs, static_cast<uint32_t>(rowvecs >> 4), n_pairs, static_cast<CVec<T, EPV> *>(out), beta, strs, tm);
+    ctx->launches++;
+    *launched = true;
+    return FP_OK;
+}
+
+// Picks the variant for one pass; *launched = false when the pass has to go through coset_kernel (K3b).
+template <typename T, int EPV>
+int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, int n_qubits, uint64_t rowvecs,
+                     void const *in, void *out, int beta, bool *launched)
+{
+    *launched = false;
+    CosetPassView<T> const &view = pd.view;
+    if (!ctx->coset_few || view.n_groups == 0 || view.n_groups > 8 || n_qubits < 8)
+        return FP_OK;
+    static FewStrings<T> const no_strings{};
+    bool const pstr = pd.few != nullptr;
+    FewStrings<T> const &strs = pstr ? *pd.few : no_strings;
+    // K3f wins on overwrite passes of large registers (measured at 20 qubits: 4 masks 0.42 -> 0.38 ms, 256 columns
+    // 1.95 -> 1.85 ms; 8 masks equal); read-modify-write passes and small registers stay on the resident-CTA kernel
+    if (ctx->coset_few == 1 && pstr && beta == 0 && n_qubits >= 16 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+        is_device_ptr(in))
+    {
+        FP_TRY((launch_coset_few_tma<T, EPV>(ctx, view, strs, n_qubits, rowvecs, in, out, beta, launched)));
+        if (*launched)
+            return FP_OK;
+    }
+    if (rowvecs % 8 == 0 && pstr)
+        FP_TRY((launch_coset_few_v<T, EPV, 3, 2, true>(ctx, view, strs, n_qubits, rowvecs, in, out, beta)));
+    else if (rowvecs % 8 == 0)
+        FP_TRY((launch_coset_few_v<T, EPV, 3, 2, false>(ctx, view, strs, n_qubits, rowvecs, in, out, beta)));
+    else
+        return FP_OK;
+    *launched = true;
     return FP_OK;
 }
 
@@ -850,15 +963,12 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
         int const b = (p == 0) ? beta : 1;
         if constexpr (MODE == 0)
         {
-            auto const &view = (*passes)[p].view;
-            if (ctx->coset_few && view.n_groups <= 8 && shape.rank() == 8 && shape.log_nt == 8 &&
-                ((shape.vpt == 16 && shape.log_twc == 4) || (shape.vpt == 8 && shape.log_twc == 3)))
+            if (shape.rank() == 8 && shape.log_nt == 8)
             {
-                if (shape.log_twc == 4)
-                    FP_TRY((launch_coset_few<T, EPV, 4>(ctx, view, n_qubits, rowvecs, in, out, b)));
-                else
-                    FP_TRY((launch_coset_few<T, EPV, 3>(ctx, view, n_qubits, rowvecs, in, out, b)));
-                continue;
+                bool launched = false;
+                FP_TRY((launch_coset_few<T, EPV>(ctx, (*passes)[p], n_qubits, rowvecs, in, out, b, &launched)));
+                if (launched)
+                    continue;
             }
         }
         FP_TRY((launch_coset_pass_v<T, EPV, MODE>(ctx, shape, (*passes)[p].view, n_qubits, rowvecs, in, out, b,
@@ -1463,6 +1573,38 @@ extern "C"
     const char *fp_last_error(void)
     {
         return g_err.c_str();
+    }
+
+    // Measured FP64 FMA throughput of the context's GPU (dependent DFMA chains on every SM, best of 3): the
+    // denominator bench.py quotes FP64-bound calls against.
+    int fp_measure_fp64_tflops(fp_ctx *ctx, double *tflops)
+    {
+        if (!ctx || !tflops)
+            return set_err(FP_INVALID_ARGUMENT, "null pointer");
+        DeviceGuard g(ctx->device);
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        int const ctas = ctx->sm_count * 4, threads = 256, iters = 4096;
+        FP_TRY(ctx->work_a.ensure(static_cast<size_t>(ctas) * threads * sizeof(double)));
+        cudaEvent_t e0, e1;
+        FP_CU(cudaEventCreate(&e0));
+        FP_CU(cudaEventCreate(&e1));
+        float best = 0;
+        for (int rep = 0; rep < 4; ++rep)
+        {
+            FP_CU(cudaEventRecord(e0, ctx->stream));
+            fpk::fp64_peak_kernel<<<ctas, threads, 0, ctx->stream>>>(static_cast<double *>(ctx->work_a.p), iters);
+            FP_CU(cudaEventRecord(e1, ctx->stream));
+            FP_CU(cudaEventSynchronize(e1));
+            float ms = 0;
+            FP_CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && (best == 0 || ms < best))
+                best = ms;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        double const fma = static_cast<double>(ctas) * threads * iters * 16.0;
+        *tflops = 2.0 * fma / (best * 1e-3) / 1e12;
+        return FP_OK;
     }
 
     int fp_version(void)

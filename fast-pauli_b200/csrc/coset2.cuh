@@ -16,12 +16,82 @@
 // Reference semantics: PauliOp::apply (PO:399-468): out(i,t) (+)= sum_s h_s m_s(i) psi(i ^ x_s, t).
 #pragma once
 #include <cstdint>
+#include <cuda.h> // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint on the host)
 #include <cuda_runtime.h>
 
 #include "coset.cuh"
 
 namespace fpk
 {
+
+#ifdef FP_FEW_PROFILE
+__device__ unsigned long long g_few_prof[8];
+#define FEW_T(i)                                                                                                       \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (threadIdx.x == 0)                                                                                          \
+        {                                                                                                              \
+            long long now_ = clock64();                                                                                \
+            atomicAdd(&g_few_prof[i], static_cast<unsigned long long>(now_ - t_prev_));                               \
+            t_prev_ = now_;                                                                                            \
+        }                                                                                                              \
+    } while (0)
+#else
+#define FEW_T(i)
+#endif
+
+constexpr uint32_t kFewMaxStrings = 256; // strings staged in shared memory per round of the row-factor phase
+constexpr uint32_t kFewParamStrings = 128; // strings that fit the kernel parameter block (constant bank)
+
+// Strings of one pass as kernel parameters: coefficient (already times (-i)^nY) and full z-mask per string, group
+// boundaries.  ~3 KiB for complex128: inside the 4 KiB parameter space every driver supports.
+template <typename T> struct FewStrings
+{
+    Cx<T> c[kFewParamStrings];
+    uint64_t z[kFewParamStrings];
+    uint32_t gs[9]; // first string of each group (GMAX = 8), gs[n_groups] = number of strings
+    uint32_t gxl[8];
+};
+
+
+// Row factors D_g = sum_{s in g} c_s (-1)^par(row & z_s) of one row from the strings in the constant bank.
+// Registers of <= 32 qubits use 32-bit masks (one POPC per string instead of two).
+template <typename T, int GMAX>
+__device__ __forceinline__ void few_row_factors(FewStrings<T> const &strs, uint32_t ng, uint64_t my_row, bool narrow, Cx<T> (&D)[GMAX])
+{
+#pragma unroll
+    for (int g = 0; g < GMAX; ++g)
+    {
+        D[g] = Cx<T>{0, 0};
+        if (static_cast<uint32_t>(g) < ng)
+        {
+            uint32_t const s1 = strs.gs[g + 1];
+            if (narrow)
+            {
+                uint32_t const r32 = static_cast<uint32_t>(my_row);
+#pragma unroll 4
+                for (uint32_t s = strs.gs[g]; s < s1; ++s)
+                {
+                    Cx<T> const c = strs.c[s];
+                    uint32_t const odd = __popc(r32 & static_cast<uint32_t>(strs.z[s])) & 1u;
+                    D[g].re += flip_sign(c.re, odd);
+                    D[g].im += flip_sign(c.im, odd);
+                }
+            }
+            else
+            {
+#pragma unroll 4
+                for (uint32_t s = strs.gs[g]; s < s1; ++s)
+                {
+                    Cx<T> const c = strs.c[s];
+                    uint32_t const odd = parity64(my_row & strs.z[s]);
+                    D[g].re += flip_sign(c.re, odd);
+                    D[g].im += flip_sign(c.im, odd);
+                }
+            }
+        }
+    }
+}
 
 template <int LOG_TWC> struct FewCfg
 {
@@ -30,14 +100,22 @@ template <int LOG_TWC> struct FewCfg
     static constexpr int TWC = 1 << LOG_TWC;        // vectors per row segment
     static constexpr int RPS = NT >> LOG_TWC;       // rows covered by one cooperative load/store step
     static constexpr int STEPS = NT / RPS;          // = TWC
-    static constexpr size_t TILE_BYTES = static_cast<size_t>(NT) * TWC * 16;
+    static constexpr size_t TILE_BYTES = static_cast<size_t>(NT) * TWC * 16; // one buffer
     static_assert(LOG_TWC == 3 || LOG_TWC == 4, "row segments of 128 or 256 bytes");
 };
 
-template <typename T, int EPV, int LOG_TWC, int GMAX>
-__global__ void __launch_bounds__(256, 2)
+// NBUF = 2: the next column tile is requested (cp.async) before the current one is evaluated, so the CTA never waits
+// for HBM in steady state; MINB = resident CTAs per SM the register budget is compiled for.
+// PSTR: the pass' strings (<= kFewParamStrings) travel in the kernel parameter block, i.e. the constant bank: the
+// row-factor phase then needs no shared-memory staging, no barrier and -- the point -- no LDS at all, so it no longer
+// queues behind the other resident CTA's gathers in the load/store unit (measured: 13 k -> 4 k cycles per CTA).
+// DSM: the row factors are parked in shared memory (GMAX x 256 x 16 B behind the tile buffers, conflict-free) between
+// the row-factor phase and the gathers: 32 registers freed for gathered vectors in flight.
+template <typename T, int EPV, int LOG_TWC, int GMAX, int NBUF = 1, int MINB = 2, bool PSTR = false, bool DSM = false>
+__global__ void __launch_bounds__(256, MINB)
     coset_few_kernel(CosetPassView<T> pass, uint64_t rowvecs, uint32_t nColTiles, uint32_t ctPerCta, uint32_t nCtGroups,
-                     CVec<T, EPV> const *__restrict__ in, CVec<T, EPV> *__restrict__ out, int beta)
+                     CVec<T, EPV> const *__restrict__ in, CVec<T, EPV> *__restrict__ out, int beta,
+                     const __grid_constant__ FewStrings<T> strs)
 {
     using Cfg = FewCfg<LOG_TWC>;
     using Vec = CVec<T, EPV>;
@@ -47,9 +125,14 @@ __global__ void __launch_bounds__(256, 2)
     extern __shared__ __align__(1024) unsigned char smem_few[];
     __shared__ uint64_t s_comb_hi[STEPS];
     __shared__ uint32_t s_gxl[GMAX];
-    Vec *tile = reinterpret_cast<Vec *>(smem_few);
+    __shared__ uint32_t s_gs[GMAX + 1];
+    __shared__ Cx<T> s_c[kFewMaxStrings];
+    __shared__ uint32_t s_zl[kFewMaxStrings];
 
     uint32_t const tid = threadIdx.x;
+#ifdef FP_FEW_PROFILE
+    long long t_prev_ = clock64();
+#endif
     uint32_t const ng = pass.n_groups;
     uint64_t const coset = blockIdx.x / nCtGroups;
     uint32_t const ctg = static_cast<uint32_t>(blockIdx.x - coset * nCtGroups);
@@ -60,15 +143,15 @@ __global__ void __launch_bounds__(256, 2)
     if (tid < STEPS)
         s_comb_hi[tid] = comb_of<Cfg::R>(pass.basis, tid * RPS);
     if (tid < ng)
-        s_gxl[tid] = pass.gxl[tid];
+        s_gxl[tid] = PSTR ? strs.gxl[tid] : pass.gxl[tid];
     uint32_t const l_lo = tid >> LOG_TWC;
     uint32_t const jv = tid & (TWC - 1);
     uint64_t const row_lo = base ^ comb_of<Cfg::R>(pass.basis, l_lo);
-    uint64_t const my_row = base ^ comb_of<Cfg::R>(pass.basis, tid);
     __syncthreads();
 
-    auto fill = [&](uint32_t c) {
+    auto fill = [&](uint32_t c, uint32_t buf) {
         uint64_t const vcol = static_cast<uint64_t>(c) * TWC + jv;
+        Vec *tile = reinterpret_cast<Vec *>(smem_few + buf * Cfg::TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < STEPS; ++k)
         {
@@ -77,34 +160,83 @@ __global__ void __launch_bounds__(256, 2)
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    fill(ct);
+    fill(ct, 0);
+    if (NBUF == 2 && ct + 1 < ct_end)
+        fill(ct + 1, 1);
 
-    // ---- row factors of this thread's row, once per coset (the first tile is in flight meanwhile)
+    // ---- row factors of this thread's row, once per coset (the first tile is in flight meanwhile).  The strings are
+    // staged in shared memory in rounds of kFewMaxStrings with the coset-base sign par(base & z_s) folded into the
+    // coefficient, so the per-thread loop is broadcast LDS + the row-local sign par(l & zl_s) only.
     Cx<T> D[GMAX];
 #pragma unroll
     for (int g = 0; g < GMAX; ++g)
-    {
         D[g] = Cx<T>{0, 0};
-        if (static_cast<uint32_t>(g) < ng)
+    if (PSTR)
+    {
+        // strings in the constant bank: sign from the thread's global row, no shared memory, no barrier
+        few_row_factors<T, GMAX>(strs, ng, base ^ comb_of<Cfg::R>(pass.basis, tid), (pass.nonpivot_mask >> 32) == 0, D);
+    }
+    uint32_t const n_str = PSTR ? 0u : pass.gstart[ng];
+    for (uint32_t r0 = 0; r0 < n_str; r0 += kFewMaxStrings)
+    {
+        uint32_t const cnt = min(kFewMaxStrings, n_str - r0);
+        if (r0)
+            __syncthreads();
+        if (tid < cnt)
         {
-            uint32_t const s0 = pass.gstart[g], s1 = pass.gstart[g + 1];
-            for (uint32_t s = s0; s < s1; ++s)
+            Cx<T> c = pass.scoef[r0 + tid];
+            uint32_t const odd = parity64(base & pass.sz[r0 + tid]);
+            c.re = flip_sign(c.re, odd);
+            c.im = flip_sign(c.im, odd);
+            s_c[tid] = c;
+            s_zl[tid] = pass.szl[r0 + tid];
+        }
+        if (tid <= ng)
+        {
+            uint32_t const gs = pass.gstart[tid];
+            s_gs[tid] = gs < r0 ? 0u : min(gs - r0, cnt);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < GMAX; ++g)
+        {
+            if (static_cast<uint32_t>(g) < ng)
             {
-                Cx<T> const c = pass.scoef[s];
-                uint32_t const odd = parity64(my_row & pass.sz[s]);
-                D[g].re += flip_sign(c.re, odd);
-                D[g].im += flip_sign(c.im, odd);
+                uint32_t const s1 = s_gs[g + 1];
+#pragma unroll 4
+                for (uint32_t s = s_gs[g]; s < s1; ++s)
+                {
+                    Cx<T> const c = s_c[s];
+                    uint32_t const odd = __popc(tid & s_zl[s]) & 1u;
+                    D[g].re += flip_sign(c.re, odd);
+                    D[g].im += flip_sign(c.im, odd);
+                }
             }
         }
     }
 
+    Cx<T> *const s_D = reinterpret_cast<Cx<T> *>(smem_few + NBUF * Cfg::TILE_BYTES);
+    if (DSM)
+    {
+#pragma unroll
+        for (int g = 0; g < GMAX; ++g)
+            s_D[g * 256 + tid] = D[g]; // only this thread ever reads its slots: no barrier needed
+    }
+    FEW_T(0); // setup + row factors
     uint32_t const key_off = (tid & (TWC - 1)) << 4;             // column rotation of this thread, in bytes
     uint32_t const own_off = (tid << ROW_SHIFT) | key_off;       // own row, rotated column 0
 
-    for (; ct < ct_end; ++ct)
+    for (uint32_t it = 0; ct < ct_end; ++ct, ++it)
     {
-        asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+        uint32_t const buf = NBUF == 2 ? (it & 1u) : 0u;
+        unsigned char *const tb = smem_few + buf * Cfg::TILE_BYTES;
+        Vec *const tile = reinterpret_cast<Vec *>(tb);
+        if (NBUF == 2 && ct + 1 < ct_end)
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory"); // the tile after this one may still be in flight
+        else
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();
+        FEW_T(1); // waiting for the tile
 
         Cx<T> acc[TWC][EPV];
 #pragma unroll
@@ -118,17 +250,19 @@ __global__ void __launch_bounds__(256, 2)
             if (static_cast<uint32_t>(g) < ng)
             {
                 uint32_t const src = own_off ^ (s_gxl[g] << ROW_SHIFT);
+                Cx<T> const d = DSM ? s_D[g * 256 + tid] : D[g];
 #pragma unroll
                 for (int j = 0; j < TWC; ++j)
                 {
-                    Vec const v = *reinterpret_cast<Vec const *>(smem_few + (src ^ (j << 4)));
+                    Vec const v = *reinterpret_cast<Vec const *>(tb + (src ^ (j << 4)));
 #pragma unroll
                     for (int e = 0; e < EPV; ++e)
-                        cfma(acc[j][e], D[g], v.e[e]);
+                        cfma(acc[j][e], d, v.e[e]);
                 }
             }
         }
         __syncthreads(); // every gather of this tile is done: the buffer becomes the store staging area
+        FEW_T(2); // gathers + FMAs
 
 #pragma unroll
         for (int j = 0; j < TWC; ++j)
@@ -137,9 +271,10 @@ __global__ void __launch_bounds__(256, 2)
 #pragma unroll
             for (int e = 0; e < EPV; ++e)
                 v.e[e] = acc[j][e];
-            *reinterpret_cast<Vec *>(smem_few + (own_off ^ (j << 4))) = v;
+            *reinterpret_cast<Vec *>(tb + (own_off ^ (j << 4))) = v;
         }
         __syncthreads();
+        FEW_T(3); // accumulators -> staging
 
         uint64_t const vcol = static_cast<uint64_t>(ct) * TWC + jv;
         if (beta)
@@ -167,10 +302,234 @@ __global__ void __launch_bounds__(256, 2)
             for (int k = 0; k < STEPS; ++k)
                 out[(row_lo ^ s_comb_hi[k]) * rowvecs + vcol] = tile[(l_lo + k * RPS) * TWC + jv];
         }
-        if (ct + 1 < ct_end)
+        FEW_T(4); // issuing the stores
+        if (ct + NBUF < ct_end)
         {
-            __syncthreads(); // staged rows have been read: refill the buffer with the next column tile
-            fill(ct + 1);
+            __syncthreads(); // staged rows have been read: refill this buffer
+            fill(ct + NBUF, buf);
+            FEW_T(5);
+        }
+    }
+}
+
+
+// ================================================================ K3f: TMA-fed, warp-specialised variant of K3e
+// One persistent CTA per SM: a producer warp streams coset tiles into a ring of three 64 KiB shared-memory buffers
+// with TMA tile::gather4 (four scattered 256-byte row segments per operation, completion on an mbarrier), and two
+// consumer groups of 256 threads evaluate alternate tiles exactly like coset_few_kernel.  Why: cp.async costs the
+// load/store unit ~15 cycles per 512-byte warp operation (measured: the gather phase of a resident CTA shortens from
+// 7.6 k to 5.8 k cycles when the OTHER CTA's fill moves to the TMA), and with the fill off the LSU and off the
+// consumers' critical path the kernel is bound by its gathers and HBM only.
+//
+// Tile order of a CTA (deterministic, so buffer = tile index mod 3): coset pairs p = blockIdx.x + k * gridDim.x;
+// consumer group g owns coset 2p + g; tiles alternate between the groups: i -> group i & 1, column tile (i / 2) % nct.
+__device__ __forceinline__ uint32_t few_smem_u32(void const *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void few_mbar_init(uint64_t *b, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(few_smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void few_mbar_expect_tx(uint64_t *b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(few_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void few_mbar_arrive(uint64_t *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(few_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void few_mbar_wait(uint64_t *b, uint32_t parity)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\n"
+                 "DONE_%=:\n}" ::"r"(few_smem_u32(b)),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void few_tma_gather4(void *dst, CUtensorMap const *tm, int c0, int r0, int r1, int r2, int r3,
+                                                uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
+                 "%5, %6}], [%7];" ::"r"(few_smem_u32(dst)),
+                 "l"(tm), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(few_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void few_group_sync(uint32_t group)
+{
+    asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
+}
+
+constexpr int kFewTmaThreads = 2 * 256 + 128; // two consumer groups + the producer warpgroup (one live warp)
+constexpr int kFewTmaBufs = 3;
+constexpr size_t kFewTmaTile = 256 * 16 * 16; // 256 rows x 16 vectors x 16 bytes
+
+template <typename T, int EPV, int GMAX>
+__global__ void __launch_bounds__(kFewTmaThreads, 1)
+    coset_few_tma_kernel(CosetPassView<T> pass, uint64_t rowvecs, uint32_t nColTiles, uint64_t nPairs,
+                         CVec<T, EPV> *__restrict__ out, int beta, const __grid_constant__ FewStrings<T> strs,
+                         const __grid_constant__ CUtensorMap tm_in)
+{
+    using Vec = CVec<T, EPV>;
+    constexpr int TWC = 16, RPS = 16, STEPS = 16, R = 8;
+    constexpr uint32_t ROW_SHIFT = 8;
+
+    extern __shared__ __align__(1024) unsigned char smem_ft[];
+    __shared__ uint64_t s_full[kFewTmaBufs], s_empty[kFewTmaBufs];
+    __shared__ uint32_t s_comb[256];    // XOR offsets of the 256 local rows
+    __shared__ uint64_t s_comb_hi[STEPS];
+
+    uint32_t const tid = threadIdx.x;
+    uint32_t const ng = pass.n_groups;
+    if (tid < 256)
+        s_comb[tid] = static_cast<uint32_t>(comb_of<R>(pass.basis, tid));
+    if (tid < STEPS)
+        s_comb_hi[tid] = comb_of<R>(pass.basis, tid * RPS);
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int b = 0; b < kFewTmaBufs; ++b)
+        {
+            few_mbar_init(&s_full[b], 1);
+            few_mbar_init(&s_empty[b], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint64_t const my_pairs = blockIdx.x < nPairs ? (nPairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    uint64_t const n_tiles = my_pairs * 2 * nColTiles;
+
+    if (tid >= 512)
+    {
+        // ------------------------------------------------ producer warpgroup: hand its registers to the consumers
+        // (640 threads are launched with 96 registers each; 24 are enough here, the consumers grow to 112: a CTA can only re-use what its own warps released)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (tid >= 544)
+            return;
+        uint32_t const lane = tid & 31u;
+        for (uint64_t i = 0; i < n_tiles; ++i)
+        {
+            uint32_t const buf = static_cast<uint32_t>(i % kFewTmaBufs);
+            if (i >= kFewTmaBufs)
+                few_mbar_wait(&s_empty[buf], static_cast<uint32_t>((i / kFewTmaBufs) - 1) & 1u);
+            // group 1 runs half a coset behind group 0, so the two row-factor phases never coincide
+            uint64_t const v = (i >> 1) + ((i & 1u) ? (nColTiles >> 1) : 0u);
+            uint64_t const pair = blockIdx.x + ((v / nColTiles) % my_pairs) * gridDim.x;
+            uint64_t const coset = 2 * pair + (i & 1u);
+            uint32_t const ct = static_cast<uint32_t>(v % nColTiles);
+            uint32_t const base = static_cast<uint32_t>(deposit_bits(coset, pass.nonpivot_mask));
+            if (lane == 0)
+                few_mbar_expect_tx(&s_full[buf], static_cast<uint32_t>(kFewTmaTile));
+            __syncwarp();
+            int const c0 = static_cast<int>(ct) * TWC * static_cast<int>(16 / sizeof(T));
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+            {
+                uint32_t const op = lane + 32 * h; // rows 4*op .. 4*op+3
+                few_tma_gather4(smem_ft + buf * kFewTmaTile + (static_cast<size_t>(op) << (ROW_SHIFT + 2)), &tm_in, c0,
+                                base ^ s_comb[4 * op], base ^ s_comb[4 * op + 1], base ^ s_comb[4 * op + 2],
+                                base ^ s_comb[4 * op + 3], &s_full[buf]);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------- consumer groups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    uint32_t const grp = tid >> 8;
+    uint32_t const l = tid & 255u; // local row of this thread
+    uint32_t const l_lo = l >> 4, jv = l & 15u;
+    uint32_t const key_off = (l & 15u) << 4;
+    uint32_t const own_off = (l << ROW_SHIFT) | key_off;
+
+    uint64_t const n_q = my_pairs * nColTiles; // tiles of this group
+    uint64_t const shift = grp ? (nColTiles >> 1) : 0u;
+    uint64_t cur_k = ~0ull, row_lo = 0;
+    Cx<T> D[GMAX];
+    for (uint64_t q = 0; q < n_q; ++q)
+    {
+        uint64_t const v = q + shift;
+        uint64_t const k = (v / nColTiles) % my_pairs;
+        uint32_t const ct = static_cast<uint32_t>(v % nColTiles);
+        if (k != cur_k)
+        {
+            cur_k = k;
+            uint64_t const coset = 2 * (blockIdx.x + k * gridDim.x) + grp;
+            uint64_t const base = deposit_bits(coset, pass.nonpivot_mask);
+            row_lo = base ^ s_comb[l_lo];
+            few_row_factors<T, GMAX>(strs, ng, base ^ s_comb[l], true, D); // launched for <= 30 qubits only
+        }
+        {
+            uint64_t const i = q * 2 + grp; // position in the CTA's tile order
+            uint32_t const buf = static_cast<uint32_t>(i % kFewTmaBufs);
+            unsigned char *const tb = smem_ft + buf * kFewTmaTile;
+            Vec *const tile = reinterpret_cast<Vec *>(tb);
+            few_mbar_wait(&s_full[buf], static_cast<uint32_t>(i / kFewTmaBufs) & 1u);
+
+            Cx<T> acc[TWC][EPV];
+#pragma unroll
+            for (int j = 0; j < TWC; ++j)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    acc[j][e] = Cx<T>{0, 0};
+#pragma unroll
+            for (int g = 0; g < GMAX; ++g)
+            {
+                if (static_cast<uint32_t>(g) < ng)
+                {
+                    uint32_t const src = own_off ^ (strs.gxl[g] << ROW_SHIFT);
+#pragma unroll
+                    for (int j = 0; j < TWC; ++j)
+                    {
+                        Vec const v = *reinterpret_cast<Vec const *>(tb + (src ^ (j << 4)));
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e)
+                            cfma(acc[j][e], D[g], v.e[e]);
+                    }
+                }
+            }
+            few_group_sync(grp); // every gather of this tile is done: the buffer becomes the store staging area
+#pragma unroll
+            for (int j = 0; j < TWC; ++j)
+            {
+                Vec v;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    v.e[e] = acc[j][e];
+                *reinterpret_cast<Vec *>(tb + (own_off ^ (j << 4))) = v;
+            }
+            few_group_sync(grp);
+            uint64_t const vcol = static_cast<uint64_t>(ct) * TWC + jv;
+            if (beta)
+            {
+                Vec o[STEPS];
+#pragma unroll
+                for (int q = 0; q < STEPS; ++q)
+                    o[q] = out[(row_lo ^ s_comb_hi[q]) * rowvecs + vcol];
+#pragma unroll
+                for (int q = 0; q < STEPS; ++q)
+                {
+                    Vec v = tile[(l_lo + q * RPS) * TWC + jv];
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                    {
+                        v.e[e].re += o[q].e[e].re;
+                        v.e[e].im += o[q].e[e].im;
+                    }
+                    out[(row_lo ^ s_comb_hi[q]) * rowvecs + vcol] = v;
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int q = 0; q < STEPS; ++q)
+                    out[(row_lo ^ s_comb_hi[q]) * rowvecs + vcol] = tile[(l_lo + q * RPS) * TWC + jv];
+            }
+            // the staged rows were read through the generic proxy; the TMA refill writes through the asynchronous one
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            few_group_sync(grp);
+            if (l == 0)
+                few_mbar_arrive(&s_empty[buf]);
         }
     }
 }

@@ -84,6 +84,27 @@ struct Geom
 
 constexpr int kThreads = 256;
 
+// FP64 peak probe (fp_measure_fp64_tflops): 16 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters)
+{
+    double const a = 1.0 + threadIdx.x * 1e-9, b = threadIdx.x * 1e-7;
+    double c[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        c[i] = i;
+    for (int it = 0; it < iters; ++it)
+    {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            c[i] = fma(a, c[i], b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ---------------------------------------------------------------- K1/K3: (grouped) operator apply
 //   out(i,t) (+)= sum_g D_g(i) psi(i ^ x_g, t),  D_g(i) = sum_{s in g} scoef_s (-1)^popc(i & z_s)
 // Covers PauliString::apply / apply_batch (PS:296-436; INLINE1, one group of one string),

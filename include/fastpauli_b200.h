@@ -78,6 +78,9 @@ extern "C"
     int fp_ctx_set_stream(fp_ctx *ctx, void *cuda_stream, int external);
     int fp_ctx_set_async(fp_ctx *ctx, int async);
     int fp_ctx_sync(fp_ctx *ctx);
+    /* Measured FP64 FMA throughput (TFLOP/s) of the context's GPU: a short DFMA microkernel on every SM, best of 3.
+     * Measurement aid for the roofline of compute-bound operators (no reference counterpart). */
+    int fp_measure_fp64_tflops(fp_ctx *ctx, double *tflops);
     /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
     int fp_ctx_launch_count(const fp_ctx *ctx, uint64_t *count);
     /* Pinned (page-locked) HOST buffers passed to the single-string entry points are read and written in place by

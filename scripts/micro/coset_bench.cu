@@ -4,10 +4,11 @@
 //
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --expt-relaxed-constexpr \
 //             -I fast-pauli_b200/csrc -o scripts/micro/coset_bench scripts/micro/coset_bench.cu
-// run:   coset_bench <case: few|rand|few16> <n_qubits> <B> <ctPerCta> [log_twc]
+// run:   coset_bench <case: few|rand|few16> <n_qubits> <B> <ctPerCta> [log_twc] [scatter 0|1]
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <random>
 #include <vector>
 
@@ -60,6 +61,7 @@ int main(int argc, char **argv)
     int B = argc > 3 ? atoi(argv[3]) : 64;
     int ctPer = argc > 4 ? atoi(argv[4]) : 0;
     int log_twc = argc > 5 ? atoi(argv[5]) : 4;
+    int scatter = argc > 6 ? atoi(argv[6]) : 0;
     using T = double;
 
     std::mt19937_64 rng(1234);
@@ -133,6 +135,7 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&res, 16));
     CK(cudaMemset(res, 0, 16));
     k_fill<<<1184, 256>>>(in, n_dbl);
+
     uint64_t const rowvecs = B;
     using Vec = CVec<T, 1>;
 
@@ -146,28 +149,108 @@ int main(int argc, char **argv)
                 views[p], rowvecs, nct, reinterpret_cast<Vec const *>(in), reinterpret_cast<Vec *>(out), p ? 1 : 0, nullptr, 0,
                 nullptr, nullptr, B);
     };
+    int const nbuf = scatter; // 7th argument: 1 = single buffer, 2 = double buffer; 8th: min CTAs/SM; 9th: TMA fill
+    int const minb = argc > 7 ? atoi(argv[7]) : 2;
+    int const tma = argc > 8 ? atoi(argv[8]) : 0;
+    (void)minb;
+    std::vector<FewStrings<T>> pstr(views.size());
+    bool pstr_ok = true;
+    for (size_t p = 0; p < passes.size(); ++p)
+    {
+        auto const &hp = passes[p];
+        memset(&pstr[p], 0, sizeof(FewStrings<T>));
+        if (hp.gxl.size() > 8 || hp.sz.size() > kFewParamStrings)
+        {
+            pstr_ok = false;
+            continue;
+        }
+        for (size_t i = 0; i < hp.sz.size(); ++i)
+        {
+            pstr[p].c[i] = Cx<T>{hp.sc[i].real(), hp.sc[i].imag()};
+            pstr[p].z[i] = hp.sz[i];
+        }
+        for (size_t g = 0; g <= hp.gxl.size(); ++g)
+            pstr[p].gs[g] = hp.gstart[g];
+        for (size_t g = 0; g < hp.gxl.size(); ++g)
+            pstr[p].gxl[g] = hp.gxl[g];
+    }
+    bool const use_pstr = tma && pstr_ok; // 9th argument now selects the parameter-block row-factor phase
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, cuuint64_t const *, cuuint64_t const *,
+                                 cuuint32_t const *, cuuint32_t const *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    EncodeFn enc = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", reinterpret_cast<void **>(&enc), cudaEnableDefault, &qres));
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)B * 2, (cuuint64_t)dim};
+        cuuint64_t strides[1] = {(cuuint64_t)B * 16};
+        cuuint32_t box[2] = {32, 1};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, in, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+        {
+            printf("cuTensorMapEncodeTiled failed: %d\n", (int)r);
+            exit(3);
+        }
+    }
+    int const grid_f = minb > 2 ? minb : 148; // K3f: 8th argument > 2 overrides the persistent grid size
     auto run_new = [&](double *out) {
         for (size_t p = 0; p < views.size(); ++p)
         {
-            if (log_twc == 4)
+            if (nbuf == 3)
             {
-                using Cfg = FewCfg<4>;
-                CK(cudaFuncSetAttribute(coset_few_kernel<T, 1, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::TILE_BYTES));
-                uint32_t const nct = rowvecs >> 4;
-                uint32_t per = ctPer > 0 ? std::min<uint32_t>(ctPer, nct) : nct;
-                uint32_t groups = (nct + per - 1) / per;
-                coset_few_kernel<T, 1, 4, 8><<<(unsigned)((dim >> 8) * groups), 256, Cfg::TILE_BYTES>>>(
-                    views[p], rowvecs, nct, per, groups, reinterpret_cast<Vec const *>(in), reinterpret_cast<Vec *>(out), p ? 1 : 0);
+                size_t const smem = kFewTmaBufs * kFewTmaTile;
+                CK(cudaFuncSetAttribute(coset_few_tma_kernel<T, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                uint64_t const n_pairs = (dim >> 8) / 2;
+                unsigned const g = (unsigned)std::min<uint64_t>(grid_f, n_pairs);
+                coset_few_tma_kernel<T, 1, 8><<<g, kFewTmaThreads, smem>>>(views[p], rowvecs, (uint32_t)(rowvecs >> 4), n_pairs,
+                                                                           reinterpret_cast<Vec *>(out), p ? 1 : 0, pstr[p], tm);
+                continue;
             }
+#define LAUNCH_FEW(LT, NB, MB, TM)                                                                                     \
+    if (ctPer < 0)                                                                                                     \
+    {                                                                                                                  \
+        using Cfg = FewCfg<LT>;                                                                                        \
+        size_t const sm = NB * Cfg::TILE_BYTES + 8 * 256 * 16;                                                         \
+        CK(cudaFuncSetAttribute(coset_few_kernel<T, 1, LT, 8, NB, MB, TM, true>,                                       \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));                                \
+        uint32_t const nct = rowvecs >> LT;                                                                            \
+        coset_few_kernel<T, 1, LT, 8, NB, MB, TM, true><<<(unsigned)(dim >> 8), 256, sm>>>(                            \
+            views[p], rowvecs, nct, nct, 1, reinterpret_cast<Vec const *>(in), reinterpret_cast<Vec *>(out), p ? 1 : 0, \
+            pstr[p]);                                                                                                  \
+    }                                                                                                                  \
+    else                                                                                                               \
+    {                                                                                                                  \
+        using Cfg = FewCfg<LT>;                                                                                        \
+        CK(cudaFuncSetAttribute(coset_few_kernel<T, 1, LT, 8, NB, MB, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)(NB * Cfg::TILE_BYTES)));                                                         \
+        uint32_t const nct = rowvecs >> LT;                                                                            \
+        uint32_t per = ctPer > 0 ? std::min<uint32_t>(ctPer, nct) : nct;                                               \
+        uint32_t groups = (nct + per - 1) / per;                                                                       \
+        coset_few_kernel<T, 1, LT, 8, NB, MB, TM><<<(unsigned)((dim >> 8) * groups), 256, NB * Cfg::TILE_BYTES>>>(     \
+            views[p], rowvecs, nct, per, groups, reinterpret_cast<Vec const *>(in), reinterpret_cast<Vec *>(out),      \
+            p ? 1 : 0, pstr[p]);                                                                                            \
+    }
+            bool const tma = use_pstr;
+            if (log_twc == 4 && nbuf <= 1 && !tma)
+                LAUNCH_FEW(4, 1, 2, false)
+            else if (log_twc == 4 && nbuf <= 1 && tma)
+                LAUNCH_FEW(4, 1, 2, true)
+            else if (log_twc == 3 && nbuf <= 1 && !tma)
+                LAUNCH_FEW(3, 1, 2, false)
+            else if (log_twc == 3 && nbuf == 2 && !tma)
+                LAUNCH_FEW(3, 2, 2, false)
+            else if (log_twc == 3 && nbuf == 2 && tma)
+                LAUNCH_FEW(3, 2, 2, true)
+            else if (log_twc == 3 && nbuf <= 1 && tma)
+                LAUNCH_FEW(3, 1, 2, true)
             else
             {
-                using Cfg = FewCfg<3>;
-                CK(cudaFuncSetAttribute(coset_few_kernel<T, 1, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::TILE_BYTES));
-                uint32_t const nct = rowvecs >> 3;
-                uint32_t per = ctPer > 0 ? std::min<uint32_t>(ctPer, nct) : nct;
-                uint32_t groups = (nct + per - 1) / per;
-                coset_few_kernel<T, 1, 3, 8><<<(unsigned)((dim >> 8) * groups), 256, Cfg::TILE_BYTES>>>(
-                    views[p], rowvecs, nct, per, groups, reinterpret_cast<Vec const *>(in), reinterpret_cast<Vec *>(out), p ? 1 : 0);
+                printf("unsupported variant\n");
+                exit(1);
             }
         }
     };
@@ -208,6 +291,19 @@ int main(int argc, char **argv)
     };
     time_it(run_old, out_a, "K3b");
     if (few_ok)
+    {
+#ifdef FP_FEW_PROFILE
+        unsigned long long z[8] = {};
+        CK(cudaMemcpyToSymbol(g_few_prof, z, sizeof z));
+#endif
         time_it(run_new, out_b, "K3e");
+#ifdef FP_FEW_PROFILE
+        CK(cudaMemcpyFromSymbol(z, g_few_prof, sizeof z));
+        double const ctas = 7.0 * views.size() * (dim >> 8) * ((rowvecs >> log_twc) / std::max(1, ctPer ? ctPer : (int)(rowvecs >> log_twc)));
+        double const tiles = 7.0 * views.size() * (dim >> 8) * (rowvecs >> log_twc);
+        printf("  phases (cycles): setup+D %.0f /CTA | per tile: wait-fill %.0f  compute %.0f  stage %.0f  store %.0f  refill-issue %.0f\n",
+               z[0] / ctas, z[1] / tiles, z[2] / tiles, z[3] / tiles, z[4] / tiles, z[5] / tiles);
+#endif
+    }
     return 0;
 }
