@@ -57,7 +57,12 @@ def _check(rc: int) -> None:
 
 
 def _dtype_code(dtype) -> int:
-    return FP_C64 if np.dtype(dtype) == np.complex64 else FP_C128
+    dt = np.dtype(dtype)
+    if dt == np.complex64:
+        return FP_C64
+    if dt == np.complex128:
+        return FP_C128
+    raise TypeError(f"fast_pauli_b200 handles complex64 / complex128 states, not {dt}")
 
 
 def _encode(strings: Iterable[str]) -> tuple[np.ndarray, int]:
@@ -182,6 +187,10 @@ class Context:
     def set_pipeline(self, enable: bool = True, min_bytes: int = 0, chunk_bytes: int = 0) -> None:
         """Chunked upload / kernel / download pipeline of PauliString.apply on host arrays (0 keeps a size)."""
         _check(lib.fp_ctx_set_pipeline(self._h, C.c_int(bool(enable)), C.c_size_t(min_bytes), C.c_size_t(chunk_bytes)))
+
+    def set_coset_few(self, mode: int = 1, column_tiles_per_cta: int = 0) -> None:
+        """Few-mask coset passes (K3e / K3f): 0 off, 1 automatic, 2 without the TMA-fed kernel."""
+        _check(lib.fp_ctx_set_coset_few(self._h, C.c_int(mode), C.c_int(column_tiles_per_cta)))
 
     def set_rcoset(self, mode: int = 1, log_nt: int = 0) -> None:
         """Register-resident coset kernels (x-mask rank <= 4): mode 0 never / 1 automatic / 2 whenever applicable."""
@@ -325,6 +334,12 @@ class _Arg:
                 raise ValueError("array must be C-contiguous (row-major)")  # NB:55-74
             self.ptr, self.shape = int(cai["data"][0]), tuple(cai["shape"])
             self.dtype, self.on_device, self.keep = np.dtype(cai["typestr"]), True, obj
+            # device arrays are used in place: there is no implicit conversion as for host arrays, so the element
+            # type must already be what the kernels read (a float64 / int buffer read as complex128 is out of bounds)
+            ok = (np.float32, np.float64) if want_real else (np.complex64, np.complex128)
+            if self.dtype not in ok:
+                raise TypeError(f"device array of dtype {self.dtype}: expected "
+                                f"{' or '.join(np.dtype(t).name for t in ok)} (device arrays are not converted)")
             return
         arr = np.asarray(obj)
         if want_real:

@@ -14,6 +14,7 @@
 #include "fast_pauli_b200/pauli.hpp"
 #include "fast_pauli_b200/pauli_op.hpp"
 #include "fast_pauli_b200/pauli_string.hpp"
+#include "fast_pauli_b200/sharded.hpp"
 #include "fast_pauli_b200/summed_pauli_op.hpp"
 #if __has_include(<fmt/format.h>)
 #include "fast_pauli_b200/fmt_support.hpp" // fmt::formatter<Pauli / PauliString / std::complex<double>>, as the reference

@@ -4,6 +4,7 @@
 // host/device pointer staging, plan packing (pack.hpp), geometry selection and kernel launches (kernels.cuh).
 // No compute happens on the host and there is no CPU fallback: without a CUDA device every compute call fails.
 #include "../../include/fastpauli_b200.h"
+#include "internal.h"
 
 #include <complex>
 #include <cstdio>
@@ -1607,6 +1608,11 @@ extern "C"
         return FP_OK;
     }
 
+    int fp_internal_set_error(int code, const char *msg)
+    {
+        return set_err(code, msg ? msg : "");
+    }
+
     int fp_version(void)
     {
         return 100; // 0.1.0
@@ -1638,7 +1644,7 @@ extern "C"
             return set_err(FP_NO_DEVICE, "no CUDA device visible: fastpauli_b200 has no CPU fallback");
         if (device < 0 || device >= n)
             return set_err(FP_INVALID_ARGUMENT, "device index out of range");
-        FP_CU(cudaSetDevice(device));
+        DeviceGuard guard(device); // the caller's current device (e.g. torch's) is restored on return
         cudaDeviceProp prop;
         FP_CU(cudaGetDeviceProperties(&prop, device));
         std::unique_ptr<fp_ctx> ctx(new fp_ctx);
@@ -1784,6 +1790,15 @@ extern "C"
             ctx->pipeline_min_bytes = min_bytes;
         if (chunk_bytes)
             ctx->pipeline_chunk_bytes = chunk_bytes;
+        return FP_OK;
+    }
+
+    int fp_ctx_set_coset_few(fp_ctx *ctx, int mode, int column_tiles_per_cta)
+    {
+        if (!ctx || mode < 0 || mode > 2 || column_tiles_per_cta < 0)
+            return set_err(FP_INVALID_ARGUMENT, "bad few-mask coset mode");
+        ctx->coset_few = mode;
+        ctx->coset_few_ct = column_tiles_per_cta;
         return FP_OK;
     }
 
@@ -2710,9 +2725,17 @@ extern "C"
         std::lock_guard<std::mutex> lk(mu);
         if (!ctx)
         {
+            // same rule as the Python package's default_context(): FASTPAULI_DEVICE, else the launcher's LOCAL_RANK
+            // (one process per GPU under torchrun / mpirun wrappers), else device 0
             int dev = 0;
             if (char const *env = getenv("FASTPAULI_DEVICE"))
                 dev = atoi(env);
+            else if (char const *lr = getenv("LOCAL_RANK"))
+            {
+                int n = 0;
+                if (fp_device_count(&n) == FP_OK && n > 0)
+                    dev = atoi(lr) % n;
+            }
             FP_TRY(fp_ctx_create(dev, &ctx));
         }
         *out = ctx;

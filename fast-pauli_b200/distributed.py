@@ -1,5 +1,10 @@
-"""Multi-GPU drivers of the hot path: one process per GPU, ``torch.distributed`` (NCCL over NVLink / NVSwitch) for
-the plumbing, the C-ABI kernels for all arithmetic.  Neither sharding exists in the reference.
+"""Multi-GPU helpers of the hot path: one process per GPU.  Neither sharding exists in the reference.
+
+The production path of the high-qubit sharding is the C ABI (``fp_comm_*`` / ``fp_sharded_op_*``, csrc/sharded.cpp,
+front-end :mod:`fast_pauli_b200.sharded`): NCCL inside the library, no torch on the data path.  This module keeps
+the host-side planning in Python form (``plan_high_qubit`` / ``ShardedStateOp`` with injected arithmetic and
+exchange, exercised on CPU by the world-size 2 / 4 gloo tests), the batch-axis helpers, and the fused CUDA-IPC
+peer-memory variant (``PeerShards`` + ``ShardedStateOp.apply_peer``).
 
 1. **Batch-axis sharding** (BASELINE configs 2-4): every hot-path formula is independent per batch column, so rank
    ``r`` of ``g`` owns the column block ``shard_columns(B, g, r)`` of the ``(dim, B)`` batch and runs the ordinary
@@ -134,7 +139,7 @@ class ShardedStateOp:
         self.plan = plan_high_qubit(list(strings), list(coeffs), world)
         self.world, self.rank = world, rank
         self._make = make_local_op or _cuda_local_op
-        self._exchange = exchange or _nccl_exchange
+        self._exchange = exchange or _no_exchange
         self.local_ops = [self._make(c.strings, _rank_coeffs(c, rank), self.plan.n_local) for c in self.plan.classes]
 
     def apply(self, out, psi, recv_bufs, accumulate: bool = False):
@@ -203,7 +208,7 @@ class ShardedStateOp:
         return all_reduce(total)
 
 
-# ------------------------------------------------------------------------------------------------ CUDA / NCCL defaults
+# ------------------------------------------------------------------------------------------------ CUDA defaults
 def _cuda_local_op(strings, coeffs, n_local):
     import fast_pauli_b200 as fp
 
@@ -211,66 +216,32 @@ def _cuda_local_op(strings, coeffs, n_local):
 
 
 class _CudaLocalOp:
-    """A class' local operator on the GPU: torch CUDA tensors in, C-ABI kernels on torch's current stream."""
+    """A class' local operator on the GPU, addressed by raw device pointers (torch-free).  Used by the fused
+    peer-memory path (``ShardedStateOp.apply_peer``); the exchange-based production path is the C ABI's
+    ``fp_sharded_op_apply`` (:mod:`fast_pauli_b200.sharded`), which owns its context, streams and NCCL communicator."""
 
     def __init__(self, fp, strings, coeffs):
         self.fp = fp
         self.op = fp.PauliOp(coeffs, strings)
 
-    def apply_into(self, out, src, accumulate: bool):
-        import ctypes as C
-        import torch
-
-        fp = self.fp
-        ctx = fp.default_context()
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        ctx.set_async(True)
-        dim = src.shape[0]
-        B = 1 if src.dim() == 1 else src.shape[1]
-        dt = np.complex128 if src.dtype == torch.complex128 else np.complex64
-        fp._check(fp.lib.fp_op_apply(ctx._h, self.op._plan(dt), C.c_void_p(out.data_ptr()), C.c_void_p(src.data_ptr()),
-                                     C.c_size_t(dim), C.c_size_t(B), C.c_int(int(accumulate))))
-
     def apply_ptr(self, out_ptr: int, src_ptr: int, dim: int, n_states: int, dtype, accumulate: bool):
-        """Same on raw device pointers (``src_ptr`` may be a peer GPU's memory mapped through CUDA IPC)."""
+        """``src_ptr`` may be a peer GPU's memory mapped through CUDA IPC."""
         import ctypes as C
 
         fp = self.fp
-        ctx = fp.default_context()
+        ctx = self.op._context()
         fp._check(fp.lib.fp_op_apply(ctx._h, self.op._plan(np.dtype(dtype)), C.c_void_p(out_ptr), C.c_void_p(src_ptr),
                                      C.c_size_t(dim), C.c_size_t(n_states), C.c_int(int(accumulate))))
 
-    def expval(self, bra_side, src):
-        """sum_i conj(bra_side[i]) (A src)[i] per column (fp_op_expval_bra), as a torch tensor on the device."""
-        import ctypes as C
-        import torch
+    def apply_into(self, out, src, accumulate: bool):
+        raise NotImplementedError("exchange-based sharded apply on GPUs: use fast_pauli_b200.sharded.ShardedPauliOp "
+                                  "(C ABI fp_sharded_op_apply, NCCL inside the library)")
 
-        fp = self.fp
-        ctx = fp.default_context()
-        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        ctx.set_async(True)
-        dim = src.shape[0]
-        B = 1 if src.dim() == 1 else src.shape[1]
-        dt = np.complex128 if src.dtype == torch.complex128 else np.complex64
-        out = torch.empty(B, dtype=src.dtype, device=src.device)
-        fp._check(fp.lib.fp_op_expval_bra(ctx._h, self.op._plan(dt), C.c_void_p(out.data_ptr()),
-                                          C.c_void_p(bra_side.data_ptr()), C.c_void_p(src.data_ptr()),
-                                          C.c_size_t(dim), C.c_size_t(B), C.c_int(0)))
-        return out
+    expval = apply_into
 
 
-def _nccl_exchange(send, recv, peer):
-    """Pairwise whole-shard swap with ``peer``; returns a callable that blocks the current stream until it landed."""
-    import torch.distributed as dist
-
-    ops = [dist.P2POp(dist.isend, send, peer), dist.P2POp(dist.irecv, recv, peer)]
-    reqs = dist.batch_isend_irecv(ops)
-
-    def wait():
-        for r in reqs:
-            r.wait()
-
-    return wait
+def _no_exchange(send, recv, peer):
+    raise NotImplementedError("inject `exchange` (CPU tests) or use fast_pauli_b200.sharded.ShardedPauliOp on GPUs")
 
 
 class PeerShards:

@@ -101,6 +101,11 @@ extern "C"
      * (default; stands aside when fp_ctx_set_coset forces a mode or shape), 2 = whenever applicable.  log_nt = 7 or 8
      * picks 128- or 256-thread CTAs (0 = default, 128). */
     int fp_ctx_set_rcoset(fp_ctx *ctx, int mode, int log_nt);
+    /* Passes of a coset plan with at most 8 x-masks (K3e / K3f, csrc/coset2.cuh: row factors in registers, strings in
+     * the constant bank, TMA-fed persistent variant): mode 0 = never (such passes run on the general coset kernel),
+     * 1 = automatic (default), 2 = never the TMA-fed kernel.  column_tiles_per_cta > 0 forces how many column tiles
+     * one CTA walks (0 = automatic). */
+    int fp_ctx_set_coset_few(fp_ctx *ctx, int mode, int column_tiles_per_cta);
     /* Override the L2 working-set budget (bytes) used to pick the batch-tile width of multi-group kernels. */
     int fp_ctx_set_l2_budget(fp_ctx *ctx, size_t bytes);
 
@@ -188,6 +193,51 @@ extern "C"
     int fp_ipc_export(fp_ctx *ctx, const void *dev_ptr, unsigned char *handle);
     int fp_ipc_open(fp_ctx *ctx, const unsigned char *handle, void **peer_ptr);
     int fp_ipc_close(fp_ctx *ctx, void *peer_ptr);
+
+    /* ---- sharded state (BASELINE config 5): one state vector split by its high index bits over the GPUs of a box ---
+     * One process per GPU.  NCCL is used by the library itself (dlopen of libnccl.so.2, no link-time dependency, no
+     * torch / MPI): rank 0 calls fp_comm_unique_id and ships the FP_COMM_ID_BYTES bytes to every rank by any means;
+     * every rank then calls fp_comm_create (collective).  world must be a power of two; rank r owns the rows whose
+     * top log2(world) index bits equal r, i.e. a contiguous shard of dim / world rows.
+     * fp_sharded_op_apply: out_shard (+)= (A psi)_shard (PauliOp::apply 1-D / 2-D, PO:362-468, on the whole state):
+     * strings whose x-mask leaves the high bits alone run as one fused local PauliOp; every other group of strings
+     * (one per peer offset x_hi) streams the peer's shard in chunks (default 256 MiB, two receive buffers) with
+     * ncclSend / ncclRecv inside ncclGroupStart / End on a communication stream while the previous chunk is applied
+     * by the streaming single-string kernel.  Device pointers only; synchronous; collective (every rank calls it).
+     * fp_sharded_op_expval: <psi|A|psi> per column (PO:482-549) = apply into `work` (a shard-sized device buffer of
+     * the caller) + local <psi|work> + one all-reduce; out_host receives n_states complex on EVERY rank. */
+#define FP_COMM_ID_BYTES 128
+    typedef struct fp_comm fp_comm;
+    typedef struct fp_sharded_op fp_sharded_op;
+    int fp_comm_unique_id(unsigned char *id /* FP_COMM_ID_BYTES */);
+    int fp_comm_create(fp_ctx *ctx, const unsigned char *id, int world, int rank, fp_comm **comm);
+    /* Single-process stand-in for rank `rank` of `world` (tests on one GPU): no NCCL; the sharded apply then takes a
+     * device buffer holding ALL shards back to back (fp_sharded_op_apply_emulated) and copies the peer chunks from it,
+     * every other step -- classes, chunk schedule, block signs, kernels -- being the production code. */
+    int fp_comm_create_emulated(fp_ctx *ctx, int world, int rank, fp_comm **comm);
+    int fp_comm_destroy(fp_comm *comm);
+    int fp_comm_info(const fp_comm *comm, int *world, int *rank, int *nccl_version);
+    int fp_comm_barrier(fp_comm *comm);
+    /* in-place sum (op = 0) or max (op = 1) of n <= 64 host doubles over the ranks (timing, small reductions) */
+    int fp_comm_allreduce_f64(fp_comm *comm, double *values, size_t n, int op);
+    /* every rank swaps `bytes` with rank ^ 1 through ncclSend / ncclRecv `iters` times: GB/s per direction per GPU
+     * (device time of the slowest rank) -- the measured NVLink denominator of the sharded apply */
+    int fp_comm_measure_p2p(fp_comm *comm, size_t bytes, int iters, double *gbps);
+    int fp_sharded_op_create(fp_comm *comm, int dtype, int n_qubits, size_t n_strings, const uint8_t *codes,
+                             const void *coeffs, fp_sharded_op **op);
+    int fp_sharded_op_destroy(fp_sharded_op *op);
+    int fp_sharded_op_set_chunk_bytes(fp_sharded_op *op, size_t bytes); /* 0 = default (256 MiB) */
+    int fp_sharded_op_apply(fp_sharded_op *op, void *out_shard, const void *in_shard, size_t local_dim, size_t n_states,
+                            int accumulate);
+    int fp_sharded_op_expval(fp_sharded_op *op, void *out_host, const void *in_shard, void *work_shard, size_t local_dim,
+                             size_t n_states);
+    int fp_sharded_op_apply_emulated(fp_sharded_op *op, void *out_shard, const void *all_shards, size_t local_dim,
+                                     size_t n_states, int accumulate);
+    /* remote classes (= peer offsets in use), and of the last apply: bytes sent per rank, chunks, kernels launched */
+    int fp_sharded_op_info(const fp_sharded_op *op, size_t *n_remote_classes, uint64_t *peer_offsets,
+                           uint64_t *bytes_sent_last, uint64_t *chunks_last, uint64_t *kernels_last);
+    /* device time (ms) of this rank's last fp_sharded_op_apply: CUDA events around the call's compute stream */
+    int fp_sharded_op_last_ms(const fp_sharded_op *op, float *ms);
 
     /* ---- diagnostics ----------------------------------------------------------------------------
      * The contraction engine on its own: C[split_k][M x N] = A[M x Kd] * B[Kd x N] (row-major fp32, split-K planes

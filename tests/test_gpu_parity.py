@@ -1047,6 +1047,119 @@ def test_headline_size_dense_local_operator_sampled_rows(k_local):
     assert rel_err(ev[cols], acc) < 1e-12
 
 
+def _chain_strings(n: int, kind: str) -> list[str]:
+    out = []
+    for i in range(n - 1):
+        for pp in (("XX", "YY", "ZZ") if kind == "heisenberg" else ("ZZ",)):
+            t = ["I"] * n
+            t[i], t[i + 1] = pp[0], pp[1]
+            out.append("".join(t))
+    if kind == "tfim":
+        for i in range(n):
+            t = ["I"] * n
+            t[i] = "X"
+            out.append("".join(t))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["few_group", "random", "heisenberg", "tfim"])
+def test_headline_size_multi_pass_operators_sampled_rows(kind):
+    """The bench's own headline operators at FULL size (PauliOp.apply, 20 qubits x 64 complex128): 64 strings over 8
+    x-masks (one K3e / K3f pass), 64 random strings (8 read-modify-write passes) and the two nearest-neighbour chain
+    Hamiltonians (multi-pass plans of the general coset kernel).  Checked three ways: sampled output rows against the
+    closed form on regenerated inputs; the few-mask kernels against the general coset kernel they replace (same
+    summation order: bit-identical); the accumulating form (the C++ methods' +=) against out0 + result."""
+    import ctypes as C
+
+    import bench
+    from fast_pauli_b200.synth import uniform_host
+
+    ctx = fp.default_context()
+    n, B = 20, 64
+    dim = 2**n
+    if kind in ("few_group", "random"):
+        strings, h = bench.headline_operators(n)[kind]
+    else:
+        strings = _chain_strings(n, kind)
+        r = np.random.default_rng(77)
+        h = r.uniform(-1, 1, len(strings)) + 1j * r.uniform(-1, 1, len(strings))
+    psi = ctx.uniform((dim, B), np.complex128, seed=18)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    ctx.set_coset_few(1)
+    l0 = ctx.launch_count
+    out = op.apply(psi)
+    launches = ctx.launch_count - l0
+    # the launch path: one pass per rank-8 span of x-masks (few: 1, random: 8; the chains need 2-3 passes)
+    assert launches == {"few_group": 1, "random": 8}.get(kind, launches) and 1 <= launches <= 8
+    masks = [orc.masks(s) for s in strings]
+    phase = np.array([1, -1j, -1, 1j])
+    rng = np.random.default_rng(3)
+    rows = [0, dim - 1] + [int(r) for r in rng.integers(0, dim, size=10)]
+    expect_rows = {}
+    for i in rows:
+        expect = np.zeros((1, B), dtype=np.complex128)
+        cache = {}
+        for (x, z, ny), hs in zip(masks, h):
+            j = i ^ x
+            if j not in cache:
+                cache[j] = uniform_host((1, B), np.complex128, seed=18, first=j * B)
+            sign = -1.0 if bin(i & z).count("1") & 1 else 1.0
+            expect += (hs * phase[ny] * sign) * cache[j]
+        expect_rows[i] = expect
+        assert rel_err(out.get_rows(i, i + 1), expect) < 1e-12
+    # the same call with the few-mask kernels switched off (general coset kernel) and without the TMA-fed variant
+    for mode in (0, 2):
+        ctx.set_coset_few(mode)
+        other = op.apply(psi)
+        for r0 in (0, dim // 2 - 4096, dim - 8192):
+            np.testing.assert_array_equal(other.get_rows(r0, r0 + 8192), out.get_rows(r0, r0 + 8192))
+        del other
+    ctx.set_coset_few(1)
+    # accumulate = 1 through the C ABI: out0 + A psi (first pass is read-modify-write too)
+    acc = ctx.uniform((dim, B), np.complex128, seed=5)
+    fp._check(fp.lib.fp_op_apply(ctx._h, op._plan(np.complex128), C.c_void_p(acc.ptr), C.c_void_p(psi.ptr),
+                                 C.c_size_t(dim), C.c_size_t(B), C.c_int(1)))
+    ctx.sync()
+    for i in rows[:6]:
+        base = uniform_host((1, B), np.complex128, seed=5, first=i * B)
+        assert rel_err(acc.get_rows(i, i + 1), base + expect_rows[i]) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,B,masks,per", [(9, 16, 8, 8), (12, 16, 8, 20), (13, 32, 5, 3), (16, 16, 8, 1), (16, 8, 3, 40),
+                                          (12, 48, 8, 2), (16, 32, 4, 2), (17, 16, 8, 4)])
+def test_few_mask_coset_kernels_small_shapes(dtype, n, B, masks, per):
+    """K3e / K3f on small registers and odd shapes: <= 8 x-masks with several z-variants each (more than 128 strings in
+    one pass takes the shared-memory staged row-factor phase), batch widths that are not multiples of 16 vectors,
+    complex64 (two columns per vector); against the oracle and against the general coset kernel."""
+    rng = np.random.default_rng(1000 * n + B + masks)
+    ctx = fp.default_context()
+    strings = []
+    for s in rand_strings(rng, n, masks):
+        for _ in range(per):
+            t = list(s)
+            for q in range(n):
+                if rng.random() < 0.5:
+                    t[q] = {"X": "Y", "Y": "X", "I": "Z", "Z": "I"}[t[q]]
+            strings.append("".join(t))
+    h = (rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))).astype(dtype)
+    psi = rand_states(rng, 2**n, B, dtype)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    d_psi = ctx.to_device(psi)
+    ref = ORC.op_apply(strings, h.astype(np.complex128), psi.astype(np.complex128), par=True)
+    results = []
+    for mode in (1, 2, 0):
+        ctx.set_coset_few(mode)
+        ctx.set_coset(2)  # whenever applicable: small problems would otherwise use the generic kernel
+        got = op.apply(d_psi).get()
+        assert rel_err(got, ref) < tol(dtype)
+        results.append(got)
+    ctx.set_coset(1)
+    ctx.set_coset_few(1)
+    np.testing.assert_array_equal(results[0], results[2])
+    np.testing.assert_array_equal(results[1], results[2])
+
+
 def test_two_devices_in_one_process():
     """One context per GPU in a single process: every kernel family that needs opt-in shared memory must be configured
     on each device it runs on (cudaFuncSetAttribute is per device).  Skipped on single-GPU boxes."""
