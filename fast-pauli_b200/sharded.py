@@ -104,6 +104,10 @@ class ShardedPauliOp:
     def local_dim(self) -> int:
         return 1 << self.n_local
 
+    def set_mode(self, mode: int) -> None:
+        """0 automatic, 1 chunked streaming (two chunk buffers), 2 whole-shard receive + fused class operator."""
+        fp._check(_lib.fp_sharded_op_set_mode(self._h, C.c_int(mode)))
+
     def set_chunk_bytes(self, nbytes: int) -> None:
         fp._check(_lib.fp_sharded_op_set_chunk_bytes(self._h, C.c_size_t(nbytes)))
 
@@ -126,9 +130,11 @@ class ShardedPauliOp:
         offs = (C.c_uint64 * max(self.comm.world, 1))()
         sent, chunks, kernels = C.c_uint64(), C.c_uint64(), C.c_uint64()
         ms = C.c_float()
+        mode = C.c_int()
         fp._check(_lib.fp_sharded_op_info(self._h, C.byref(n), offs, C.byref(sent), C.byref(chunks), C.byref(kernels)))
         fp._check(_lib.fp_sharded_op_last_ms(self._h, C.byref(ms)))
-        return {"n_remote_classes": int(n.value), "peer_offsets": [int(offs[i]) for i in range(n.value)],
+        fp._check(_lib.fp_sharded_op_last_mode(self._h, C.byref(mode)))
+        return {"mode_last": {1: "chunked", 2: "whole-shard"}.get(int(mode.value), "none"),"n_remote_classes": int(n.value), "peer_offsets": [int(offs[i]) for i in range(n.value)],
                 "bytes_sent_last": int(sent.value), "chunks_last": int(chunks.value), "kernels_last": int(kernels.value),
                 "device_ms_last": float(ms.value)}
 
@@ -161,7 +167,7 @@ def closed_form_rows(strings, coeffs, rows: np.ndarray, seed: int) -> np.ndarray
 
 
 def bench_config5(fp_mod, ctx, dist, torch, rank: int, world: int, local_rank: int, seed: int = 18,
-                  string_seed: int = 1234, n_qubits: int | None = None, n_strings: int = 16) -> dict:
+                  string_seed: int = 1234, n_qubits: int | None = None, n_strings: int = 16, mode: int = 0) -> dict:
     """BASELINE config 5 scaled to `world` ranks: PauliOp.apply on one complex128 state of 31 + log2(world) qubits
     (34 qubits = 256 GiB at 8 ranks), 32 GiB shard in + 32 GiB out per GPU.  Parity on sampled rows before timing;
     device time of the slowest rank; NVLink GB/s per direction against a pairwise ncclSend/Recv probe measured in the
@@ -179,6 +185,7 @@ def bench_config5(fp_mod, ctx, dist, torch, rank: int, world: int, local_rank: i
     strings = random_strings(rng, n, n_strings)
     h = rng.uniform(-1, 1, n_strings) + 1j * rng.uniform(-1, 1, n_strings)
     op = ShardedPauliOp(comm, h, strings)
+    op.set_mode(mode)
     psi = ctx.uniform((local_dim,), np.complex128, seed=seed, first=rank * local_dim)
     out = ctx.empty((local_dim,), np.complex128)
     try:
@@ -209,9 +216,11 @@ def bench_config5(fp_mod, ctx, dist, torch, rank: int, world: int, local_rank: i
                "nvlink_bytes_sent_per_gpu": sent, "nvlink_GBps_per_direction": gbps,
                "nvlink_peak_GBps_measured": p2p, "nvlink_frac": gbps / p2p if p2p > 0 else None,
                "nvlink_peak_source": "pairwise ncclSend/ncclRecv swap of 1 GiB with rank^1, same run (fp_comm_measure_p2p)",
-               "chunks": info["chunks_last"], "kernels": info["kernels_last"], "exchange": "ncclSend/ncclRecv in "
-               "ncclGroupStart/End, 256 MiB chunks, two receive buffers, overlapped with the per-chunk kernels "
-               "(C ABI: fp_sharded_op_apply; no torch on the data path)",
+               "exchange_mode": info["mode_last"], "transfers": info["chunks_last"], "kernel_calls": info["kernels_last"],
+               "exchange": "ncclSend/ncclRecv in ncclGroupStart/End on a communication stream, double-buffered against "
+                           "the kernels: whole-shard mode = one fused PauliOp per peer offset on the received shard, "
+                           "chunked mode = 256 MiB chunks + the streaming single-string kernel (C ABI: "
+                           "fp_sharded_op_apply; no torch on the data path)",
                "nccl_version": comm.nccl_version(), "timing": "CUDA events inside the call, best of 3, max over ranks"}
     finally:
         op.close()

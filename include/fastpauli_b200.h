@@ -227,6 +227,11 @@ extern "C"
                              const void *coeffs, fp_sharded_op **op);
     int fp_sharded_op_destroy(fp_sharded_op *op);
     int fp_sharded_op_set_chunk_bytes(fp_sharded_op *op, size_t bytes); /* 0 = default (256 MiB) */
+    /* How a peer's shard reaches the kernels: 1 = chunked streaming (two chunk buffers; one streaming single-string
+     * kernel per string and chunk), 2 = whole shard (one or two shard-sized receive buffers; each group of strings
+     * runs as ONE fused PauliOp on the received shard while the next group's exchange is in flight), 0 = automatic:
+     * whole shard when the device has room for it (it is 2-4x faster with several strings per peer offset). */
+    int fp_sharded_op_set_mode(fp_sharded_op *op, int mode);
     int fp_sharded_op_apply(fp_sharded_op *op, void *out_shard, const void *in_shard, size_t local_dim, size_t n_states,
                             int accumulate);
     int fp_sharded_op_expval(fp_sharded_op *op, void *out_host, const void *in_shard, void *work_shard, size_t local_dim,
@@ -238,6 +243,7 @@ extern "C"
                            uint64_t *bytes_sent_last, uint64_t *chunks_last, uint64_t *kernels_last);
     /* device time (ms) of this rank's last fp_sharded_op_apply: CUDA events around the call's compute stream */
     int fp_sharded_op_last_ms(const fp_sharded_op *op, float *ms);
+    int fp_sharded_op_last_mode(const fp_sharded_op *op, int *mode); /* 1 chunked, 2 whole shard */
 
     /* ---- diagnostics ----------------------------------------------------------------------------
      * The contraction engine on its own: C[split_k][M x N] = A[M x Kd] * B[Kd x N] (row-major fp32, split-K planes

@@ -29,7 +29,8 @@ def main():
     dist.broadcast_object_list(box, src=0)
     comm = sharded.Comm(ctx, box[0], world, rank)
     rng = np.random.default_rng(11)  # same stream on every rank: identical global problem
-    for n, B, S, chunk in ((12, None, 20, 4096), (14, 3, 12, 1 << 16), (16, None, 30, 1 << 18)):
+    for n, B, S, chunk, mode in ((12, None, 20, 4096, 1), (14, 3, 12, 1 << 16, 2), (16, None, 30, 1 << 18, 1),
+                                 (16, None, 30, 1 << 18, 0), (13, 2, 9, 1 << 12, 2)):
         strings = random_strings(rng, n, S) + ["X" + "Z" * (n - 1), "I" * n]
         h = rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))
         shape = (1 << n,) if B is None else (1 << n, B)
@@ -37,6 +38,7 @@ def main():
         local = (1 << n) // world
         op = sharded.ShardedPauliOp(comm, h, strings)
         op.set_chunk_bytes(chunk)
+        op.set_mode(mode)
         d_in = ctx.to_device(np.ascontiguousarray(psi[rank * local:(rank + 1) * local]))
         d_out = ctx.empty(d_in.shape, np.complex128)
         op.apply(d_out, d_in)
@@ -49,6 +51,7 @@ def main():
         assert err < 1e-12, f"sharded apply n={n} B={B}: {err:.3e}"
         info = op.info()
         assert info["n_remote_classes"] >= 1 and info["bytes_sent_last"] > 0
+        assert info["mode_last"] == ("chunked" if mode == 1 else "whole-shard")
         ev = op.expectation_value(d_in, d_out)
         ev_ref = orc.best().op_expval(strings, h, psi if B is not None else psi[:, None])
         err_e = float(np.max(np.abs(ev - ev_ref)) / np.max(np.abs(ev_ref)))

@@ -26,7 +26,7 @@ fp = load_package()
 ORC = orc.best()
 
 
-def emulated_apply(strings, h, psi, world, dtype, chunk_bytes, accumulate=False, out0=None):
+def emulated_apply(strings, h, psi, world, dtype, chunk_bytes, accumulate=False, out0=None, mode=1):
     """Gather of the emulated per-rank results: (dim,) or (dim, B)."""
     ctx = fp.default_context()
     dt = np.dtype(dtype)
@@ -44,6 +44,7 @@ def emulated_apply(strings, h, psi, world, dtype, chunk_bytes, accumulate=False,
         fp._check(fp.lib.fp_sharded_op_create(comm, C.c_int(fp._dtype_code(dt)), C.c_int(n), C.c_size_t(len(strings)),
                                               C.c_void_p(codes.ctypes.data), C.c_void_p(hh.ctypes.data), C.byref(op)))
         fp._check(fp.lib.fp_sharded_op_set_chunk_bytes(op, C.c_size_t(chunk_bytes)))
+        fp._check(fp.lib.fp_sharded_op_set_mode(op, C.c_int(mode)))
         shape = (local,) if psi.ndim == 1 else (local, B)
         if out0 is not None:
             d_out = ctx.to_device(np.ascontiguousarray(out0[rank * local:(rank + 1) * local], dtype=dt))
@@ -58,15 +59,16 @@ def emulated_apply(strings, h, psi, world, dtype, chunk_bytes, accumulate=False,
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 2, 0])
 @pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
 @pytest.mark.parametrize("world,n,B,chunk", [(2, 10, None, 1 << 20), (4, 11, None, 4096), (8, 12, None, 2048),
                                              (4, 10, 3, 4096), (8, 13, 4, 16384), (2, 9, 16, 1024)])
-def test_emulated_sharded_apply_matches_oracle(dtype, world, n, B, chunk, rng):
+def test_emulated_sharded_apply_matches_oracle(mode, dtype, world, n, B, chunk, rng):
     strings = rand_strings(rng, n, 24)
     strings += ["I" * n, "Z" * n, "X" + "I" * (n - 1), "Y" * n]  # identity, diagonal, pure high-bit flip, all-Y
     h = rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))
     psi = rand_states(rng, 1 << n, B, dtype)
-    got = emulated_apply(strings, h, psi, world, dtype, chunk)
+    got = emulated_apply(strings, h, psi, world, dtype, chunk, mode=mode)
     ref = ORC.op_apply(strings, h.astype(dtype), psi)
     assert rel_err(got, ref) < TOL[np.dtype(dtype)]
 
@@ -78,10 +80,11 @@ def test_emulated_sharded_apply_accumulates(rng):
     h = rng.uniform(-1, 1, 9) + 1j * rng.uniform(-1, 1, 9)
     psi = rand_states(rng, 1 << n, None)
     out0 = rand_states(rng, 1 << n, None)
-    got = emulated_apply(strings, h, psi, world, np.complex128, 2048, accumulate=True, out0=out0)
     ref = out0.copy()
     ORC.op_apply(strings, h, psi, out=ref)  # the C++ methods accumulate (PO:419,432)
-    assert rel_err(got, ref) < 1e-12
+    for mode in (1, 2):
+        got = emulated_apply(strings, h, psi, world, np.complex128, 2048, accumulate=True, out0=out0, mode=mode)
+        assert rel_err(got, ref) < 1e-12
 
 
 @pytest.mark.gpu
@@ -91,8 +94,9 @@ def test_emulated_only_remote_classes(rng):
     strings = ["XX" + s for s in rand_strings(rng, n - 2, 5)] + ["YI" + s for s in rand_strings(rng, n - 2, 3)]
     h = rng.uniform(-1, 1, 8) + 1j * rng.uniform(-1, 1, 8)
     psi = rand_states(rng, 1 << n, 2)
-    got = emulated_apply(strings, h, psi, world, np.complex128, 1024)
-    assert rel_err(got, ORC.op_apply(strings, h, psi)) < 1e-12
+    for mode in (1, 2):
+        got = emulated_apply(strings, h, psi, world, np.complex128, 1024, mode=mode)
+        assert rel_err(got, ORC.op_apply(strings, h, psi)) < 1e-12
 
 
 @pytest.mark.gpu
@@ -143,7 +147,8 @@ def test_sharded_entry_points_need_a_device():
     for name in ("fp_comm_unique_id", "fp_comm_create", "fp_comm_create_emulated", "fp_comm_destroy", "fp_comm_barrier",
                  "fp_comm_allreduce_f64", "fp_comm_measure_p2p", "fp_sharded_op_create", "fp_sharded_op_apply",
                  "fp_sharded_op_apply_emulated", "fp_sharded_op_expval", "fp_sharded_op_info", "fp_sharded_op_last_ms",
-                 "fp_sharded_op_set_chunk_bytes", "fp_sharded_op_destroy"):
+                 "fp_sharded_op_set_chunk_bytes", "fp_sharded_op_set_mode", "fp_sharded_op_last_mode",
+                 "fp_sharded_op_destroy"):
         assert hasattr(fp.lib, name), name
     if _n_gpus() == 0:
         ctxp = C.c_void_p()
