@@ -1515,6 +1515,69 @@ int pipelined_string_apply(fp_ctx *ctx, StringMasks const &mk, std::complex<T> c
     return FP_OK;
 }
 
+// Host-resident PauliOp::apply (PO:399-468) as a pipeline over COLUMN blocks: every hot-path formula is independent
+// per batch column, so the (dim, B) host batch is cut into blocks of `cols` columns; block j+1 is uploaded (strided 2-D
+// copy into a dense device block) while block j runs the ordinary kernels and block j-1 is downloaded, so both PCIe
+// directions are busy for the whole call.  Three device blocks per direction.
+template <typename T>
+int pipelined_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const *in, uint64_t dim, uint64_t B,
+                       int n_qubits, bool *used)
+{
+    *used = false;
+    size_t const esize = 2 * sizeof(T);
+    // block width: a multiple of 16 vectors (256-byte row segments: the widest coset tile and efficient strided DMA),
+    // at most B / 3 so that at least three blocks are in flight, about pipeline_chunk_bytes * 8 per block
+    uint64_t const vec_cols = 16 / esize;          // columns per 16-byte vector
+    uint64_t cols = 16 * vec_cols;                 // 256 bytes per row
+    if (B % cols != 0 || B / cols < 3)
+        return FP_OK;
+    while (B % (2 * cols) == 0 && B / (2 * cols) >= 4 && dim * (2 * cols) * esize <= (256ull << 20))
+        cols *= 2;
+    uint64_t const n_blocks = B / cols;
+    size_t const bbytes = dim * cols * esize;
+    if (!ctx->h2d_stream)
+    {
+        FP_CU(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+        FP_CU(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 3; ++i)
+        {
+            FP_CU(cudaEventCreateWithFlags(&ctx->pipe_in[i], cudaEventDisableTiming));
+            FP_CU(cudaEventCreateWithFlags(&ctx->pipe_k[i], cudaEventDisableTiming));
+            FP_CU(cudaEventCreateWithFlags(&ctx->pipe_out[i], cudaEventDisableTiming));
+        }
+        FP_CU(cudaEventCreateWithFlags(&ctx->pipe_start, cudaEventDisableTiming));
+    }
+    FP_TRY(ctx->stage_in.ensure(3 * bbytes));
+    FP_TRY(ctx->stage_out.ensure(3 * bbytes));
+    FP_CU(cudaEventRecord(ctx->pipe_start, ctx->stream));
+    FP_CU(cudaStreamWaitEvent(ctx->h2d_stream, ctx->pipe_start, 0));
+    size_t const host_pitch = B * esize, dev_pitch = cols * esize;
+    for (uint64_t j = 0; j < n_blocks; ++j)
+    {
+        int const b = static_cast<int>(j % 3);
+        auto *d_in = static_cast<unsigned char *>(ctx->stage_in.p) + static_cast<size_t>(b) * bbytes;
+        auto *d_out = static_cast<unsigned char *>(ctx->stage_out.p) + static_cast<size_t>(b) * bbytes;
+        if (j >= 3)
+            FP_CU(cudaStreamWaitEvent(ctx->h2d_stream, ctx->pipe_k[b], 0)); // kernel j-3 has consumed this block
+        FP_CU(cudaMemcpy2DAsync(d_in, dev_pitch, static_cast<unsigned char const *>(in) + j * dev_pitch, host_pitch,
+                                dev_pitch, dim, cudaMemcpyHostToDevice, ctx->h2d_stream));
+        FP_CU(cudaEventRecord(ctx->pipe_in[b], ctx->h2d_stream));
+        FP_CU(cudaStreamWaitEvent(ctx->stream, ctx->pipe_in[b], 0));
+        if (j >= 3)
+            FP_CU(cudaStreamWaitEvent(ctx->stream, ctx->pipe_out[b], 0)); // download j-3 has drained this block
+        FP_TRY(run_op_apply<T>(ctx, op, d_out, d_in, dim, cols, 0, n_qubits));
+        FP_CU(cudaEventRecord(ctx->pipe_k[b], ctx->stream));
+        FP_CU(cudaStreamWaitEvent(ctx->d2h_stream, ctx->pipe_k[b], 0));
+        FP_CU(cudaMemcpy2DAsync(static_cast<unsigned char *>(out) + j * dev_pitch, host_pitch, d_out, dev_pitch, dev_pitch,
+                                dim, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        FP_CU(cudaEventRecord(ctx->pipe_out[b], ctx->d2h_stream));
+    }
+    for (int b = 0; b < 3 && static_cast<uint64_t>(b) < n_blocks; ++b)
+        FP_CU(cudaStreamWaitEvent(ctx->stream, ctx->pipe_out[b], 0));
+    *used = true;
+    return FP_OK;
+}
+
 template <typename T> DeviceOp<T> &dop(fp_op *op);
 template <> DeviceOp<float> &dop<float>(fp_op *op)
 {
@@ -2139,6 +2202,21 @@ extern "C"
         DeviceGuard g(ctx->device);
         std::lock_guard<std::mutex> lk(ctx->mu);
         size_t const bytes = dim * n_states * csize(op->dtype);
+        if (ctx->pipeline && !accumulate && bytes >= ctx->pipeline_min_bytes && !is_device_ptr(in) && !is_device_ptr(out))
+        {
+            auto const *ib = static_cast<unsigned char const *>(in);
+            auto const *ob = static_cast<unsigned char const *>(out);
+            if (ib + bytes <= ob || ob + bytes <= ib) // disjoint host buffers
+            {
+                bool used = false;
+                if (op->dtype == FP_C128)
+                    FP_TRY(pipelined_op_apply<double>(ctx, op->d, out, in, dim, n_states, op->n_qubits, &used));
+                else
+                    FP_TRY(pipelined_op_apply<float>(ctx, op->f, out, in, dim, n_states, op->n_qubits, &used));
+                if (used)
+                    return finish(ctx, true);
+            }
+        }
         Staged sin, sout;
         FP_TRY(stage_in(ctx, ctx->stage_in, in, bytes, true, sin));
         FP_TRY(stage_in(ctx, ctx->stage_out, out, bytes, accumulate != 0, sout));

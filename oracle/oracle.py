@@ -309,3 +309,37 @@ def np_op_apply(strings: Sequence[str], coeffs, states: np.ndarray) -> np.ndarra
         mm = (h * m).astype(states.dtype)
         out += (mm[:, None] * states[k]) if states.ndim == 2 else mm * states[k]
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Like-ordered expectation values: numpy's pairwise summation, in the INPUT precision.
+# The reference accumulates expectation values sequentially (PS:534), so its own rounding error grows like the number of
+# terms; a tree-ordered sum in the same precision is the fair comparison for the GPU's tree reductions.  Used by the
+# tests before any appeal to a higher-precision arbiter.
+# ---------------------------------------------------------------------------------------------
+def np_string_expvals(strings: Sequence[str], states: np.ndarray) -> np.ndarray:
+    """E(s, t) = <psi_t| P_s |psi_t> with unit coefficients, in states.dtype, pairwise-summed over the rows."""
+    states = np.ascontiguousarray(states)
+    s2 = states.reshape(states.shape[0], -1)
+    out = np.zeros((len(strings), s2.shape[1]), dtype=states.dtype)
+    for k, st in enumerate(strings):
+        idx, m = np_sparse(st)
+        prod = np.conj(s2) * (m.astype(states.dtype)[:, None] * s2[idx])
+        out[k] = prod.sum(axis=0, dtype=states.dtype)
+    return out
+
+
+def np_expval_pairwise(kind: str, *args) -> np.ndarray:
+    """kind in {"string_expval", "op_expval", "sop_expval"} with the same argument lists as the Backend methods."""
+    if kind == "string_expval":
+        string, states = args[0], args[1]
+        c = complex(args[2]) if len(args) > 2 else 1.0
+        st = string if isinstance(string, str) else string[0]
+        return (np_string_expvals([st], states)[0] * np.asarray(c, dtype=states.dtype)).astype(states.dtype)
+    strings, coeffs, states = args[0], np.asarray(args[1]), args[2]
+    E = np_string_expvals(list(strings), states)
+    if kind == "op_expval":
+        return (coeffs.astype(states.dtype) @ E).astype(states.dtype)
+    if kind == "sop_expval":
+        return (coeffs.astype(states.dtype).T @ E).astype(states.dtype)
+    raise ValueError(kind)

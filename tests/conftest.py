@@ -18,6 +18,24 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+# Every time a parity check does NOT pass the plain |gpu - reference| < tol comparison and is settled some other way,
+# it is recorded here and printed at the end of the run (the relaxations must be countable).
+#   like_ordered : passed against the pairwise-summed host reference in the SAME precision (no relaxation of the bar)
+#   arbiter      : passed only against a higher-precision arbiter (the documented exception)
+AUDIT: dict[str, list[str]] = {"like_ordered": [], "arbiter": []}
+# the arbiter may only ever be needed for long reductions: below these term counts it is a failure, not an exception
+ARBITER_MIN_TERMS = {"complex64": 1 << 12, "complex128": 1 << 21}
+
+
+def pytest_terminal_summary(terminalreporter):
+    tr = terminalreporter
+    tr.write_line(f"parity audit: {len(AUDIT['like_ordered'])} check(s) settled by the like-ordered (pairwise, same "
+                  f"precision) reference, {len(AUDIT['arbiter'])} by the higher-precision arbiter")
+    for kind in ("like_ordered", "arbiter"):
+        for line in AUDIT[kind][:40]:
+            tr.write_line(f"  [{kind}] {line}")
+
+
 def rand_states(rng: np.random.Generator, dim: int, n_states: int | None, dtype=np.complex128) -> np.ndarray:
     """U[0,1) + i U[0,1) like the reference fixtures (tests/conftest.py:86-90, __factory.hpp:110-122)."""
     shape = (dim,) if n_states is None else (dim, n_states)

@@ -27,26 +27,48 @@ def tol(dtype) -> float:
     return TOL[np.dtype(dtype)]
 
 
+def _reduction_terms(args) -> int:
+    """Terms summed per output value of an expectation-value check: rows x strings."""
+    dim = next((a.shape[0] for a in args if isinstance(a, np.ndarray) and a.ndim >= 1 and a.dtype.kind == "c"
+                and a.shape[0] > 1), 1)
+    n_str = next((len(a) for a in args if isinstance(a, (list, tuple)) and a and isinstance(a[0], str)), 1)
+    return int(dim) * int(n_str)
+
+
 def assert_parity(got, ref_fn, dtype, *args):
     """North-star bar: max|gpu - ref| / |ref|_inf < 1e-12 (complex128) / 1e-5 (complex64).
 
-    One documented exception, complex64 reductions only: the reference accumulates expectation values
-    sequentially in float32 (PS:534, SPO:609), so over >= 2^12 terms ITS OWN rounding error exceeds 1e-5
-    (measured against its complex128 path on the same inputs).  When the direct comparison misses the bar,
-    the GPU result must instead be within 1e-5 of the complex128 reference AND at least as close to it as
-    the complex64 reference is -- i.e. the discrepancy is the reference's, not ours.
+    The reference accumulates expectation values sequentially in the input precision (PS:534, SPO:609), so over long
+    reductions ITS OWN rounding error can exceed the bar.  When the direct comparison misses it, the check is settled
+    in this order, and every such event is counted and printed at the end of the run (conftest.AUDIT):
+      1. like-ordered reference: the same sum, same precision, numpy pairwise (tree) order -- same bar, no relaxation;
+      2. complex64 only, and only for reductions of >= 2^12 terms: the GPU must be within 1e-5 of the complex128
+         reference AND at least as close to it as the complex64 reference is.  Below 2^12 terms this is a failure.
     """
+    import conftest
+
     ref = ref_fn(*args)
     err = rel_err(got, ref)
     if err < tol(dtype):
         return
-    assert np.dtype(dtype) == np.complex64, f"complex128 parity {err:.3e}"
+    kind = getattr(ref_fn, "__name__", "")
+    terms = _reduction_terms(args)
+    where = f"{kind} {np.dtype(dtype).name} terms=2^{np.log2(max(terms, 1)):.1f} |gpu-ref|={err:.2e}"
+    if kind in ("string_expval", "op_expval", "sop_expval"):
+        like = orc.np_expval_pairwise(kind, *args)
+        e_like = rel_err(got, like.reshape(np.shape(ref)))
+        if e_like < tol(dtype):
+            conftest.AUDIT["like_ordered"].append(f"{where} |gpu-pairwise|={e_like:.2e}")
+            return
+    assert np.dtype(dtype) == np.complex64, f"complex128 parity {err:.3e} ({where})"
+    assert terms >= conftest.ARBITER_MIN_TERMS["complex64"], f"arbiter below its term threshold: {where}"
     up = [a.astype(np.complex128) if isinstance(a, np.ndarray) and a.dtype == np.complex64 else
           (a.astype(np.float64) if isinstance(a, np.ndarray) and a.dtype == np.float32 else a) for a in args]
     exact = ref_fn(*up)
     e_gpu, e_ref = rel_err(got, exact), rel_err(ref, exact)
     assert e_gpu < tol(dtype) and e_gpu <= e_ref, (
         f"complex64 parity: |gpu-ref32| {err:.3e}, |gpu-ref64| {e_gpu:.3e}, |ref32-ref64| {e_ref:.3e}")
+    conftest.AUDIT["arbiter"].append(f"{where} |gpu-ref64|={e_gpu:.2e} |ref32-ref64|={e_ref:.2e}")
 
 
 # ------------------------------------------------------------------ golden vectors from the reference's numpy code
@@ -192,7 +214,10 @@ def test_fuzz_fixed_seeds(seed):
     dtypes and host / device residency through all seven Python entry points against the oracle."""
     import fuzz_parity  # tests/fuzz_parity.py
 
+    import conftest
+
     cases, failures = fuzz_parity.run(seconds=25, seed=seed, max_cases=200, native=(seed == 8))  # 8: both front-ends
+    conftest.AUDIT["arbiter"].extend(f"fuzz seed {seed}: {n}" for n in fuzz_parity.LAST_NOTES)
     assert cases >= 20 and not failures, "\n".join(failures[:20])
 
 
