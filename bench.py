@@ -756,6 +756,11 @@ def run_ours(args) -> None:
              "amp_strings_per_s": N_STRINGS * dim * B / t,
              "traffic": tr.get("dram_bytes_per_call"), "traffic_source": tr.get("source"),
              "kernel": tr.get("kernel", "coset_few_kernel / coset_few_tma_kernel (K3e / K3f, csrc/coset2.cuh)")}
+        # third floor, reported beside the two the SURVEY names: every complex FMA of a multi-mask pass needs one 16-byte
+        # shared-memory gather (no register-level reuse between independent masks); 128 B/clk/SM of LDS bandwidth
+        t_lds = 16.0 * G * dim * B / (148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6) if G > 4 else 0.0
+        r["t_smem_gather_ms"] = 1e3 * t_lds
+        r["frac_of_max_hbm_fp64_smem"] = max(t_hbm, t_fp, t_lds) / t
         if r["traffic"]:
             # what the implementation really moves through HBM (multi-pass plans re-stream the batch): how busy HBM is
             r["traffic_GBps"] = r["traffic"] / t / 1e9
@@ -803,6 +808,10 @@ def run_ours(args) -> None:
         e2e = {"value": world * 2.0 * N_STRINGS * dim * B * Ke / dt, "unit": UNIT,
                "h2d_bytes_per_step": 2 * h_in.nbytes, "d2h_bytes_per_step": sum(h.nbytes for h in h_out.values()),
                "steps": Ke, "ms_per_step": 1e3 * dt / Ke, "host_numa_node_rank0": numa_node,
+               # attribution of the N > 1 behaviour: what all ranks together pull through the host per second, beside
+               # a plain single-thread host memcpy of the same pinned buffers on rank 0
+               "aggregate_host_traffic_GBps": world * (2 * h_in.nbytes + sum(h.nbytes for h in h_out.values())) * Ke / dt / 1e9,
+
                "path": "fp_op_apply with pinned host pointers for input and output, once per operator: the call streams "
                        "256-byte column blocks through the GPU (strided upload of block j+1 | kernels on block j | "
                        "download of block j-1, three device blocks per direction)"}
@@ -811,6 +820,7 @@ def run_ours(args) -> None:
             chk = outs[k].get_rows(12345, 12346)
             if not np.array_equal(chk, h_out[k][12345:12346]):
                 e2e["warning"] = "host-staged result differs from device-resident result"
+        e2e["host_memcpy_GBps_rank0"] = host_memcpy_gbps(h_out["few_group"], h_in)  # after the check: it overwrites
         ctx.pinned_free(h_in)
         for h in h_out.values():
             ctx.pinned_free(h)
@@ -867,6 +877,14 @@ def run_ours(args) -> None:
         EMIT(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def host_memcpy_gbps(dst: np.ndarray, src: np.ndarray) -> float:
+    """Single-thread host memcpy bandwidth (read + write bytes per second) between two pinned buffers."""
+    np.copyto(dst, src)
+    t0 = time.perf_counter()
+    np.copyto(dst, src)
+    return 2.0 * src.nbytes / (time.perf_counter() - t0) / 1e9
 
 
 def fp64_peak(fp, ctx, clocks: dict) -> dict:
