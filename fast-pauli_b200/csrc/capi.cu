@@ -842,9 +842,10 @@ template <typename T> bool make_row_tensor_map(CUtensorMap *tm, void const *base
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename T, int EPV, int LOG_TWC, int NBUF, bool PSTR>
+template <typename T, int EPV, int LOG_TWC, int NBUF, bool PSTR, int MODE = 0>
 int launch_coset_few_v(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T> const &strs, int n_qubits,
-                       uint64_t rowvecs, void const *in, void *out, int beta)
+                       uint64_t rowvecs, void const *in, void *out, int beta, void *partials = nullptr,
+                       uint32_t Bpad = 0)
 {
     using Cfg = FewCfg<LOG_TWC>;
     constexpr int GMAX = 8;
@@ -852,7 +853,7 @@ int launch_coset_few_v(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T> 
     static PerDevice configured; // per template instance
     if (!configured.done(ctx->device))
     {
-        FP_CU(cudaFuncSetAttribute(coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR>,
+        FP_CU(cudaFuncSetAttribute(coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR, false, MODE>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured.set(ctx->device);
     }
@@ -868,9 +869,10 @@ int launch_coset_few_v(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T> 
     uint32_t const groups = (nct + per - 1) / per;
     uint64_t const grid = n_cosets * groups;
     FP_TRY(check_grid(grid));
-    coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR><<<static_cast<unsigned>(grid), Cfg::NT, smem, ctx->stream>>>(
-        view, rowvecs, nct, per, groups, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta,
-        strs);
+    coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR, false, MODE>
+        <<<static_cast<unsigned>(grid), Cfg::NT, smem, ctx->stream>>>(
+            view, rowvecs, nct, per, groups, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta,
+            strs, static_cast<Cx<T> *>(partials), Bpad);
     ctx->launches++;
     return FP_OK;
 }
@@ -902,9 +904,9 @@ int launch_coset_few_tma(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T
 }
 
 // Picks the variant for one pass; *launched = false when the pass has to go through coset_kernel (K3b).
-template <typename T, int EPV>
+template <typename T, int EPV, int MODE = 0>
 int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, int n_qubits, uint64_t rowvecs,
-                     void const *in, void *out, int beta, bool *launched)
+                     void const *in, void *out, int beta, bool *launched, void *partials = nullptr, uint32_t Bpad = 0)
 {
     *launched = false;
     CosetPassView<T> const &view = pd.view;
@@ -915,7 +917,7 @@ int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, 
     FewStrings<T> const &strs = pstr ? *pd.few : no_strings;
     // K3f wins on overwrite passes of large registers (measured at 20 qubits: 4 masks 0.42 -> 0.38 ms, 256 columns
     // 1.95 -> 1.85 ms; 8 masks equal); read-modify-write passes and small registers stay on the resident-CTA kernel
-    if (ctx->coset_few == 1 && pstr && beta == 0 && n_qubits >= 16 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+    if (MODE == 0 && ctx->coset_few == 1 && pstr && beta == 0 && n_qubits >= 16 && n_qubits <= 30 && rowvecs % 16 == 0 &&
         is_device_ptr(in))
     {
         FP_TRY((launch_coset_few_tma<T, EPV>(ctx, view, strs, n_qubits, rowvecs, in, out, beta, launched)));
@@ -923,9 +925,11 @@ int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, 
             return FP_OK;
     }
     if (rowvecs % 8 == 0 && pstr)
-        FP_TRY((launch_coset_few_v<T, EPV, 3, 2, true>(ctx, view, strs, n_qubits, rowvecs, in, out, beta)));
+        FP_TRY((launch_coset_few_v<T, EPV, 3, 2, true, MODE>(ctx, view, strs, n_qubits, rowvecs, in, out, beta, partials,
+                                                             Bpad)));
     else if (rowvecs % 8 == 0)
-        FP_TRY((launch_coset_few_v<T, EPV, 3, 2, false>(ctx, view, strs, n_qubits, rowvecs, in, out, beta)));
+        FP_TRY((launch_coset_few_v<T, EPV, 3, 2, false, MODE>(ctx, view, strs, n_qubits, rowvecs, in, out, beta, partials,
+                                                              Bpad)));
     else
         return FP_OK;
     *launched = true;
@@ -962,14 +966,24 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
     for (size_t p = 0; p < passes->size(); ++p)
     {
         int const b = (p == 0) ? beta : 1;
-        if constexpr (MODE == 0)
+        if constexpr (MODE == 0 || MODE == 1)
         {
             if (shape.rank() == 8 && shape.log_nt == 8)
             {
                 bool launched = false;
-                FP_TRY((launch_coset_few<T, EPV>(ctx, (*passes)[p], n_qubits, rowvecs, in, out, b, &launched)));
+                FP_TRY((launch_coset_few<T, EPV, MODE>(ctx, (*passes)[p], n_qubits, rowvecs, in, out, b, &launched,
+                                                       ctx->partials.p, Bpad)));
                 if (launched)
+                {
+                    if (MODE == 1)
+                    {
+                        unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
+                        finalize_complex_kernel<T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
+                            static_cast<Cx<T> const *>(ctx->partials.p), n_cosets, Bpad, B, static_cast<Cx<T> *>(out), b);
+                        ctx->launches++;
+                    }
                     continue;
+                }
             }
         }
         FP_TRY((launch_coset_pass_v<T, EPV, MODE>(ctx, shape, (*passes)[p].view, n_qubits, rowvecs, in, out, b,

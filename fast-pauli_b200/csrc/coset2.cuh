@@ -111,11 +111,16 @@ template <int LOG_TWC> struct FewCfg
 // queues behind the other resident CTA's gathers in the load/store unit (measured: 13 k -> 4 k cycles per CTA).
 // DSM: the row factors are parked in shared memory (GMAX x 256 x 16 B behind the tile buffers, conflict-free) between
 // the row-factor phase and the gathers: 32 registers freed for gathered vectors in flight.
-template <typename T, int EPV, int LOG_TWC, int GMAX, int NBUF = 1, int MINB = 2, bool PSTR = false, bool DSM = false>
+// MODE 1: PauliOp::expectation_value partials (PO:482-549) instead of the store: e(t) = sum over the tile's rows of
+// conj(psi(l,t)) (A psi)(l,t), written to partials[coset][t] (fixed summation order; finalize_complex_kernel sums the
+// cosets).  The products are staged in the (dead) tile buffer and column-summed by the cooperative row mapping.
+template <typename T, int EPV, int LOG_TWC, int GMAX, int NBUF = 1, int MINB = 2, bool PSTR = false, bool DSM = false,
+          int MODE = 0>
 __global__ void __launch_bounds__(256, MINB)
     coset_few_kernel(CosetPassView<T> pass, uint64_t rowvecs, uint32_t nColTiles, uint32_t ctPerCta, uint32_t nCtGroups,
                      CVec<T, EPV> const *__restrict__ in, CVec<T, EPV> *__restrict__ out, int beta,
-                     const __grid_constant__ FewStrings<T> strs)
+                     const __grid_constant__ FewStrings<T> strs, Cx<T> *__restrict__ partials = nullptr,
+                     uint32_t Bpad = 0)
 {
     using Cfg = FewCfg<LOG_TWC>;
     using Vec = CVec<T, EPV>;
@@ -128,6 +133,7 @@ __global__ void __launch_bounds__(256, MINB)
     __shared__ uint32_t s_gs[GMAX + 1];
     __shared__ Cx<T> s_c[kFewMaxStrings];
     __shared__ uint32_t s_zl[kFewMaxStrings];
+    __shared__ CVec<T, EPV> s_red[MODE == 1 ? 8 * (1 << LOG_TWC) : 1];
 
     uint32_t const tid = threadIdx.x;
 #ifdef FP_FEW_PROFILE
@@ -268,13 +274,79 @@ __global__ void __launch_bounds__(256, MINB)
         for (int j = 0; j < TWC; ++j)
         {
             Vec v;
+            if (MODE == 1)
+            {
+                // conj(psi) * acc for the thread's own row: read and rewritten in place (no other thread touches
+                // these slots after the barrier above)
+                Vec const a = *reinterpret_cast<Vec const *>(tb + (own_off ^ (j << 4)));
 #pragma unroll
-            for (int e = 0; e < EPV; ++e)
-                v.e[e] = acc[j][e];
+                for (int e = 0; e < EPV; ++e)
+                {
+                    v.e[e].re = fma(a.e[e].re, acc[j][e].re, a.e[e].im * acc[j][e].im);
+                    v.e[e].im = fma(a.e[e].re, acc[j][e].im, -a.e[e].im * acc[j][e].re);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    v.e[e] = acc[j][e];
+            }
             *reinterpret_cast<Vec *>(tb + (own_off ^ (j << 4))) = v;
         }
         __syncthreads();
         FEW_T(3); // accumulators -> staging
+
+        if (MODE == 1)
+        {
+            // column sums: this thread adds rows l_lo + k * RPS of vector column jv, the warp's 32 / TWC row groups are
+            // folded by shuffles, the 8 warps through shared memory (fixed order)
+            Vec sum;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+                sum.e[e] = Cx<T>{0, 0};
+#pragma unroll
+            for (int k = 0; k < STEPS; ++k)
+            {
+                Vec const v = tile[(l_lo + k * RPS) * TWC + jv];
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                {
+                    sum.e[e].re += v.e[e].re;
+                    sum.e[e].im += v.e[e].im;
+                }
+            }
+#pragma unroll
+            for (int off = TWC; off < 32; off <<= 1)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                {
+                    sum.e[e].re += __shfl_xor_sync(0xffffffffu, sum.e[e].re, off);
+                    sum.e[e].im += __shfl_xor_sync(0xffffffffu, sum.e[e].im, off);
+                }
+            __syncthreads(); // every staged product has been read: s_red may alias nothing, but the tile is reused below
+            if ((tid & 31u) < static_cast<uint32_t>(TWC))
+                s_red[(tid >> 5) * TWC + jv] = sum;
+            __syncthreads();
+            if (tid < static_cast<uint32_t>(TWC))
+            {
+                Vec tot = s_red[tid];
+#pragma unroll
+                for (int w = 1; w < 8; ++w)
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                    {
+                        tot.e[e].re += s_red[w * TWC + tid].e[e].re;
+                        tot.e[e].im += s_red[w * TWC + tid].e[e].im;
+                    }
+                uint64_t const col0 = (static_cast<uint64_t>(ct) * TWC + tid) * EPV;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    partials[coset * Bpad + col0 + e] = tot.e[e];
+            }
+        }
+        else
+        {
 
         uint64_t const vcol = static_cast<uint64_t>(ct) * TWC + jv;
         if (beta)
@@ -301,6 +373,7 @@ __global__ void __launch_bounds__(256, MINB)
 #pragma unroll
             for (int k = 0; k < STEPS; ++k)
                 out[(row_lo ^ s_comb_hi[k]) * rowvecs + vcol] = tile[(l_lo + k * RPS) * TWC + jv];
+        }
         }
         FEW_T(4); // issuing the stores
         if (ct + NBUF < ct_end)

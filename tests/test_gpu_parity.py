@@ -29,8 +29,9 @@ def tol(dtype) -> float:
 
 def _reduction_terms(args) -> int:
     """Terms summed per output value of an expectation-value check: rows x strings."""
-    dim = next((a.shape[0] for a in args if isinstance(a, np.ndarray) and a.ndim >= 1 and a.dtype.kind == "c"
-                and a.shape[0] > 1), 1)
+    # the states are the LAST complex array of every signature (string, states, c) / (strings, coeffs, states)
+    dim = next((a.shape[0] for a in reversed(args) if isinstance(a, np.ndarray) and a.ndim >= 1 and a.dtype.kind == "c"),
+               1)
     n_str = next((len(a) for a in args if isinstance(a, (list, tuple)) and a and isinstance(a[0], str)), 1)
     return int(dim) * int(n_str)
 
@@ -1140,6 +1141,20 @@ def test_headline_size_multi_pass_operators_sampled_rows(kind):
             np.testing.assert_array_equal(other.get_rows(r0, r0 + 8192), out.get_rows(r0, r0 + 8192))
         del other
     ctx.set_coset_few(1)
+    # expectation values at full size (few-mask passes: K3e's reduction mode): two columns against host sums of
+    # conj(psi) . (A psi) with A psi taken from the apply verified row-wise above
+    from fast_pauli_b200.synth import uniform_complex_at
+
+    ev = op.expectation_value(psi).get()
+    cols = [1, B - 2]
+    acc_ev = np.zeros(2, dtype=np.complex128)
+    chunk = 1 << 16
+    for r0 in range(0, dim, chunk):
+        o = out.get_rows(r0, r0 + chunk)[:, cols]
+        rr = np.arange(r0, r0 + chunk, dtype=np.uint64)
+        pp = np.stack([uniform_complex_at(rr * np.uint64(B) + np.uint64(cc), np.complex128, 18) for cc in cols], axis=1)
+        acc_ev += np.sum(np.conj(pp) * o, axis=0)
+    assert rel_err(ev[cols], acc_ev) < 1e-12
     # accumulate = 1 through the C ABI: out0 + A psi (first pass is read-modify-write too)
     acc = ctx.uniform((dim, B), np.complex128, seed=5)
     fp._check(fp.lib.fp_op_apply(ctx._h, op._plan(np.complex128), C.c_void_p(acc.ptr), C.c_void_p(psi.ptr),
@@ -1179,10 +1194,18 @@ def test_few_mask_coset_kernels_small_shapes(dtype, n, B, masks, per):
         got = op.apply(d_psi).get()
         assert rel_err(got, ref) < tol(dtype)
         results.append(got)
-    ctx.set_coset(1)
-    ctx.set_coset_few(1)
     np.testing.assert_array_equal(results[0], results[2])
     np.testing.assert_array_equal(results[1], results[2])
+    # expectation values: K3e's reduction mode against the oracle, and against the general coset kernel
+    evs = []
+    for mode in (1, 0):
+        ctx.set_coset_few(mode)
+        ev = op.expectation_value(d_psi).get()
+        assert_parity(ev, ORC.op_expval, dtype, strings, h, psi)
+        evs.append(ev)
+    assert rel_err(evs[0], evs[1]) < tol(dtype)
+    ctx.set_coset(1)
+    ctx.set_coset_few(1)
 
 
 def test_two_devices_in_one_process():
