@@ -185,6 +185,8 @@ template <typename T> struct DeviceOp
         uint8_t const *esodd = nullptr;
         // the pass' strings as a kernel-parameter block (K3e / K3f): passes with <= 8 groups and <= 128 strings
         std::shared_ptr<FewStrings<T>> few;
+        // ... and for passes with any number of groups (K3g): <= 768 strings, <= 256 groups, <= 30 qubits
+        std::shared_ptr<GenStrings<T>> gen;
         std::vector<void *> allocs;
     };
     mutable std::map<int, std::vector<CosetPassDev>> coset_plans;
@@ -370,6 +372,20 @@ int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank, int reserve_lo
                 d.few->gs[g] = h.gstart[g];
             for (size_t g = 0; g < h.gxl.size(); ++g)
                 d.few->gxl[g] = h.gxl[g];
+        }
+        if (rank == 8 && n_qubits <= 30 && h.gxl.size() > 8 && h.gxl.size() <= kGenMaxGroups && h.sz.size() <= kGenMaxStrings)
+        {
+            d.gen = std::make_shared<GenStrings<T>>();
+            std::memset(d.gen.get(), 0, sizeof(GenStrings<T>));
+            for (size_t i = 0; i < h.sz.size(); ++i)
+            {
+                d.gen->c[i] = Cx<T>{h.sc[i].real(), h.sc[i].imag()};
+                d.gen->z[i] = static_cast<uint32_t>(h.sz[i]);
+            }
+            for (size_t g = 0; g <= h.gxl.size(); ++g)
+                d.gen->gs[g] = static_cast<uint16_t>(h.gstart[g]);
+            for (size_t g = 0; g < h.gxl.size(); ++g)
+                d.gen->gxl[g] = static_cast<uint8_t>(h.gxl[g]);
         }
         CosetChunk *chunks = nullptr;
         uint32_t *gxl = nullptr, *gstart = nullptr, *szl = nullptr, *sidx = nullptr;
@@ -669,8 +685,11 @@ struct CosetShape
 };
 
 // Pick the tile shape, or an invalid shape for "use the generic gather kernel".
+// tma_kernels: the call can use the TMA-fed rank-8 kernels (K3f / K3g: apply on device-resident batches with rows of
+// >= 256 bytes), whose passes are cheaper than the general kernel's
 template <typename T>
-CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, uint64_t rowvecs, int epv)
+CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, uint64_t rowvecs, int epv,
+                        bool tma_kernels = false)
 {
     CosetShape none;
     if (ctx->coset_mode == 0 || op.host.sz.size() < 2)
@@ -718,7 +737,10 @@ CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, 
             int const reserve = std::max(0, 2 - v);
             if (get_coset_plan<T>(op, n_qubits, 4 + lnt_pref - v, reserve, &passes) != FP_OK)
                 continue;
-            double const cost = static_cast<double>(passes->size()) * seg_cost[v];
+            // measured (20 q x 64 chains, 16 q x 1024 config 3): a rank-8 pass of K3e / K3f / K3g costs ~0.7 of a
+            // general-kernel pass of the same width
+            double const cost = static_cast<double>(passes->size()) * seg_cost[v] *
+                                ((tma_kernels && v == 4 && lnt_pref == 8) ? 0.7 : 1.0);
             if (best == 0 || cost < best)
             {
                 best = cost;
@@ -903,6 +925,38 @@ int launch_coset_few_tma(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T
     return FP_OK;
 }
 
+// K3g: persistent TMA-fed kernel for passes with more than 8 x-masks (row factors per tile from the constant bank)
+template <typename T, int EPV>
+int launch_coset_gen_tma(fp_ctx *ctx, CosetPassView<T> const &view, GenStrings<T> const &gstr, int n_qubits,
+                         uint64_t rowvecs, void const *in, void *out, int beta, bool *launched)
+{
+    *launched = false;
+    CUtensorMap tm;
+    if (!make_row_tensor_map<T>(&tm, in, 1ull << n_qubits, rowvecs))
+        return FP_OK;
+    constexpr size_t smem = kFewTmaBufs * kFewTmaTile + kGenMetaBytes;
+    static PerDevice configured;
+    if (!configured.done(ctx->device))
+    {
+        FP_CU(cudaFuncSetAttribute(coset_gen_tma_kernel<T, EPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+        configured.set(ctx->device);
+    }
+    uint64_t const n_pairs = 1ull << (n_qubits - 9);
+    uint32_t const nct = static_cast<uint32_t>(rowvecs >> 4);
+    // work items = coset pairs x chunks of column tiles: enough of them to balance 148 persistent CTAs
+    uint32_t chunk = nct;
+    while (chunk > 1 && chunk % 2 == 0 && n_pairs * (nct / chunk) < 6ull * static_cast<uint64_t>(ctx->sm_count))
+        chunk /= 2;
+    uint64_t const items = n_pairs * (nct / chunk);
+    unsigned const grid = static_cast<unsigned>(std::min<uint64_t>(items, static_cast<uint64_t>(ctx->sm_count)));
+    coset_gen_tma_kernel<T, EPV, true><<<grid, kFewTmaThreads, smem, ctx->stream>>>(
+        view, rowvecs, nct, n_pairs, chunk, static_cast<CVec<T, EPV> *>(out), beta, tm, gstr);
+    ctx->launches++;
+    *launched = true;
+    return FP_OK;
+}
+
 // Picks the variant for one pass; *launched = false when the pass has to go through coset_kernel (K3b).
 template <typename T, int EPV, int MODE = 0>
 int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, int n_qubits, uint64_t rowvecs,
@@ -910,6 +964,9 @@ int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, 
 {
     *launched = false;
     CosetPassView<T> const &view = pd.view;
+    if (MODE == 0 && ctx->coset_few == 1 && pd.gen && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+        is_device_ptr(in))
+        return launch_coset_gen_tma<T, EPV>(ctx, view, *pd.gen, n_qubits, rowvecs, in, out, beta, launched);
     if (!ctx->coset_few || view.n_groups == 0 || view.n_groups > 8 || n_qubits < 8)
         return FP_OK;
     static FewStrings<T> const no_strings{};
@@ -949,7 +1006,9 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
     if (epv != EPV)
         return FP_OK;
     uint64_t const rowvecs = B / EPV;
-    CosetShape const shape = choose_coset<T>(ctx, op, n_qubits, rowvecs, epv);
+    bool const tma_ok = MODE == 0 && ctx->coset_few == 1 && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+                        is_device_ptr(in) && tensor_map_encoder() != nullptr;
+    CosetShape const shape = choose_coset<T>(ctx, op, n_qubits, rowvecs, epv, tma_ok);
     if (!shape.ok())
         return FP_OK;
     std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;

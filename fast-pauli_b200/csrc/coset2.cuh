@@ -485,9 +485,8 @@ __global__ void __launch_bounds__(kFewTmaThreads, 1)
             uint32_t const buf = static_cast<uint32_t>(i % kFewTmaBufs);
             if (i >= kFewTmaBufs)
                 few_mbar_wait(&s_empty[buf], static_cast<uint32_t>((i / kFewTmaBufs) - 1) & 1u);
-            // group 1 runs half a coset behind group 0, so the two row-factor phases never coincide
-            uint64_t const v = (i >> 1) + ((i & 1u) ? (nColTiles >> 1) : 0u);
-            uint64_t const pair = blockIdx.x + ((v / nColTiles) % my_pairs) * gridDim.x;
+            uint64_t const v = i >> 1;
+            uint64_t const pair = blockIdx.x + (v / nColTiles) * gridDim.x;
             uint64_t const coset = 2 * pair + (i & 1u);
             uint32_t const ct = static_cast<uint32_t>(v % nColTiles);
             uint32_t const base = static_cast<uint32_t>(deposit_bits(coset, pass.nonpivot_mask));
@@ -516,7 +515,7 @@ __global__ void __launch_bounds__(kFewTmaThreads, 1)
     uint32_t const own_off = (l << ROW_SHIFT) | key_off;
 
     uint64_t const n_q = my_pairs * nColTiles; // tiles of this group
-    uint64_t const shift = grp ? (nColTiles >> 1) : 0u;
+    uint64_t const shift = 0;
     uint64_t cur_k = ~0ull, row_lo = 0;
     Cx<T> D[GMAX];
     for (uint64_t q = 0; q < n_q; ++q)
@@ -599,6 +598,232 @@ __global__ void __launch_bounds__(kFewTmaThreads, 1)
                     out[(row_lo ^ s_comb_hi[q]) * rowvecs + vcol] = tile[(l_lo + q * RPS) * TWC + jv];
             }
             // the staged rows were read through the generic proxy; the TMA refill writes through the asynchronous one
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            few_group_sync(grp);
+            if (l == 0)
+                few_mbar_arrive(&s_empty[buf]);
+        }
+    }
+}
+
+
+// ================================================================ K3g: K3f for passes with ANY number of x-masks
+// Same persistent producer / two-consumer-group structure and tile ring as K3f.  The row factors cannot live in
+// registers (a pass of BASELINE config 3 has 25-50 x-masks), so they are formed per (tile, x-mask) from the pass'
+// strings, which are staged in shared memory ONCE per CTA (the CTA is persistent: once per launch) -- the general coset
+// kernel K3b re-stages them for every tile.  Work items are (coset pair, chunk of column tiles), dealt round-robin to
+// the CTAs, so small registers with wide batches (16 qubits x 1024 columns: 128 coset pairs) still fill 148 SMs.
+// Tile order inside an item: column tile ct of the chunk for group 0 (coset 2p), then for group 1 (coset 2p + 1), ...
+constexpr uint32_t kGenMaxStrings = 768;
+constexpr uint32_t kGenMaxGroups = 256;
+constexpr size_t kGenMetaBytes = kGenMaxStrings * 24 + (kGenMaxGroups + 1) * 4 + kGenMaxGroups * 4;
+
+// The strings of one pass as a (large) kernel-parameter block: the row-factor loop then reads the constant bank only.
+// ~21 KiB for complex128: needs the 32 KiB parameter space of CUDA >= 12.1 on sm_70+ (the library targets sm_100a).
+template <typename T> struct GenStrings
+{
+    Cx<T> c[kGenMaxStrings];
+    uint32_t z[kGenMaxStrings]; // <= 30 qubits: one word
+    uint16_t gs[kGenMaxGroups + 1];
+    uint8_t gxl[kGenMaxGroups];
+};
+
+template <typename T, int EPV, bool CMETA = false>
+__global__ void __launch_bounds__(kFewTmaThreads, 1)
+    coset_gen_tma_kernel(CosetPassView<T> pass, uint64_t rowvecs, uint32_t nColTiles, uint64_t nPairs, uint32_t chunkTiles,
+                         CVec<T, EPV> *__restrict__ out, int beta, const __grid_constant__ CUtensorMap tm_in,
+                         const __grid_constant__ GenStrings<T> gstr)
+{
+    using Vec = CVec<T, EPV>;
+    constexpr int TWC = 16, RPS = 16, STEPS = 16, R = 8;
+    constexpr uint32_t ROW_SHIFT = 8;
+
+    extern __shared__ __align__(1024) unsigned char smem_gt[];
+    __shared__ uint64_t s_full[kFewTmaBufs], s_empty[kFewTmaBufs];
+    __shared__ uint32_t s_comb[256];
+    __shared__ uint64_t s_comb_hi[STEPS];
+    unsigned char *const meta = smem_gt + kFewTmaBufs * kFewTmaTile;
+    uint64_t *const s_z = reinterpret_cast<uint64_t *>(meta);                              // [S]
+    Cx<double> *const s_c = reinterpret_cast<Cx<double> *>(meta + kGenMaxStrings * 8);     // [S] (as double pairs)
+    uint32_t *const s_gs = reinterpret_cast<uint32_t *>(meta + kGenMaxStrings * 24);       // [G + 1]
+    uint32_t *const s_gxl = s_gs + kGenMaxGroups + 1;                                      // [G]
+
+    uint32_t const tid = threadIdx.x;
+    uint32_t const ng = pass.n_groups;
+    uint32_t const n_str = pass.gstart[ng];
+    if (tid < 256)
+        s_comb[tid] = static_cast<uint32_t>(comb_of<R>(pass.basis, tid));
+    if (tid < STEPS)
+        s_comb_hi[tid] = comb_of<R>(pass.basis, tid * RPS);
+    if (!CMETA)
+    {
+        for (uint32_t s = tid; s < n_str; s += blockDim.x)
+        {
+            s_z[s] = pass.sz[s];
+            Cx<T> const c = pass.scoef[s];
+            s_c[s] = Cx<double>{static_cast<double>(c.re), static_cast<double>(c.im)};
+        }
+        for (uint32_t g = tid; g <= ng; g += blockDim.x)
+        {
+            s_gs[g] = pass.gstart[g];
+            if (g < ng)
+                s_gxl[g] = pass.gxl[g];
+        }
+    }
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int b = 0; b < kFewTmaBufs; ++b)
+        {
+            few_mbar_init(&s_full[b], 1);
+            few_mbar_init(&s_empty[b], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint32_t const n_chunks = nColTiles / chunkTiles; // the host picks a divisor
+    uint64_t const n_items = nPairs * n_chunks;
+    uint64_t const my_items = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    uint64_t const tiles_per_item = 2ull * chunkTiles;
+    uint64_t const n_tiles = my_items * tiles_per_item;
+
+    if (tid >= 512)
+    {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (tid >= 544)
+            return;
+        uint32_t const lane = tid & 31u;
+        for (uint64_t i = 0; i < n_tiles; ++i)
+        {
+            uint32_t const buf = static_cast<uint32_t>(i % kFewTmaBufs);
+            if (i >= kFewTmaBufs)
+                few_mbar_wait(&s_empty[buf], static_cast<uint32_t>((i / kFewTmaBufs) - 1) & 1u);
+            uint64_t const item = blockIdx.x + (i / tiles_per_item) * gridDim.x;
+            uint32_t const within = static_cast<uint32_t>(i % tiles_per_item);
+            uint64_t const coset = 2 * (item / n_chunks) + (within & 1u);
+            uint32_t const ct = static_cast<uint32_t>(item % n_chunks) * chunkTiles + (within >> 1);
+            uint32_t const base = static_cast<uint32_t>(deposit_bits(coset, pass.nonpivot_mask));
+            if (lane == 0)
+                few_mbar_expect_tx(&s_full[buf], static_cast<uint32_t>(kFewTmaTile));
+            __syncwarp();
+            int const c0 = static_cast<int>(ct) * TWC * static_cast<int>(16 / sizeof(T));
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+            {
+                uint32_t const op = lane + 32 * h;
+                few_tma_gather4(smem_gt + buf * kFewTmaTile + (static_cast<size_t>(op) << (ROW_SHIFT + 2)), &tm_in, c0,
+                                base ^ s_comb[4 * op], base ^ s_comb[4 * op + 1], base ^ s_comb[4 * op + 2],
+                                base ^ s_comb[4 * op + 3], &s_full[buf]);
+            }
+        }
+        return;
+    }
+
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    uint32_t const grp = tid >> 8;
+    uint32_t const l = tid & 255u;
+    uint32_t const l_lo = l >> 4, jv = l & 15u;
+    uint32_t const own_off = (l << ROW_SHIFT) | ((l & 15u) << 4);
+
+    for (uint64_t k = 0; k < my_items; ++k)
+    {
+        uint64_t const item = blockIdx.x + k * gridDim.x;
+        uint64_t const coset = 2 * (item / n_chunks) + grp;
+        uint32_t const ct0 = static_cast<uint32_t>(item % n_chunks) * chunkTiles;
+        uint64_t const base = deposit_bits(coset, pass.nonpivot_mask);
+        uint32_t const my_row = static_cast<uint32_t>(base) ^ s_comb[l]; // launched for <= 30 qubits only
+        uint64_t const row_lo = base ^ s_comb[l_lo];
+        for (uint32_t q = 0; q < chunkTiles; ++q)
+        {
+            uint32_t const ct = ct0 + q;
+            uint64_t const i = k * tiles_per_item + 2ull * q + grp;
+            uint32_t const buf = static_cast<uint32_t>(i % kFewTmaBufs);
+            unsigned char *const tb = smem_gt + buf * kFewTmaTile;
+            Vec *const tile = reinterpret_cast<Vec *>(tb);
+            few_mbar_wait(&s_full[buf], static_cast<uint32_t>(i / kFewTmaBufs) & 1u);
+
+            Cx<T> acc[TWC][EPV];
+#pragma unroll
+            for (int j = 0; j < TWC; ++j)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    acc[j][e] = Cx<T>{0, 0};
+            for (uint32_t g = 0; g < ng; ++g)
+            {
+                Cx<T> d{0, 0};
+                uint32_t xl;
+                if (CMETA)
+                {
+                    uint32_t const s1 = gstr.gs[g + 1];
+                    for (uint32_t s = gstr.gs[g]; s < s1; ++s)
+                    {
+                        Cx<T> const c = gstr.c[s];
+                        uint32_t const odd = __popc(my_row & gstr.z[s]) & 1u;
+                        d.re += flip_sign(c.re, odd);
+                        d.im += flip_sign(c.im, odd);
+                    }
+                    xl = gstr.gxl[g];
+                }
+                else
+                {
+                    uint32_t const s1 = s_gs[g + 1];
+                    for (uint32_t s = s_gs[g]; s < s1; ++s)
+                    {
+                        Cx<double> const c = s_c[s];
+                        uint32_t const odd = __popc(my_row & static_cast<uint32_t>(s_z[s])) & 1u;
+                        d.re += flip_sign(static_cast<T>(c.re), odd);
+                        d.im += flip_sign(static_cast<T>(c.im), odd);
+                    }
+                    xl = s_gxl[g];
+                }
+                uint32_t const src = own_off ^ (xl << ROW_SHIFT);
+#pragma unroll
+                for (int j = 0; j < TWC; ++j)
+                {
+                    Vec const v = *reinterpret_cast<Vec const *>(tb + (src ^ (j << 4)));
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                        cfma(acc[j][e], d, v.e[e]);
+                }
+            }
+            few_group_sync(grp);
+#pragma unroll
+            for (int j = 0; j < TWC; ++j)
+            {
+                Vec v;
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    v.e[e] = acc[j][e];
+                *reinterpret_cast<Vec *>(tb + (own_off ^ (j << 4))) = v;
+            }
+            few_group_sync(grp);
+            uint64_t const vcol = static_cast<uint64_t>(ct) * TWC + jv;
+            if (beta)
+            {
+                Vec o[STEPS];
+#pragma unroll
+                for (int t = 0; t < STEPS; ++t)
+                    o[t] = out[(row_lo ^ s_comb_hi[t]) * rowvecs + vcol];
+#pragma unroll
+                for (int t = 0; t < STEPS; ++t)
+                {
+                    Vec v = tile[(l_lo + t * RPS) * TWC + jv];
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                    {
+                        v.e[e].re += o[t].e[e].re;
+                        v.e[e].im += o[t].e[e].im;
+                    }
+                    out[(row_lo ^ s_comb_hi[t]) * rowvecs + vcol] = v;
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int t = 0; t < STEPS; ++t)
+                    out[(row_lo ^ s_comb_hi[t]) * rowvecs + vcol] = tile[(l_lo + t * RPS) * TWC + jv];
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             few_group_sync(grp);
             if (l == 0)

@@ -95,6 +95,37 @@ int main(int argc, char **argv)
         variants(16, 4);
     else if (kind == "few4")
         variants(4, 16);
+    else if (kind == "cfg3")
+    {
+        // BASELINE config 3's operator: 2000 strings of weight <= 4 (weight uniform in 1..4, positions without replacement)
+        for (int t = 0; t < 2000; ++t)
+        {
+            std::vector<uint8_t> s(n, 0);
+            int w = 1 + static_cast<int>(rng() % 4);
+            for (int k = 0; k < w; ++k)
+            {
+                int pos;
+                do
+                    pos = static_cast<int>(rng() % n);
+                while (s[pos]);
+                s[pos] = 1 + static_cast<uint8_t>(rng() % 3);
+            }
+            push(s);
+            ++S;
+        }
+    }
+    else if (kind == "chain")
+    {
+        for (int i = 0; i + 1 < n; ++i)
+            for (uint8_t pp : {1, 2, 3})
+            {
+                std::vector<uint8_t> s(n, 0);
+                s[i] = pp;
+                s[i + 1] = pp;
+                push(s);
+                ++S;
+            }
+    }
     else
         variants(64, 1);
     std::vector<std::complex<T>> h(S);
@@ -174,7 +205,8 @@ int main(int argc, char **argv)
         for (size_t g = 0; g < hp.gxl.size(); ++g)
             pstr[p].gxl[g] = hp.gxl[g];
     }
-    bool const use_pstr = tma && pstr_ok; // 9th argument now selects the parameter-block row-factor phase
+    bool const use_pstr = tma && pstr_ok;
+    (void)use_pstr; // 9th argument now selects the parameter-block row-factor phase
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, cuuint64_t const *, cuuint64_t const *,
                                  cuuint32_t const *, cuuint32_t const *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -200,6 +232,52 @@ int main(int argc, char **argv)
     auto run_new = [&](double *out) {
         for (size_t p = 0; p < views.size(); ++p)
         {
+            if (nbuf == 4)
+            {
+                size_t const smem = kFewTmaBufs * kFewTmaTile + kGenMetaBytes;
+                CK(cudaFuncSetAttribute(coset_gen_tma_kernel<T, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                uint64_t const n_pairs = (dim >> 8) / 2;
+                uint32_t const nct = (uint32_t)(rowvecs >> 4);
+                uint32_t chunk = ctPer > 0 ? (uint32_t)ctPer : nct;
+                while (nct % chunk)
+                    --chunk;
+                uint64_t const items = n_pairs * (nct / chunk);
+                unsigned const g = (unsigned)std::min<uint64_t>(grid_f, items);
+                static std::vector<GenStrings<T>> gstrs;
+                if (gstrs.empty())
+                {
+                    gstrs.resize(passes.size());
+                    for (size_t q = 0; q < passes.size(); ++q)
+                    {
+                        auto const &hp = passes[q];
+                        memset(&gstrs[q], 0, sizeof(GenStrings<T>));
+                        if (hp.sz.size() > kGenMaxStrings || hp.gxl.size() > kGenMaxGroups)
+                        {
+                            printf("pass too large for K3g\n");
+                            exit(1);
+                        }
+                        for (size_t i = 0; i < hp.sz.size(); ++i)
+                        {
+                            gstrs[q].c[i] = Cx<T>{hp.sc[i].real(), hp.sc[i].imag()};
+                            gstrs[q].z[i] = (uint32_t)hp.sz[i];
+                        }
+                        for (size_t gg = 0; gg <= hp.gxl.size(); ++gg)
+                            gstrs[q].gs[gg] = (uint16_t)hp.gstart[gg];
+                        for (size_t gg = 0; gg < hp.gxl.size(); ++gg)
+                            gstrs[q].gxl[gg] = (uint8_t)hp.gxl[gg];
+                    }
+                }
+                if (tma)
+                {
+                    CK(cudaFuncSetAttribute(coset_gen_tma_kernel<T, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    coset_gen_tma_kernel<T, 1, true><<<g, kFewTmaThreads, smem>>>(views[p], rowvecs, nct, n_pairs, chunk,
+                                                                                  reinterpret_cast<Vec *>(out), p ? 1 : 0, tm, gstrs[p]);
+                }
+                else
+                    coset_gen_tma_kernel<T, 1, false><<<g, kFewTmaThreads, smem>>>(views[p], rowvecs, nct, n_pairs, chunk,
+                                                                                   reinterpret_cast<Vec *>(out), p ? 1 : 0, tm, gstrs[p]);
+                continue;
+            }
             if (nbuf == 3)
             {
                 size_t const smem = kFewTmaBufs * kFewTmaTile;
@@ -256,7 +334,7 @@ int main(int argc, char **argv)
     };
     bool const few_ok = [&]() {
         for (auto const &v : views)
-            if (v.n_groups > 8)
+            if (v.n_groups > 8 && nbuf != 4)
                 return false;
         return true;
     }();

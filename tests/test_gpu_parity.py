@@ -1134,11 +1134,16 @@ def test_headline_size_multi_pass_operators_sampled_rows(kind):
         expect_rows[i] = expect
         assert rel_err(out.get_rows(i, i + 1), expect) < 1e-12
     # the same call with the few-mask kernels switched off (general coset kernel) and without the TMA-fed variant
+    # (for the chains the general kernel prefers wider cosets, i.e. another pass structure and summation order: there
+    # the two results agree to rounding, not bit for bit)
     for mode in (0, 2):
         ctx.set_coset_few(mode)
         other = op.apply(psi)
         for r0 in (0, dim // 2 - 4096, dim - 8192):
-            np.testing.assert_array_equal(other.get_rows(r0, r0 + 8192), out.get_rows(r0, r0 + 8192))
+            if kind in ("few_group", "random"):
+                np.testing.assert_array_equal(other.get_rows(r0, r0 + 8192), out.get_rows(r0, r0 + 8192))
+            else:
+                assert rel_err(other.get_rows(r0, r0 + 8192), out.get_rows(r0, r0 + 8192)) < 1e-13
         del other
     ctx.set_coset_few(1)
     # expectation values at full size (few-mask passes: K3e's reduction mode): two columns against host sums of
@@ -1206,6 +1211,40 @@ def test_few_mask_coset_kernels_small_shapes(dtype, n, B, masks, per):
     assert rel_err(evs[0], evs[1]) < tol(dtype)
     ctx.set_coset(1)
     ctx.set_coset_few(1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,B,S,w", [(12, 32, 200, 3), (14, 32, 400, 4), (16, 64, 600, 4), (13, 16, 120, 2)])
+def test_many_mask_tma_kernel_against_general_coset_kernel(dtype, n, B, S, w):
+    """K3g (persistent TMA-fed kernel, passes with more than 8 x-masks: low-weight operators like BASELINE config 3)
+    on device-resident batches: against the oracle, bit-identical to the general coset kernel it replaces, and the
+    accumulating form."""
+    import ctypes as C
+
+    rng = np.random.default_rng(31 * n + B)
+    ctx = fp.default_context()
+    strings = rand_strings(rng, n, S, max_weight=w)
+    h = (rng.uniform(-1, 1, S) + 1j * rng.uniform(-1, 1, S)).astype(dtype)
+    psi = rand_states(rng, 2**n, B, dtype)
+    d_psi = ctx.to_device(psi)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    ref = ORC.op_apply(strings, h.astype(np.complex128), psi.astype(np.complex128), par=True)
+    ctx.set_coset(2, 4, 8)  # rank-8 tiles of 16 vectors per row: the shape the TMA-fed kernels take
+    res = []
+    for mode in (1, 0):
+        ctx.set_coset_few(mode)
+        got = op.apply(d_psi).get()
+        assert rel_err(got, ref) < tol(dtype)
+        res.append(got)
+    np.testing.assert_array_equal(res[0], res[1])
+    ctx.set_coset_few(1)
+    out0 = rand_states(rng, 2**n, B, dtype)
+    acc = ctx.to_device(out0)
+    fp._check(fp.lib.fp_op_apply(ctx._h, op._plan(dtype), C.c_void_p(acc.ptr), C.c_void_p(d_psi.ptr), C.c_size_t(2**n),
+                                 C.c_size_t(B), C.c_int(1)))
+    ctx.sync()
+    assert rel_err(acc.get(), out0.astype(np.complex128) + ref) < tol(dtype)
+    ctx.set_coset(1)
 
 
 def test_two_devices_in_one_process():
