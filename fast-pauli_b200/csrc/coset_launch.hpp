@@ -1,0 +1,516 @@
+// Host side of the coset-blocked kernel family (K3b / K6 coset.cuh, K3e / K3f / K3g coset2.cuh): plan cache, tile-shape
+// cost model, launchers and the per-pass dispatch.  Templates in an anonymous namespace: a translation unit only
+// instantiates (and compiles kernels for) the modes it calls -- capi.cu MODE 0 / 1, sop_capi.cu MODE 2.
+#pragma once
+#include <cuda.h>
+#include "capi_internal.hpp"
+
+namespace
+{
+// ---------------------------------------------------------------- coset-blocked path: plan cache + launch
+template <typename T>
+int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank, int reserve_low_bits,
+                   std::vector<typename DeviceOp<T>::CosetPassDev> const **out)
+{
+    int const key = rank * 8 + reserve_low_bits;
+    auto it = op.coset_plans.find(key);
+    if (it != op.coset_plans.end())
+    {
+        *out = &it->second;
+        return FP_OK;
+    }
+    std::vector<CosetPassHost<T>> host = plan_coset<T>(op.host, n_qubits, rank, reserve_low_bits);
+    std::vector<typename DeviceOp<T>::CosetPassDev> dev(host.size());
+    for (size_t p = 0; p < host.size(); ++p)
+    {
+        CosetPassHost<T> const &h = host[p];
+        auto &d = dev[p];
+        for (int k = 0; k < kCosetMaxRank; ++k)
+            d.view.basis[k] = k < h.basis.r ? h.basis.b[k] : 0;
+        d.view.nonpivot_mask = h.nonpivot_mask;
+        d.view.n_chunks = static_cast<uint32_t>(h.chunks.size());
+        d.view.n_groups = static_cast<uint32_t>(h.gxl.size());
+        if (h.gxl.size() <= 8 && h.sz.size() <= kFewParamStrings && !h.gxl.empty())
+        {
+            d.few = std::make_shared<FewStrings<T>>();
+            std::memset(d.few.get(), 0, sizeof(FewStrings<T>));
+            for (size_t i = 0; i < h.sz.size(); ++i)
+            {
+                d.few->c[i] = Cx<T>{h.sc[i].real(), h.sc[i].imag()};
+                d.few->z[i] = h.sz[i];
+            }
+            for (size_t g = 0; g <= h.gxl.size(); ++g)
+                d.few->gs[g] = h.gstart[g];
+            for (size_t g = 0; g < h.gxl.size(); ++g)
+                d.few->gxl[g] = h.gxl[g];
+        }
+        if (rank == 8 && n_qubits <= 30 && h.gxl.size() > 8 && h.gxl.size() <= kGenMaxGroups && h.sz.size() <= kGenMaxStrings)
+        {
+            d.gen = std::make_shared<GenStrings<T>>();
+            std::memset(d.gen.get(), 0, sizeof(GenStrings<T>));
+            for (size_t i = 0; i < h.sz.size(); ++i)
+            {
+                d.gen->c[i] = Cx<T>{h.sc[i].real(), h.sc[i].imag()};
+                d.gen->z[i] = static_cast<uint32_t>(h.sz[i]);
+            }
+            for (size_t g = 0; g <= h.gxl.size(); ++g)
+                d.gen->gs[g] = static_cast<uint16_t>(h.gstart[g]);
+            for (size_t g = 0; g < h.gxl.size(); ++g)
+                d.gen->gxl[g] = static_cast<uint8_t>(h.gxl[g]);
+        }
+        CosetChunk *chunks = nullptr;
+        uint32_t *gxl = nullptr, *gstart = nullptr, *szl = nullptr, *sidx = nullptr;
+        uint64_t *sz = nullptr;
+        Cx<T> *sc = nullptr;
+        std::vector<Cx<T>> scv(h.sc.size());
+        for (size_t i = 0; i < scv.size(); ++i)
+            scv[i] = Cx<T>{h.sc[i].real(), h.sc[i].imag()};
+        int rc = upload_vec(&chunks, h.chunks);
+        if (rc == FP_OK) { d.allocs.push_back(chunks); rc = upload_vec(&gxl, h.gxl); }
+        if (rc == FP_OK) { d.allocs.push_back(gxl); rc = upload_vec(&gstart, h.gstart); }
+        if (rc == FP_OK) { d.allocs.push_back(gstart); rc = upload_vec(&szl, h.szl); }
+        if (rc == FP_OK) { d.allocs.push_back(szl); rc = upload_vec(&sz, h.sz); }
+        if (rc == FP_OK) { d.allocs.push_back(sz); rc = upload_vec(&sc, scv); }
+        if (rc == FP_OK) { d.allocs.push_back(sc); rc = upload_vec(&sidx, h.sidx); }
+        if (rc == FP_OK) d.allocs.push_back(sidx);
+        if (rc == FP_OK)
+        {
+            std::vector<PairChunk> ech;
+            std::vector<uint8_t> esodd(h.sidx.size());
+            for (size_t i = 0; i < h.sidx.size(); ++i)
+                esodd[i] = op.host.sodd[h.sidx[i]];
+            for (size_t g = 0; g + 1 < h.gstart.size(); ++g)
+            {
+                uint32_t const xl = h.gxl[g];
+                for (uint32_t s0 = h.gstart[g]; s0 < h.gstart[g + 1]; s0 += kPairMS)
+                {
+                    PairChunk c;
+                    c.x = xl;
+                    c.s0 = s0;
+                    c.count = std::min<uint32_t>(kPairMS, h.gstart[g + 1] - s0);
+                    c.hbit = xl ? 31u - static_cast<uint32_t>(__builtin_clz(xl)) : 0u;
+                    c.diag = xl == 0;
+                    ech.push_back(c);
+                }
+            }
+            PairChunk *d_ech = nullptr;
+            uint8_t *d_esodd = nullptr;
+            rc = upload_vec(&d_ech, ech);
+            if (rc == FP_OK) { d.allocs.push_back(d_ech); rc = upload_vec(&d_esodd, esodd); }
+            if (rc == FP_OK) d.allocs.push_back(d_esodd);
+            d.echunks = d_ech;
+            d.n_echunks = static_cast<uint32_t>(ech.size());
+            d.esodd = d_esodd;
+        }
+        if (rc != FP_OK)
+        {
+            for (auto &dd : dev)
+                for (void *a : dd.allocs)
+                    cudaFree(a);
+            return rc;
+        }
+        d.view.chunks = chunks;
+        d.view.gxl = gxl;
+        d.view.gstart = gstart;
+        d.view.szl = szl;
+        d.view.sz = sz;
+        d.view.scoef = sc;
+        d.view.sidx = sidx;
+    }
+    auto ins = op.coset_plans.emplace(key, std::move(dev));
+    *out = &ins.first->second;
+    return FP_OK;
+}
+
+// ---------------------------------------------------------------- coset-blocked path: heuristics + launch
+struct CosetShape
+{
+    int log_twc = -1; // TWc = 2^log_twc vectors per row segment
+    int log_nt = 8;   // threads per CTA
+    int vpt = 16;     // vectors per thread (tile = vpt * NT vectors)
+    int rank() const
+    {
+        return (vpt == 16 ? 4 : 3) + log_nt - log_twc;
+    }
+    bool ok() const
+    {
+        return log_twc >= 0;
+    }
+};
+
+// Pick the tile shape, or an invalid shape for "use the generic gather kernel".
+// tma_kernels: the call can use the TMA-fed rank-8 kernels (K3f / K3g: apply on device-resident batches with rows of
+// >= 256 bytes), whose passes are cheaper than the general kernel's
+template <typename T>
+CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, uint64_t rowvecs, int epv,
+                        bool tma_kernels = false)
+{
+    CosetShape none;
+    if (ctx->coset_mode == 0 || op.host.sz.size() < 2)
+        return none;
+    if (n_qubits > 12 && op.host.gx.size() > 20000)
+        return none; // pass planning is quadratic in the number of x-groups: huge operators use the generic kernel
+    if (sizeof(T) == 4 && epv != 2)
+        return none;
+    auto valid = [&](int v, int lnt) {
+        return v >= 0 && v <= 4 && (lnt == 7 || lnt == 8) && (rowvecs % (1ull << v)) == 0 && (4 + lnt - v) <= n_qubits;
+    };
+    CosetShape pick;
+    if (ctx->coset_log_twc >= 0)
+    {
+        int lnt = ctx->coset_log_nt > 0 ? ctx->coset_log_nt : 8;
+        int vpt = ctx->coset_vpt == 8 ? 8 : 16;
+        bool ok = vpt == 16 ? valid(ctx->coset_log_twc, lnt)
+                            : (lnt == 8 && ctx->coset_log_twc <= 3 && (rowvecs % (1ull << ctx->coset_log_twc)) == 0 &&
+                               (3 + lnt - ctx->coset_log_twc) <= n_qubits);
+        if (ok)
+        {
+            pick.log_twc = ctx->coset_log_twc;
+            pick.log_nt = lnt;
+            pick.vpt = vpt;
+        }
+    }
+    else
+    {
+        int const lnt_pref = ctx->coset_log_nt > 0 ? ctx->coset_log_nt : 8;
+        // the whole state column fits one tile: single pass whatever the operator
+        if (n_qubits <= 12 && valid(12 - n_qubits, 8))
+        {
+            pick.log_twc = 12 - n_qubits;
+            pick.log_nt = 8;
+        }
+        // otherwise: the candidate whose (number of passes) x (relative cost of a pass at that row-segment width)
+        // is smallest; pass counts come from the real planner (plans are cached on the operator)
+        static double const seg_cost[5] = {3.5, 2.0, 1.45, 1.05, 1.0}; // measured, HBM-bound passes, v = 0..4
+        double best = 0;
+        for (int v = 4; v >= 0 && !pick.ok(); --v)
+        {
+            if (!valid(v, lnt_pref))
+                continue;
+            std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
+            int const reserve = std::max(0, 2 - v);
+            if (get_coset_plan<T>(op, n_qubits, 4 + lnt_pref - v, reserve, &passes) != FP_OK)
+                continue;
+            // measured (20 q x 64 chains, 16 q x 1024 config 3): a rank-8 pass of K3e / K3f / K3g costs ~0.7 of a
+            // general-kernel pass of the same width
+            double const cost = static_cast<double>(passes->size()) * seg_cost[v] *
+                                ((tma_kernels && v == 4 && lnt_pref == 8) ? 0.7 : 1.0);
+            if (best == 0 || cost < best)
+            {
+                best = cost;
+                none.log_twc = v; // remember the best so far in `none` (returned through `pick` below)
+                none.log_nt = lnt_pref;
+            }
+        }
+        if (!pick.ok() && none.ok())
+            pick = none;
+        none = CosetShape{};
+    }
+    if (!pick.ok())
+        return none;
+    uint64_t const ctas = (1ull << (n_qubits - pick.rank())) * (rowvecs >> pick.log_twc);
+    if (ctx->coset_mode == 1 && ctas < static_cast<uint64_t>(ctx->sm_count))
+        return none;
+    return pick;
+}
+
+template <typename T, int EPV, int LOG_TWC, int LOG_NT, int MODE, int VPT = 16>
+int launch_coset_pass(fp_ctx *ctx, CosetPassView<T> const &view, int n_qubits, uint64_t rowvecs, void const *in,
+                      void *out, int beta, void *partials, uint32_t Bpad, T const *Wre, T const *Wim, uint64_t B)
+{
+    using Cfg = CosetCfg<LOG_TWC, LOG_NT, VPT>;
+    size_t const smem = coset_smem_bytes<T, LOG_TWC, LOG_NT, VPT>();
+    static PerDevice configured; // per template instance
+    if (!configured.done(ctx->device))
+    {
+        FP_CU(cudaFuncSetAttribute(coset_kernel<T, EPV, LOG_TWC, LOG_NT, MODE, VPT>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured.set(ctx->device);
+    }
+    uint32_t const nct = static_cast<uint32_t>(rowvecs >> LOG_TWC);
+    uint64_t const grid = (1ull << (n_qubits - Cfg::R)) * nct;
+    FP_TRY(check_grid(grid));
+    coset_kernel<T, EPV, LOG_TWC, LOG_NT, MODE, VPT><<<static_cast<unsigned>(grid), Cfg::NT, smem, ctx->stream>>>(
+        view, rowvecs, nct, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta,
+        static_cast<Cx<T> *>(partials), Bpad, Wre, Wim, B);
+    ctx->launches++;
+    return FP_OK;
+}
+
+template <typename T, int EPV, int MODE>
+int launch_coset_pass_v(fp_ctx *ctx, CosetShape shape, CosetPassView<T> const &view, int n_qubits, uint64_t rowvecs,
+                        void const *in, void *out, int beta, void *partials, uint32_t Bpad, T const *Wre, T const *Wim,
+                        uint64_t B)
+{
+#define FP_COSET_CASE(V, LNT)                                                                                          \
+    if (shape.vpt == 16 && shape.log_twc == V && shape.log_nt == LNT)                                                  \
+        return launch_coset_pass<T, EPV, V, LNT, MODE>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad,    \
+                                                       Wre, Wim, B);
+    if constexpr (MODE == 2)
+    {
+        // weighted apply on a whole-column tile (rank 12, one vector per row): 512 threads x 8 rows halve the
+        // per-thread accumulator + D registers, so 16 warps are resident per SM instead of 8
+        if (shape.vpt == 16 && shape.log_twc == 0 && shape.log_nt == 8 && ctx->coset_wide_cta)
+            return launch_coset_pass<T, EPV, 0, 9, MODE, 8>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad,
+                                                           Wre, Wim, B);
+    }
+#define FP_COSET_CASE8(V)                                                                                              \
+    if (shape.vpt == 8 && shape.log_twc == V && shape.log_nt == 8)                                                     \
+        return launch_coset_pass<T, EPV, V, 8, MODE, 8>(ctx, view, n_qubits, rowvecs, in, out, beta, partials, Bpad,   \
+                                                        Wre, Wim, B);
+    if constexpr (MODE != 2)
+    {
+        FP_COSET_CASE8(0)
+        FP_COSET_CASE8(1)
+        FP_COSET_CASE8(2)
+        FP_COSET_CASE8(3)
+    }
+#undef FP_COSET_CASE8
+    FP_COSET_CASE(0, 8)
+    FP_COSET_CASE(1, 8)
+    FP_COSET_CASE(2, 8)
+    FP_COSET_CASE(3, 8)
+    FP_COSET_CASE(4, 8)
+    FP_COSET_CASE(0, 7)
+    FP_COSET_CASE(1, 7)
+    FP_COSET_CASE(2, 7)
+    FP_COSET_CASE(3, 7)
+    FP_COSET_CASE(4, 7)
+#undef FP_COSET_CASE
+    return set_err(FP_UNSUPPORTED, "unsupported coset tile shape");
+}
+
+// ---------------------------------------------------------------- K3e / K3f (coset2.cuh): passes with <= 8 x-masks
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, cuuint64_t const *,
+                                      cuuint64_t const *, cuuint32_t const *, cuuint32_t const *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda); nullptr when unavailable
+TensorMapEncodeFn tensor_map_encoder()
+{
+    static TensorMapEncodeFn fn = []() -> TensorMapEncodeFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+        {
+            (void)cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<TensorMapEncodeFn>(p);
+    }();
+    return fn;
+}
+
+// The batch as a 2-D tensor (rows = dim, inner = real scalars of one row) with a box of one 256-byte row segment:
+// the shape TMA tile::gather4 wants (four arbitrary rows per operation).
+template <typename T> bool make_row_tensor_map(CUtensorMap *tm, void const *base, uint64_t dim, uint64_t rowvecs)
+{
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc)
+        return false;
+    cuuint64_t dims[2] = {rowvecs * (16 / sizeof(T)), dim};
+    cuuint64_t strides[1] = {rowvecs * 16};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(256 / sizeof(T)), 1};
+    cuuint32_t es[2] = {1, 1};
+    return enc(tm, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+               const_cast<void *>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename T, int EPV, int LOG_TWC, int NBUF, bool PSTR, int MODE = 0>
+int launch_coset_few_v(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T> const &strs, int n_qubits,
+                       uint64_t rowvecs, void const *in, void *out, int beta, void *partials = nullptr,
+                       uint32_t Bpad = 0)
+{
+    using Cfg = FewCfg<LOG_TWC>;
+    constexpr int GMAX = 8;
+    constexpr size_t smem = NBUF * Cfg::TILE_BYTES;
+    static PerDevice configured; // per template instance
+    if (!configured.done(ctx->device))
+    {
+        FP_CU(cudaFuncSetAttribute(coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR, false, MODE>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        configured.set(ctx->device);
+    }
+    uint32_t const nct = static_cast<uint32_t>(rowvecs >> LOG_TWC);
+    uint64_t const n_cosets = 1ull << (n_qubits - Cfg::R);
+    // column tiles per CTA: as many as possible (the row factors are formed once per CTA) while >= 4 waves remain
+    uint32_t per = nct;
+    if (ctx->coset_few_ct > 0)
+        per = std::min<uint32_t>(nct, static_cast<uint32_t>(ctx->coset_few_ct));
+    else
+        while (per > 1 && n_cosets * ((nct + per - 1) / per) < 8ull * static_cast<uint64_t>(ctx->sm_count))
+            per = (per + 1) / 2;
+    uint32_t const groups = (nct + per - 1) / per;
+    uint64_t const grid = n_cosets * groups;
+    FP_TRY(check_grid(grid));
+    coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR, false, MODE>
+        <<<static_cast<unsigned>(grid), Cfg::NT, smem, ctx->stream>>>(
+            view, rowvecs, nct, per, groups, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta,
+            strs, static_cast<Cx<T> *>(partials), Bpad);
+    ctx->launches++;
+    return FP_OK;
+}
+
+// K3f: persistent TMA-fed kernel, overwrite or accumulate, 12..30 qubits, rows of >= 256 bytes
+template <typename T, int EPV>
+int launch_coset_few_tma(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T> const &strs, int n_qubits,
+                         uint64_t rowvecs, void const *in, void *out, int beta, bool *launched)
+{
+    *launched = false;
+    CUtensorMap tm;
+    if (!make_row_tensor_map<T>(&tm, in, 1ull << n_qubits, rowvecs))
+        return FP_OK;
+    constexpr size_t smem = kFewTmaBufs * kFewTmaTile;
+    static PerDevice configured;
+    if (!configured.done(ctx->device))
+    {
+        FP_CU(cudaFuncSetAttribute(coset_few_tma_kernel<T, EPV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+        configured.set(ctx->device);
+    }
+    uint64_t const n_pairs = 1ull << (n_qubits - 9);
+    unsigned const grid = static_cast<unsigned>(std::min<uint64_t>(n_pairs, static_cast<uint64_t>(ctx->sm_count)));
+    coset_few_tma_kernel<T, EPV, 8><<<grid, kFewTmaThreads, smem, ctx->stream>>>(
+        view, rowvecs, static_cast<uint32_t>(rowvecs >> 4), n_pairs, static_cast<CVec<T, EPV> *>(out), beta, strs, tm);
+    ctx->launches++;
+    *launched = true;
+    return FP_OK;
+}
+
+// K3g: persistent TMA-fed kernel for passes with more than 8 x-masks (row factors per tile from the constant bank)
+template <typename T, int EPV>
+int launch_coset_gen_tma(fp_ctx *ctx, CosetPassView<T> const &view, GenStrings<T> const &gstr, int n_qubits,
+                         uint64_t rowvecs, void const *in, void *out, int beta, bool *launched)
+{
+    *launched = false;
+    CUtensorMap tm;
+    if (!make_row_tensor_map<T>(&tm, in, 1ull << n_qubits, rowvecs))
+        return FP_OK;
+    constexpr size_t smem = kFewTmaBufs * kFewTmaTile + kGenMetaBytes;
+    static PerDevice configured;
+    if (!configured.done(ctx->device))
+    {
+        FP_CU(cudaFuncSetAttribute(coset_gen_tma_kernel<T, EPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+        configured.set(ctx->device);
+    }
+    uint64_t const n_pairs = 1ull << (n_qubits - 9);
+    uint32_t const nct = static_cast<uint32_t>(rowvecs >> 4);
+    // work items = coset pairs x chunks of column tiles: enough of them to balance 148 persistent CTAs
+    uint32_t chunk = nct;
+    while (chunk > 1 && chunk % 2 == 0 && n_pairs * (nct / chunk) < 6ull * static_cast<uint64_t>(ctx->sm_count))
+        chunk /= 2;
+    uint64_t const items = n_pairs * (nct / chunk);
+    unsigned const grid = static_cast<unsigned>(std::min<uint64_t>(items, static_cast<uint64_t>(ctx->sm_count)));
+    coset_gen_tma_kernel<T, EPV, true><<<grid, kFewTmaThreads, smem, ctx->stream>>>(
+        view, rowvecs, nct, n_pairs, chunk, static_cast<CVec<T, EPV> *>(out), beta, tm, gstr);
+    ctx->launches++;
+    *launched = true;
+    return FP_OK;
+}
+
+// Picks the variant for one pass; *launched = false when the pass has to go through coset_kernel (K3b).
+template <typename T, int EPV, int MODE = 0>
+int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, int n_qubits, uint64_t rowvecs,
+                     void const *in, void *out, int beta, bool *launched, void *partials = nullptr, uint32_t Bpad = 0)
+{
+    *launched = false;
+    CosetPassView<T> const &view = pd.view;
+    if (MODE == 0 && ctx->coset_few == 1 && pd.gen && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+        is_device_ptr(in))
+        return launch_coset_gen_tma<T, EPV>(ctx, view, *pd.gen, n_qubits, rowvecs, in, out, beta, launched);
+    if (!ctx->coset_few || view.n_groups == 0 || view.n_groups > 8 || n_qubits < 8)
+        return FP_OK;
+    static FewStrings<T> const no_strings{};
+    bool const pstr = pd.few != nullptr;
+    FewStrings<T> const &strs = pstr ? *pd.few : no_strings;
+    // K3f wins on overwrite passes of large registers (measured at 20 qubits: 4 masks 0.42 -> 0.38 ms, 256 columns
+    // 1.95 -> 1.85 ms; 8 masks equal); read-modify-write passes and small registers stay on the resident-CTA kernel
+    if (MODE == 0 && ctx->coset_few == 1 && pstr && beta == 0 && n_qubits >= 16 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+        is_device_ptr(in))
+    {
+        FP_TRY((launch_coset_few_tma<T, EPV>(ctx, view, strs, n_qubits, rowvecs, in, out, beta, launched)));
+        if (*launched)
+            return FP_OK;
+    }
+    if (rowvecs % 8 == 0 && pstr)
+        FP_TRY((launch_coset_few_v<T, EPV, 3, 2, true, MODE>(ctx, view, strs, n_qubits, rowvecs, in, out, beta, partials,
+                                                             Bpad)));
+    else if (rowvecs % 8 == 0)
+        FP_TRY((launch_coset_few_v<T, EPV, 3, 2, false, MODE>(ctx, view, strs, n_qubits, rowvecs, in, out, beta, partials,
+                                                              Bpad)));
+    else
+        return FP_OK;
+    *launched = true;
+    return FP_OK;
+}
+
+// Runs all passes.  Returns FP_OK with *used = false when the generic kernel should be used instead.
+template <typename T, int MODE>
+int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void const *in, uint64_t dim, uint64_t B,
+              int beta, T const *Wre, T const *Wim, bool *used)
+{
+    *used = false;
+    constexpr int EPV = sizeof(T) == 4 ? 2 : 1;
+    if (n_qubits <= 0 || dim != (1ull << n_qubits))
+        return FP_OK;
+    int const epv = pick_epv<T>(in, MODE == 1 ? in : out, B);
+    if (epv != EPV)
+        return FP_OK;
+    uint64_t const rowvecs = B / EPV;
+    bool const tma_ok = MODE == 0 && ctx->coset_few == 1 && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+                        is_device_ptr(in) && tensor_map_encoder() != nullptr;
+    CosetShape const shape = choose_coset<T>(ctx, op, n_qubits, rowvecs, epv, tma_ok);
+    if (!shape.ok())
+        return FP_OK;
+    std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
+    // narrow row segments (16 / 32 bytes): force the lowest row bits into the tile so it is made of >= 64-byte runs
+    int const reserve = std::max(0, 2 - shape.log_twc);
+    FP_TRY(get_coset_plan<T>(op, n_qubits, shape.rank(), reserve, &passes));
+    // every pass re-streams the batch (read in, read-modify-write out): only worth it while passes << groups
+    if (ctx->coset_mode == 1 && passes->size() * 3 > op.host.gx.size() && passes->size() > 1)
+        return FP_OK;
+    uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
+    uint64_t const n_cosets = 1ull << (n_qubits - shape.rank());
+    if (MODE == 1)
+        FP_TRY(ctx->partials.ensure(n_cosets * Bpad * 2 * sizeof(T)));
+    for (size_t p = 0; p < passes->size(); ++p)
+    {
+        int const b = (p == 0) ? beta : 1;
+        if constexpr (MODE == 0 || MODE == 1)
+        {
+            if (shape.rank() == 8 && shape.log_nt == 8)
+            {
+                bool launched = false;
+                FP_TRY((launch_coset_few<T, EPV, MODE>(ctx, (*passes)[p], n_qubits, rowvecs, in, out, b, &launched,
+                                                       ctx->partials.p, Bpad)));
+                if (launched)
+                {
+                    if (MODE == 1)
+                    {
+                        unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
+                        finalize_complex_kernel<T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
+                            static_cast<Cx<T> const *>(ctx->partials.p), n_cosets, Bpad, B, static_cast<Cx<T> *>(out), b);
+                        ctx->launches++;
+                    }
+                    continue;
+                }
+            }
+        }
+        FP_TRY((launch_coset_pass_v<T, EPV, MODE>(ctx, shape, (*passes)[p].view, n_qubits, rowvecs, in, out, b,
+                                                   ctx->partials.p, Bpad, Wre, Wim, B)));
+        if (MODE == 1)
+        {
+            unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
+            finalize_complex_kernel<T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
+                static_cast<Cx<T> const *>(ctx->partials.p), n_cosets, Bpad, B, static_cast<Cx<T> *>(out), b);
+            ctx->launches++;
+        }
+    }
+    *used = true;
+    return FP_OK;
+}
+
+} // namespace

@@ -85,7 +85,7 @@ struct Geom
 constexpr int kThreads = 256;
 
 // FP64 peak probe (fp_measure_fp64_tflops): 16 independent DFMA chains per thread
-__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters)
+static __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters)
 {
     double const a = 1.0 + threadIdx.x * 1e-9, b = threadIdx.x * 1e-7;
     double c[16];
