@@ -219,7 +219,9 @@ def run_reference_arm(args) -> None:
     from oracle import oracle as orc
 
     be = orc.reference() or orc.port()
-    be.use_all_threads()  # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every host core
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm gets every host core, up to 64: its par path allocates
+    # n_threads x (dim x B) private copies of the 1 GiB batch (PO:427-429) and zero-fills / reduces them every call
+    be.use_all_threads(cap=64)
     threads = be.max_threads()
     step = CpuStep(be)
     for _ in range(args.warmup):
@@ -835,7 +837,7 @@ def run_ours(args) -> None:
             from oracle import oracle as orc
 
             be = orc.reference() or orc.port()
-            be.use_all_threads()
+            be.use_all_threads(cap=64)
             step = CpuStep(be)
             step.run(("few_group",))  # warm-up: first touch of the n_threads x dim x B private copies (PO:427)
             dt = step.run()

@@ -95,12 +95,15 @@ class Backend:
         c = complex(c)
         return np.array([c.real, c.imag], dtype=real)
 
-    def use_all_threads(self) -> int:
-        """Let the OpenMP reference use every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    def use_all_threads(self, cap: int | None = None) -> int:
+        """Let the OpenMP reference use every core this process may run on (torchrun exports OMP_NUM_THREADS=1);
+        `cap` bounds the count where the reference's par path allocates per-thread copies of the batch (PO:427)."""
         try:
             n = len(os.sched_getaffinity(0))
         except AttributeError:
             n = os.cpu_count() or 1
+        if cap:
+            n = min(n, cap)
         if self.prefix == "ref_":
             self.lib.ref_set_threads(C.c_int(n))
         else:

@@ -51,10 +51,12 @@ def test_sass_carries_the_blackwell_instructions_the_design_claims():
     """DESIGN.md section 3 names the hardware paths; the compiled sm_100a code must contain them (no GPU needed):
     tcgen05 MMA / TMEM load / commit / alloc for the coefficient contraction (K5), FP64 tensor-core MMA for the dense
     coset kernels (K3d), cp.async 16-byte fills for the shared-memory coset tiles (K3b), packed FP32 arithmetic for
-    the SummedPauliOp tiles (K6b / K4c), 16-byte vector loads and stores for the streaming kernels (K1 / K2)."""
+    the SummedPauliOp tiles (K6b / K4c), 16-byte vector loads and stores for the streaming kernels (K1 / K2), TMA
+    tile::gather4 loads with mbarrier completion and register re-balancing for the persistent few-mask / many-mask coset
+    kernels (K3f / K3g), constant-bank row factors (K3e)."""
     sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "UTCATOMSWS", "DMMA.8x8x4", "LDGSTS.E.BYPASS.128", "FFMA2", "FADD2",
-                     "LDG.E.128", "STG.E.128"):
+                     "LDG.E.128", "STG.E.128", "UTMALDG.2D.GATHER4", "SYNCS.ARRIVE.TRANS64", "USETMAXREG", "LDCU.64"):
         assert mnemonic in sass, f"{mnemonic} not found in the SASS of {LIB}"
 
 
