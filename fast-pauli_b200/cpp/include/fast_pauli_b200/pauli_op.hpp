@@ -7,6 +7,7 @@
 // dim-sized lookup tables for every string on every call (PS:323,408,499).
 #pragma once
 #include <memory>
+#include <cstring>
 #include <mutex>
 #include <unordered_map>
 
@@ -17,12 +18,26 @@ namespace fast_pauli
 
 namespace gpu
 {
-// owns one fp_op plan keyed by a fingerprint of (codes, coeffs)
+// owns one fp_op plan together with a byte-exact snapshot of the (codes, coeffs) it was built from: the public
+// `coeffs` / `pauli_strings` members are mutable, and a plan is reused only while both still compare equal (memcmp,
+// not a hash: no collision can hand back a stale plan)
 struct OpPlanCache
 {
     fp_op *plan = nullptr;
-    uint64_t key = 0;
+    std::vector<unsigned char> snap_codes, snap_coeffs;
     std::mutex mu;
+    bool matches(std::vector<uint8_t> const &codes, void const *coeffs, size_t coeff_bytes) const
+    {
+        return plan && snap_codes.size() == codes.size() && snap_coeffs.size() == coeff_bytes &&
+               (codes.empty() || std::memcmp(snap_codes.data(), codes.data(), codes.size()) == 0) &&
+               (coeff_bytes == 0 || std::memcmp(snap_coeffs.data(), coeffs, coeff_bytes) == 0);
+    }
+    void remember(std::vector<uint8_t> const &codes, void const *coeffs, size_t coeff_bytes)
+    {
+        snap_codes.assign(codes.begin(), codes.end());
+        auto const *p = static_cast<unsigned char const *>(coeffs);
+        snap_coeffs.assign(p, p + coeff_bytes);
+    }
     OpPlanCache() = default;
     OpPlanCache(OpPlanCache const &)
     {
@@ -41,7 +56,8 @@ struct OpPlanCache
         if (plan)
             fp_op_destroy(plan);
         plan = nullptr;
-        key = 0;
+        snap_codes.clear();
+        snap_coeffs.clear();
     }
 };
 } // namespace gpu
@@ -270,15 +286,13 @@ template <std::floating_point T, typename H = std::complex<T>> struct PauliOp
         for (size_t s = 0; s < S; ++s)
             for (size_t q = 0; q < n; ++q)
                 codes[s * n + q] = pauli_strings[s].paulis[q].code;
-        uint64_t key = gpu::fnv1a(codes.data(), codes.size());
-        key = gpu::fnv1a(coeffs.data(), coeffs.size() * sizeof(H), key) ^ (uint64_t(n) << 56) ^ S;
         std::lock_guard<std::mutex> lk(cache_.mu);
-        if (!cache_.plan || cache_.key != key)
+        if (!cache_.matches(codes, coeffs.data(), coeffs.size() * sizeof(H)))
         {
             cache_.reset();
             gpu::check(fp_op_create(gpu::context(), gpu::dtype_of<T>(), static_cast<int>(n), S, codes.data(),
                                     coeffs.data(), &cache_.plan));
-            cache_.key = key;
+            cache_.remember(codes, coeffs.data(), coeffs.size() * sizeof(H));
         }
         return cache_.plan;
     }

@@ -188,17 +188,31 @@ template <std::floating_point T> struct SummedPauliOp
     }
 
   private:
+    // the plan is reused only while a byte-exact snapshot of (codes, coeffs) still compares equal (memcmp, no hash)
     struct PlanCache
     {
         fp_sop *plan = nullptr;
-        uint64_t key = 0;
+        std::vector<unsigned char> snap_codes, snap_coeffs;
         std::mutex mu;
+        bool matches(std::vector<uint8_t> const &codes, void const *c, size_t bytes) const
+        {
+            return plan && snap_codes.size() == codes.size() && snap_coeffs.size() == bytes &&
+                   (codes.empty() || std::memcmp(snap_codes.data(), codes.data(), codes.size()) == 0) &&
+                   (bytes == 0 || std::memcmp(snap_coeffs.data(), c, bytes) == 0);
+        }
+        void remember(std::vector<uint8_t> const &codes, void const *c, size_t bytes)
+        {
+            snap_codes.assign(codes.begin(), codes.end());
+            auto const *p = static_cast<unsigned char const *>(c);
+            snap_coeffs.assign(p, p + bytes);
+        }
         void reset()
         {
             if (plan)
                 fp_sop_destroy(plan);
             plan = nullptr;
-            key = 0;
+            snap_codes.clear();
+            snap_coeffs.clear();
         }
     };
     mutable PlanCache cache_;
@@ -226,15 +240,14 @@ template <std::floating_point T> struct SummedPauliOp
         for (size_t s = 0; s < S; ++s)
             for (size_t q = 0; q < n; ++q)
                 codes[s * n + q] = pauli_strings[s].paulis[q].code;
-        uint64_t key = gpu::fnv1a(codes.data(), codes.size());
-        key = gpu::fnv1a(coeffs.data_handle(), coeffs.size() * sizeof(std::complex<T>), key) ^ (uint64_t(n) << 56) ^ S;
+        size_t const bytes = coeffs.size() * sizeof(std::complex<T>);
         std::lock_guard<std::mutex> lk(cache_.mu);
-        if (!cache_.plan || cache_.key != key)
+        if (!cache_.matches(codes, coeffs.data_handle(), bytes))
         {
             cache_.reset();
             gpu::check(fp_sop_create(gpu::context(), gpu::dtype_of<T>(), static_cast<int>(n), S, codes.data(),
                                      n_operators(), coeffs.data_handle(), &cache_.plan));
-            cache_.key = key;
+            cache_.remember(codes, coeffs.data_handle(), bytes);
         }
         return cache_.plan;
     }
