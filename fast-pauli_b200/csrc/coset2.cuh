@@ -109,12 +109,13 @@ template <int LOG_TWC> struct FewCfg
 // PSTR: the pass' strings (<= kFewParamStrings) travel in the kernel parameter block, i.e. the constant bank: the
 // row-factor phase then needs no shared-memory staging, no barrier and -- the point -- no LDS at all, so it no longer
 // queues behind the other resident CTA's gathers in the load/store unit (measured: 13 k -> 4 k cycles per CTA).
-// DSM: the row factors are parked in shared memory (GMAX x 256 x 16 B behind the tile buffers, conflict-free) between
-// the row-factor phase and the gathers: 32 registers freed for gathered vectors in flight.
+// RMWPF: accumulating passes (beta != 0) prefetch the OLD output rows of a tile with cp.async into one more
+// shared-memory buffer while the tile's gathers run, instead of loading them (LDG, 8-16 vectors live in registers, a
+// full memory round trip exposed) in the store phase.
 // MODE 1: PauliOp::expectation_value partials (PO:482-549) instead of the store: e(t) = sum over the tile's rows of
 // conj(psi(l,t)) (A psi)(l,t), written to partials[coset][t] (fixed summation order; finalize_complex_kernel sums the
 // cosets).  The products are staged in the (dead) tile buffer and column-summed by the cooperative row mapping.
-template <typename T, int EPV, int LOG_TWC, int GMAX, int NBUF = 1, int MINB = 2, bool PSTR = false, bool DSM = false,
+template <typename T, int EPV, int LOG_TWC, int GMAX, int NBUF = 1, int MINB = 2, bool PSTR = false, bool RMWPF = false,
           int MODE = 0>
 __global__ void __launch_bounds__(256, MINB)
     coset_few_kernel(CosetPassView<T> pass, uint64_t rowvecs, uint32_t nColTiles, uint32_t ctPerCta, uint32_t nCtGroups,
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(256, MINB)
     uint64_t const row_lo = base ^ comb_of<Cfg::R>(pass.basis, l_lo);
     __syncthreads();
 
-    auto fill = [&](uint32_t c, uint32_t buf) {
+    auto fill = [&](uint32_t c, uint32_t buf, bool commit) {
         uint64_t const vcol = static_cast<uint64_t>(c) * TWC + jv;
         Vec *tile = reinterpret_cast<Vec *>(smem_few + buf * Cfg::TILE_BYTES);
 #pragma unroll
@@ -164,11 +165,25 @@ __global__ void __launch_bounds__(256, MINB)
             uint64_t const row = row_lo ^ s_comb_hi[k];
             cp_async16(&tile[(l_lo + k * RPS) * TWC + jv], &in[row * rowvecs + vcol]);
         }
-        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        if (commit)
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
     };
-    fill(ct, 0);
+    bool const pf = RMWPF && beta != 0;
+    unsigned char *const ob = smem_few + NBUF * Cfg::TILE_BYTES; // old output rows of the current tile (RMWPF)
+    auto fill_old = [&](uint32_t c) {
+        uint64_t const vcol = static_cast<uint64_t>(c) * TWC + jv;
+        Vec *o = reinterpret_cast<Vec *>(ob);
+#pragma unroll
+        for (int k = 0; k < STEPS; ++k)
+            cp_async16(&o[(l_lo + k * RPS) * TWC + jv], &out[(row_lo ^ s_comb_hi[k]) * rowvecs + vcol]);
+    };
+    fill(ct, 0, true);
     if (NBUF == 2 && ct + 1 < ct_end)
-        fill(ct + 1, 1);
+        fill(ct + 1, 1, false);
+    if (pf)
+        fill_old(ct);
+    if (pf || (NBUF == 2 && ct + 1 < ct_end))
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
 
     // ---- row factors of this thread's row, once per coset (the first tile is in flight meanwhile).  The strings are
     // staged in shared memory in rounds of kFewMaxStrings with the coset-base sign par(base & z_s) folded into the
@@ -221,13 +236,6 @@ __global__ void __launch_bounds__(256, MINB)
         }
     }
 
-    Cx<T> *const s_D = reinterpret_cast<Cx<T> *>(smem_few + NBUF * Cfg::TILE_BYTES);
-    if (DSM)
-    {
-#pragma unroll
-        for (int g = 0; g < GMAX; ++g)
-            s_D[g * 256 + tid] = D[g]; // only this thread ever reads its slots: no barrier needed
-    }
     FEW_T(0); // setup + row factors
     uint32_t const key_off = (tid & (TWC - 1)) << 4;             // column rotation of this thread, in bytes
     uint32_t const own_off = (tid << ROW_SHIFT) | key_off;       // own row, rotated column 0
@@ -237,8 +245,8 @@ __global__ void __launch_bounds__(256, MINB)
         uint32_t const buf = NBUF == 2 ? (it & 1u) : 0u;
         unsigned char *const tb = smem_few + buf * Cfg::TILE_BYTES;
         Vec *const tile = reinterpret_cast<Vec *>(tb);
-        if (NBUF == 2 && ct + 1 < ct_end)
-            asm volatile("cp.async.wait_group 1;\n" ::: "memory"); // the tile after this one may still be in flight
+        if (pf || (NBUF == 2 && ct + 1 < ct_end))
+            asm volatile("cp.async.wait_group 1;\n" ::: "memory"); // a newer group (next tile / old rows) may be in flight
         else
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
         __syncthreads();
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(256, MINB)
             if (static_cast<uint32_t>(g) < ng)
             {
                 uint32_t const src = own_off ^ (s_gxl[g] << ROW_SHIFT);
-                Cx<T> const d = DSM ? s_D[g * 256 + tid] : D[g];
+                Cx<T> const d = D[g];
 #pragma unroll
                 for (int j = 0; j < TWC; ++j)
                 {
@@ -294,6 +302,8 @@ __global__ void __launch_bounds__(256, MINB)
             }
             *reinterpret_cast<Vec *>(tb + (own_off ^ (j << 4))) = v;
         }
+        if (pf)
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory"); // the old output rows of this tile have landed
         __syncthreads();
         FEW_T(3); // accumulators -> staging
 
@@ -349,7 +359,24 @@ __global__ void __launch_bounds__(256, MINB)
         {
 
         uint64_t const vcol = static_cast<uint64_t>(ct) * TWC + jv;
-        if (beta)
+        if (pf)
+        {
+            Vec const *o = reinterpret_cast<Vec const *>(ob);
+#pragma unroll
+            for (int k = 0; k < STEPS; ++k)
+            {
+                Vec v = tile[(l_lo + k * RPS) * TWC + jv];
+                Vec const w = o[(l_lo + k * RPS) * TWC + jv];
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                {
+                    v.e[e].re += w.e[e].re;
+                    v.e[e].im += w.e[e].im;
+                }
+                out[(row_lo ^ s_comb_hi[k]) * rowvecs + vcol] = v;
+            }
+        }
+        else if (beta)
         {
             Vec o[STEPS];
 #pragma unroll
@@ -376,10 +403,14 @@ __global__ void __launch_bounds__(256, MINB)
         }
         }
         FEW_T(4); // issuing the stores
-        if (ct + NBUF < ct_end)
+        if (ct + NBUF < ct_end || (pf && ct + 1 < ct_end))
         {
-            __syncthreads(); // staged rows have been read: refill this buffer
-            fill(ct + NBUF, buf);
+            __syncthreads(); // staged (and old) rows have been read: refill this buffer / the old-row buffer
+            if (ct + NBUF < ct_end)
+                fill(ct + NBUF, buf, false);
+            if (pf && ct + 1 < ct_end)
+                fill_old(ct + 1);
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
             FEW_T(5);
         }
     }

@@ -318,18 +318,25 @@ template <typename T> bool make_row_tensor_map(CUtensorMap *tm, void const *base
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <typename T, int EPV, int LOG_TWC, int NBUF, bool PSTR, int MODE = 0>
+template <typename T, int EPV, int LOG_TWC, int NBUF, bool PSTR, int MODE = 0, bool RMWPF = false>
 int launch_coset_few_v(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T> const &strs, int n_qubits,
                        uint64_t rowvecs, void const *in, void *out, int beta, void *partials = nullptr,
                        uint32_t Bpad = 0)
 {
     using Cfg = FewCfg<LOG_TWC>;
     constexpr int GMAX = 8;
-    constexpr size_t smem = NBUF * Cfg::TILE_BYTES;
+    if constexpr (MODE == 0 && !RMWPF)
+    {
+        // accumulating passes prefetch the old output rows through one more shared-memory buffer
+        if (beta)
+            return launch_coset_few_v<T, EPV, LOG_TWC, NBUF, PSTR, MODE, true>(ctx, view, strs, n_qubits, rowvecs, in, out,
+                                                                               beta, partials, Bpad);
+    }
+    constexpr size_t smem = (NBUF + (RMWPF ? 1 : 0)) * Cfg::TILE_BYTES;
     static PerDevice configured; // per template instance
     if (!configured.done(ctx->device))
     {
-        FP_CU(cudaFuncSetAttribute(coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR, false, MODE>,
+        FP_CU(cudaFuncSetAttribute(coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR, RMWPF, MODE>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         configured.set(ctx->device);
     }
@@ -345,7 +352,7 @@ int launch_coset_few_v(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T> 
     uint32_t const groups = (nct + per - 1) / per;
     uint64_t const grid = n_cosets * groups;
     FP_TRY(check_grid(grid));
-    coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR, false, MODE>
+    coset_few_kernel<T, EPV, LOG_TWC, GMAX, NBUF, 2, PSTR, RMWPF, MODE>
         <<<static_cast<unsigned>(grid), Cfg::NT, smem, ctx->stream>>>(
             view, rowvecs, nct, per, groups, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta,
             strs, static_cast<Cx<T> *>(partials), Bpad);

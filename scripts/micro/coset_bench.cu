@@ -292,7 +292,7 @@ int main(int argc, char **argv)
     if (ctPer < 0)                                                                                                     \
     {                                                                                                                  \
         using Cfg = FewCfg<LT>;                                                                                        \
-        size_t const sm = NB * Cfg::TILE_BYTES + 8 * 256 * 16;                                                         \
+        size_t const sm = (NB + 1) * Cfg::TILE_BYTES;                                                                  \
         CK(cudaFuncSetAttribute(coset_few_kernel<T, 1, LT, 8, NB, MB, TM, true>,                                       \
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));                                \
         uint32_t const nct = rowvecs >> LT;                                                                            \
