@@ -309,7 +309,7 @@ extern "C"
         return OK;
     }
 
-    // sum (op = 0) or max (op = 1) of n <= 64 host doubles over the ranks, in place; also a barrier
+    // sum (op = 0), max (op = 1) or min (op = 2) of n <= 64 host doubles over the ranks, in place; also a barrier
     int fp_comm_allreduce_f64(fp_comm *c, double *values, size_t n, int op)
     {
         if (!c || (!values && n))
@@ -326,7 +326,8 @@ extern "C"
             n = 1;
         }
         SH_CU(cudaMemcpyAsync(c->scratch, values, n * sizeof(double), cudaMemcpyHostToDevice, c->comm_stream));
-        SH_NCCL(nccl().AllReduce(c->scratch, c->scratch, n, ncclDouble, op == 1 ? ncclMax : ncclSum, c->comm, c->comm_stream));
+        SH_NCCL(nccl().AllReduce(c->scratch, c->scratch, n, ncclDouble, op == 1 ? ncclMax : (op == 2 ? ncclMin : ncclSum),
+                                 c->comm, c->comm_stream));
         SH_CU(cudaMemcpyAsync(values, c->scratch, n * sizeof(double), cudaMemcpyDeviceToHost, c->comm_stream));
         SH_CU(cudaStreamSynchronize(c->comm_stream));
         return OK;
@@ -594,6 +595,14 @@ extern "C"
                 n_whole_bufs = free_b >= 2 * shard_bytes + margin ? 2 : (free_b >= shard_bytes + margin ? 1 : 0);
                 if (op->mode == 0 && op->remote.size() == 1 && n_whole_bufs == 2)
                     n_whole_bufs = 1;
+            }
+            // the exchange schedule is collective: every rank must pick the same mode, so the ranks agree on the
+            // smallest buffer count any of them can afford
+            if (!c->emulated && c->world > 1)
+            {
+                double v = n_whole_bufs;
+                SH_TRY(fp_comm_allreduce_f64(c, &v, 1, 2));
+                n_whole_bufs = static_cast<int>(v);
             }
             whole = n_whole_bufs > 0 && (op->mode == 2 || shard_bytes > op->chunk_bytes);
             if (op->mode == 2 && n_whole_bufs == 0)

@@ -218,7 +218,8 @@ extern "C"
     int fp_comm_destroy(fp_comm *comm);
     int fp_comm_info(const fp_comm *comm, int *world, int *rank, int *nccl_version);
     int fp_comm_barrier(fp_comm *comm);
-    /* in-place sum (op = 0) or max (op = 1) of n <= 64 host doubles over the ranks (timing, small reductions) */
+    /* in-place sum (op = 0), max (op = 1) or min (op = 2) of n <= 64 host doubles over the ranks (timing, small
+     * reductions) */
     int fp_comm_allreduce_f64(fp_comm *comm, double *values, size_t n, int op);
     /* every rank swaps `bytes` with rank ^ 1 through ncclSend / ncclRecv `iters` times: GB/s per direction per GPU
      * (device time of the slowest rank) -- the measured NVLink denominator of the sharded apply */
