@@ -509,7 +509,9 @@ int pipelined_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const
     // block width: a multiple of 16 vectors (256-byte row segments: the widest coset tile and efficient strided DMA),
     // at most B / 3 so that at least three blocks are in flight, about pipeline_chunk_bytes * 8 per block
     uint64_t const vec_cols = 16 / esize;          // columns per 16-byte vector
-    uint64_t cols = 16 * vec_cols;                 // 256 bytes per row
+    uint64_t cols = 16 * vec_cols;                 // 256 bytes per row (128-byte segments: strided DMA drops to 2/3)
+    if (char const *env = getenv("FASTPAULI_PIPE_VECS"))
+        cols = std::max<uint64_t>(1, strtoull(env, nullptr, 10)) * vec_cols;
     if (B % cols != 0 || B / cols < 3)
         return FP_OK;
     while (B % (2 * cols) == 0 && B / (2 * cols) >= 4 && dim * (2 * cols) * esize <= (256ull << 20))
