@@ -772,6 +772,15 @@ __global__ void __launch_bounds__(kFewTmaThreads, 1)
             uint32_t const buf = static_cast<uint32_t>(i % kFewTmaBufs);
             unsigned char *const tb = smem_gt + buf * kFewTmaTile;
             Vec *const tile = reinterpret_cast<Vec *>(tb);
+            if (beta)
+            {
+                // accumulating pass: pull the old output rows of this tile into L2 now, so that the read-modify-write
+                // loads of the store phase (many thousand cycles from here) do not wait for HBM
+                uint64_t const vc = static_cast<uint64_t>(ct) * TWC + jv;
+#pragma unroll
+                for (int t = 0; t < STEPS; ++t)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(&out[(row_lo ^ s_comb_hi[t]) * rowvecs + vc]));
+            }
             few_mbar_wait(&s_full[buf], static_cast<uint32_t>(i / kFewTmaBufs) & 1u);
 
             Cx<T> acc[TWC][EPV];
