@@ -792,10 +792,20 @@ extern "C"
 
     int fp_ctx_set_coset_few(fp_ctx *ctx, int mode, int column_tiles_per_cta)
     {
-        if (!ctx || mode < 0 || mode > 2 || column_tiles_per_cta < 0)
+        if (!ctx || mode < 0 || mode > 3 || column_tiles_per_cta < 0)
             return set_err(FP_INVALID_ARGUMENT, "bad few-mask coset mode");
         ctx->coset_few = mode;
         ctx->coset_few_ct = column_tiles_per_cta;
+        return FP_OK;
+    }
+
+    int fp_ctx_coset_kernels_used(fp_ctx *ctx, uint32_t *mask, int reset)
+    {
+        if (!ctx || !mask)
+            return set_err(FP_INVALID_ARGUMENT, "null argument");
+        *mask = ctx->coset_kernels;
+        if (reset)
+            ctx->coset_kernels = 0;
         return FP_OK;
     }
 

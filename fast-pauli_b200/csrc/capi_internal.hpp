@@ -20,6 +20,7 @@
 
 #include "coset.cuh"
 #include "coset2.cuh"
+#include "coset3.cuh"
 #include "rcoset.cuh"
 #include "kernels.cuh"
 #include "pack.hpp"
@@ -123,6 +124,7 @@ struct fp_ctx
     bool tensor_core = true;
     bool zero_copy = true; // single-pass kernels read/write pinned host buffers in place
     uint64_t launches = 0;
+    uint32_t coset_kernels = 0; // coset-family kernels launched since the last reset: 1 K3b, 2 K3e, 4 K3f, 8 K3g, 16 K3i
     int last_gemm_engine = -1; // 0 = SIMT, 1 = tcgen05 (diagnostics)
     size_t l2_budget = 40ull << 20;
     int coset_mode = 1;       // 0: never use the coset-blocked kernels, 1: heuristic, 2: whenever applicable
@@ -130,7 +132,7 @@ struct fp_ctx
     int coset_log_nt = 0;     // 7 or 8 forces the CTA size (128 / 256 threads); 0 = default (256)
     int coset_vpt = 16;       // vectors per thread when the shape is forced (8 or 16)
     bool coset_wide_cta = true; // 512-thread CTAs for the rank-12 weighted-apply tile
-    int coset_few = 1;          // K3e / K3f (coset2.cuh) for passes with <= 8 x-masks: 0 off, 1 auto, 2 never the TMA
+    int coset_few = 1;          // K3e / K3f / K3i for passes with <= 8 x-masks: 0 off, 1 auto, 2 never the TMA, 3 auto without K3i
                                 // kernel (K3f)
     int coset_few_ct = 0;       // column tiles per CTA of K3e (0 = all of them while the grid still fills the chip)
     bool pipeline = true;       // chunked H2D / kernel / D2H pipeline for large host-resident single-string applies
@@ -178,6 +180,8 @@ template <typename T> struct DeviceOp
         std::shared_ptr<FewStrings<T>> few;
         // ... and for passes with any number of groups (K3g): <= 768 strings, <= 256 groups, <= 30 qubits
         std::shared_ptr<GenStrings<T>> gen;
+        // ... and for passes whose x-masks carry one string each (K3i, coset3.cuh): <= 32 masks, <= 30 qubits
+        std::shared_ptr<DirStrings<T>> dir;
         std::vector<void *> allocs;
     };
     mutable std::map<int, std::vector<CosetPassDev>> coset_plans;

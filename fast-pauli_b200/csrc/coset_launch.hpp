@@ -58,6 +58,21 @@ int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank, int reserve_lo
             for (size_t g = 0; g < h.gxl.size(); ++g)
                 d.gen->gxl[g] = static_cast<uint8_t>(h.gxl[g]);
         }
+        if (rank == 8 && n_qubits <= 30 && !h.gxl.empty() && h.gxl.size() == h.sz.size() &&
+            h.gxl.size() <= static_cast<size_t>(kDirMaxMasks))
+        {
+            // one string per x-mask: the row factor is +-c_g (K3i)
+            d.dir = std::make_shared<DirStrings<T>>();
+            std::memset(d.dir.get(), 0, sizeof(DirStrings<T>));
+            d.dir->n = static_cast<uint32_t>(h.gxl.size());
+            for (size_t g = 0; g < h.gxl.size(); ++g)
+            {
+                d.dir->c[g] = Cx<T>{h.sc[g].real(), h.sc[g].imag()};
+                d.dir->z[g] = h.sz[g];
+                d.dir->xl[g] = h.gxl[g];
+                d.dir->zl[g] = h.szl[g];
+            }
+        }
         CosetChunk *chunks = nullptr;
         uint32_t *gxl = nullptr, *gstart = nullptr, *szl = nullptr, *sidx = nullptr;
         uint64_t *sz = nullptr;
@@ -234,6 +249,7 @@ int launch_coset_pass(fp_ctx *ctx, CosetPassView<T> const &view, int n_qubits, u
         view, rowvecs, nct, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta,
         static_cast<Cx<T> *>(partials), Bpad, Wre, Wim, B);
     ctx->launches++;
+    ctx->coset_kernels |= 1u;
     return FP_OK;
 }
 
@@ -357,6 +373,7 @@ int launch_coset_few_v(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T> 
             view, rowvecs, nct, per, groups, static_cast<CVec<T, EPV> const *>(in), static_cast<CVec<T, EPV> *>(out), beta,
             strs, static_cast<Cx<T> *>(partials), Bpad);
     ctx->launches++;
+    ctx->coset_kernels |= 2u;
     return FP_OK;
 }
 
@@ -382,6 +399,7 @@ int launch_coset_few_tma(fp_ctx *ctx, CosetPassView<T> const &view, FewStrings<T
     coset_few_tma_kernel<T, EPV, 8><<<grid, kFewTmaThreads, smem, ctx->stream>>>(
         view, rowvecs, static_cast<uint32_t>(rowvecs >> 4), n_pairs, static_cast<CVec<T, EPV> *>(out), beta, strs, tm);
     ctx->launches++;
+    ctx->coset_kernels |= 4u;
     *launched = true;
     return FP_OK;
 }
@@ -414,6 +432,45 @@ int launch_coset_gen_tma(fp_ctx *ctx, CosetPassView<T> const &view, GenStrings<T
     coset_gen_tma_kernel<T, EPV, true><<<grid, kFewTmaThreads, smem, ctx->stream>>>(
         view, rowvecs, nct, n_pairs, chunk, static_cast<CVec<T, EPV> *>(out), beta, tm, gstr);
     ctx->launches++;
+    ctx->coset_kernels |= 8u;
+    *launched = true;
+    return FP_OK;
+}
+
+// K3i: persistent TMA-fed kernel with direct stores for passes whose x-masks carry one string each (coset3.cuh)
+template <typename T, int EPV>
+int launch_coset_dir_tma(fp_ctx *ctx, CosetPassView<T> const &view, DirStrings<T> const &strs, int n_qubits,
+                         uint64_t rowvecs, void const *in, void *out, int beta, bool *launched)
+{
+    *launched = false;
+    CUtensorMap tm;
+    if (!make_row_tensor_map<T>(&tm, in, 1ull << n_qubits, rowvecs))
+        return FP_OK;
+    constexpr size_t smem = kFewTmaBufs * kFewTmaTile;
+    uint32_t const nct = static_cast<uint32_t>(rowvecs >> 4);
+    uint64_t const n_tiles = (1ull << (n_qubits - 8)) * nct;
+    unsigned const grid = static_cast<unsigned>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(ctx->sm_count)));
+#define FP_LAUNCH_DIR(NCH)                                                                                             \
+    {                                                                                                                  \
+        static PerDevice configured;                                                                                   \
+        if (!configured.done(ctx->device))                                                                             \
+        {                                                                                                              \
+            FP_CU(cudaFuncSetAttribute(coset_dir_tma_kernel<T, EPV, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                       static_cast<int>(smem)));                                                       \
+            configured.set(ctx->device);                                                                               \
+        }                                                                                                              \
+        coset_dir_tma_kernel<T, EPV, NCH><<<grid, kDirThreads, smem, ctx->stream>>>(                                   \
+            view, rowvecs, nct, n_tiles, static_cast<CVec<T, EPV> *>(out), beta, strs, tm);                            \
+    }
+    if (strs.n <= 8)
+        FP_LAUNCH_DIR(1)
+    else if (strs.n <= 16)
+        FP_LAUNCH_DIR(2)
+    else
+        FP_LAUNCH_DIR(4)
+#undef FP_LAUNCH_DIR
+    ctx->launches++;
+    ctx->coset_kernels |= 16u;
     *launched = true;
     return FP_OK;
 }
@@ -425,7 +482,17 @@ int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, 
 {
     *launched = false;
     CosetPassView<T> const &view = pd.view;
-    if (MODE == 0 && ctx->coset_few == 1 && pd.gen && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+    bool const tma_mode = ctx->coset_few == 1 || ctx->coset_few == 3;
+    // one string per x-mask (random strings): direct-store kernel, overwrite and read-modify-write passes alike
+    // (measured at 20 qubits x 64: 8 masks 0.49 -> 0.43 ms, the 8 passes of 64 random strings 4.55 -> 4.16 ms)
+    if (MODE == 0 && ctx->coset_few == 1 && pd.dir && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+        is_device_ptr(in) && (rowvecs >> 4) << (n_qubits - 8) >= 4ull * static_cast<uint64_t>(ctx->sm_count))
+    {
+        FP_TRY((launch_coset_dir_tma<T, EPV>(ctx, view, *pd.dir, n_qubits, rowvecs, in, out, beta, launched)));
+        if (*launched)
+            return FP_OK;
+    }
+    if (MODE == 0 && tma_mode && pd.gen && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
         is_device_ptr(in))
         return launch_coset_gen_tma<T, EPV>(ctx, view, *pd.gen, n_qubits, rowvecs, in, out, beta, launched);
     if (!ctx->coset_few || view.n_groups == 0 || view.n_groups > 8 || n_qubits < 8)
@@ -435,7 +502,7 @@ int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, 
     FewStrings<T> const &strs = pstr ? *pd.few : no_strings;
     // K3f wins on overwrite passes of large registers (measured at 20 qubits: 4 masks 0.42 -> 0.38 ms, 256 columns
     // 1.95 -> 1.85 ms; 8 masks equal); read-modify-write passes and small registers stay on the resident-CTA kernel
-    if (MODE == 0 && ctx->coset_few == 1 && pstr && beta == 0 && n_qubits >= 16 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+    if (MODE == 0 && tma_mode && pstr && beta == 0 && n_qubits >= 16 && n_qubits <= 30 && rowvecs % 16 == 0 &&
         is_device_ptr(in))
     {
         FP_TRY((launch_coset_few_tma<T, EPV>(ctx, view, strs, n_qubits, rowvecs, in, out, beta, launched)));
@@ -467,7 +534,7 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
     if (epv != EPV)
         return FP_OK;
     uint64_t const rowvecs = B / EPV;
-    bool const tma_ok = MODE == 0 && ctx->coset_few == 1 && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+    bool const tma_ok = MODE == 0 && (ctx->coset_few == 1 || ctx->coset_few == 3) && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
                         is_device_ptr(in) && tensor_map_encoder() != nullptr;
     CosetShape const shape = choose_coset<T>(ctx, op, n_qubits, rowvecs, epv, tma_ok);
     if (!shape.ok())

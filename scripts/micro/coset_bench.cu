@@ -14,6 +14,7 @@
 
 #include "coset.cuh"
 #include "coset2.cuh"
+#include "coset3.cuh"
 #include "coset_plan.hpp"
 
 using namespace fpk;
@@ -95,6 +96,8 @@ int main(int argc, char **argv)
         variants(16, 4);
     else if (kind == "few4")
         variants(4, 16);
+    else if (kind.rfind("rand", 0) == 0 && kind.size() > 4)
+        variants(atoi(kind.c_str() + 4), 1); // randN: N random strings
     else if (kind == "cfg3")
     {
         // BASELINE config 3's operator: 2000 strings of weight <= 4 (weight uniform in 1..4, positions without replacement)
@@ -232,6 +235,53 @@ int main(int argc, char **argv)
     auto run_new = [&](double *out) {
         for (size_t p = 0; p < views.size(); ++p)
         {
+            if (nbuf == 5)
+            {
+                // K3i: direct-store TMA-fed kernel (one string per x-mask)
+                auto const &hp = passes[p];
+                if (hp.sz.size() != hp.gxl.size() || hp.gxl.size() > (size_t)kDirMaxMasks)
+                {
+                    printf("pass not eligible for K3i\n");
+                    exit(1);
+                }
+                DirStrings<T> ds;
+                memset(&ds, 0, sizeof ds);
+                ds.n = (uint32_t)hp.gxl.size();
+                for (size_t g = 0; g < hp.gxl.size(); ++g)
+                {
+                    ds.c[g] = Cx<T>{hp.sc[g].real(), hp.sc[g].imag()};
+                    ds.z[g] = hp.sz[g];
+                    ds.xl[g] = hp.gxl[g];
+                    ds.zl[g] = hp.szl[g];
+                }
+                size_t const smem = kFewTmaBufs * kFewTmaTile;
+                uint32_t const nct = (uint32_t)(rowvecs >> 4);
+                uint64_t const n_tiles = (dim >> 8) * nct;
+                unsigned const g = (unsigned)std::min<uint64_t>(grid_f, n_tiles);
+                int const nch = (int)((ds.n + 7) / 8);
+#define LAUNCH_DIR2(NCH, IB)                                                                                           \
+    {                                                                                                                  \
+        CK(cudaFuncSetAttribute(coset_dir_tma_kernel<T, 1, NCH, IB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        coset_dir_tma_kernel<T, 1, NCH, IB><<<g, kDirThreads, smem>>>(views[p], rowvecs, nct, n_tiles,                 \
+                                                                      reinterpret_cast<Vec *>(out), p ? 1 : 0, ds, tm); \
+    }
+#define LAUNCH_DIR(NCH)                                                                                                \
+    {                                                                                                                  \
+        if (log_twc == 8)                                                                                              \
+            LAUNCH_DIR2(NCH, 8)                                                                                        \
+        else if (log_twc == 2)                                                                                         \
+            LAUNCH_DIR2(NCH, 2)                                                                                        \
+        else                                                                                                           \
+            LAUNCH_DIR2(NCH, 4)                                                                                        \
+    }
+                if (nch <= 1)
+                    LAUNCH_DIR(1)
+                else if (nch == 2)
+                    LAUNCH_DIR(2)
+                else
+                    LAUNCH_DIR(4)
+                continue;
+            }
             if (nbuf == 4)
             {
                 size_t const smem = kFewTmaBufs * kFewTmaTile + kGenMetaBytes;
@@ -334,7 +384,7 @@ int main(int argc, char **argv)
     };
     bool const few_ok = [&]() {
         for (auto const &v : views)
-            if (v.n_groups > 8 && nbuf != 4)
+            if (v.n_groups > 8 && nbuf != 4 && nbuf != 5)
                 return false;
         return true;
     }();
@@ -375,6 +425,15 @@ int main(int argc, char **argv)
         CK(cudaMemcpyToSymbol(g_few_prof, z, sizeof z));
 #endif
         time_it(run_new, out_b, "K3e");
+#ifdef FP_DIR_PROFILE
+        {
+            unsigned long long z[8] = {};
+            CK(cudaMemcpyFromSymbol(z, g_dir_prof, sizeof z));
+            double const tiles = 8.0 * views.size() * (dim >> 8) * (rowvecs >> 4); // 1 check + 2 warm-up + 5 timed runs
+            printf("  K3i per tile and warp (cycles): setup %.0f  wait-full %.0f  compute+store %.0f  fence+arrive %.0f | producer: wait-empty %.0f issue %.0f\n",
+                   z[0] / tiles / 16, z[1] / tiles / 16, z[2] / tiles / 16, z[3] / tiles / 16, z[4] / tiles, z[5] / tiles);
+        }
+#endif
 #ifdef FP_FEW_PROFILE
         CK(cudaMemcpyFromSymbol(z, g_few_prof, sizeof z));
         double const ctas = 7.0 * views.size() * (dim >> 8) * ((rowvecs >> log_twc) / std::max(1, ctPer ? ctPer : (int)(rowvecs >> log_twc)));

@@ -1113,10 +1113,18 @@ def test_headline_size_multi_pass_operators_sampled_rows(kind):
     op = fp.PauliOp(h, strings, ctx=ctx)
     ctx.set_coset_few(1)
     l0 = ctx.launch_count
+    ctx.coset_kernels_used(reset=True)
     out = op.apply(psi)
     launches = ctx.launch_count - l0
-    # the launch path: one pass per rank-8 span of x-masks (few: 1, random: 8; the chains need 2-3 passes)
+    used = ctx.coset_kernels_used()
+    # the launch path: one pass per rank-8 span of x-masks (few: 1, random: 8; the chains need 2-3 passes) on the
+    # kernels the design names: K3f (4) for the 8-mask pass, K3i (16) for the single-string passes of the random
+    # operator, K3g (8) for the chains
     assert launches == {"few_group": 1, "random": 8}.get(kind, launches) and 1 <= launches <= 8
+    if kind in ("few_group", "random"):
+        assert used == {"few_group": 4, "random": 16}[kind], used
+    else:
+        assert used & 8 and not used & 1, used  # K3g, plus K3e / K3f for a last pass with <= 8 masks
     masks = [orc.masks(s) for s in strings]
     phase = np.array([1, -1j, -1, 1j])
     rng = np.random.default_rng(3)
@@ -1136,7 +1144,7 @@ def test_headline_size_multi_pass_operators_sampled_rows(kind):
     # the same call with the few-mask kernels switched off (general coset kernel) and without the TMA-fed variant
     # (for the chains the general kernel prefers wider cosets, i.e. another pass structure and summation order: there
     # the two results agree to rounding, not bit for bit)
-    for mode in (0, 2):
+    for mode in (0, 2, 3):
         ctx.set_coset_few(mode)
         other = op.apply(psi)
         for r0 in (0, dim // 2 - 4096, dim - 8192):
@@ -1243,6 +1251,51 @@ def test_many_mask_tma_kernel_against_general_coset_kernel(dtype, n, B, S, w):
     fp._check(fp.lib.fp_op_apply(ctx._h, op._plan(dtype), C.c_void_p(acc.ptr), C.c_void_p(d_psi.ptr), C.c_size_t(2**n),
                                  C.c_size_t(B), C.c_int(1)))
     ctx.sync()
+    assert rel_err(acc.get(), out0.astype(np.complex128) + ref) < tol(dtype)
+    ctx.set_coset(1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,B,S", [(16, 96, 8), (16, 128, 5), (17, 64, 20), (14, 512, 13), (18, 32, 3)])
+def test_direct_store_tma_kernel_single_string_masks(dtype, n, B, S):
+    """K3i (coset_dir_tma_kernel: TMA-fed, direct stores, sign bits instead of row factors) on passes whose x-masks
+    carry one string each -- i.i.d. random strings: against the oracle, bit-identical to the few-mask kernels (K3e /
+    K3f) and to the general coset kernel it replaces, read-modify-write passes (S > 8 needs several), the accumulating
+    form, and the launch path."""
+    import ctypes as C
+
+    rng = np.random.default_rng(97 * n + B + S)
+    ctx = fp.default_context()
+    strings = rand_strings(rng, n, S)
+    assert len({orc.masks(s)[0] for s in strings}) == S  # all x-masks different
+    h = (rng.uniform(-1, 1, S) + 1j * rng.uniform(-1, 1, S)).astype(dtype)
+    psi = rand_states(rng, 2**n, B, dtype)
+    d_psi = ctx.to_device(psi)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    ref = ORC.op_apply(strings, h.astype(np.complex128), psi.astype(np.complex128), par=True)
+    ctx.set_coset(2, 4, 8)  # rank-8 tiles of 16 vectors per row: the shape the TMA-fed kernels take
+    res = []
+    for mode in (1, 3, 0):
+        ctx.set_coset_few(mode)
+        ctx.coset_kernels_used(reset=True)
+        got = op.apply(d_psi).get()
+        used = ctx.coset_kernels_used()
+        assert rel_err(got, ref) < tol(dtype)
+        if mode == 1:
+            assert used == 16, used
+        else:
+            assert used & 16 == 0, used
+        res.append(got)
+    np.testing.assert_array_equal(res[0], res[1])
+    np.testing.assert_array_equal(res[0], res[2])
+    ctx.set_coset_few(1)
+    out0 = rand_states(rng, 2**n, B, dtype)
+    acc = ctx.to_device(out0)
+    ctx.coset_kernels_used(reset=True)
+    fp._check(fp.lib.fp_op_apply(ctx._h, op._plan(dtype), C.c_void_p(acc.ptr), C.c_void_p(d_psi.ptr), C.c_size_t(2**n),
+                                 C.c_size_t(B), C.c_int(1)))
+    ctx.sync()
+    assert ctx.coset_kernels_used() == 16
     assert rel_err(acc.get(), out0.astype(np.complex128) + ref) < tol(dtype)
     ctx.set_coset(1)
 
