@@ -48,6 +48,10 @@ __device__ unsigned long long g_dir_prof[8];
 
 constexpr int kDirMaxMasks = 32;           // x-masks (= strings) of one pass
 constexpr int kDirConsumerWarps = 16;
+#ifndef FP_DIR_NPROD
+#define FP_DIR_NPROD 1
+#endif
+constexpr int kDirProducerWarps = FP_DIR_NPROD; // live warps of the producer warpgroup (1, 2 or 4): each issues 64 / n gather4 per tile
 constexpr int kDirThreads = kDirConsumerWarps * 32 + 128; // + the producer warpgroup (one live warp, see K3f)
 
 // One pass as kernel parameters (constant bank): per x-mask the coefficient (times (-i)^nY), the full z-mask (sign of
@@ -60,6 +64,16 @@ template <typename T> struct DirStrings
     uint32_t zl[kDirMaxMasks];
     uint32_t n;
 };
+
+// flips the sign of v when bit 31 of t is set
+__device__ __forceinline__ double dir_flip(double v, uint32_t t)
+{
+    return __hiloint2double(__double2hiint(v) ^ static_cast<int>(t & 0x80000000u), __double2loint(v));
+}
+__device__ __forceinline__ float dir_flip(float v, uint32_t t)
+{
+    return __int_as_float(__float_as_int(v) ^ static_cast<int>(t & 0x80000000u));
+}
 
 template <typename T, int EPV, int NCH, int IB = 4> // NCH = ceil(n / 8): the mask loop is unrolled; IB row pairs at a time
 __global__ void __launch_bounds__(kDirThreads, 1)
@@ -98,9 +112,9 @@ __global__ void __launch_bounds__(kDirThreads, 1)
     {
         // ------------------------------------------------ producer warpgroup: hands its registers to the consumers
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (tid >= kDirConsumerWarps * 32 + 32)
+        if (tid >= kDirConsumerWarps * 32 + 32 * kDirProducerWarps)
             return;
-        uint32_t const lane = tid & 31u;
+        uint32_t const lane = tid & 31u, pw = (tid >> 5) - kDirConsumerWarps;
         uint64_t p_coset = 0;
         uint32_t p_ct = 0, p_base = 0;
 #ifdef FP_DIR_PROFILE
@@ -121,7 +135,7 @@ __global__ void __launch_bounds__(kDirThreads, 1)
                 p_base = static_cast<uint32_t>(deposit_bits(p_coset, pass.nonpivot_mask));
             }
             uint32_t const ct = p_ct, base = p_base;
-            if (lane == 0)
+            if (lane == 0 && pw == 0)
                 few_mbar_expect_tx(&s_full[buf], static_cast<uint32_t>(kFewTmaTile));
             __syncwarp();
             int const c0 = static_cast<int>(ct) * TWC * static_cast<int>(16 / sizeof(T));
@@ -129,6 +143,10 @@ __global__ void __launch_bounds__(kDirThreads, 1)
             for (int h = 0; h < 2; ++h)
             {
                 uint32_t const op = lane + 32 * h; // rows 4*op .. 4*op+3
+                if (kDirProducerWarps == 2 && static_cast<uint32_t>(h) != pw)
+                    continue;
+                if (kDirProducerWarps == 4 && (static_cast<uint32_t>(h) != (pw >> 1) || ((lane >> 4) != (pw & 1u))))
+                    continue;
                 few_tma_gather4(smem_dt + buf * kFewTmaTile + (static_cast<size_t>(op) << (ROW_SHIFT + 2)), &tm_in, c0,
                                 base ^ s_comb[4 * op], base ^ s_comb[4 * op + 1], base ^ s_comb[4 * op + 2],
                                 base ^ s_comb[4 * op + 3], &s_full[buf]);
@@ -176,7 +194,6 @@ __global__ void __launch_bounds__(kDirThreads, 1)
     uint32_t buf = 0, round = 0;
     for (uint64_t t = t0; t < t1; ++t)
     {
-        unsigned char const *const tb = smem_dt + buf * kFewTmaTile;
         if (t == t0 || ++ct == nColTiles)
         {
             coset = t == t0 ? t0 / nColTiles : coset + 1;
@@ -228,7 +245,7 @@ __global__ void __launch_bounds__(kDirThreads, 1)
             for (int b = 0; b < IB; ++b)
             {
                 uint32_t const l = 2u * (warp + kDirConsumerWarps * (i0 + b)) + half;
-                own[b] = (l << ROW_SHIFT) | col_off;
+                own[b] = buf * static_cast<uint32_t>(kFewTmaTile) + ((l << ROW_SHIFT) | col_off); // offset in the ring
                 sgn[b] = sl[i0 + b] ^ pbm;
 #pragma unroll
                 for (int e = 0; e < EPV; ++e)
@@ -244,10 +261,10 @@ __global__ void __launch_bounds__(kDirThreads, 1)
                     int const g = g2 * 2 + k;
                     if (static_cast<uint32_t>(g) < ng)
                     {
-                        uint32_t const xo = strs.xl[g] << ROW_SHIFT;
+                        uint32_t const xo = strs.xl[g] << ROW_SHIFT; // < 64 KiB: the XOR stays inside the buffer
 #pragma unroll
                         for (int b = 0; b < IB; ++b)
-                            v[k][b] = *reinterpret_cast<Vec const *>(tb + (own[b] ^ xo));
+                            v[k][b] = *reinterpret_cast<Vec const *>(smem_dt + (own[b] ^ xo));
                     }
                 }
 #pragma unroll
@@ -256,14 +273,19 @@ __global__ void __launch_bounds__(kDirThreads, 1)
                     int const g = g2 * 2 + k;
                     if (static_cast<uint32_t>(g) < ng)
                     {
+                        // +-c_g psi = c_g (+-psi): the coefficient stays a constant-bank operand of the DFMAs, the sign
+                        // bit of the row goes into the gathered value (one shift + one LOP3 per real component)
+                        Cx<T> const c = strs.c[g];
 #pragma unroll
                         for (int b = 0; b < IB; ++b)
                         {
-                            uint32_t const odd = (sgn[b] >> g) & 1u;
-                            Cx<T> const d{flip_sign(strs.c[g].re, odd), flip_sign(strs.c[g].im, odd)};
+                            uint32_t const t = sgn[b] << (31 - g);
 #pragma unroll
                             for (int e = 0; e < EPV; ++e)
-                                cfma(acc[b][e], d, v[k][b].e[e]);
+                            {
+                                Cx<T> const w{dir_flip(v[k][b].e[e].re, t), dir_flip(v[k][b].e[e].im, t)};
+                                cfma(acc[b][e], c, w);
+                            }
                         }
                     }
                 }
