@@ -60,6 +60,21 @@ def test_sass_carries_the_blackwell_instructions_the_design_claims():
         assert mnemonic in sass, f"{mnemonic} not found in the SASS of {LIB}"
 
 
+def test_direct_store_coset_kernel_has_no_staging_in_its_sass():
+    """K3i (coset_dir_tma_kernel): the tile arrives by TMA gather4, the gathers are LDS.128, the
+    results leave by STG.128 straight from the accumulators (old rows by LDG.128 after an L2 prefetch) -- no
+    shared-memory staging store and no barrier among the consumer warps (only the start-up __syncthreads)."""
+    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    parts = sass.split("Function : ")
+    k3i = [p for p in parts if "coset_dir_tma_kernelIdLi1ELi1ELi4" in p.split("\n", 1)[0]]
+    assert len(k3i) == 1, "complex128 instance of coset_dir_tma_kernel not found"
+    body = k3i[0]
+    for mnemonic in ("UTMALDG.2D.GATHER4", "LDS.128", "STG.E.128", "LDG.E.128", "CCTL.E.PF2", "USETMAXREG", "SYNCS"):
+        assert mnemonic in body, f"{mnemonic} not found in coset_dir_tma_kernel"
+    assert "STS.128" not in body and "STS.64" not in body
+    assert body.count("BAR.SYNC") == 1
+
+
 def test_no_gpu_fails_loudly(lib):
     import torch
 
