@@ -99,21 +99,23 @@ int launch_rcoset(fp_ctx *ctx, RcPassView<T> const &view, uint64_t n_cosets, uin
     return FP_OK;
 }
 
-// K3d (dcoset.cuh): FP64 tensor-core dense-coset kernel, complex128 apply, rank 4 (one warp per coset) or 5 (two)
-template <int RR, int WPC, int PFD, int MODE>
-int launch_dcoset(fp_ctx *ctx, RcPassView<double> const &view, uint32_t n_strings, uint64_t n_cosets, uint64_t rowvecs,
+// K3d (dcoset.cuh): FP64 tensor-core dense-coset kernel, rank 4 (one warp per coset) or 5 (two); complex128 batches,
+// and complex64 batches widened to double in registers (two columns per 16-byte vector)
+template <int RR, int WPC, int PFD, int MODE, typename T>
+int launch_dcoset(fp_ctx *ctx, RcPassView<T> const &view, uint32_t n_strings, uint64_t n_cosets, uint64_t rowvecs,
                   void const *in, void *out, int beta, uint64_t B)
 {
     using Cfg = DcosetCfg<RR, WPC>;
-    constexpr size_t smem = MODE == 1 ? Cfg::smem_expval : Cfg::smem;
+    constexpr int EPV = sizeof(T) == 4 ? 2 : 1;
+    constexpr size_t smem = MODE == 1 ? Cfg::smem_expval(EPV) : Cfg::smem;
     static int resident = 0; // CTAs per SM (per template instance): the kernel is persistent
     static PerDevice configured;
     if (!configured.done(ctx->device))
     {
-        FP_CU(cudaFuncSetAttribute(dcoset_kernel<RR, WPC, PFD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        FP_CU(cudaFuncSetAttribute(dcoset_kernel<RR, WPC, PFD, MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));
         int nb = 0;
-        FP_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dcoset_kernel<RR, WPC, PFD, MODE>, Cfg::NT, smem));
+        FP_CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dcoset_kernel<RR, WPC, PFD, MODE, T>, Cfg::NT, smem));
         resident = std::max(1, nb);
         configured.set(ctx->device);
     }
@@ -123,15 +125,15 @@ int launch_dcoset(fp_ctx *ctx, RcPassView<double> const &view, uint32_t n_string
     uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
     if (MODE == 1)
         FP_TRY(ctx->partials.ensure(gx * Bpad * sizeof(Cx<double>)));
-    dcoset_kernel<RR, WPC, PFD, MODE><<<dim3(static_cast<unsigned>(gx), ny), Cfg::NT, smem, ctx->stream>>>(
-        view, n_strings, n_cosets, rowvecs, static_cast<CVec<double, 1> const *>(in),
-        MODE == 1 ? nullptr : static_cast<CVec<double, 1> *>(out), beta, static_cast<Cx<double> *>(ctx->partials.p), Bpad);
+    dcoset_kernel<RR, WPC, PFD, MODE, T><<<dim3(static_cast<unsigned>(gx), ny), Cfg::NT, smem, ctx->stream>>>(
+        view, n_strings, n_cosets, rowvecs, static_cast<CVec<T, EPV> const *>(in),
+        MODE == 1 ? nullptr : static_cast<CVec<T, EPV> *>(out), beta, static_cast<Cx<double> *>(ctx->partials.p), Bpad);
     ctx->launches++;
     if (MODE == 1)
     {
         unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
-        finalize_complex_kernel<double><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
-            static_cast<Cx<double> const *>(ctx->partials.p), gx, Bpad, B, static_cast<Cx<double> *>(out), beta);
+        finalize_complex_kernel<double, T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
+            static_cast<Cx<double> const *>(ctx->partials.p), gx, Bpad, B, static_cast<Cx<T> *>(out), beta);
         ctx->launches++;
     }
     return FP_OK;
@@ -154,9 +156,10 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
     if (rowvecs < 4 && ctx->rcoset_mode != 2)
         return FP_OK; // rows shorter than 64 bytes: coalescing must come from the row index (shared-memory tiles)
     int const rr = std::min(n_qubits, std::max(2, op.x_rank)); // 2-row threads keep too few bytes in flight
-    if constexpr (sizeof(T) == 8)
     {
-        // ranks 4 and 5 are GEMM-shaped per coset (16x16 / 32x32 complex): FP64 tensor cores
+        // ranks 4 and 5 are GEMM-shaped per coset (16x16 / 32x32 complex): FP64 tensor cores (complex64 batches are
+        // widened in registers: measured at 20 qubits x 64 complex64, all Paulis on 4 / 5 qubits took 0.37 / 1.53 ms on
+        // the SIMT kernels, bound by their shared-memory traffic)
         // The tensor-core form costs 2^rr complex FMAs per amplitude however few of the 2^rr coset masks occur; the
         // SIMT forms cost one per occurring mask.  Measured at 20 qubits x 64 columns (scripts/dispatch_sweep.py,
         // profiles/r01s3_dispatch_sweep.txt): rank 4 -- DMMA 0.45 ms apply / 0.53 ms expectation value against
@@ -164,7 +167,10 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
         // kernel at 4 / 8 / 12 / 16 masks; rank 5 -- DMMA 0.82-0.94 ms against 0.49 / 0.58 / 0.68 / 0.81 / 1.09 ms for
         // the shared-memory coset kernel at 5 / 8 / 12 / 16 / 24 masks.
         size_t const n_masks = op.host.gx.size();
-        bool const dense_enough = rr == 4 ? n_masks > (MODE == 1 ? 12u : 8u) : n_masks > 16u;
+        // complex64 batches: rank 5 only -- at rank 4 the SIMT register kernel is as fast (all 256 Paulis on 4 qubits,
+        // 20 q x 64 complex64: 0.37 / 0.37 ms apply / expectation value against 0.39 / 0.48 ms here), at rank 5 the
+        // tensor-core form halves the time (all 1024 Paulis on 5 qubits: 1.53 / 1.61 -> 0.77 / 0.92 ms)
+        bool const dense_enough = rr == 4 ? (sizeof(T) == 8 && n_masks > (MODE == 1 ? 12u : 8u)) : n_masks > 16u;
         if ((ctx->dcoset == 2 || (ctx->dcoset == 1 && dense_enough)) && (rr == 4 || rr == 5) && rowvecs >= 8)
         {
             typename DeviceOp<T>::RcPlanDev const *dplan = nullptr;
@@ -172,9 +178,9 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
             uint64_t const nc = 1ull << (n_qubits - rr);
             uint32_t const ns = static_cast<uint32_t>(op.host.sz.size());
             if (rr == 4)
-                FP_TRY((launch_dcoset<4, 1, 4, MODE>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta, B)));
+                FP_TRY((launch_dcoset<4, 1, 4, MODE, T>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta, B)));
             else
-                FP_TRY((launch_dcoset<5, 2, 2, MODE>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta, B)));
+                FP_TRY((launch_dcoset<5, 2, 2, MODE, T>(ctx, dplan->view, ns, nc, rowvecs, in, out, beta, B)));
             *used = true;
             return FP_OK;
         }

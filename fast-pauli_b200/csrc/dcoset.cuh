@@ -16,7 +16,12 @@
 //     pair exchange per row tile lets every STG.128 instruction write whole 32-byte sectors.
 // WPC warps share one coset: each owns ROWS/8/WPC row tiles of the output and loads the full input tile.
 //
-// Covers PauliOp::apply (PO:399-468) / SummedPauliOp::apply (SPO:277-349) for std::complex<double>.
+// Covers PauliOp::apply (PO:399-468) / SummedPauliOp::apply (SPO:277-349) for std::complex<double> -- and, through the
+// TIO = float instance, for std::complex<float> batches: the 16-byte load then holds TWO batch columns, which feed two
+// n-tiles of MMAs (even / odd columns) after an exact float -> double conversion; arithmetic and row factors stay
+// FP64 and the result is rounded to float once, in the store.  The complex64 SIMT forms of the same operators are
+// bound by the load/store unit (all 1024 Paulis on 5 qubits, 20 q x 64: 1.53 ms through the shared-memory coset
+// kernel against 0.93 ms for the SAME operator on a complex128 batch of twice the bytes through this kernel).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -32,6 +37,26 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
+
+// batch element type of the global arrays: the 16-byte vector of one lane and the n-tiles (batch columns) it carries
+template <typename TIO> struct DcIo;
+template <> struct DcIo<double>
+{
+    using V = double2;
+    static constexpr int NH = 1;
+};
+template <> struct DcIo<float>
+{
+    using V = float4;
+    static constexpr int NH = 2;
+};
+__device__ __forceinline__ double dc_re(double2 const &v, int) { return v.x; }
+__device__ __forceinline__ double dc_im(double2 const &v, int) { return v.y; }
+__device__ __forceinline__ double dc_re(float4 const &v, int h) { return h ? v.z : v.x; }
+__device__ __forceinline__ double dc_im(float4 const &v, int h) { return h ? v.w : v.y; }
+template <typename V> __device__ __forceinline__ V dc_zero();
+template <> __device__ __forceinline__ double2 dc_zero<double2>() { return make_double2(0, 0); }
+template <> __device__ __forceinline__ float4 dc_zero<float4>() { return make_float4(0, 0, 0, 0); }
 
 // barrier among the WPC warps that share a coset (named barrier 1 + group index; a single warp needs __syncwarp only)
 template <int WPC> __device__ __forceinline__ void group_sync(uint32_t group)
@@ -55,8 +80,12 @@ template <int RR, int WPC> struct DcosetCfg
     static_assert(WPC * 32 >= 2 * ROWS, "the sign transform maps one (local x-mask, re/im) pair to a thread");
     static constexpr int MAX_STAGED = 1024; // strings whose (coefficient, z-mask) are staged in shared memory
     static constexpr size_t smem = tables + MAX_STAGED * (sizeof(Cx<double>) + 8) + (ROWS * ROWS + 1) * 4 + 12;
-    static constexpr int ECOLS = 128; // MODE 1: batch columns per CTA (blockIdx.y picks the range)
-    static constexpr size_t smem_expval = (smem + 15) / 16 * 16 + static_cast<size_t>(WARPS) * ECOLS * sizeof(Cx<double>);
+    static constexpr int ECOLS = 128; // MODE 1: 16-byte batch vectors per CTA (blockIdx.y picks the range)
+    // per-warp column sums: one entry per batch column (two per vector for complex64 batches)
+    static constexpr size_t smem_expval(int nh)
+    {
+        return (smem + 15) / 16 * 16 + static_cast<size_t>(WARPS) * ECOLS * nh * sizeof(Cx<double>);
+    }
     static_assert(RT % WPC == 0 && WARPS % WPC == 0, "warps must split the row tiles evenly");
 };
 
@@ -64,13 +93,15 @@ template <int RR, int WPC> struct DcosetCfg
 // every warp sums conj(psi) . (M_c psi) per batch column over its cosets into a private shared-memory array, the CTA
 // folds its warps at the end and writes one partial row per CTA: partials[blockIdx.x][column] (fixed order:
 // deterministic); blockIdx.y selects a range of ECOLS columns.
-template <int RR, int WPC, int PFD, int MODE>
+template <int RR, int WPC, int PFD, int MODE, typename TIO = double>
 __global__ void __launch_bounds__(128)
-    dcoset_kernel(RcPassView<double> pass, uint32_t n_strings, uint64_t n_cosets, uint64_t rowvecs_total,
-                  CVec<double, 1> const *__restrict__ in, CVec<double, 1> *__restrict__ out, int beta,
-                  Cx<double> *__restrict__ partials, uint32_t Bpad)
+    dcoset_kernel(RcPassView<TIO> pass, uint32_t n_strings, uint64_t n_cosets, uint64_t rowvecs_total,
+                  CVec<TIO, 16 / (2 * sizeof(TIO))> const *__restrict__ in, CVec<TIO, 16 / (2 * sizeof(TIO))> *__restrict__ out,
+                  int beta, Cx<double> *__restrict__ partials, uint32_t Bpad)
 {
     using Cfg = DcosetCfg<RR, WPC>;
+    using V = typename DcIo<TIO>::V;
+    constexpr int NH = DcIo<TIO>::NH;
     constexpr int ROWS = Cfg::ROWS, CPI = Cfg::CPI, PITCH = Cfg::PITCH, RT_OWN = Cfg::RT_OWN, KB = Cfg::KB;
     extern __shared__ __align__(16) unsigned char dc_smem[];
     Cx<double> *Dt = reinterpret_cast<Cx<double> *>(dc_smem); // [CPI][xl][l], rows PITCH entries apart
@@ -80,23 +111,28 @@ __global__ void __launch_bounds__(128)
     uint64_t *s_z = reinterpret_cast<uint64_t *>(s_coef + Cfg::MAX_STAGED);
     uint32_t *s_ustart = reinterpret_cast<uint32_t *>(s_z + Cfg::MAX_STAGED);
     bool const staged = n_strings <= static_cast<uint32_t>(Cfg::MAX_STAGED);
-    Cx<double> const *coefs = pass.scoef;
     uint64_t const *zs = pass.sz;
     uint32_t const *ustart = pass.ustart;
     if (staged)
     {
         for (uint32_t i = threadIdx.x; i < n_strings; i += Cfg::NT)
         {
-            s_coef[i] = pass.scoef[i];
+            Cx<TIO> const c = pass.scoef[i];
+            s_coef[i] = Cx<double>{static_cast<double>(c.re), static_cast<double>(c.im)};
             s_z[i] = pass.sz[i];
         }
         for (uint32_t i = threadIdx.x; i <= ROWS * ROWS; i += Cfg::NT)
             s_ustart[i] = pass.ustart[i];
-        coefs = s_coef;
         zs = s_z;
         ustart = s_ustart;
         __syncthreads();
     }
+    auto coef_at = [&](uint32_t s) {
+        if (staged)
+            return s_coef[s];
+        Cx<TIO> const c = pass.scoef[s];
+        return Cx<double>{static_cast<double>(c.re), static_cast<double>(c.im)};
+    };
 
     uint32_t const tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint32_t const cw = warp / WPC, part = warp % WPC; // coset slot of this warp, its share of the row tiles
@@ -104,12 +140,12 @@ __global__ void __launch_bounds__(128)
     // MODE 1 CTAs work on the column range [col0, col0 + rowvecs); the row pitch is always rowvecs_total
     uint64_t const col0 = MODE == 1 ? static_cast<uint64_t>(blockIdx.y) * Cfg::ECOLS : 0;
     uint64_t const rowvecs = MODE == 1 ? (rowvecs_total - col0 < Cfg::ECOLS ? rowvecs_total - col0 : Cfg::ECOLS) : rowvecs_total;
-    double2 const *in2 = reinterpret_cast<double2 const *>(in) + col0;
-    double2 *out2 = reinterpret_cast<double2 *>(out);
-    Cx<double> *esm = reinterpret_cast<Cx<double> *>(dc_smem + (Cfg::smem + 15) / 16 * 16) + warp * Cfg::ECOLS;
+    V const *in2 = reinterpret_cast<V const *>(in) + col0;
+    V *out2 = reinterpret_cast<V *>(out);
+    Cx<double> *esm = reinterpret_cast<Cx<double> *>(dc_smem + (Cfg::smem + 15) / 16 * 16) + warp * Cfg::ECOLS * NH;
     if (MODE == 1)
     {
-        for (uint32_t i = lane; i < Cfg::ECOLS; i += 32)
+        for (uint32_t i = lane; i < Cfg::ECOLS * NH; i += 32)
             esm[i] = Cx<double>{0, 0};
         __syncwarp();
     }
@@ -134,14 +170,14 @@ __global__ void __launch_bounds__(128)
             rowoff[kb] = (base ^ comb) * rowvecs_total;
         }
         // ---- the first PF input tiles are requested before the factor tables are built: their latency hides there
-        double2 x[PF][KB];
+        V x[PF][KB];
 #pragma unroll
         for (int u = 0; u < PF; ++u)
         {
             uint64_t const col = static_cast<uint64_t>(u) * 8 + lq;
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
-                x[u][kb] = (live && col < rowvecs) ? in2[rowoff[kb] + col] : make_double2(0, 0);
+                x[u][kb] = (live && col < rowvecs) ? in2[rowoff[kb] + col] : dc_zero<V>();
         }
 
         // ---- row factors of this warp group's coset (same two-step build as rcoset.cuh).  Every group of WPC warps
@@ -158,7 +194,7 @@ __global__ void __launch_bounds__(128)
                 uint32_t const s0 = ustart[xz], s1 = ustart[xz + 1];
                 for (uint32_t s = s0; s < s1; ++s)
                 {
-                    Cx<double> const cf = coefs[s];
+                    Cx<double> const cf = coef_at(s);
                     uint32_t const odd = parity64(base & zs[s]);
                     u.re += flip_sign(cf.re, odd);
                     u.im += flip_sign(cf.im, odd);
@@ -236,54 +272,73 @@ __global__ void __launch_bounds__(128)
                     if (nt >= n_tiles)
                         break; // warp-uniform
                     uint64_t const n0 = nt * 8;
-                    double C[2 * RT_OWN][2];
+                    double C[NH][2 * RT_OWN][2];
 #pragma unroll
-                    for (int m = 0; m < 2 * RT_OWN; ++m)
-                        C[m][0] = C[m][1] = 0.0;
+                    for (int h = 0; h < NH; ++h)
+#pragma unroll
+                        for (int m = 0; m < 2 * RT_OWN; ++m)
+                            C[h][m][0] = C[h][m][1] = 0.0;
                     // consecutive MMAs go to different accumulators (the m-tiles), never back to back into one
 #pragma unroll
                     for (int kb = 0; kb < KB; ++kb)
                     {
 #pragma unroll
-                        for (int m = 0; m < 2 * RT_OWN; ++m)
-                            dmma884(C[m][0], C[m][1], A[m][kb], x[u][kb].x);
+                        for (int h = 0; h < NH; ++h)
+                        {
+                            double const xr = dc_re(x[u][kb], h), xi = dc_im(x[u][kb], h);
 #pragma unroll
-                        for (int m = 0; m < 2 * RT_OWN; ++m)
-                            dmma884(C[m][0], C[m][1], A[m][KB + kb], x[u][kb].y);
+                            for (int m = 0; m < 2 * RT_OWN; ++m)
+                                dmma884(C[h][m][0], C[h][m][1], A[m][kb], xr);
+#pragma unroll
+                            for (int m = 0; m < 2 * RT_OWN; ++m)
+                                dmma884(C[h][m][0], C[h][m][1], A[m][KB + kb], xi);
+                        }
                     }
                     if (nt + PF < n_tiles)
                     {
                         uint64_t const col = n0 + PF * 8 + lq;
 #pragma unroll
                         for (int kb = 0; kb < KB; ++kb)
-                            x[u][kb] = col < rowvecs ? in2[rowoff[kb] + col] : make_double2(0, 0);
+                            x[u][kb] = col < rowvecs ? in2[rowoff[kb] + col] : dc_zero<V>();
                     }
                     if (MODE == 1)
                     {
                         // e(col) += sum over this lane's rows of conj(psi(l', col)) * out(l', col); the psi values are
                         // re-read (cache hits: the tile was just loaded), then the 8 row lanes are folded by shuffles
-                        double er[2] = {0, 0}, ei[2] = {0, 0};
+                        double er[2][NH], ei[2][NH];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+#pragma unroll
+                            for (int h = 0; h < NH; ++h)
+                                er[c][h] = ei[c][h] = 0.0;
 #pragma unroll
                         for (int r = 0; r < RT_OWN; ++r)
 #pragma unroll
                             for (int c = 0; c < 2; ++c)
                             {
                                 uint64_t const col = n0 + 2 * lr + c;
-                                double2 const a = col < rowvecs ? in2[orow[r] + col] : make_double2(0, 0);
-                                double const o_re = C[r][c], o_im = C[RT_OWN + r][c];
-                                er[c] = fma(a.x, o_re, er[c]);
-                                er[c] = fma(a.y, o_im, er[c]);
-                                ei[c] = fma(a.x, o_im, ei[c]);
-                                ei[c] = fma(-a.y, o_re, ei[c]);
+                                V const a = col < rowvecs ? in2[orow[r] + col] : dc_zero<V>();
+#pragma unroll
+                                for (int h = 0; h < NH; ++h)
+                                {
+                                    double const ar = dc_re(a, h), ai = dc_im(a, h);
+                                    double const o_re = C[h][r][c], o_im = C[h][RT_OWN + r][c];
+                                    er[c][h] = fma(ar, o_re, er[c][h]);
+                                    er[c][h] = fma(ai, o_im, er[c][h]);
+                                    ei[c][h] = fma(ar, o_im, ei[c][h]);
+                                    ei[c][h] = fma(-ai, o_re, ei[c][h]);
+                                }
                             }
 #pragma unroll
                         for (int off = 4; off < 32; off <<= 1)
 #pragma unroll
                             for (int c = 0; c < 2; ++c)
-                            {
-                                er[c] += __shfl_xor_sync(0xffffffffu, er[c], off);
-                                ei[c] += __shfl_xor_sync(0xffffffffu, ei[c], off);
-                            }
+#pragma unroll
+                                for (int h = 0; h < NH; ++h)
+                                {
+                                    er[c][h] += __shfl_xor_sync(0xffffffffu, er[c][h], off);
+                                    ei[c][h] += __shfl_xor_sync(0xffffffffu, ei[c][h], off);
+                                }
                         if (lq == 0)
                         {
 #pragma unroll
@@ -292,20 +347,26 @@ __global__ void __launch_bounds__(128)
                                 uint64_t const col = n0 + 2 * lr + c;
                                 if (col < rowvecs)
                                 {
-                                    esm[col].re += er[c];
-                                    esm[col].im += ei[c];
+#pragma unroll
+                                    for (int h = 0; h < NH; ++h)
+                                    {
+                                        esm[col * NH + h].re += er[c][h];
+                                        esm[col * NH + h].im += ei[c][h];
+                                    }
                                 }
                             }
                         }
                     }
                     else
                     {
-                    // lane holds rows l' (real: C[r], imaginary: C[RT_OWN + r]) x columns n0 + 2*lr + {0, 1}
+                    // lane holds rows l' (real: C[.][r], imaginary: C[.][RT_OWN + r]) x vectors n0 + 2*lr + {0, 1}
+                    if constexpr (NH == 1)
+                    {
 #pragma unroll
                     for (int r = 0; r < RT_OWN; ++r)
                     {
-                        double2 first = make_double2(C[r][0], C[RT_OWN + r][0]);  // column 2*lr
-                        double2 second = make_double2(C[r][1], C[RT_OWN + r][1]); // column 2*lr + 1
+                        double2 first = make_double2(C[0][r][0], C[0][RT_OWN + r][0]);  // column 2*lr
+                        double2 second = make_double2(C[0][r][1], C[0][RT_OWN + r][1]); // column 2*lr + 1
                         // pair exchange: even lanes end up with columns (4p, 4p+2), odd lanes with (4p+1, 4p+3), so
                         // each store instruction writes adjacent columns from adjacent lanes = whole 32-byte sectors
                         bool const oddl = lr & 1u;
@@ -318,10 +379,10 @@ __global__ void __launch_bounds__(128)
                         uint64_t const ca = n0 + 2 * (lr & ~1u) + (lr & 1u), cb = ca + 2;
                         if (ca < rowvecs)
                         {
-                            double2 *dst = &out2[orow[r] + ca];
+                            V *dst = &out2[orow[r] + ca];
                             if (beta)
                             {
-                                double2 const o = *dst;
+                                V const o = *dst;
                                 va.x += o.x;
                                 va.y += o.y;
                             }
@@ -329,15 +390,45 @@ __global__ void __launch_bounds__(128)
                         }
                         if (cb < rowvecs)
                         {
-                            double2 *dst = &out2[orow[r] + cb];
+                            V *dst = &out2[orow[r] + cb];
                             if (beta)
                             {
-                                double2 const o = *dst;
+                                V const o = *dst;
                                 vb.x += o.x;
                                 vb.y += o.y;
                             }
                             *dst = vb;
                         }
+                    }
+                    }
+                    else
+                    {
+                        // complex64: both columns of a 16-byte vector sit in this lane (n-tiles 0 / 1), the lane's two
+                        // vectors are neighbours: 32 contiguous bytes per lane, 128 per row and instruction pair
+#pragma unroll
+                        for (int r = 0; r < RT_OWN; ++r)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                            {
+                                uint64_t const col = n0 + 2 * lr + c;
+                                if (col < rowvecs)
+                                {
+                                    V *dst = &out2[orow[r] + col];
+                                    double v0 = C[0][r][c], v1 = C[0][RT_OWN + r][c], v2 = C[NH - 1][r][c],
+                                           v3 = C[NH - 1][RT_OWN + r][c];
+                                    if (beta)
+                                    {
+                                        V const o = *dst;
+                                        v0 += dc_re(o, 0);
+                                        v1 += dc_im(o, 0);
+                                        v2 += dc_re(o, 1);
+                                        v3 += dc_im(o, 1);
+                                    }
+                                    float4 const w = make_float4(static_cast<float>(v0), static_cast<float>(v1),
+                                                                 static_cast<float>(v2), static_cast<float>(v3));
+                                    *reinterpret_cast<float4 *>(dst) = w;
+                                }
+                            }
                     }
                     }
                 }
@@ -349,16 +440,16 @@ __global__ void __launch_bounds__(128)
     {
         __syncthreads();
         Cx<double> const *all = reinterpret_cast<Cx<double> const *>(dc_smem + (Cfg::smem + 15) / 16 * 16);
-        for (uint32_t i = tid; i < rowvecs; i += Cfg::NT)
+        for (uint32_t i = tid; i < rowvecs * NH; i += Cfg::NT)
         {
             Cx<double> sum{0, 0};
 #pragma unroll
             for (int w = 0; w < Cfg::WARPS; ++w)
             {
-                sum.re += all[w * Cfg::ECOLS + i].re;
-                sum.im += all[w * Cfg::ECOLS + i].im;
+                sum.re += all[w * Cfg::ECOLS * NH + i].re;
+                sum.im += all[w * Cfg::ECOLS * NH + i].im;
             }
-            partials[static_cast<uint64_t>(blockIdx.x) * Bpad + col0 + i] = sum;
+            partials[static_cast<uint64_t>(blockIdx.x) * Bpad + col0 * NH + i] = sum;
         }
     }
 }

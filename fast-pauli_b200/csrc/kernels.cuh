@@ -346,10 +346,10 @@ __device__ __forceinline__ double fin_reduce_y(double v, double (*sm)[kFinX + 1]
 }
 
 // out[t] = (beta ? out[t] : 0) + sum_rb partials[rb][t]
-template <typename T>
+template <typename T, typename TO = T> // TO: element type of the result (partials may be kept in double for float batches)
 __global__ void __launch_bounds__(kFinX *kFinY)
     finalize_complex_kernel(Cx<T> const *__restrict__ partials, uint64_t nRowBlocks, uint32_t Bpad, uint64_t B,
-                            Cx<T> *__restrict__ out, int beta)
+                            Cx<TO> *__restrict__ out, int beta)
 {
     __shared__ double sm[kFinY][kFinX + 1];
     uint64_t const t = blockIdx.x * static_cast<uint64_t>(kFinX) + threadIdx.x;
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(kFinX *kFinY)
             re += out[t].re;
             im += out[t].im;
         }
-        out[t] = Cx<T>{static_cast<T>(re), static_cast<T>(im)};
+        out[t] = Cx<TO>{static_cast<TO>(re), static_cast<TO>(im)};
     }
 }
 

@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--log-nt", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--c128", action="store_true", help="cfg4w / cfg4e in complex128 instead of complex64")
+    ap.add_argument("--c64", action="store_true", help="span* / local* in complex64 instead of complex128")
     a = ap.parse_args()
     ctx = fp.Context(0)
     ctx.set_coset(a.coset, a.log_twc, a.log_nt)
@@ -103,17 +104,19 @@ def main():
                         x ^= gens[j]
                 z = int(rng.integers(0, 1 << n))
                 strings.append("".join("IZXY"[2 * ((x >> (n - 1 - q)) & 1) + ((z >> (n - 1 - q)) & 1)] for q in range(n)))
-        h = rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))
-        psi = ctx.uniform((1 << n, B), np.complex128)
+        cdt = np.complex64 if a.c64 else np.complex128
+        h = (rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))).astype(cdt)
+        psi = ctx.uniform((1 << n, B), cdt)
         op = fp.PauliOp(h, strings, ctx=ctx)
-        y = ctx.empty((1 << n, B), np.complex128)
-        ev = ctx.empty((B,), np.complex128)
-        plan = op._plan(np.complex128)
+        y = ctx.empty((1 << n, B), cdt)
+        ev = ctx.empty((B,), cdt)
+        plan = op._plan(cdt)
         ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
         ms2 = timed(ctx, lambda: fp.lib.fp_op_expval(ctx._h, plan, vp(ev.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
         amps = (1 << n) * B
-        print(f"{a.case}: apply {ms:.3f} ms  {amps*32/ms/1e6:.0f} GB/s | expval {ms2:.3f} ms {amps*16/ms2/1e6:.0f} GB/s "
-              f"groups={op.plan_info()['n_x_groups']}")
+        bpa = 16 if a.c64 else 32
+        print(f"{a.case}{' c64' if a.c64 else ''} B={B}: apply {ms:.3f} ms  {amps*bpa/ms/1e6:.0f} GB/s | expval {ms2:.3f} ms "
+              f"{amps*bpa/2/ms2/1e6:.0f} GB/s groups={op.plan_info()['n_x_groups']}")
     elif a.case in ("heis20", "tfim20"):
         # nearest-neighbour chain Hamiltonians on 20 qubits: x-masks of rank ~20 but weight <= 2
         n, B = 20, a.batch or 64

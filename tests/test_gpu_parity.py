@@ -677,6 +677,61 @@ def test_dense_coset_tensor_core_kernel(rank, n, B):
         assert rel_err(opf.expectation_value(psi), ORC.op_expval(few, hf, psi, par=True)) < 1e-12
 
 
+@pytest.mark.parametrize("rank", [4, 5])
+@pytest.mark.parametrize("n,B", [(7, 16), (9, 34), (12, 300), (10, 18), (8, 1100), (14, 64)])
+def test_dense_coset_tensor_core_kernel_complex64(rank, n, B):
+    """K3d on complex64 batches (TIO = float instance: two columns per 16-byte vector widened to double in registers,
+    FP64 tensor-core arithmetic, one rounding to float in the store): one launch for apply, kernel + finaliser for the
+    expectation value; parity vs the oracle at the complex64 tolerance, accumulate forms, partial column tiles, and
+    agreement with the SIMT kernels."""
+    import ctypes as C
+    import os as _os
+
+    dtype = np.complex64
+    _os.environ["FASTPAULI_DCOSET"] = "2"
+    try:
+        ctx = fp.Context(0)
+    finally:
+        del _os.environ["FASTPAULI_DCOSET"]
+    rng = np.random.default_rng(9000 + 10 * rank + n)
+    S = 90
+    strings = _span_strings(rng, n, rank, S)
+    strings[-1] = strings[0]
+    strings[-2] = "Z" * n
+    h = (rand_states(rng, S, None) * 2 - (1 + 1j)).astype(dtype)
+    psi = rand_states(rng, 2**n, B, dtype)
+    base = rand_states(rng, 2**n, B, dtype)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    l0 = ctx.launch_count
+    got = op.apply(psi)
+    assert ctx.launch_count - l0 == 1
+    assert got.dtype == dtype
+    ref = ORC.op_apply(strings, h.astype(np.complex128), psi.astype(np.complex128), par=True)
+    assert rel_err(got, ref) < tol(dtype)
+    # FP64 arithmetic on exactly widened inputs, one rounding at the end: within a few float ulps of the double result
+    assert rel_err(got, ref) < 5e-7
+    out = base.copy()
+    rc = fp.lib.fp_op_apply(ctx._h, op._plan(dtype), C.c_void_p(out.ctypes.data), C.c_void_p(psi.ctypes.data),
+                            C.c_size_t(2**n), C.c_size_t(B), C.c_int(1))
+    assert rc == 0
+    assert rel_err(out, base.astype(np.complex128) + ref) < tol(dtype)
+    l0 = ctx.launch_count
+    ev = op.expectation_value(psi)
+    assert ctx.launch_count - l0 == 2  # tensor-core kernel (MODE 1) + finaliser
+    assert_parity(ev, ORC.op_expval, dtype, strings, h, psi)
+    ev_acc = np.full(B, 1.5 - 2j, dtype=dtype)
+    rc = fp.lib.fp_op_expval(ctx._h, op._plan(dtype), C.c_void_p(ev_acc.ctypes.data), C.c_void_p(psi.ctypes.data),
+                             C.c_size_t(2**n), C.c_size_t(B), C.c_int(1))
+    assert rc == 0
+    assert rel_err(ev_acc - dtype(1.5 - 2j), ev) < tol(dtype)
+    _os.environ["FASTPAULI_DCOSET"] = "0"
+    try:
+        ctx0 = fp.Context(0)
+    finally:
+        del _os.environ["FASTPAULI_DCOSET"]
+    assert rel_err(fp.PauliOp(h, strings, ctx=ctx0).apply(psi), got) < tol(dtype)
+
+
 def test_register_coset_default_path_headline_shape():
     """The north-star headline shape at reduced batch: 64 strings over 8 x-masks (rank 3) at 16 qubits takes the
     register-resident kernel by default; a diagonal-only operator (rank 0) does too."""
