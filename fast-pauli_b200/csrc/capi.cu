@@ -241,9 +241,26 @@ int try_rcoset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void
     if (MODE == 1)
     {
         unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
-        finalize_complex_kernel<T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
-            static_cast<Cx<T> const *>(ctx->partials.p), n_blocks, Bpad, B, static_cast<Cx<T> *>(out), beta);
-        ctx->launches++;
+        if (n_blocks > 2048)
+        {
+            // thousands of partial rows (many small independent CTAs keep HBM busy the way the apply form does): fold
+            // them with a wide first stage -- the single-stage finaliser has only B / 32 CTAs
+            uint64_t const per = (n_blocks + 127) / 128;
+            unsigned const slices = static_cast<unsigned>((n_blocks + per - 1) / per);
+            FP_TRY(ctx->partials2.ensure(static_cast<size_t>(slices) * Bpad * sizeof(Cx<double>)));
+            fold_partials_kernel<T><<<dim3(fgrid, slices), dim3(kFinX, kFinY), 0, ctx->stream>>>(
+                static_cast<Cx<T> const *>(ctx->partials.p), n_blocks, per, Bpad, B,
+                static_cast<Cx<double> *>(ctx->partials2.p));
+            finalize_complex_kernel<double, T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
+                static_cast<Cx<double> const *>(ctx->partials2.p), slices, Bpad, B, static_cast<Cx<T> *>(out), beta);
+            ctx->launches += 2;
+        }
+        else
+        {
+            finalize_complex_kernel<T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
+                static_cast<Cx<T> const *>(ctx->partials.p), n_blocks, Bpad, B, static_cast<Cx<T> *>(out), beta);
+            ctx->launches++;
+        }
     }
     *used = true;
     return FP_OK;
@@ -705,7 +722,7 @@ extern "C"
             return FP_OK;
         DeviceGuard g(ctx->device);
         cudaStreamSynchronize(ctx->stream);
-        for (Scratch *s : {&ctx->stage_in, &ctx->stage_out, &ctx->stage_data, &ctx->partials, &ctx->work_a, &ctx->work_b,
+        for (Scratch *s : {&ctx->stage_in, &ctx->stage_out, &ctx->stage_data, &ctx->partials, &ctx->partials2, &ctx->work_a, &ctx->work_b,
                            &ctx->meta})
             s->release();
         if (ctx->own_stream)

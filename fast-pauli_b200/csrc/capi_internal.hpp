@@ -142,11 +142,11 @@ struct fp_ctx
     bool etile = true;          // packed-FP32 per-string expectation kernel (complex64, 9-12 qubits)
     bool wtile = true;          // dedicated whole-column weighted-apply kernel (complex64, 11-12 qubits)
     int rcoset_mode = 1;        // register-resident coset kernel (x-mask rank <= 4): 0 never, 1 auto, 2 whenever applicable
-    int rc_expval_ctas_per_sm = 16; // MODE 1 grid target: CTAs per SM (each walks n_sets / grid coset sets in turn)
+    int rc_expval_ctas_per_sm = 64; // MODE 1 grid target: CTAs per SM (each walks n_sets / grid coset sets in turn)
     int dcoset = 1;             // FP64 tensor-core dense-coset kernel (complex128, x-mask rank 4 or 5): 0 never,
                                 // 1 when the cost model below prefers it, 2 whenever applicable
     int rcoset_log_nt = 7;      // its CTA size (128 / 256 threads)
-    Scratch stage_in, stage_out, stage_data, partials, work_a, work_b, meta;
+    Scratch stage_in, stage_out, stage_data, partials, partials2, work_a, work_b, meta;
     std::mutex mu;
 };
 

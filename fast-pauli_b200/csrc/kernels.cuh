@@ -376,6 +376,34 @@ __global__ void __launch_bounds__(kFinX *kFinY)
     }
 }
 
+// First stage of a two-stage column sum for long partial lists (thousands of rows: the single-stage finaliser has only
+// B / 32 CTAs): CTA (x, s) adds the rows [s * rowsPerSlice, (s + 1) * rowsPerSlice) of its 32 columns in double and
+// writes slice row s; finalize_complex_kernel<double, T> then folds the slices.  Fixed order: deterministic.
+template <typename T>
+__global__ void __launch_bounds__(kFinX *kFinY)
+    fold_partials_kernel(Cx<T> const *__restrict__ partials, uint64_t nRowBlocks, uint64_t rowsPerSlice, uint32_t Bpad,
+                         uint64_t B, Cx<double> *__restrict__ slices)
+{
+    __shared__ double sm[kFinY][kFinX + 1];
+    uint64_t const t = blockIdx.x * static_cast<uint64_t>(kFinX) + threadIdx.x;
+    uint64_t const r0 = blockIdx.y * rowsPerSlice;
+    uint64_t const r1 = r0 + rowsPerSlice < nRowBlocks ? r0 + rowsPerSlice : nRowBlocks;
+    double re = 0, im = 0;
+    if (t < B)
+    {
+        for (uint64_t rb = r0 + threadIdx.y; rb < r1; rb += kFinY)
+        {
+            Cx<T> p = partials[rb * Bpad + t];
+            re += p.re;
+            im += p.im;
+        }
+    }
+    re = fin_reduce_y(re, sm);
+    im = fin_reduce_y(im, sm);
+    if (threadIdx.y == 0 && t < B)
+        slices[static_cast<uint64_t>(blockIdx.y) * Bpad + t] = Cx<double>{re, im};
+}
+
 // ---------------------------------------------------------------- K2/K4: paired expectation values
 // For strings sharing one x-mask, rows are visited as unordered pairs {i, j = i ^ x} (i has the top bit of x
 // clear), so every amplitude is read ONCE (16 B/amp for complex128 instead of 32):
