@@ -49,12 +49,15 @@ def main():
     ap.add_argument("--log-twc", type=int, default=-1)
     ap.add_argument("--log-nt", type=int, default=0)
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--few", type=int, default=-1, help="fp_ctx_set_coset_few mode (0 general kernel, 1 default dispatch, 2 K3e only, 3 K3e/K3f)")
     ap.add_argument("--c128", action="store_true", help="cfg4w / cfg4e in complex128 instead of complex64")
     ap.add_argument("--c64", action="store_true", help="span* / local* in complex64 instead of complex128")
     a = ap.parse_args()
     ctx = fp.Context(0)
     ctx.set_coset(a.coset, a.log_twc, a.log_nt)
     ctx.set_async(True)
+    if a.few >= 0:
+        ctx.set_coset_few(a.few)
     rng = np.random.default_rng(1234)
     if a.case in ("few20", "rand20", "few20low", "few20one"):
         n, B = 20, a.batch or 64
@@ -79,7 +82,10 @@ def main():
         plan = op._plan(np.complex128)
         ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
         amps = (1 << n) * B
-        print(f"{a.case}: {ms:.3f} ms  {amps*32/ms/1e6:.0f} GB/s algorithmic  groups={op.plan_info()['n_x_groups']}")
+        ev = ctx.empty((B,), np.complex128)
+        ms2 = timed(ctx, lambda: fp.lib.fp_op_expval(ctx._h, plan, vp(ev.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
+        print(f"{a.case}: {ms:.3f} ms  {amps*32/ms/1e6:.0f} GB/s algorithmic  groups={op.plan_info()['n_x_groups']} | "
+              f"expval {ms2:.3f} ms {amps*16/ms2/1e6:.0f} GB/s  kernels_used={ctx.coset_kernels_used()}")
     elif a.case in ("span1", "span2", "span3", "span4", "span5", "local2", "local3", "local4", "local5"):
         # x-masks confined to a GF(2) span of rank r (register-resident coset kernel): 64 strings over 2^r masks;
         # local3 = all 64 Pauli strings on 3 fixed qubits (8 x-masks x 8 z-masks)
