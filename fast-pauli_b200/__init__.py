@@ -189,11 +189,12 @@ class Context:
         _check(lib.fp_ctx_set_pipeline(self._h, C.c_int(bool(enable)), C.c_size_t(min_bytes), C.c_size_t(chunk_bytes)))
 
     def set_coset_few(self, mode: int = 1, column_tiles_per_cta: int = 0) -> None:
-        """Few-mask coset passes (K3e / K3f / K3i): 0 off, 1 automatic, 2 without the TMA-fed kernels, 3 without K3i."""
+        """Few-mask coset passes (K3e / K3f / K3i / K3j): 0 off, 1 automatic, 2 without the TMA-fed kernels, 3 without
+        K3i and K3j, 4 without K3j, 5 automatic with K3j on single-string masks as well (default: K3i)."""
         _check(lib.fp_ctx_set_coset_few(self._h, C.c_int(mode), C.c_int(column_tiles_per_cta)))
 
     def coset_kernels_used(self, reset: bool = True) -> int:
-        """Bit mask of the coset-family kernels launched since the last reset: 1 K3b, 2 K3e, 4 K3f, 8 K3g, 16 K3i."""
+        """Bit mask of the coset-family kernels launched since the last reset: 1 K3b, 2 K3e, 4 K3f, 8 K3g, 16 K3i, 32 K3j."""
         m = C.c_uint32()
         _check(lib.fp_ctx_coset_kernels_used(self._h, C.byref(m), C.c_int(bool(reset))))
         return int(m.value)

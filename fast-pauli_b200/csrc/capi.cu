@@ -685,7 +685,10 @@ extern "C"
         if (char const *env = getenv("FASTPAULI_COSET_WIDE"))
             ctx->coset_wide_cta = atoi(env) != 0;
         if (char const *env = getenv("FASTPAULI_COSET_FEW"))
-            ctx->coset_few = atoi(env);
+        {
+            ctx->coset_few = atoi(env) == 5 ? 1 : atoi(env);
+            ctx->coset_pair_all = atoi(env) == 5;
+        }
         if (char const *env = getenv("FASTPAULI_COSET_FEW_CT"))
             ctx->coset_few_ct = atoi(env);
         if (char const *env = getenv("FASTPAULI_PIPELINE"))
@@ -815,9 +818,10 @@ extern "C"
 
     int fp_ctx_set_coset_few(fp_ctx *ctx, int mode, int column_tiles_per_cta)
     {
-        if (!ctx || mode < 0 || mode > 3 || column_tiles_per_cta < 0)
+        if (!ctx || mode < 0 || mode > 5 || column_tiles_per_cta < 0)
             return set_err(FP_INVALID_ARGUMENT, "bad few-mask coset mode");
-        ctx->coset_few = mode;
+        ctx->coset_few = mode == 5 ? 1 : mode;
+        ctx->coset_pair_all = mode == 5;
         ctx->coset_few_ct = column_tiles_per_cta;
         return FP_OK;
     }

@@ -21,6 +21,7 @@
 #include "coset.cuh"
 #include "coset2.cuh"
 #include "coset3.cuh"
+#include "coset4.cuh"
 #include "rcoset.cuh"
 #include "kernels.cuh"
 #include "pack.hpp"
@@ -132,8 +133,9 @@ struct fp_ctx
     int coset_log_nt = 0;     // 7 or 8 forces the CTA size (128 / 256 threads); 0 = default (256)
     int coset_vpt = 16;       // vectors per thread when the shape is forced (8 or 16)
     bool coset_wide_cta = true; // 512-thread CTAs for the rank-12 weighted-apply tile
-    int coset_few = 1;          // K3e / K3f / K3i for passes with <= 8 x-masks: 0 off, 1 auto, 2 never the TMA, 3 auto without K3i
-                                // kernel (K3f)
+    int coset_few = 1;          // K3e / K3f / K3i / K3j for passes with few x-masks: 0 off, 1 auto, 2 never the TMA-fed
+                                // kernels, 3 auto without K3i / K3j, 4 auto without K3j
+    bool coset_pair_all = false; // K3j also for passes whose masks carry one string each (set by mode 5 = mode 1 + this)
     int coset_few_ct = 0;       // column tiles per CTA of K3e (0 = all of them while the grid still fills the chip)
     bool pipeline = true;       // chunked H2D / kernel / D2H pipeline for large host-resident single-string applies
     size_t pipeline_min_bytes = 128ull << 20, pipeline_chunk_bytes = 32ull << 20;
@@ -182,6 +184,8 @@ template <typename T> struct DeviceOp
         std::shared_ptr<GenStrings<T>> gen;
         // ... and for passes whose x-masks carry one string each (K3i, coset3.cuh): <= 32 masks, <= 30 qubits
         std::shared_ptr<DirStrings<T>> dir;
+        // ... and for passes of eight independent x-masks with <= 64 strings (K3j, coset4.cuh): paired-mask basis
+        std::shared_ptr<PairStrings<T>> pair;
         std::vector<void *> allocs;
     };
     mutable std::map<int, std::vector<CosetPassDev>> coset_plans;

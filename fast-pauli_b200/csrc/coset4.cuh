@@ -1,0 +1,267 @@
+// K3j: TMA-fed coset kernel with direct stores for passes of EIGHT INDEPENDENT x-masks with any number of strings
+// each -- the north-star operator (64 strings over 8 x-masks) in one pass, and every pass of 64 i.i.d. strings.
+//
+// Same ring and producer as K3i (coset3.cuh): a persistent CTA per SM, a producer warp streaming 256-row coset tiles
+// (256 bytes per row) into three 64 KiB buffers with TMA tile::gather4, 16 consumer warps whose lanes run along the
+// batch axis and store their accumulators straight to global memory.  Two things are new:
+//
+//  * PAIRED MASKS.  A thread owns the 8 rows l_i = l_0 + 32 i of the tile (local bits 5..7 = i) at one column offset.
+//    The pass' basis is re-chosen on the host from the masks themselves:
+//        b_0 = m_0, b_1 = m_2, b_2 = m_4, b_3 = m_6, b_4 = m_7,   b_5 = m_0^m_1, b_6 = m_2^m_3, b_7 = m_4^m_5
+//    so that in local coordinates m_0 = e_0 and m_1 = e_0 ^ e_5, ...: the eight vectors psi(l_i ^ e_0) gathered for
+//    mask 0 are, permuted over i, exactly the ones mask 1 needs (psi(l_i ^ e_0 ^ e_5) = psi(l_{i^1} ^ e_0)).  Three
+//    pairs + two single masks = 40 gathers (LDS.128) per thread and tile instead of 64; the accumulation order per
+//    output element stays mask 0, 1, ..., 7, so results are bit-identical to K3e / K3b on the same plan.
+//  * ROW FACTORS FROM A TABLE.  D_g(l) = sum_{s in g} +-c_s (any number of strings per mask) depends on the coset and
+//    the row, not on the column tile: the 8 x 256 factors of a coset are formed once (4 per consumer thread, strings in
+//    plan order from the constant bank) into a 32 KiB shared-memory table whenever the CTA moves to a new coset (column
+//    tiles run fastest), between two named barriers of the consumer warps.  The main loop reads a factor with one
+//    broadcast load per (row, mask): a half-warp shares the row, so the load is a single wavefront against four for a
+//    gather -- 40 x 4 + 64 = 224 shared-memory wavefronts per thread and tile (K3i: 256, K3e: 256 + 64 of staging).
+//
+// Reference semantics: PauliOp::apply (PO:399-468): out(i,t) (+)= sum_s h_s m_s(i) psi(i ^ x_s, t).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "coset3.cuh"
+
+namespace fpk
+{
+
+constexpr int kPairMasks = 8;
+constexpr int kPairMaxStrings = 64;
+constexpr int kPairConsumerWarps = 16;
+constexpr int kPairThreads = kPairConsumerWarps * 32 + 128; // + the producer warpgroup (one live warp)
+
+// One pass as kernel parameters (constant bank); masks in plan order, local coordinates in the re-chosen basis
+template <typename T> struct PairStrings
+{
+    Cx<T> c[kPairMaxStrings];     // coefficient times (-i)^nY
+    uint32_t z[kPairMaxStrings];  // full z-mask (<= 30 qubits): sign of a global row = parity(row & z)
+    uint8_t gs[kPairMasks + 1];   // strings of mask g: gs[g] .. gs[g + 1]
+    uint64_t basis[kPairMasks];   // the re-chosen basis (see above)
+};
+
+template <typename T> constexpr size_t pair_table_bytes()
+{
+    return static_cast<size_t>(kPairMasks) * 256 * sizeof(Cx<T>);
+}
+
+template <typename T, int EPV>
+__global__ void __launch_bounds__(kPairThreads, 1)
+    coset_pair_tma_kernel(uint64_t nonpivot_mask, uint64_t rowvecs, uint32_t nColTiles, uint64_t nTiles,
+                          CVec<T, EPV> *__restrict__ out, int beta, const __grid_constant__ PairStrings<T> strs,
+                          const __grid_constant__ CUtensorMap tm_in)
+{
+    using Vec = CVec<T, EPV>;
+    constexpr int TWC = 16, R = 8, ITERS = 8;
+    constexpr uint32_t ROW_SHIFT = 8;
+
+    extern __shared__ __align__(1024) unsigned char smem_pt[];
+    __shared__ uint64_t s_full[kFewTmaBufs], s_empty[kFewTmaBufs];
+    __shared__ uint32_t s_comb[256]; // XOR offsets of the 256 local rows
+    Cx<T> *const tab = reinterpret_cast<Cx<T> *>(smem_pt + kFewTmaBufs * kFewTmaTile); // [mask][local row]
+
+    uint32_t const tid = threadIdx.x;
+    if (tid < 256)
+        s_comb[tid] = static_cast<uint32_t>(comb_of<R>(strs.basis, tid));
+    if (tid == 0)
+    {
+#pragma unroll
+        for (int b = 0; b < kFewTmaBufs; ++b)
+        {
+            few_mbar_init(&s_full[b], 1);
+            few_mbar_init(&s_empty[b], kPairConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // this CTA's contiguous range of (coset, column tile) work items, column tiles fastest
+    uint64_t const t0 = nTiles * blockIdx.x / gridDim.x, t1 = nTiles * (blockIdx.x + 1) / gridDim.x;
+
+    if (tid >= kPairConsumerWarps * 32)
+    {
+        // ------------------------------------------------ producer warpgroup: hands its registers to the consumers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (tid >= kPairConsumerWarps * 32 + 32)
+            return;
+        uint32_t const lane = tid & 31u;
+        uint64_t p_coset = 0;
+        uint32_t p_ct = 0, p_base = 0;
+        uint32_t buf = 0, round = 0; // ring position: tile i of this CTA sits in buffer i % 3, round = i / 3
+        for (uint64_t t = t0; t < t1; ++t)
+        {
+            if (round)
+                few_mbar_wait(&s_empty[buf], (round - 1) & 1u);
+            if (t == t0 || ++p_ct == nColTiles)
+            {
+                p_coset = t == t0 ? t0 / nColTiles : p_coset + 1;
+                p_ct = t == t0 ? static_cast<uint32_t>(t0 - p_coset * nColTiles) : 0u;
+                p_base = static_cast<uint32_t>(deposit_bits(p_coset, nonpivot_mask));
+            }
+            if (lane == 0)
+                few_mbar_expect_tx(&s_full[buf], static_cast<uint32_t>(kFewTmaTile));
+            __syncwarp();
+            int const c0 = static_cast<int>(p_ct) * TWC * static_cast<int>(16 / sizeof(T));
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+            {
+                uint32_t const op = lane + 32 * h; // rows 4*op .. 4*op+3
+                few_tma_gather4(smem_pt + buf * kFewTmaTile + (static_cast<size_t>(op) << (ROW_SHIFT + 2)), &tm_in, c0,
+                                p_base ^ s_comb[4 * op], p_base ^ s_comb[4 * op + 1], p_base ^ s_comb[4 * op + 2],
+                                p_base ^ s_comb[4 * op + 3], &s_full[buf]);
+            }
+            if (++buf == kFewTmaBufs)
+            {
+                buf = 0;
+                ++round;
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------- consumer warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    uint32_t const warp = tid >> 5, lane = tid & 31u;
+    uint32_t const half = lane >> 4, jv = lane & 15u;
+    uint32_t const l0 = 2u * warp + half;                    // local row of step i: l0 + 32 i
+    uint32_t const own0 = (l0 << ROW_SHIFT) | (jv << 4);     // byte offset of (l0, this lane's vector) in a buffer
+    Cx<T> const *const my_tab = tab + l0;                    // factor of (mask g, step i): my_tab[g * 256 + 32 * i]
+    uint32_t const lb = tid & 255u, g_lo = (tid >> 8) * 4u;  // table builder: row lb, masks g_lo .. g_lo + 3
+
+    uint64_t coset = 0;
+    uint32_t ct = 0, base = 0;
+    uint32_t buf = 0, round = 0;
+    for (uint64_t t = t0; t < t1; ++t)
+    {
+        if (t == t0 || ++ct == nColTiles)
+        {
+            coset = t == t0 ? t0 / nColTiles : coset + 1;
+            ct = t == t0 ? static_cast<uint32_t>(t0 - coset * nColTiles) : 0u;
+            base = static_cast<uint32_t>(deposit_bits(coset, nonpivot_mask)); // launched for <= 30 qubits
+            // new coset: row factors D_g(l) = sum_{s in g} (-1)^{popc(row & z_s)} c_s, strings in plan order
+            asm volatile("bar.sync 1, %0;" ::"n"(kPairConsumerWarps * 32) : "memory"); // the old table has been read
+            uint32_t const row = base ^ s_comb[lb];
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+            {
+                uint32_t const g = g_lo + k;
+                Cx<T> d{0, 0};
+                uint32_t const s1 = strs.gs[g + 1];
+                for (uint32_t s = strs.gs[g]; s < s1; ++s)
+                {
+                    Cx<T> const c = strs.c[s];
+                    uint32_t const odd = __popc(row & strs.z[s]) & 1u;
+                    d.re += flip_sign(c.re, odd);
+                    d.im += flip_sign(c.im, odd);
+                }
+                tab[g * 256u + lb] = d;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kPairConsumerWarps * 32) : "memory");
+        }
+        uint64_t const vcol = static_cast<uint64_t>(ct) * TWC + jv;
+
+        if (beta && t + 1 < t1)
+        {
+            // accumulating pass: the next tile's old output rows -> L2, a whole tile of gathers away from their use
+            bool const same = ct + 1 < nColTiles;
+            uint32_t const base_n = same ? base : static_cast<uint32_t>(deposit_bits(coset + 1, nonpivot_mask));
+            uint64_t const vcol_n = static_cast<uint64_t>(same ? ct + 1 : 0u) * TWC + jv;
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&out[static_cast<uint64_t>(base_n ^ s_comb[l0 + 32 * i]) * rowvecs + vcol_n]));
+        }
+        few_mbar_wait(&s_full[buf], round & 1u);
+        unsigned char const *const tb = smem_pt + buf * kFewTmaTile;
+
+        Cx<T> acc[ITERS][EPV];
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i)
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+                acc[i][e] = Cx<T>{0, 0};
+        Vec v[ITERS];
+        // pairs (2p, 2p + 1): local x = e_p and e_p ^ e_{5 + p}
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+        {
+            uint32_t const off = own0 ^ (1u << (ROW_SHIFT + p));
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i)
+                v[i] = *reinterpret_cast<Vec const *>(tb + off + i * (32 << ROW_SHIFT));
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i)
+            {
+                Cx<T> const f = my_tab[(2 * p) * 256 + 32 * i];
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    cfma(acc[i][e], f, v[i].e[e]);
+            }
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i)
+            {
+                Cx<T> const f = my_tab[(2 * p + 1) * 256 + 32 * i];
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    cfma(acc[i][e], f, v[i ^ (1 << p)].e[e]);
+            }
+        }
+        // single masks 6, 7: local x = e_3, e_4
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+        {
+            uint32_t const off = own0 ^ (1u << (ROW_SHIFT + 3 + q));
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i)
+                v[i] = *reinterpret_cast<Vec const *>(tb + off + i * (32 << ROW_SHIFT));
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i)
+            {
+                Cx<T> const f = my_tab[(6 + q) * 256 + 32 * i];
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                    cfma(acc[i][e], f, v[i].e[e]);
+            }
+        }
+        // this warp's gathers of the buffer are done: order them before the asynchronous-proxy refill and hand it back
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0)
+            few_mbar_arrive(&s_empty[buf]);
+        if (++buf == kFewTmaBufs)
+        {
+            buf = 0;
+            ++round;
+        }
+
+        if (beta)
+        {
+            // old output rows (in L2 since the previous tile) into the registers the gathers have left
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i)
+                v[i] = out[static_cast<uint64_t>(base ^ s_comb[l0 + 32 * i]) * rowvecs + vcol];
+#pragma unroll
+            for (int i = 0; i < ITERS; ++i)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                {
+                    acc[i][e].re += v[i].e[e].re;
+                    acc[i][e].im += v[i].e[e].im;
+                }
+        }
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i)
+        {
+            Vec r;
+#pragma unroll
+            for (int e = 0; e < EPV; ++e)
+                r.e[e] = acc[i][e];
+            out[static_cast<uint64_t>(base ^ s_comb[l0 + 32 * i]) * rowvecs + vcol] = r;
+        }
+    }
+}
+
+} // namespace fpk

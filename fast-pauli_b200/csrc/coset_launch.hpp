@@ -73,6 +73,44 @@ int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank, int reserve_lo
                 d.dir->zl[g] = h.szl[g];
             }
         }
+        if (rank == 8 && n_qubits <= 30 && h.basis.r == 8 && h.gxl.size() == static_cast<size_t>(kPairMasks) &&
+            h.sz.size() <= static_cast<size_t>(kPairMaxStrings))
+        {
+            // eight x-masks: if they are independent they ARE a basis of the pass' span; K3j re-chooses the local
+            // coordinates from them so that masks (0,1), (2,3), (4,5) differ in one of the three row bits a thread owns
+            uint64_t m[kPairMasks];
+            for (int g = 0; g < kPairMasks; ++g)
+            {
+                m[g] = 0;
+                for (int k = 0; k < 8; ++k)
+                    if ((h.gxl[g] >> k) & 1u)
+                        m[g] ^= h.basis.b[k];
+            }
+            uint32_t red[kPairMasks], rk = 0; // GF(2) rank of the local coordinates
+            for (int g = 0; g < kPairMasks; ++g)
+            {
+                uint32_t v = h.gxl[g];
+                for (uint32_t j = 0; j < rk; ++j)
+                    v = std::min(v, v ^ red[j]);
+                if (v)
+                    red[rk++] = v;
+            }
+            if (rk == kPairMasks)
+            {
+                d.pair = std::make_shared<PairStrings<T>>();
+                std::memset(d.pair.get(), 0, sizeof(PairStrings<T>));
+                uint64_t const nb[kPairMasks] = {m[0], m[2], m[4], m[6], m[7], m[0] ^ m[1], m[2] ^ m[3], m[4] ^ m[5]};
+                for (int k = 0; k < kPairMasks; ++k)
+                    d.pair->basis[k] = nb[k];
+                for (size_t i = 0; i < h.sz.size(); ++i)
+                {
+                    d.pair->c[i] = Cx<T>{h.sc[i].real(), h.sc[i].imag()};
+                    d.pair->z[i] = static_cast<uint32_t>(h.sz[i]);
+                }
+                for (size_t g = 0; g <= h.gxl.size(); ++g)
+                    d.pair->gs[g] = static_cast<uint8_t>(h.gstart[g]);
+            }
+        }
         CosetChunk *chunks = nullptr;
         uint32_t *gxl = nullptr, *gstart = nullptr, *szl = nullptr, *sidx = nullptr;
         uint64_t *sz = nullptr;
@@ -475,6 +513,35 @@ int launch_coset_dir_tma(fp_ctx *ctx, CosetPassView<T> const &view, DirStrings<T
     return FP_OK;
 }
 
+// K3j: persistent TMA-fed kernel with direct stores, paired masks and a row-factor table, for passes of eight
+// independent x-masks with any number of strings each (coset4.cuh)
+template <typename T, int EPV>
+int launch_coset_pair_tma(fp_ctx *ctx, CosetPassView<T> const &view, PairStrings<T> const &strs, int n_qubits,
+                          uint64_t rowvecs, void const *in, void *out, int beta, bool *launched)
+{
+    *launched = false;
+    CUtensorMap tm;
+    if (!make_row_tensor_map<T>(&tm, in, 1ull << n_qubits, rowvecs))
+        return FP_OK;
+    constexpr size_t smem = kFewTmaBufs * kFewTmaTile + pair_table_bytes<T>();
+    uint32_t const nct = static_cast<uint32_t>(rowvecs >> 4);
+    uint64_t const n_tiles = (1ull << (n_qubits - 8)) * nct;
+    unsigned const grid = static_cast<unsigned>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(ctx->sm_count)));
+    static PerDevice configured;
+    if (!configured.done(ctx->device))
+    {
+        FP_CU(cudaFuncSetAttribute(coset_pair_tma_kernel<T, EPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+        configured.set(ctx->device);
+    }
+    coset_pair_tma_kernel<T, EPV><<<grid, kPairThreads, smem, ctx->stream>>>(
+        view.nonpivot_mask, rowvecs, nct, n_tiles, static_cast<CVec<T, EPV> *>(out), beta, strs, tm);
+    ctx->launches++;
+    ctx->coset_kernels |= 32u;
+    *launched = true;
+    return FP_OK;
+}
+
 // Picks the variant for one pass; *launched = false when the pass has to go through coset_kernel (K3b).
 template <typename T, int EPV, int MODE = 0>
 int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, int n_qubits, uint64_t rowvecs,
@@ -482,10 +549,20 @@ int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, 
 {
     *launched = false;
     CosetPassView<T> const &view = pd.view;
-    bool const tma_mode = ctx->coset_few == 1 || ctx->coset_few == 3;
+    bool const tma_mode = ctx->coset_few == 1 || ctx->coset_few == 3 || ctx->coset_few == 4;
+    // eight independent x-masks with several strings each: direct stores + paired masks + row-factor table (measured at
+    // 20 qubits x 64: 64 strings over 8 masks 0.512 -> 0.445 ms; single-string masks stay on K3i, whose early loads of
+    // the old output rows suit read-modify-write passes better: 64 random strings 4.28 against 4.44 ms)
+    if (MODE == 0 && ctx->coset_few == 1 && pd.pair && (!pd.dir || ctx->coset_pair_all) && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+        is_device_ptr(in) && (rowvecs >> 4) << (n_qubits - 8) >= 4ull * static_cast<uint64_t>(ctx->sm_count))
+    {
+        FP_TRY((launch_coset_pair_tma<T, EPV>(ctx, view, *pd.pair, n_qubits, rowvecs, in, out, beta, launched)));
+        if (*launched)
+            return FP_OK;
+    }
     // one string per x-mask (random strings): direct-store kernel, overwrite and read-modify-write passes alike
     // (measured at 20 qubits x 64: 8 masks 0.49 -> 0.43 ms, the 8 passes of 64 random strings 4.55 -> 4.16 ms)
-    if (MODE == 0 && ctx->coset_few == 1 && pd.dir && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+    if (MODE == 0 && (ctx->coset_few == 1 || ctx->coset_few == 4) && pd.dir && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
         is_device_ptr(in) && (rowvecs >> 4) << (n_qubits - 8) >= 4ull * static_cast<uint64_t>(ctx->sm_count))
     {
         FP_TRY((launch_coset_dir_tma<T, EPV>(ctx, view, *pd.dir, n_qubits, rowvecs, in, out, beta, launched)));
@@ -534,7 +611,7 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
     if (epv != EPV)
         return FP_OK;
     uint64_t const rowvecs = B / EPV;
-    bool const tma_ok = MODE == 0 && (ctx->coset_few == 1 || ctx->coset_few == 3) && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+    bool const tma_ok = MODE == 0 && (ctx->coset_few == 1 || ctx->coset_few == 3 || ctx->coset_few == 4) && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
                         is_device_ptr(in) && tensor_map_encoder() != nullptr;
     CosetShape const shape = choose_coset<T>(ctx, op, n_qubits, rowvecs, epv, tma_ok);
     if (!shape.ok())

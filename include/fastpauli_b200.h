@@ -102,14 +102,16 @@ extern "C"
      * picks 128- or 256-thread CTAs (0 = default, 128). */
     int fp_ctx_set_rcoset(fp_ctx *ctx, int mode, int log_nt);
     /* Passes of a coset plan with at most 8 x-masks (K3e / K3f, csrc/coset2.cuh: row factors in registers, strings in
-     * the constant bank, TMA-fed persistent variant) and passes whose x-masks carry one string each (K3i,
-     * csrc/coset3.cuh: TMA-fed, direct stores): mode 0 = never (such passes run on the general coset kernel),
-     * 1 = automatic (default), 2 = never the TMA-fed kernels, 3 = automatic without K3i.  column_tiles_per_cta > 0
+     * the constant bank, TMA-fed persistent variant), passes whose x-masks carry one string each (K3i,
+     * csrc/coset3.cuh: TMA-fed, direct stores) and passes of eight independent x-masks (K3j, csrc/coset4.cuh: direct
+     * stores, paired masks, row-factor table): mode 0 = never (such passes run on the general coset kernel),
+     * 1 = automatic (default), 2 = never the TMA-fed kernels, 3 = automatic without K3i and K3j, 4 = automatic
+     * without K3j, 5 = automatic with K3j also on single-string masks (by default those stay on K3i).  column_tiles_per_cta > 0
      * forces how many column tiles one CTA of K3e walks (0 = automatic). */
     int fp_ctx_set_coset_few(fp_ctx *ctx, int mode, int column_tiles_per_cta);
     /* Which kernels of the coset family ran on this context since the last reset (bit mask: 1 = K3b coset_kernel,
      * 2 = K3e coset_few_kernel, 4 = K3f coset_few_tma_kernel, 8 = K3g coset_gen_tma_kernel, 16 = K3i
-     * coset_dir_tma_kernel); reset != 0 clears it.  For tests and benchmarks that assert the launch path. */
+     * coset_dir_tma_kernel, 32 = K3j coset_pair_tma_kernel); reset != 0 clears it.  For tests and benchmarks that assert the launch path. */
     int fp_ctx_coset_kernels_used(fp_ctx *ctx, uint32_t *mask, int reset);
     /* Override the L2 working-set budget (bytes) used to pick the batch-tile width of multi-group kernels. */
     int fp_ctx_set_l2_budget(fp_ctx *ctx, size_t bytes);

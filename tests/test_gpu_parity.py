@@ -1173,11 +1173,11 @@ def test_headline_size_multi_pass_operators_sampled_rows(kind):
     launches = ctx.launch_count - l0
     used = ctx.coset_kernels_used()
     # the launch path: one pass per rank-8 span of x-masks (few: 1, random: 8; the chains need 2-3 passes) on the
-    # kernels the design names: K3f (4) for the 8-mask pass, K3i (16) for the single-string passes of the random
+    # kernels the design names: K3j (32) for the 8-mask pass, K3i (16) for the single-string passes of the random
     # operator, K3g (8) for the chains
     assert launches == {"few_group": 1, "random": 8}.get(kind, launches) and 1 <= launches <= 8
     if kind in ("few_group", "random"):
-        assert used == {"few_group": 4, "random": 16}[kind], used
+        assert used == {"few_group": 32, "random": 16}[kind], used
     else:
         assert used & 8 and not used & 1, used  # K3g, plus K3e / K3f for a last pass with <= 8 masks
     masks = [orc.masks(s) for s in strings]
@@ -1352,6 +1352,67 @@ def test_direct_store_tma_kernel_single_string_masks(dtype, n, B, S):
     ctx.sync()
     assert ctx.coset_kernels_used() == 16
     assert rel_err(acc.get(), out0.astype(np.complex128) + ref) < tol(dtype)
+    ctx.set_coset_few(1)
+    ctx.set_coset(1)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("n,B,masks,per", [(16, 96, 8, 8), (16, 96, 8, 1), (17, 64, 8, 3), (14, 512, 8, 5), (18, 32, 16, 2),
+                                           (16, 128, 24, 1)])
+def test_paired_mask_tma_kernel(dtype, n, B, masks, per):
+    """K3j (coset_pair_tma_kernel: TMA-fed, direct stores, masks paired through the pass' basis, row factors from a
+    per-coset shared-memory table) on passes of eight independent x-masks with `per` strings each -- the north-star
+    operator shape and i.i.d. random strings: against the oracle, bit-identical to the kernels it replaces (K3i / K3e /
+    K3f, and the general coset kernel), read-modify-write passes (more than 8 masks), the accumulating form, and the
+    launch path."""
+    import ctypes as C
+
+    rng = np.random.default_rng(131 * n + B + 7 * masks + per)
+    ctx = fp.default_context()
+    strings = []
+    for s in rand_strings(rng, n, masks):
+        seen = set()
+        while len(seen) < per:
+            t = list(s)
+            for q in range(n):
+                if rng.random() < 0.5:
+                    t[q] = {"X": "Y", "Y": "X", "I": "Z", "Z": "I"}[t[q]]
+            seen.add("".join(t))
+        strings += sorted(seen)
+    assert len({orc.masks(s)[0] for s in strings}) == masks
+    h = (rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))).astype(dtype)
+    psi = rand_states(rng, 2**n, B, dtype)
+    d_psi = ctx.to_device(psi)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    ref = ORC.op_apply(strings, h.astype(np.complex128), psi.astype(np.complex128), par=True)
+    ctx.set_coset(2, 4, 8)  # rank-8 tiles of 16 vectors per row: the shape the TMA-fed kernels take
+    res = []
+    auto = 1 if per > 1 else 5  # single-string masks stay on K3i unless mode 5 asks for K3j
+    for mode in (auto, 4, 0):
+        ctx.set_coset_few(mode)
+        ctx.coset_kernels_used(reset=True)
+        got = op.apply(d_psi).get()
+        used = ctx.coset_kernels_used()
+        assert rel_err(got, ref) < tol(dtype)
+        if mode == auto:
+            assert used & 32, used
+            if masks == 8:
+                assert used == 32, used  # one pass of eight independent masks
+        else:
+            assert used & 32 == 0, used
+        res.append(got)
+    np.testing.assert_array_equal(res[0], res[1])
+    np.testing.assert_array_equal(res[0], res[2])
+    ctx.set_coset_few(auto)
+    out0 = rand_states(rng, 2**n, B, dtype)
+    acc = ctx.to_device(out0)
+    ctx.coset_kernels_used(reset=True)
+    fp._check(fp.lib.fp_op_apply(ctx._h, op._plan(dtype), C.c_void_p(acc.ptr), C.c_void_p(d_psi.ptr), C.c_size_t(2**n),
+                                 C.c_size_t(B), C.c_int(1)))
+    ctx.sync()
+    assert ctx.coset_kernels_used() & 32
+    assert rel_err(acc.get(), out0.astype(np.complex128) + ref) < tol(dtype)
+    ctx.set_coset_few(1)
     ctx.set_coset(1)
 
 
