@@ -736,7 +736,7 @@ def run_ours(args) -> None:
     fp64 = fp64_peak(fp, ctx, clocks)
     alg_bytes = dim * B * 32.0
     traffic_db = {}
-    tpath = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02c_dram_traffic.json")
     if os.path.exists(tpath):
         try:
             traffic_db = json.load(open(tpath))
@@ -757,7 +757,7 @@ def run_ours(args) -> None:
              "t_hbm_ms": 1e3 * t_hbm, "t_fp64_ms": 1e3 * t_fp,
              "amp_strings_per_s": N_STRINGS * dim * B / t,
              "traffic": tr.get("dram_bytes_per_call"), "traffic_source": tr.get("source"),
-             "kernel": tr.get("kernel", "coset_few_kernel / coset_few_tma_kernel / coset_dir_tma_kernel (K3e / K3f / K3i, csrc/coset2.cuh, coset3.cuh)")}
+             "kernel": tr.get("kernel", "coset_pair_tma_kernel / coset_dir_tma_kernel (K3j / K3i, csrc/coset4.cuh, coset3.cuh)")}
         # third floor, reported beside the two the SURVEY names: every complex FMA of a multi-mask pass needs one 16-byte
         # shared-memory gather (no register-level reuse between independent masks); 128 B/clk/SM of LDS bandwidth
         t_lds = 16.0 * G * dim * B / (148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6) if G > 4 else 0.0

@@ -15,7 +15,9 @@
 //  * ROW FACTORS FROM A TABLE.  D_g(l) = sum_{s in g} +-c_s (any number of strings per mask) depends on the coset and
 //    the row, not on the column tile: the 8 x 256 factors of a coset are formed once (4 per consumer thread, strings in
 //    plan order from the constant bank) into a 32 KiB shared-memory table whenever the CTA moves to a new coset (column
-//    tiles run fastest), between two named barriers of the consumer warps.  The main loop reads a factor with one
+//    tiles run fastest); a warp forms exactly the 16 rows x 8 masks it reads itself, so the table costs no barrier among
+//    the consumer warps (a CTA-wide barrier per coset was measured: the drain costs ~3 us per coset, 0.08 ms at 20 qubits
+//    x 64).  The main loop reads a factor with one
 //    broadcast load per (row, mask): a half-warp shares the row, so the load is a single wavefront against four for a
 //    gather -- 40 x 4 + 64 = 224 shared-memory wavefronts per thread and tile (K3i: 256, K3e: 256 + 64 of staging).
 //
@@ -130,7 +132,9 @@ __global__ void __launch_bounds__(kPairThreads, 1)
     uint32_t const l0 = 2u * warp + half;                    // local row of step i: l0 + 32 i
     uint32_t const own0 = (l0 << ROW_SHIFT) | (jv << 4);     // byte offset of (l0, this lane's vector) in a buffer
     Cx<T> const *const my_tab = tab + l0;                    // factor of (mask g, step i): my_tab[g * 256 + 32 * i]
-    uint32_t const lb = tid & 255u, g_lo = (tid >> 8) * 4u;  // table builder: row lb, masks g_lo .. g_lo + 3
+    // table builder: a warp forms exactly the 16 rows x 8 masks it reads itself (lane -> row 2 warp + hb + 32 ib, masks
+    // g_lo .. g_lo + 3), so the table needs no barrier among the warps and they keep drifting apart
+    uint32_t const lb = 2u * warp + (lane >> 4) + 32u * ((lane >> 1) & 7u), g_lo = (lane & 1u) * 4u;
 
     uint64_t coset = 0;
     uint32_t ct = 0, base = 0;
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(kPairThreads, 1)
             ct = t == t0 ? static_cast<uint32_t>(t0 - coset * nColTiles) : 0u;
             base = static_cast<uint32_t>(deposit_bits(coset, nonpivot_mask)); // launched for <= 30 qubits
             // new coset: row factors D_g(l) = sum_{s in g} (-1)^{popc(row & z_s)} c_s, strings in plan order
-            asm volatile("bar.sync 1, %0;" ::"n"(kPairConsumerWarps * 32) : "memory"); // the old table has been read
+            __syncwarp(); // the warp's slice of the old table has been read
             uint32_t const row = base ^ s_comb[lb];
 #pragma unroll
             for (uint32_t k = 0; k < 4; ++k)
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kPairThreads, 1)
                 }
                 tab[g * 256u + lb] = d;
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kPairConsumerWarps * 32) : "memory");
+            __syncwarp();
         }
         uint64_t const vcol = static_cast<uint64_t>(ct) * TWC + jv;
 

@@ -550,10 +550,11 @@ int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, 
     *launched = false;
     CosetPassView<T> const &view = pd.view;
     bool const tma_mode = ctx->coset_few == 1 || ctx->coset_few == 3 || ctx->coset_few == 4;
-    // eight independent x-masks with several strings each: direct stores + paired masks + row-factor table (measured at
-    // 20 qubits x 64: 64 strings over 8 masks 0.512 -> 0.445 ms; single-string masks stay on K3i, whose early loads of
-    // the old output rows suit read-modify-write passes better: 64 random strings 4.28 against 4.44 ms)
-    if (MODE == 0 && ctx->coset_few == 1 && pd.pair && (!pd.dir || ctx->coset_pair_all) && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+    // eight independent x-masks: direct stores + paired masks + row-factor table (measured at 20 qubits x 64: 64 strings
+    // over 8 masks 0.512 -> 0.416 ms, 8 single-string masks 0.417 -> 0.382 ms); read-modify-write passes of single-string
+    // masks stay on K3i, whose early loads of the old output rows suit them slightly better (64 random strings: 4.25
+    // against 4.28 ms with K3j on all eight passes)
+    if (MODE == 0 && ctx->coset_few == 1 && pd.pair && (!pd.dir || beta == 0 || ctx->coset_pair_all) && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
         is_device_ptr(in) && (rowvecs >> 4) << (n_qubits - 8) >= 4ull * static_cast<uint64_t>(ctx->sm_count))
     {
         FP_TRY((launch_coset_pair_tma<T, EPV>(ctx, view, *pd.pair, n_qubits, rowvecs, in, out, beta, launched)));
