@@ -43,7 +43,7 @@ template <typename T> struct PairStrings
     Cx<T> c[kPairMaxStrings];     // coefficient times (-i)^nY
     uint32_t z[kPairMaxStrings];  // full z-mask (<= 30 qubits): sign of a global row = parity(row & z)
     uint8_t gs[kPairMasks + 1];   // strings of mask g: gs[g] .. gs[g + 1]
-    uint64_t basis[kPairMasks];   // the re-chosen basis (see above)
+    uint64_t basis[2][kPairMasks]; // the re-chosen basis (see above) for RB = 3 ([0]) and RB = 2 ([1]: two pairs)
 };
 
 template <typename T> constexpr size_t pair_table_bytes()
@@ -51,14 +51,14 @@ template <typename T> constexpr size_t pair_table_bytes()
     return static_cast<size_t>(kPairMasks) * 256 * sizeof(Cx<T>);
 }
 
-template <typename T, int EPV>
+template <typename T, int EPV, int RB = 3>
 __global__ void __launch_bounds__(kPairThreads, 1)
     coset_pair_tma_kernel(uint64_t nonpivot_mask, uint64_t rowvecs, uint32_t nColTiles, uint64_t nTiles,
                           CVec<T, EPV> *__restrict__ out, int beta, const __grid_constant__ PairStrings<T> strs,
                           const __grid_constant__ CUtensorMap tm_in)
 {
     using Vec = CVec<T, EPV>;
-    constexpr int TWC = 16, R = 8, ITERS = 8;
+    constexpr int TWC = 16, R = 8;
     constexpr uint32_t ROW_SHIFT = 8;
 
     extern __shared__ __align__(1024) unsigned char smem_pt[];
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kPairThreads, 1)
 
     uint32_t const tid = threadIdx.x;
     if (tid < 256)
-        s_comb[tid] = static_cast<uint32_t>(comb_of<R>(strs.basis, tid));
+        s_comb[tid] = static_cast<uint32_t>(comb_of<R>(strs.basis[RB == 3 ? 0 : 1], tid));
     if (tid == 0)
     {
 #pragma unroll
@@ -127,14 +127,18 @@ __global__ void __launch_bounds__(kPairThreads, 1)
 
     // ---------------------------------------------------- consumer warps
     asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // A lane owns NR = 2^RB rows (the top RB local bits) x NV = 8 / NR vectors of the 256-byte row segment; LPR lanes
+    // share a row, a warp instruction covers RW rows.  RB = 3: 8 rows x 1 vector, three mask pairs (40 gathers + 64 factor
+    // loads per lane and tile); RB = 2: 4 rows x 2 vectors, two pairs (48 gathers + 32 factor loads).
+    constexpr int NR = 1 << RB, NV = 8 / NR, LPR = 16 / NV, RW = 32 / LPR, RSTEP = RW * 16, NSINGLE = 8 - 2 * RB;
     uint32_t const warp = tid >> 5, lane = tid & 31u;
-    uint32_t const half = lane >> 4, jv = lane & 15u;
-    uint32_t const l0 = 2u * warp + half;                    // local row of step i: l0 + 32 i
-    uint32_t const own0 = (l0 << ROW_SHIFT) | (jv << 4);     // byte offset of (l0, this lane's vector) in a buffer
-    Cx<T> const *const my_tab = tab + l0;                    // factor of (mask g, step i): my_tab[g * 256 + 32 * i]
-    // table builder: a warp forms exactly the 16 rows x 8 masks it reads itself (lane -> row 2 warp + hb + 32 ib, masks
-    // g_lo .. g_lo + 3), so the table needs no barrier among the warps and they keep drifting apart
-    uint32_t const lb = 2u * warp + (lane >> 4) + 32u * ((lane >> 1) & 7u), g_lo = (lane & 1u) * 4u;
+    uint32_t const rq = lane / LPR, jl = lane % LPR;
+    uint32_t const l0 = RW * warp + rq;                      // local row of step i: l0 + RSTEP i
+    uint32_t const own0 = (l0 << ROW_SHIFT) | (jl << 4);     // byte offset of (l0, this lane's first vector) in a buffer
+    Cx<T> const *const my_tab = tab + l0;                    // factor of (mask g, step i): my_tab[g * 256 + RSTEP * i]
+    // table builder: a warp forms exactly the 16 rows x 8 masks it reads itself (lane -> one row, masks g_lo .. g_lo + 3),
+    // so the table needs no barrier among the warps and they keep drifting apart
+    uint32_t const lb = RW * warp + ((lane >> 1) % RW) + RSTEP * ((lane >> 1) / RW), g_lo = (lane & 1u) * 4u;
 
     uint64_t coset = 0;
     uint32_t ct = 0, base = 0;
@@ -166,68 +170,83 @@ __global__ void __launch_bounds__(kPairThreads, 1)
             }
             __syncwarp();
         }
-        uint64_t const vcol = static_cast<uint64_t>(ct) * TWC + jv;
+        uint64_t const vcol = static_cast<uint64_t>(ct) * TWC + jl;
 
         if (beta && t + 1 < t1)
         {
             // accumulating pass: the next tile's old output rows -> L2, a whole tile of gathers away from their use
             bool const same = ct + 1 < nColTiles;
             uint32_t const base_n = same ? base : static_cast<uint32_t>(deposit_bits(coset + 1, nonpivot_mask));
-            uint64_t const vcol_n = static_cast<uint64_t>(same ? ct + 1 : 0u) * TWC + jv;
+            uint64_t const vcol_n = static_cast<uint64_t>(same ? ct + 1 : 0u) * TWC + jl;
 #pragma unroll
-            for (int i = 0; i < ITERS; ++i)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(&out[static_cast<uint64_t>(base_n ^ s_comb[l0 + 32 * i]) * rowvecs + vcol_n]));
+            for (int i = 0; i < NR; ++i)
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                        &out[static_cast<uint64_t>(base_n ^ s_comb[l0 + RSTEP * i]) * rowvecs + vcol_n + c * LPR]));
         }
         few_mbar_wait(&s_full[buf], round & 1u);
         unsigned char const *const tb = smem_pt + buf * kFewTmaTile;
 
-        Cx<T> acc[ITERS][EPV];
+        Cx<T> acc[NR][NV][EPV];
 #pragma unroll
-        for (int i = 0; i < ITERS; ++i)
+        for (int i = 0; i < NR; ++i)
 #pragma unroll
-            for (int e = 0; e < EPV; ++e)
-                acc[i][e] = Cx<T>{0, 0};
-        Vec v[ITERS];
-        // pairs (2p, 2p + 1): local x = e_p and e_p ^ e_{5 + p}
+            for (int c = 0; c < NV; ++c)
 #pragma unroll
-        for (int p = 0; p < 3; ++p)
+                for (int e = 0; e < EPV; ++e)
+                    acc[i][c][e] = Cx<T>{0, 0};
+        Vec v[NR][NV];
+        // pairs (2p, 2p + 1): local x = e_p and e_p ^ e_{8 - RB + p}
+#pragma unroll
+        for (int p = 0; p < RB; ++p)
         {
             uint32_t const off = own0 ^ (1u << (ROW_SHIFT + p));
 #pragma unroll
-            for (int i = 0; i < ITERS; ++i)
-                v[i] = *reinterpret_cast<Vec const *>(tb + off + i * (32 << ROW_SHIFT));
+            for (int i = 0; i < NR; ++i)
 #pragma unroll
-            for (int i = 0; i < ITERS; ++i)
+                for (int c = 0; c < NV; ++c)
+                    v[i][c] = *reinterpret_cast<Vec const *>(tb + off + i * (RSTEP << ROW_SHIFT) + c * (LPR * 16));
+#pragma unroll
+            for (int i = 0; i < NR; ++i)
             {
-                Cx<T> const f = my_tab[(2 * p) * 256 + 32 * i];
+                Cx<T> const f = my_tab[(2 * p) * 256 + RSTEP * i];
 #pragma unroll
-                for (int e = 0; e < EPV; ++e)
-                    cfma(acc[i][e], f, v[i].e[e]);
+                for (int c = 0; c < NV; ++c)
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                        cfma(acc[i][c][e], f, v[i][c].e[e]);
             }
 #pragma unroll
-            for (int i = 0; i < ITERS; ++i)
+            for (int i = 0; i < NR; ++i)
             {
-                Cx<T> const f = my_tab[(2 * p + 1) * 256 + 32 * i];
+                Cx<T> const f = my_tab[(2 * p + 1) * 256 + RSTEP * i];
 #pragma unroll
-                for (int e = 0; e < EPV; ++e)
-                    cfma(acc[i][e], f, v[i ^ (1 << p)].e[e]);
+                for (int c = 0; c < NV; ++c)
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                        cfma(acc[i][c][e], f, v[i ^ (1 << p)][c].e[e]);
             }
         }
-        // single masks 6, 7: local x = e_3, e_4
+        // single masks 2 RB .. 7: local x = e_{RB + q}
 #pragma unroll
-        for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < NSINGLE; ++q)
         {
-            uint32_t const off = own0 ^ (1u << (ROW_SHIFT + 3 + q));
+            uint32_t const off = own0 ^ (1u << (ROW_SHIFT + RB + q));
 #pragma unroll
-            for (int i = 0; i < ITERS; ++i)
-                v[i] = *reinterpret_cast<Vec const *>(tb + off + i * (32 << ROW_SHIFT));
+            for (int i = 0; i < NR; ++i)
 #pragma unroll
-            for (int i = 0; i < ITERS; ++i)
+                for (int c = 0; c < NV; ++c)
+                    v[i][c] = *reinterpret_cast<Vec const *>(tb + off + i * (RSTEP << ROW_SHIFT) + c * (LPR * 16));
+#pragma unroll
+            for (int i = 0; i < NR; ++i)
             {
-                Cx<T> const f = my_tab[(6 + q) * 256 + 32 * i];
+                Cx<T> const f = my_tab[(2 * RB + q) * 256 + RSTEP * i];
 #pragma unroll
-                for (int e = 0; e < EPV; ++e)
-                    cfma(acc[i][e], f, v[i].e[e]);
+                for (int c = 0; c < NV; ++c)
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                        cfma(acc[i][c][e], f, v[i][c].e[e]);
             }
         }
         // this warp's gathers of the buffer are done: order them before the asynchronous-proxy refill and hand it back
@@ -245,26 +264,32 @@ __global__ void __launch_bounds__(kPairThreads, 1)
         {
             // old output rows (in L2 since the previous tile) into the registers the gathers have left
 #pragma unroll
-            for (int i = 0; i < ITERS; ++i)
-                v[i] = out[static_cast<uint64_t>(base ^ s_comb[l0 + 32 * i]) * rowvecs + vcol];
+            for (int i = 0; i < NR; ++i)
 #pragma unroll
-            for (int i = 0; i < ITERS; ++i)
+                for (int c = 0; c < NV; ++c)
+                    v[i][c] = out[static_cast<uint64_t>(base ^ s_comb[l0 + RSTEP * i]) * rowvecs + vcol + c * LPR];
+#pragma unroll
+            for (int i = 0; i < NR; ++i)
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                    {
+                        acc[i][c][e].re += v[i][c].e[e].re;
+                        acc[i][c][e].im += v[i][c].e[e].im;
+                    }
+        }
+#pragma unroll
+        for (int i = 0; i < NR; ++i)
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+            {
+                Vec r;
 #pragma unroll
                 for (int e = 0; e < EPV; ++e)
-                {
-                    acc[i][e].re += v[i].e[e].re;
-                    acc[i][e].im += v[i].e[e].im;
-                }
-        }
-#pragma unroll
-        for (int i = 0; i < ITERS; ++i)
-        {
-            Vec r;
-#pragma unroll
-            for (int e = 0; e < EPV; ++e)
-                r.e[e] = acc[i][e];
-            out[static_cast<uint64_t>(base ^ s_comb[l0 + 32 * i]) * rowvecs + vcol] = r;
-        }
+                    r.e[e] = acc[i][c][e];
+                out[static_cast<uint64_t>(base ^ s_comb[l0 + RSTEP * i]) * rowvecs + vcol + c * LPR] = r;
+            }
     }
 }
 

@@ -99,9 +99,13 @@ int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank, int reserve_lo
             {
                 d.pair = std::make_shared<PairStrings<T>>();
                 std::memset(d.pair.get(), 0, sizeof(PairStrings<T>));
-                uint64_t const nb[kPairMasks] = {m[0], m[2], m[4], m[6], m[7], m[0] ^ m[1], m[2] ^ m[3], m[4] ^ m[5]};
+                uint64_t const nb3[kPairMasks] = {m[0], m[2], m[4], m[6], m[7], m[0] ^ m[1], m[2] ^ m[3], m[4] ^ m[5]};
+                uint64_t const nb2[kPairMasks] = {m[0], m[2], m[4], m[5], m[6], m[7], m[0] ^ m[1], m[2] ^ m[3]};
                 for (int k = 0; k < kPairMasks; ++k)
-                    d.pair->basis[k] = nb[k];
+                {
+                    d.pair->basis[0][k] = nb3[k];
+                    d.pair->basis[1][k] = nb2[k];
+                }
                 for (size_t i = 0; i < h.sz.size(); ++i)
                 {
                     d.pair->c[i] = Cx<T>{h.sc[i].real(), h.sc[i].imag()};
@@ -527,15 +531,24 @@ int launch_coset_pair_tma(fp_ctx *ctx, CosetPassView<T> const &view, PairStrings
     uint32_t const nct = static_cast<uint32_t>(rowvecs >> 4);
     uint64_t const n_tiles = (1ull << (n_qubits - 8)) * nct;
     unsigned const grid = static_cast<unsigned>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(ctx->sm_count)));
-    static PerDevice configured;
-    if (!configured.done(ctx->device))
-    {
-        FP_CU(cudaFuncSetAttribute(coset_pair_tma_kernel<T, EPV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
-        configured.set(ctx->device);
+#define FP_LAUNCH_PAIR(RB)                                                                                             \
+    {                                                                                                                  \
+        static PerDevice configured;                                                                                   \
+        if (!configured.done(ctx->device))                                                                             \
+        {                                                                                                              \
+            FP_CU(cudaFuncSetAttribute(coset_pair_tma_kernel<T, EPV, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       static_cast<int>(smem)));                                                       \
+            configured.set(ctx->device);                                                                               \
+        }                                                                                                              \
+        coset_pair_tma_kernel<T, EPV, RB><<<grid, kPairThreads, smem, ctx->stream>>>(                                  \
+            view.nonpivot_mask, rowvecs, nct, n_tiles, static_cast<CVec<T, EPV> *>(out), beta, strs, tm);              \
     }
-    coset_pair_tma_kernel<T, EPV><<<grid, kPairThreads, smem, ctx->stream>>>(
-        view.nonpivot_mask, rowvecs, nct, n_tiles, static_cast<CVec<T, EPV> *>(out), beta, strs, tm);
+    static int const rb = getenv("FASTPAULI_PAIR_RB") ? atoi(getenv("FASTPAULI_PAIR_RB")) : 2;
+    if (rb == 3)
+        FP_LAUNCH_PAIR(3)
+    else
+        FP_LAUNCH_PAIR(2)
+#undef FP_LAUNCH_PAIR
     ctx->launches++;
     ctx->coset_kernels |= 32u;
     *launched = true;

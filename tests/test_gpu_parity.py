@@ -1416,6 +1416,50 @@ def test_paired_mask_tma_kernel(dtype, n, B, masks, per):
     ctx.set_coset(1)
 
 
+def test_paired_mask_tma_kernel_three_register_bits():
+    """K3j's other lane mapping (FASTPAULI_PAIR_RB=3: 8 rows x 1 vector per lane, three mask pairs; the default is 4 rows
+    x 2 vectors, two pairs) in a fresh process -- the knob is read once: against the oracle and bit-identical to K3e."""
+    import subprocess
+    import sys
+
+    code = """
+import numpy as np, sys
+sys.path.insert(0, %r)
+from __graft_entry__ import load_package
+fp = load_package()
+from oracle import oracle as orc
+rng = np.random.default_rng(11)
+n, B = 16, 96
+ctx = fp.default_context()
+strings = []
+for _ in range(8):
+    s = "".join("IXYZ"[k] for k in rng.integers(0, 4, size=n))
+    for _ in range(3):
+        t = list(s)
+        for q in range(n):
+            if rng.random() < 0.5:
+                t[q] = {"X": "Y", "Y": "X", "I": "Z", "Z": "I"}[t[q]]
+        strings.append("".join(t))
+strings = sorted(set(strings))
+h = rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))
+psi = rng.random((2**n, B)) + 1j * rng.random((2**n, B))
+d_psi = ctx.to_device(psi)
+op = fp.PauliOp(h, strings, ctx=ctx)
+ctx.set_coset(2, 4, 8)
+ctx.coset_kernels_used(reset=True)
+got = op.apply(d_psi).get()
+assert ctx.coset_kernels_used() == 32
+ref = orc.best().op_apply(strings, h, psi, par=True)
+assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < 1e-12
+ctx.set_coset_few(2)
+np.testing.assert_array_equal(op.apply(d_psi).get(), got)
+print("ok")
+""" % (ROOT,)
+    env = dict(os.environ, FASTPAULI_PAIR_RB="3")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_two_devices_in_one_process():
     """One context per GPU in a single process: every kernel family that needs opt-in shared memory must be configured
     on each device it runs on (cudaFuncSetAttribute is per device).  Skipped on single-GPU boxes."""
