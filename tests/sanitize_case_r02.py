@@ -5,7 +5,8 @@
     compute-sanitizer --tool racecheck python tests/sanitize_case_r02.py
 
 K3e (coset_few_kernel, overwrite + read-modify-write + expectation value), K3f (coset_few_tma_kernel), K3g
-(coset_gen_tma_kernel), K3i (coset_dir_tma_kernel, overwrite + read-modify-write) in both precisions, and K3d on
+(coset_gen_tma_kernel), K3i (coset_dir_tma_kernel, overwrite + read-modify-write), K3j (coset_pair_tma_kernel, overwrite +
+read-modify-write) in both precisions, and K3d on
 complex64 batches; every result is checked against the oracle and the launch path is asserted.
 """
 import os
@@ -69,6 +70,10 @@ for dtype in (np.complex128, np.complex64):
     check(rand_strings(rng, 13, 150, max_weight=3), 13, 32 * wide, dtype, 8)
     # K3i: random strings (one per mask), enough tiles for the persistent grid; 12 strings = overwrite + accumulate
     check(rand_strings(rng, 14, 12), 14, 256 * wide, dtype, 16)
+    # K3j: eight independent masks x 3 strings (overwrite: table build + paired gathers), 16 masks x 2 strings (the
+    # second pass is read-modify-write)
+    check(variants(rand_strings(rng, 14, 8), 3), 14, 256 * wide, dtype, 32)
+    check(variants(rand_strings(rng, 14, 16), 2), 14, 256 * wide, dtype, 32)
     ctx.set_coset(1)
 
 # K3d on complex64: dense 5-local operator
