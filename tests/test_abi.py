@@ -75,6 +75,24 @@ def test_direct_store_coset_kernel_has_no_staging_in_its_sass():
     assert body.count("BAR.SYNC") == 1
 
 
+def test_paired_mask_coset_kernel_sass_structure():
+    """K3j (coset_pair_tma_kernel), default lane mapping (4 rows x 2 vectors): per tile and lane 48
+    gathers + 32 row-factor loads (LDS.128) feed 8 x 8 complex FMAs = 256 DFMA; the only shared-memory stores are the
+    4 table entries a lane forms per coset; results leave by STG.128 straight from the accumulators; no barrier among
+    the consumer warps (only the start-up __syncthreads)."""
+    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    parts = sass.split("Function : ")
+    k3j = [p for p in parts if "coset_pair_tma_kernelIdLi1ELi2" in p.split("\n", 1)[0]]
+    assert len(k3j) == 1, "complex128 RB = 2 instance of coset_pair_tma_kernel not found"
+    body = k3j[0]
+    for mnemonic in ("UTMALDG.2D.GATHER4", "LDS.128", "STG.E.128", "LDG.E.128", "CCTL.E.PF2", "USETMAXREG", "SYNCS", "POPC"):
+        assert mnemonic in body, f"{mnemonic} not found in coset_pair_tma_kernel"
+    assert body.count("DFMA") == 256
+    assert 80 <= body.count("LDS.128") <= 84, body.count("LDS.128")
+    assert body.count("STS.128") == 4
+    assert body.count("BAR.SYNC") == 1
+
+
 def test_no_gpu_fails_loudly(lib):
     import torch
 
