@@ -51,11 +51,17 @@ template <typename T> constexpr size_t pair_table_bytes()
     return static_cast<size_t>(kPairMasks) * 256 * sizeof(Cx<T>);
 }
 
-template <typename T, int EPV, int RB = 3>
+// MODE 1: PauliOp::expectation_value partials (PO:482-549) instead of the store: e(t) += conj(psi(l, t)) (A psi)(l, t)
+// with psi(l, t) read from the tile.  Per tile a warp folds its 16 rows (in-lane over the lane's rows, two shuffles over
+// the lanes that share a column) and adds the column sums to ITS OWN row of `partials` ([CTA][warp][column], zeroed by
+// the host) with fire-and-forget reductions: every address has exactly one writing thread, so the order of the additions
+// is the program order and the result is reproducible; finalize_complex_kernel adds the rows in a fixed order.
+template <typename T, int EPV, int RB = 3, int MODE = 0>
 __global__ void __launch_bounds__(kPairThreads, 1)
     coset_pair_tma_kernel(uint64_t nonpivot_mask, uint64_t rowvecs, uint32_t nColTiles, uint64_t nTiles,
                           CVec<T, EPV> *__restrict__ out, int beta, const __grid_constant__ PairStrings<T> strs,
-                          const __grid_constant__ CUtensorMap tm_in)
+                          const __grid_constant__ CUtensorMap tm_in, Cx<T> *__restrict__ partials = nullptr,
+                          uint32_t Bpad = 0)
 {
     using Vec = CVec<T, EPV>;
     constexpr int TWC = 16, R = 8;
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(kPairThreads, 1)
         }
         uint64_t const vcol = static_cast<uint64_t>(ct) * TWC + jl;
 
-        if (beta && t + 1 < t1)
+        if (MODE == 0 && beta && t + 1 < t1)
         {
             // accumulating pass: the next tile's old output rows -> L2, a whole tile of gathers away from their use
             bool const same = ct + 1 < nColTiles;
@@ -249,6 +255,33 @@ __global__ void __launch_bounds__(kPairThreads, 1)
                         cfma(acc[i][c][e], f, v[i][c].e[e]);
             }
         }
+        Cx<T> esum[NV][EPV];
+        if (MODE == 1)
+        {
+            // conj(psi(l, t)) * (A psi)(l, t), summed over the lane's rows; psi of the lane's own rows from the tile
+#pragma unroll
+            for (int i = 0; i < NR; ++i)
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+                    v[i][c] = *reinterpret_cast<Vec const *>(tb + own0 + i * (RSTEP << ROW_SHIFT) + c * (LPR * 16));
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+                {
+                    Cx<T> sacc{0, 0};
+#pragma unroll
+                    for (int i = 0; i < NR; ++i)
+                    {
+                        Cx<T> const a = v[i][c].e[e];
+                        sacc.re = fma(a.re, acc[i][c][e].re, sacc.re);
+                        sacc.re = fma(a.im, acc[i][c][e].im, sacc.re);
+                        sacc.im = fma(a.re, acc[i][c][e].im, sacc.im);
+                        sacc.im = fma(-a.im, acc[i][c][e].re, sacc.im);
+                    }
+                    esum[c][e] = sacc;
+                }
+        }
         // this warp's gathers of the buffer are done: order them before the asynchronous-proxy refill and hand it back
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -260,6 +293,34 @@ __global__ void __launch_bounds__(kPairThreads, 1)
             ++round;
         }
 
+        if (MODE == 1)
+        {
+            // fold over the RW lanes that share a column, then one writer per (warp, column)
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+#pragma unroll
+                for (int e = 0; e < EPV; ++e)
+#pragma unroll
+                    for (int sh = LPR; sh < 32; sh <<= 1)
+                    {
+                        esum[c][e].re += __shfl_xor_sync(0xffffffffu, esum[c][e].re, sh);
+                        esum[c][e].im += __shfl_xor_sync(0xffffffffu, esum[c][e].im, sh);
+                    }
+            if (rq == 0)
+            {
+                Cx<T> *const prow = partials + (static_cast<uint64_t>(blockIdx.x) * kPairConsumerWarps + warp) * Bpad;
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+                    {
+                        Cx<T> *const dst = prow + (vcol + c * LPR) * EPV + e;
+                        atomicAdd(&dst->re, esum[c][e].re);
+                        atomicAdd(&dst->im, esum[c][e].im);
+                    }
+            }
+            continue;
+        }
         if (beta)
         {
             // old output rows (in L2 since the previous tile) into the registers the gathers have left

@@ -519,9 +519,11 @@ int launch_coset_dir_tma(fp_ctx *ctx, CosetPassView<T> const &view, DirStrings<T
 
 // K3j: persistent TMA-fed kernel with direct stores, paired masks and a row-factor table, for passes of eight
 // independent x-masks with any number of strings each (coset4.cuh)
-template <typename T, int EPV>
+// MODE 1: expectation-value partials, one row per (CTA, consumer warp), zeroed here and folded by the caller
+template <typename T, int EPV, int MODE = 0>
 int launch_coset_pair_tma(fp_ctx *ctx, CosetPassView<T> const &view, PairStrings<T> const &strs, int n_qubits,
-                          uint64_t rowvecs, void const *in, void *out, int beta, bool *launched)
+                          uint64_t rowvecs, void const *in, void *out, int beta, bool *launched, void *partials = nullptr,
+                          uint32_t Bpad = 0, uint64_t *n_partial_rows = nullptr)
 {
     *launched = false;
     CUtensorMap tm;
@@ -531,17 +533,24 @@ int launch_coset_pair_tma(fp_ctx *ctx, CosetPassView<T> const &view, PairStrings
     uint32_t const nct = static_cast<uint32_t>(rowvecs >> 4);
     uint64_t const n_tiles = (1ull << (n_qubits - 8)) * nct;
     unsigned const grid = static_cast<unsigned>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(ctx->sm_count)));
+    if (MODE == 1)
+    {
+        uint64_t const rows = static_cast<uint64_t>(grid) * kPairConsumerWarps;
+        FP_CU(cudaMemsetAsync(partials, 0, rows * Bpad * sizeof(Cx<T>), ctx->stream));
+        *n_partial_rows = rows;
+    }
 #define FP_LAUNCH_PAIR(RB)                                                                                             \
     {                                                                                                                  \
         static PerDevice configured;                                                                                   \
         if (!configured.done(ctx->device))                                                                             \
         {                                                                                                              \
-            FP_CU(cudaFuncSetAttribute(coset_pair_tma_kernel<T, EPV, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       static_cast<int>(smem)));                                                       \
+            FP_CU(cudaFuncSetAttribute(coset_pair_tma_kernel<T, EPV, RB, MODE>,                                        \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));          \
             configured.set(ctx->device);                                                                               \
         }                                                                                                              \
-        coset_pair_tma_kernel<T, EPV, RB><<<grid, kPairThreads, smem, ctx->stream>>>(                                  \
-            view.nonpivot_mask, rowvecs, nct, n_tiles, static_cast<CVec<T, EPV> *>(out), beta, strs, tm);              \
+        coset_pair_tma_kernel<T, EPV, RB, MODE><<<grid, kPairThreads, smem, ctx->stream>>>(                            \
+            view.nonpivot_mask, rowvecs, nct, n_tiles, MODE == 1 ? nullptr : static_cast<CVec<T, EPV> *>(out), beta,   \
+            strs, tm, static_cast<Cx<T> *>(partials), Bpad);                                                           \
     }
     static int const rb = getenv("FASTPAULI_PAIR_RB") ? atoi(getenv("FASTPAULI_PAIR_RB")) : 2;
     if (rb == 3)
@@ -558,7 +567,8 @@ int launch_coset_pair_tma(fp_ctx *ctx, CosetPassView<T> const &view, PairStrings
 // Picks the variant for one pass; *launched = false when the pass has to go through coset_kernel (K3b).
 template <typename T, int EPV, int MODE = 0>
 int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, int n_qubits, uint64_t rowvecs,
-                     void const *in, void *out, int beta, bool *launched, void *partials = nullptr, uint32_t Bpad = 0)
+                     void const *in, void *out, int beta, bool *launched, void *partials = nullptr, uint32_t Bpad = 0,
+                     uint64_t *n_partial_rows = nullptr)
 {
     *launched = false;
     CosetPassView<T> const &view = pd.view;
@@ -567,10 +577,15 @@ int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, 
     // over 8 masks 0.512 -> 0.416 ms, 8 single-string masks 0.417 -> 0.382 ms); read-modify-write passes of single-string
     // masks stay on K3i, whose early loads of the old output rows suit them slightly better (64 random strings: 4.25
     // against 4.28 ms with K3j on all eight passes)
-    if (MODE == 0 && ctx->coset_few == 1 && pd.pair && (!pd.dir || beta == 0 || ctx->coset_pair_all) && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
-        is_device_ptr(in) && (rowvecs >> 4) << (n_qubits - 8) >= 4ull * static_cast<uint64_t>(ctx->sm_count))
+    // (expectation values -- MODE 1 -- take it for every such pass: 8-mask operator 0.50 -> 0.39 ms, 64 random strings 3.96 -> 3.01 ms)
+    if ((MODE == 0 || MODE == 1) && ctx->coset_few == 1 && pd.pair &&
+        (MODE == 1 ? n_partial_rows != nullptr : (!pd.dir || beta == 0 || ctx->coset_pair_all)) && n_qubits >= 12 &&
+        n_qubits <= 30 && rowvecs % 16 == 0 && is_device_ptr(in) &&
+        (rowvecs >> 4) << (n_qubits - 8) >= 4ull * static_cast<uint64_t>(ctx->sm_count))
     {
-        FP_TRY((launch_coset_pair_tma<T, EPV>(ctx, view, *pd.pair, n_qubits, rowvecs, in, out, beta, launched)));
+        if constexpr (MODE == 0 || MODE == 1)
+            FP_TRY((launch_coset_pair_tma<T, EPV, MODE>(ctx, view, *pd.pair, n_qubits, rowvecs, in, out, beta, launched,
+                                                        partials, Bpad, n_partial_rows)));
         if (*launched)
             return FP_OK;
     }
@@ -639,8 +654,9 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
         return FP_OK;
     uint32_t const Bpad = static_cast<uint32_t>((B + 3) & ~3ull);
     uint64_t const n_cosets = 1ull << (n_qubits - shape.rank());
-    if (MODE == 1)
-        FP_TRY(ctx->partials.ensure(n_cosets * Bpad * 2 * sizeof(T)));
+    if (MODE == 1) // one row per coset, or (K3j) one per consumer warp of a persistent grid
+        FP_TRY(ctx->partials.ensure(std::max<uint64_t>(n_cosets, static_cast<uint64_t>(ctx->sm_count) * kPairConsumerWarps) *
+                                    Bpad * 2 * sizeof(T)));
     for (size_t p = 0; p < passes->size(); ++p)
     {
         int const b = (p == 0) ? beta : 1;
@@ -649,15 +665,16 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
             if (shape.rank() == 8 && shape.log_nt == 8)
             {
                 bool launched = false;
+                uint64_t partial_rows = n_cosets; // K3j writes one partial row per consumer warp instead of one per coset
                 FP_TRY((launch_coset_few<T, EPV, MODE>(ctx, (*passes)[p], n_qubits, rowvecs, in, out, b, &launched,
-                                                       ctx->partials.p, Bpad)));
+                                                       ctx->partials.p, Bpad, &partial_rows)));
                 if (launched)
                 {
                     if (MODE == 1)
                     {
                         unsigned fgrid = static_cast<unsigned>((B + kFinX - 1) / kFinX);
                         finalize_complex_kernel<T><<<fgrid, dim3(kFinX, kFinY), 0, ctx->stream>>>(
-                            static_cast<Cx<T> const *>(ctx->partials.p), n_cosets, Bpad, B, static_cast<Cx<T> *>(out), b);
+                            static_cast<Cx<T> const *>(ctx->partials.p), partial_rows, Bpad, B, static_cast<Cx<T> *>(out), b);
                         ctx->launches++;
                     }
                     continue;

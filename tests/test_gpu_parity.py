@@ -1412,6 +1412,19 @@ def test_paired_mask_tma_kernel(dtype, n, B, masks, per):
     ctx.sync()
     assert ctx.coset_kernels_used() & 32
     assert rel_err(acc.get(), out0.astype(np.complex128) + ref) < tol(dtype)
+    # expectation values: K3j's reduction mode (one partial row per consumer warp, single-writer reductions) against the
+    # oracle and against K3e's; reproducible run to run
+    evs = []
+    for mode in (1, 4, 1):
+        ctx.set_coset_few(mode)
+        ctx.coset_kernels_used(reset=True)
+        ev = op.expectation_value(d_psi).get()
+        used = ctx.coset_kernels_used()
+        assert_parity(ev, ORC.op_expval, dtype, strings, h, psi)
+        assert (used & 32) if mode == 1 else (used & 32 == 0), (mode, used)
+        evs.append(ev)
+    assert rel_err(evs[0], evs[1]) < tol(dtype)
+    np.testing.assert_array_equal(evs[0], evs[2])
     ctx.set_coset_few(1)
     ctx.set_coset(1)
 
