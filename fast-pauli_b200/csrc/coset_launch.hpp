@@ -200,7 +200,7 @@ struct CosetShape
 // >= 256 bytes), whose passes are cheaper than the general kernel's
 template <typename T>
 CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, uint64_t rowvecs, int epv,
-                        bool tma_kernels = false)
+                        bool tma_kernels = false, bool pair_expval = false)
 {
     CosetShape none;
     if (ctx->coset_mode == 0 || op.host.sz.size() < 2)
@@ -250,8 +250,16 @@ CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, 
                 continue;
             // measured (20 q x 64 chains, 16 q x 1024 config 3): a rank-8 pass of K3e / K3f / K3g costs ~0.7 of a
             // general-kernel pass of the same width
-            double const cost = static_cast<double>(passes->size()) * seg_cost[v] *
-                                ((tma_kernels && v == 4 && lnt_pref == 8) ? 0.7 : 1.0);
+            double cost = static_cast<double>(passes->size()) * seg_cost[v] *
+                          ((tma_kernels && v == 4 && lnt_pref == 8) ? 0.7 : 1.0);
+            if (pair_expval && v == 4 && lnt_pref == 8)
+            {
+                // expectation values: only K3j has a TMA-fed reduction mode; its passes cost ~0.6 of a general one
+                // (measured at 20 q x 64: 0.38 against 0.6 ms)
+                cost = 0;
+                for (auto const &pd : *passes)
+                    cost += seg_cost[v] * (pd.pair ? 0.6 : 1.0);
+            }
             if (best == 0 || cost < best)
             {
                 best = cost;
@@ -642,7 +650,10 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
     uint64_t const rowvecs = B / EPV;
     bool const tma_ok = MODE == 0 && (ctx->coset_few == 1 || ctx->coset_few == 3 || ctx->coset_few == 4) && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
                         is_device_ptr(in) && tensor_map_encoder() != nullptr;
-    CosetShape const shape = choose_coset<T>(ctx, op, n_qubits, rowvecs, epv, tma_ok);
+    bool const pair_ok = MODE == 1 && ctx->coset_few == 1 && n_qubits >= 12 && n_qubits <= 30 && rowvecs % 16 == 0 &&
+                         is_device_ptr(in) && tensor_map_encoder() != nullptr &&
+                         (rowvecs >> 4) << (n_qubits - 8) >= 4ull * static_cast<uint64_t>(ctx->sm_count);
+    CosetShape const shape = choose_coset<T>(ctx, op, n_qubits, rowvecs, epv, tma_ok, pair_ok);
     if (!shape.ok())
         return FP_OK;
     std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;

@@ -207,11 +207,22 @@ inline std::vector<CosetPassHost<T>> plan_coset(PackedOp<T> const &op, int n_qub
         pass.basis.sort_by_pivot();
         pass.nonpivot_mask = full & ~pass.basis.pivot_mask();
 
-        // ---- collect every not-yet-done group inside the span
+        // ---- collect every not-yet-done group inside the span.  The diagonal group (x = 0) lies in every span: it goes
+        // to the first pass that holds fewer than 8 other groups, or to the last pass, so that passes of exactly eight
+        // independent x-masks (chain Hamiltonians: 8 bond masks + the ZZ terms) stay eligible for K3j
+        size_t in_span = 0, others_left = 0;
+        for (size_t g = 0; g < G; ++g)
+            if (!done[g] && op.gx[g] != 0)
+            {
+                ++others_left;
+                if (pass.basis.contains(op.gx[g]))
+                    ++in_span;
+            }
+        bool const take_diagonal = in_span < 8 || in_span == others_left;
         pass.gstart.push_back(0);
         for (size_t g = 0; g < G; ++g)
         {
-            if (done[g] || !pass.basis.contains(op.gx[g]))
+            if (done[g] || !pass.basis.contains(op.gx[g]) || (op.gx[g] == 0 && !take_diagonal))
                 continue;
             done[g] = 1;
             --remaining;

@@ -1174,12 +1174,14 @@ def test_headline_size_multi_pass_operators_sampled_rows(kind):
     used = ctx.coset_kernels_used()
     # the launch path: one pass per rank-8 span of x-masks (few: 1, random: 8; the chains need 2-3 passes) on the
     # kernels the design names: K3j (32) for the 8-mask pass and the overwrite pass of the random operator, K3i (16)
-    # for its read-modify-write passes, K3g (8) for the chains
+    # for its read-modify-write passes; the chains: see below
     assert launches == {"few_group": 1, "random": 8}.get(kind, launches) and 1 <= launches <= 8
     if kind in ("few_group", "random"):
         assert used == {"few_group": 32, "random": 48}[kind], used  # random: K3j overwrite pass + 7 K3i passes
     else:
-        assert used & 8 and not used & 1, used  # K3g, plus K3e / K3f for a last pass with <= 8 masks
+        # passes of eight bond / X masks on K3j (K3i for single-string read-modify-write passes), the rest + the diagonal
+        # ZZ group on K3e; never the general kernel
+        assert used & 32 and not used & 1, used
     masks = [orc.masks(s) for s in strings]
     phase = np.array([1, -1j, -1, 1j])
     rng = np.random.default_rng(3)
