@@ -314,6 +314,12 @@ int run_op_apply(fp_ctx *ctx, DeviceOp<T> const &op, void *out, void const *in, 
     if (op.host.sz.size() > 1 && n_qubits > 0)
     {
         bool used = false;
+        if (B == 1 && dim == (1ull << n_qubits))
+        {
+            FP_TRY((try_single_state<T>(ctx, op, n_qubits, out, in, beta, &used)));
+            if (used)
+                return FP_OK;
+        }
         FP_TRY((try_rcoset<T, 0>(ctx, op, n_qubits, out, in, dim, B, beta, &used)));
         if (used)
             return FP_OK;
@@ -689,6 +695,8 @@ extern "C"
             ctx->coset_few = atoi(env) == 5 ? 1 : atoi(env);
             ctx->coset_pair_all = atoi(env) == 5;
         }
+        if (char const *env = getenv("FASTPAULI_COSET_RUN_LOG"))
+            ctx->coset_run_log = std::max(0, std::min(4, atoi(env)));
         if (char const *env = getenv("FASTPAULI_COSET_FEW_CT"))
             ctx->coset_few_ct = atoi(env);
         if (char const *env = getenv("FASTPAULI_PIPELINE"))

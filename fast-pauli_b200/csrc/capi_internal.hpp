@@ -135,6 +135,8 @@ struct fp_ctx
     bool coset_wide_cta = true; // 512-thread CTAs for the rank-12 weighted-apply tile
     int coset_few = 1;          // K3e / K3f / K3i / K3j for passes with few x-masks: 0 off, 1 auto, 2 never the TMA-fed
                                 // kernels, 3 auto without K3i / K3j, 4 auto without K3j
+    int coset_run_log = 2;      // narrow row segments: lowest row bits forced into every tile so that it is made of runs of
+                                // 2^run_log vectors (FASTPAULI_COSET_RUN_LOG)
     bool coset_pair_all = false; // K3j also for passes whose masks carry one string each (set by mode 5 = mode 1 + this)
     int coset_few_ct = 0;       // column tiles per CTA of K3e (0 = all of them while the grid still fills the chip)
     bool pipeline = true;       // chunked H2D / kernel / D2H pipeline for large host-resident single-string applies
@@ -189,6 +191,16 @@ template <typename T> struct DeviceOp
         std::vector<void *> allocs;
     };
     mutable std::map<int, std::vector<CosetPassDev>> coset_plans;
+
+    // single-state form (batch of ONE complex128 state of >= 22 qubits, K3i): the state is viewed as 2^(n-4) rows x 16
+    // columns (the 4 lowest index bits), the operator re-planned on the upper n-4 bits; built lazily, see coset_launch.hpp
+    struct SingleStatePass
+    {
+        CosetPassView<T> view{}; // basis + nonpivot_mask only
+        DirStrings<T> strs{};
+    };
+    mutable std::vector<SingleStatePass> single_state_plan;
+    mutable int single_state_tried = 0; // 0 not yet, 1 plan usable, -1 not applicable
 
     // register-resident coset plan (x-mask rank <= kRcMaxRank), built lazily
     struct RcPlanDev

@@ -62,6 +62,10 @@ template <typename T> struct DirStrings
     uint64_t z[kDirMaxMasks];
     uint32_t xl[kDirMaxMasks];
     uint32_t zl[kDirMaxMasks];
+    // single-state form (one 2^n vector viewed as 2^(n-4) rows x 16 "columns" = the 4 lowest index bits): the string
+    // also permutes the columns (j -> j ^ xlo) and signs them ((-1)^popc(j & zlo)); both 0 for ordinary batches
+    uint8_t xlo[kDirMaxMasks];
+    uint8_t zlo[kDirMaxMasks];
     uint32_t n;
 };
 
@@ -180,7 +184,7 @@ __global__ void __launch_bounds__(kDirThreads, 1)
         uint32_t const l = 2u * (warp + kDirConsumerWarps * i) + half;
         uint32_t w = 0;
         for (uint32_t g = 0; g < ng; ++g)
-            w |= (__popc(l & strs.zl[g]) & 1u) << g;
+            w |= (__popc((l & strs.zl[g]) ^ ((jv & strs.zlo[g]) << 8)) & 1u) << g; // + the column's own sign (single state)
         sl[i] = w;
     }
     uint32_t const col_off = jv << 4;
@@ -261,7 +265,8 @@ __global__ void __launch_bounds__(kDirThreads, 1)
                     int const g = g2 * 2 + k;
                     if (static_cast<uint32_t>(g) < ng)
                     {
-                        uint32_t const xo = strs.xl[g] << ROW_SHIFT; // < 64 KiB: the XOR stays inside the buffer
+                        // < 64 KiB: the XOR stays inside the buffer (xlo: column permutation of the single-state form)
+                        uint32_t const xo = (strs.xl[g] << ROW_SHIFT) | (static_cast<uint32_t>(strs.xlo[g]) << 4);
 #pragma unroll
                         for (int b = 0; b < IB; ++b)
                             v[k][b] = *reinterpret_cast<Vec const *>(smem_dt + (own[b] ^ xo));

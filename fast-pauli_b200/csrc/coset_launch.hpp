@@ -245,7 +245,7 @@ CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, 
             if (!valid(v, lnt_pref))
                 continue;
             std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
-            int const reserve = std::max(0, 2 - v);
+            int const reserve = std::max(0, ctx->coset_run_log - v);
             if (get_coset_plan<T>(op, n_qubits, 4 + lnt_pref - v, reserve, &passes) != FP_OK)
                 continue;
             // measured (20 q x 64 chains, 16 q x 1024 config 3): a rank-8 pass of K3e / K3f / K3g costs ~0.7 of a
@@ -572,6 +572,110 @@ int launch_coset_pair_tma(fp_ctx *ctx, CosetPassView<T> const &view, PairStrings
     return FP_OK;
 }
 
+// PauliOp::apply on ONE state (PO:362-383 through PO:399-468 with one column; the local piece of the sharded 34-qubit
+// state, BASELINE config 5).  A row of a one-column batch is 16 bytes, so the coset kernels gather single vectors and
+// form a row factor per vector (measured: 2.1 TB/s algorithmic at 28 qubits).  Here the state is VIEWED as 2^(n-4) rows x
+// 16 columns -- the column is the 4 lowest index bits j -- so rows are 256-byte segments again; a string then also
+// permutes the columns (j -> j ^ (x & 15)) and signs them ((-1)^popc(j & z & 15)), which K3i takes as one more XOR in the
+// gather address and one more parity in the lane's sign word.  The operator is re-planned on the upper n-4 bits (strings
+// that differ only in the low bits share a row offset; K3i treats every string as its own mask).
+template <typename T>
+int try_single_state(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void const *in, int beta, bool *used)
+{
+    *used = false;
+    if constexpr (sizeof(T) != 8)
+        return FP_OK;
+    else
+    {
+        int const nr = n_qubits - 4;
+        if (ctx->coset_few != 1 || ctx->coset_mode == 0 || n_qubits < 22 || nr > 30 || op.single_state_tried < 0 ||
+            !is_device_ptr(in) || tensor_map_encoder() == nullptr || op.host.sz.size() < 2)
+            return FP_OK;
+        if (op.single_state_tried == 0)
+        {
+            op.single_state_tried = -1;
+            // the operator on the upper bits: (x >> 4, z >> 4) with the low nibbles kept per string
+            struct Rs
+            {
+                uint64_t x, z;
+                uint8_t xlo, zlo;
+                std::complex<T> c;
+            };
+            std::vector<Rs> rs;
+            for (size_t g = 0; g + 1 < op.host.gstart.size(); ++g)
+                for (uint32_t t = op.host.gstart[g]; t < op.host.gstart[g + 1]; ++t)
+                    rs.push_back(Rs{op.host.gx[g] >> 4, op.host.sz[t] >> 4, static_cast<uint8_t>(op.host.gx[g] & 15u),
+                                    static_cast<uint8_t>(op.host.sz[t] & 15u), op.host.sc[t]});
+            std::stable_sort(rs.begin(), rs.end(), [](Rs const &a, Rs const &b) { return a.x != b.x ? a.x < b.x : a.z < b.z; });
+            PackedOp<T> r;
+            r.n_qubits = nr;
+            r.n_strings_in = rs.size();
+            for (size_t i = 0; i < rs.size(); ++i)
+            {
+                if (i == 0 || rs[i].x != rs[i - 1].x)
+                {
+                    r.gx.push_back(rs[i].x);
+                    r.gstart.push_back(static_cast<uint32_t>(i));
+                }
+                r.sz.push_back(rs[i].z);
+                r.sc.push_back(rs[i].c);
+            }
+            r.gstart.push_back(static_cast<uint32_t>(rs.size()));
+            std::vector<CosetPassHost<T>> host = plan_coset<T>(r, nr, 8, 0);
+            std::vector<typename DeviceOp<T>::SingleStatePass> plan(host.size());
+            // every pass re-streams the state: only worth it while the passes stay few (the general path needs one
+            // pass per 10..12 independent masks at a third of the speed)
+            bool ok = !host.empty() && host.size() <= 8;
+            for (size_t p = 0; ok && p < host.size(); ++p)
+            {
+                CosetPassHost<T> const &h = host[p];
+                if (h.sz.size() > static_cast<size_t>(kDirMaxMasks) || h.sz.empty())
+                {
+                    ok = false;
+                    break;
+                }
+                auto &d = plan[p];
+                for (int k = 0; k < kCosetMaxRank; ++k)
+                    d.view.basis[k] = k < h.basis.r ? h.basis.b[k] : 0;
+                d.view.nonpivot_mask = h.nonpivot_mask;
+                std::memset(&d.strs, 0, sizeof(d.strs));
+                d.strs.n = static_cast<uint32_t>(h.sz.size());
+                for (size_t g = 0; g < h.gxl.size(); ++g)
+                    for (uint32_t t = h.gstart[g]; t < h.gstart[g + 1]; ++t)
+                    {
+                        d.strs.c[t] = Cx<T>{h.sc[t].real(), h.sc[t].imag()};
+                        d.strs.z[t] = h.sz[t];
+                        d.strs.xl[t] = h.gxl[g];
+                        d.strs.zl[t] = h.szl[t];
+                        d.strs.xlo[t] = rs[h.sidx[t]].xlo;
+                        d.strs.zlo[t] = rs[h.sidx[t]].zlo;
+                    }
+            }
+            if (ok)
+            {
+                op.single_state_plan = std::move(plan);
+                op.single_state_tried = 1;
+            }
+        }
+        if (op.single_state_tried != 1)
+            return FP_OK;
+        for (size_t p = 0; p < op.single_state_plan.size(); ++p)
+        {
+            bool launched = false;
+            auto const &d = op.single_state_plan[p];
+            FP_TRY((launch_coset_dir_tma<T, 1>(ctx, d.view, d.strs, nr, 16, in, out, p == 0 ? beta : 1, &launched)));
+            if (!launched)
+            {
+                if (p == 0)
+                    return FP_OK; // no tensor map: the caller's general path
+                return set_err(FP_CUDA_ERROR, "single-state PauliOp.apply: tensor map creation failed mid-plan");
+            }
+        }
+        *used = true;
+        return FP_OK;
+    }
+}
+
 // Picks the variant for one pass; *launched = false when the pass has to go through coset_kernel (K3b).
 template <typename T, int EPV, int MODE = 0>
 int launch_coset_few(fp_ctx *ctx, typename DeviceOp<T>::CosetPassDev const &pd, int n_qubits, uint64_t rowvecs,
@@ -658,7 +762,7 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
         return FP_OK;
     std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
     // narrow row segments (16 / 32 bytes): force the lowest row bits into the tile so it is made of >= 64-byte runs
-    int const reserve = std::max(0, 2 - shape.log_twc);
+    int const reserve = std::max(0, ctx->coset_run_log - shape.log_twc);
     FP_TRY(get_coset_plan<T>(op, n_qubits, shape.rank(), reserve, &passes));
     // every pass re-streams the batch (read in, read-modify-write out): only worth it while passes << groups
     if (ctx->coset_mode == 1 && passes->size() * 3 > op.host.gx.size() && passes->size() > 1)

@@ -229,7 +229,8 @@ def main():
         op = fp.PauliOp(h, strings, ctx=ctx)
         plan = op._plan(np.complex128)
         ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(1), 0), a.iters)
-        print(f"b1 n={n}: {ms:.3f} ms  {(1 << n) * 32 / ms / 1e6:.0f} GB/s algorithmic")
+        print(f"b1 n={n}: {ms:.3f} ms  {(1 << n) * 32 / ms / 1e6:.0f} GB/s algorithmic  kernels_used={ctx.coset_kernels_used()} "
+              f"launches/call={ctx.launch_count // (a.iters + 1)}")
     elif a.case == "str20":
         n, B = 20, a.batch or 256
         psi = ctx.uniform((1 << n, B), np.complex128)

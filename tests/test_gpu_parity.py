@@ -1475,6 +1475,59 @@ print("ok")
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("n,S", [(22, 8), (22, 20), (23, 3), (22, 40)])
+def test_single_state_apply_on_the_direct_store_kernel(n, S):
+    """PauliOp.apply on ONE complex128 state of >= 22 qubits (PO:362-383; the local piece of the sharded state, config
+    5): the state is viewed as 2^(n-4) rows x 16 columns (the 4 lowest index bits) and every pass runs on K3i with the
+    strings' low nibbles as column permutation + column sign.  Against the closed form on sampled rows AND the full
+    result of the general path (coset mode 0 = generic gather kernel), the accumulating form, the launch path; strings
+    that differ only in their 4 lowest qubits share a row offset."""
+    import ctypes as C
+
+    rng = np.random.default_rng(17 * n + S)
+    ctx = fp.default_context()
+    strings = rand_strings(rng, n, S)
+    # two strings that differ only in the lowest qubits (same x >> 4, different x & 15 / z & 15)
+    strings[1] = strings[0][:-4] + "".join("IXYZ"[k] for k in rng.integers(0, 4, size=4))
+    if strings[1] == strings[0]:
+        strings[1] = strings[0][:-1] + ("X" if strings[0][-1] != "X" else "Z")
+    h = rng.uniform(-1, 1, S) + 1j * rng.uniform(-1, 1, S)
+    dim = 2**n
+    psi = ctx.uniform((dim,), np.complex128, seed=7)
+    op = fp.PauliOp(h, strings, ctx=ctx)
+    ctx.coset_kernels_used(reset=True)
+    l0 = ctx.launch_count
+    out = op.apply(psi)
+    launches = ctx.launch_count - l0
+    used = ctx.coset_kernels_used()
+    if S <= 32:
+        assert used == 16 and launches <= 4, (used, launches)  # K3i only, one launch per rank-8 span of x >> 4
+    # general path of the same call
+    ctx.set_coset(0)
+    ref = op.apply(psi)
+    ctx.set_coset(1)
+    got = out.get()
+    assert rel_err(got, ref.get()) < 1e-12
+    # closed form on sampled rows: out[i] = sum_s h_s (-i)^nY (-1)^popc(i & z) psi[i ^ x]
+    from fast_pauli_b200.synth import uniform_host
+
+    masks = [orc.masks(s) for s in strings]
+    phase = np.array([1, -1j, -1, 1j])
+    for i in [0, dim - 1, 5, 16, 4097] + [int(r) for r in rng.integers(0, dim, size=8)]:
+        expect = 0j
+        for (x, z, ny), hs in zip(masks, h):
+            v = uniform_host((1,), np.complex128, seed=7, first=i ^ x)[0]
+            expect += hs * phase[ny] * (-1.0 if bin(i & z).count("1") & 1 else 1.0) * v
+        assert abs(got[i] - expect) < 1e-12 * max(1.0, abs(expect)), i
+    # accumulate through the C ABI
+    acc = ctx.uniform((dim,), np.complex128, seed=9)
+    acc0 = acc.get()
+    fp._check(fp.lib.fp_op_apply(ctx._h, op._plan(np.complex128), C.c_void_p(acc.ptr), C.c_void_p(psi.ptr), C.c_size_t(dim),
+                                 C.c_size_t(1), C.c_int(1)))
+    ctx.sync()
+    assert rel_err(acc.get(), acc0 + got) < 1e-12
+
+
 def test_two_devices_in_one_process():
     """One context per GPU in a single process: every kernel family that needs opt-in shared memory must be configured
     on each device it runs on (cudaFuncSetAttribute is per device).  Skipped on single-GPU boxes."""
