@@ -695,8 +695,6 @@ extern "C"
             ctx->coset_few = atoi(env) == 5 ? 1 : atoi(env);
             ctx->coset_pair_all = atoi(env) == 5;
         }
-        if (char const *env = getenv("FASTPAULI_COSET_RUN_LOG"))
-            ctx->coset_run_log = std::max(0, std::min(4, atoi(env)));
         if (char const *env = getenv("FASTPAULI_COSET_FEW_CT"))
             ctx->coset_few_ct = atoi(env);
         if (char const *env = getenv("FASTPAULI_PIPELINE"))

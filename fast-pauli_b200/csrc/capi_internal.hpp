@@ -135,8 +135,6 @@ struct fp_ctx
     bool coset_wide_cta = true; // 512-thread CTAs for the rank-12 weighted-apply tile
     int coset_few = 1;          // K3e / K3f / K3i / K3j for passes with few x-masks: 0 off, 1 auto, 2 never the TMA-fed
                                 // kernels, 3 auto without K3i / K3j, 4 auto without K3j
-    int coset_run_log = 2;      // narrow row segments: lowest row bits forced into every tile so that it is made of runs of
-                                // 2^run_log vectors (FASTPAULI_COSET_RUN_LOG)
     bool coset_pair_all = false; // K3j also for passes whose masks carry one string each (set by mode 5 = mode 1 + this)
     int coset_few_ct = 0;       // column tiles per CTA of K3e (0 = all of them while the grid still fills the chip)
     bool pipeline = true;       // chunked H2D / kernel / D2H pipeline for large host-resident single-string applies

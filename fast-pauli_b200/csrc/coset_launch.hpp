@@ -245,7 +245,7 @@ CosetShape choose_coset(fp_ctx const *ctx, DeviceOp<T> const &op, int n_qubits, 
             if (!valid(v, lnt_pref))
                 continue;
             std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
-            int const reserve = std::max(0, ctx->coset_run_log - v);
+            int const reserve = std::max(0, 2 - v);
             if (get_coset_plan<T>(op, n_qubits, 4 + lnt_pref - v, reserve, &passes) != FP_OK)
                 continue;
             // measured (20 q x 64 chains, 16 q x 1024 config 3): a rank-8 pass of K3e / K3f / K3g costs ~0.7 of a
@@ -762,7 +762,7 @@ int try_coset(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out, void 
         return FP_OK;
     std::vector<typename DeviceOp<T>::CosetPassDev> const *passes = nullptr;
     // narrow row segments (16 / 32 bytes): force the lowest row bits into the tile so it is made of >= 64-byte runs
-    int const reserve = std::max(0, ctx->coset_run_log - shape.log_twc);
+    int const reserve = std::max(0, 2 - shape.log_twc);
     FP_TRY(get_coset_plan<T>(op, n_qubits, shape.rank(), reserve, &passes));
     // every pass re-streams the batch (read in, read-modify-write out): only worth it while passes << groups
     if (ctx->coset_mode == 1 && passes->size() * 3 > op.host.gx.size() && passes->size() > 1)
