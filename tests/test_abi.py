@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import functools
 import re
 import subprocess
 
@@ -41,6 +42,13 @@ def test_every_declared_symbol_is_exported(lib):
     assert not missing, f"declared in include/fastpauli_b200.h but not exported: {missing}"
 
 
+@functools.lru_cache(maxsize=1)
+def _sass() -> str:
+    """SASS of the product library (one cuobjdump run for all the tests that read it)."""
+    return subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+
+
+
 def test_sass_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_\d+a?", out))
@@ -54,7 +62,7 @@ def test_sass_carries_the_blackwell_instructions_the_design_claims():
     the SummedPauliOp tiles (K6b / K4c), 16-byte vector loads and stores for the streaming kernels (K1 / K2), TMA
     tile::gather4 loads with mbarrier completion and register re-balancing for the persistent few-mask / many-mask coset
     kernels (K3f / K3g), constant-bank row factors (K3e)."""
-    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    sass = _sass()
     for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "UTCATOMSWS", "DMMA.8x8x4", "LDGSTS.E.BYPASS.128", "FFMA2", "FADD2",
                      "LDG.E.128", "STG.E.128", "UTMALDG.2D.GATHER4", "SYNCS.ARRIVE.TRANS64", "USETMAXREG", "LDCU.64"):
         assert mnemonic in sass, f"{mnemonic} not found in the SASS of {LIB}"
@@ -64,7 +72,7 @@ def test_direct_store_coset_kernel_has_no_staging_in_its_sass():
     """K3i (coset_dir_tma_kernel): the tile arrives by TMA gather4, the gathers are LDS.128, the
     results leave by STG.128 straight from the accumulators (old rows by LDG.128 after an L2 prefetch) -- no
     shared-memory staging store and no barrier among the consumer warps (only the start-up __syncthreads)."""
-    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    sass = _sass()
     parts = sass.split("Function : ")
     k3i = [p for p in parts if "coset_dir_tma_kernelIdLi1ELi1ELi4" in p.split("\n", 1)[0]]
     assert len(k3i) == 1, "complex128 instance of coset_dir_tma_kernel not found"
@@ -80,10 +88,10 @@ def test_paired_mask_coset_kernel_sass_structure():
     gathers + 32 row-factor loads (LDS.128) feed 8 x 8 complex FMAs = 256 DFMA; the only shared-memory stores are the
     4 table entries a lane forms per coset; results leave by STG.128 straight from the accumulators; no barrier among
     the consumer warps (only the start-up __syncthreads)."""
-    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+    sass = _sass()
     parts = sass.split("Function : ")
-    k3j = [p for p in parts if "coset_pair_tma_kernelIdLi1ELi2" in p.split("\n", 1)[0]]
-    assert len(k3j) == 1, "complex128 RB = 2 instance of coset_pair_tma_kernel not found"
+    k3j = [p for p in parts if "coset_pair_tma_kernelIdLi1ELi2ELi0" in p.split("\n", 1)[0]]
+    assert len(k3j) == 1, "complex128 RB = 2 MODE 0 instance of coset_pair_tma_kernel not found"
     body = k3j[0]
     for mnemonic in ("UTMALDG.2D.GATHER4", "LDS.128", "STG.E.128", "LDG.E.128", "CCTL.E.PF2", "USETMAXREG", "SYNCS", "POPC"):
         assert mnemonic in body, f"{mnemonic} not found in coset_pair_tma_kernel"
