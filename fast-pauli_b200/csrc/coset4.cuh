@@ -5,21 +5,23 @@
 // (256 bytes per row) into three 64 KiB buffers with TMA tile::gather4, 16 consumer warps whose lanes run along the
 // batch axis and store their accumulators straight to global memory.  Two things are new:
 //
-//  * PAIRED MASKS.  A thread owns the 8 rows l_i = l_0 + 32 i of the tile (local bits 5..7 = i) at one column offset.
-//    The pass' basis is re-chosen on the host from the masks themselves:
-//        b_0 = m_0, b_1 = m_2, b_2 = m_4, b_3 = m_6, b_4 = m_7,   b_5 = m_0^m_1, b_6 = m_2^m_3, b_7 = m_4^m_5
-//    so that in local coordinates m_0 = e_0 and m_1 = e_0 ^ e_5, ...: the eight vectors psi(l_i ^ e_0) gathered for
-//    mask 0 are, permuted over i, exactly the ones mask 1 needs (psi(l_i ^ e_0 ^ e_5) = psi(l_{i^1} ^ e_0)).  Three
-//    pairs + two single masks = 40 gathers (LDS.128) per thread and tile instead of 64; the accumulation order per
-//    output element stays mask 0, 1, ..., 7, so results are bit-identical to K3e / K3b on the same plan.
+//  * PAIRED MASKS.  A lane owns 2^RB rows of the tile (its top RB local bits) x 8 / 2^RB vectors of the row segment.
+//    The pass' basis is re-chosen on the host from the masks themselves, for RB = 2:
+//        b_0..5 = m_0, m_2, m_4, m_5, m_6, m_7,   b_6 = m_0^m_1, b_7 = m_2^m_3
+//    (RB = 3: b_0..4 = m_0, m_2, m_4, m_6, m_7, b_5..7 = m_0^m_1, m_2^m_3, m_4^m_5), so that in local coordinates
+//    m_0 = e_0 and m_1 = e_0 ^ e_6: the vectors psi(l_i ^ e_0) gathered for mask 0 are, permuted over the lane's rows
+//    i, exactly the ones mask 1 needs (psi(l_i ^ e_0 ^ e_6) = psi(l_{i^1} ^ e_0)).  RB pairs + (8 - 2 RB) single masks:
+//    48 gathers (LDS.128) per lane and tile at RB = 2, 40 at RB = 3, instead of 64; the accumulation order per output
+//    element stays mask 0, 1, ..., 7, so results are bit-identical to K3e / K3b on the same plan.
 //  * ROW FACTORS FROM A TABLE.  D_g(l) = sum_{s in g} +-c_s (any number of strings per mask) depends on the coset and
 //    the row, not on the column tile: the 8 x 256 factors of a coset are formed once (4 per consumer thread, strings in
 //    plan order from the constant bank) into a 32 KiB shared-memory table whenever the CTA moves to a new coset (column
 //    tiles run fastest); a warp forms exactly the 16 rows x 8 masks it reads itself, so the table costs no barrier among
-//    the consumer warps (a CTA-wide barrier per coset was measured: the drain costs ~3 us per coset, 0.08 ms at 20 qubits
-//    x 64).  The main loop reads a factor with one
-//    broadcast load per (row, mask): a half-warp shares the row, so the load is a single wavefront against four for a
-//    gather -- 40 x 4 + 64 = 224 shared-memory wavefronts per thread and tile (K3i: 256, K3e: 256 + 64 of staging).
+//    the consumer warps (a CTA-wide barrier per coset was measured: the drain costs ~3 us per coset, 0.03 ms at 20 qubits
+//    x 64).  The main loop reads a factor with one 16-byte load per (row, mask) -- 8 x 2^RB per lane and tile.  These
+//    loads weigh like gathers (a 16-byte shared load is served a quarter-warp at a time whether or not the lanes share
+//    the address), which is why RB = 2 (48 + 32 loads, 76.8 M shared-memory wavefronts per launch at 20 qubits x 64)
+//    beats RB = 3 (40 + 64 loads, 94.7 M): 0.397 against 0.411 ms.
 //
 // Reference semantics: PauliOp::apply (PO:399-468): out(i,t) (+)= sum_s h_s m_s(i) psi(i ^ x_s, t).
 #pragma once
@@ -56,7 +58,7 @@ template <typename T> constexpr size_t pair_table_bytes()
 // the lanes that share a column) and adds the column sums to ITS OWN row of `partials` ([CTA][warp][column], zeroed by
 // the host) with fire-and-forget reductions: every address has exactly one writing thread, so the order of the additions
 // is the program order and the result is reproducible; finalize_complex_kernel adds the rows in a fixed order.
-template <typename T, int EPV, int RB = 3, int MODE = 0>
+template <typename T, int EPV, int RB = 2, int MODE = 0>
 __global__ void __launch_bounds__(kPairThreads, 1)
     coset_pair_tma_kernel(uint64_t nonpivot_mask, uint64_t rowvecs, uint32_t nColTiles, uint64_t nTiles,
                           CVec<T, EPV> *__restrict__ out, int beta, const __grid_constant__ PairStrings<T> strs,
