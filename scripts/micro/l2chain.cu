@@ -60,6 +60,45 @@ __device__ __forceinline__ void do_tile(double2 const *__restrict__ in, double2 
     }
 }
 
+// read-modify-write by reduction: out += f(in) with fire-and-forget RED.ADD.F64 (the addition happens in the L2, the old
+// value never travels to the SM): 2 units of SM <-> L2 traffic per pass instead of 3
+__device__ __forceinline__ void do_tile_red(double2 const *__restrict__ in, double2 *__restrict__ out, uint64_t first,
+                                            uint64_t stride)
+{
+    uint32_t const warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    uint32_t const half = lane >> 4, jv = lane & 15u;
+    double2 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+        uint64_t const row = first + (2u * (warp + 16u * i) + half) * stride;
+        v[i] = __ldcg(&in[row * 16 + jv]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+    {
+        uint64_t const row = first + (2u * (warp + 16u * i) + half) * stride;
+        double *dst = reinterpret_cast<double *>(&out[row * 16 + jv]);
+        atomicAdd(dst, v[i].x * 1.0000001);
+        atomicAdd(dst + 1, v[i].y * 1.0000001);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+    pass_red_kernel(double2 const *in, double2 *out, uint64_t nChunks, uint32_t chunkTiles, int strided)
+{
+    uint64_t const total = nChunks * chunkTiles;
+    for (uint64_t q = blockIdx.x; q < total; q += gridDim.x)
+    {
+        uint64_t const c = q / chunkTiles, j = q % chunkTiles;
+        uint64_t const base = c * chunkTiles * kTileRows;
+        if (strided)
+            do_tile_red(in, out, base + j, chunkTiles);
+        else
+            do_tile_red(in, out, base + j * kTileRows, 1);
+    }
+}
+
 // plain pass: tiles of contiguous (stride 1) or strided rows inside each chunk, round-robin over a persistent grid
 __global__ void __launch_bounds__(kThreads, 1)
     pass_kernel(double2 const *in, double2 *out, uint64_t nChunks, uint32_t chunkTiles, int strided, int rmw)
@@ -195,6 +234,23 @@ int main(int argc, char **argv)
         if (rep)
             printf("unchained: %.3f ms per %d passes (%.2f TB/s on %.0f GiB of HBM traffic)\n", ms / 5, passes,
                    units * bytes / (ms / 5) / 1e9, units);
+    }
+    for (int rep = 0; rep < 2; ++rep)
+    {
+        CK(cudaEventRecord(e0));
+        for (int it = 0; it < 5; ++it)
+            for (int p = 0; p < passes; ++p)
+            {
+                if (p == 0)
+                    pass_kernel<<<grid, kThreads>>>(in, out, nChunks, chunkTiles, 0, 0);
+                else
+                    pass_red_kernel<<<grid, kThreads>>>(in, out, nChunks, chunkTiles, p & 1);
+            }
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep)
+            printf("unchained, read-modify-write passes by RED.ADD.F64: %.3f ms per %d passes\n", ms / 5, passes);
     }
     for (int deferred = 0; deferred < 2; ++deferred)
         for (int dist = 1; dist <= 2; ++dist)
