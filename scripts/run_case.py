@@ -75,17 +75,19 @@ def main():
                     strings.append("".join(t))
         else:
             strings = random_strings(rng, n, 64)
-        h = rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))
-        psi = ctx.uniform((1 << n, B), np.complex128)
+        cdt = np.complex64 if a.c64 else np.complex128
+        h = (rng.uniform(-1, 1, len(strings)) + 1j * rng.uniform(-1, 1, len(strings))).astype(cdt)
+        psi = ctx.uniform((1 << n, B), cdt)
         op = fp.PauliOp(h, strings, ctx=ctx)
-        y = ctx.empty((1 << n, B), np.complex128)
-        plan = op._plan(np.complex128)
+        y = ctx.empty((1 << n, B), cdt)
+        plan = op._plan(cdt)
         ms = timed(ctx, lambda: fp.lib.fp_op_apply(ctx._h, plan, vp(y.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
         amps = (1 << n) * B
-        ev = ctx.empty((B,), np.complex128)
+        ev = ctx.empty((B,), cdt)
         ms2 = timed(ctx, lambda: fp.lib.fp_op_expval(ctx._h, plan, vp(ev.ptr), vp(psi.ptr), sz(1 << n), sz(B), 0), a.iters)
-        print(f"{a.case}: {ms:.3f} ms  {amps*32/ms/1e6:.0f} GB/s algorithmic  groups={op.plan_info()['n_x_groups']} | "
-              f"expval {ms2:.3f} ms {amps*16/ms2/1e6:.0f} GB/s  kernels_used={ctx.coset_kernels_used()}")
+        bpa = 16 if a.c64 else 32
+        print(f"{a.case}{' c64' if a.c64 else ''}: {ms:.3f} ms  {amps*bpa/ms/1e6:.0f} GB/s algorithmic  groups={op.plan_info()['n_x_groups']} | "
+              f"expval {ms2:.3f} ms {amps*bpa/2/ms2/1e6:.0f} GB/s  kernels_used={ctx.coset_kernels_used()}")
     elif a.case in ("span1", "span2", "span3", "span4", "span5", "local2", "local3", "local4", "local5"):
         # x-masks confined to a GF(2) span of rank r (register-resident coset kernel): 64 strings over 2^r masks;
         # local3 = all 64 Pauli strings on 3 fixed qubits (8 x-masks x 8 z-masks)
