@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(kPairThreads, 1)
             {
                 p_coset = t == t0 ? t0 / nColTiles : p_coset + 1;
                 p_ct = t == t0 ? static_cast<uint32_t>(t0 - p_coset * nColTiles) : 0u;
-                p_base = static_cast<uint32_t>(deposit_bits(p_coset, nonpivot_mask));
+                p_base = t == t0 ? static_cast<uint32_t>(deposit_bits(p_coset, nonpivot_mask))
+                                 : next_coset_base(p_base, static_cast<uint32_t>(nonpivot_mask));
             }
             if (lane == 0)
                 few_mbar_expect_tx(&s_full[buf], static_cast<uint32_t>(kFewTmaTile));
@@ -157,7 +158,8 @@ __global__ void __launch_bounds__(kPairThreads, 1)
         {
             coset = t == t0 ? t0 / nColTiles : coset + 1;
             ct = t == t0 ? static_cast<uint32_t>(t0 - coset * nColTiles) : 0u;
-            base = static_cast<uint32_t>(deposit_bits(coset, nonpivot_mask)); // launched for <= 30 qubits
+            base = t == t0 ? static_cast<uint32_t>(deposit_bits(coset, nonpivot_mask)) // launched for <= 30 qubits
+                           : next_coset_base(base, static_cast<uint32_t>(nonpivot_mask));
             // new coset: row factors D_g(l) = sum_{s in g} (-1)^{popc(row & z_s)} c_s, strings in plan order
             __syncwarp(); // the warp's slice of the old table has been read
             uint32_t const row = base ^ s_comb[lb];
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kPairThreads, 1)
         {
             // accumulating pass: the next tile's old output rows -> L2, a whole tile of gathers away from their use
             bool const same = ct + 1 < nColTiles;
-            uint32_t const base_n = same ? base : static_cast<uint32_t>(deposit_bits(coset + 1, nonpivot_mask));
+            uint32_t const base_n = same ? base : next_coset_base(base, static_cast<uint32_t>(nonpivot_mask));
             uint64_t const vcol_n = static_cast<uint64_t>(same ? ct + 1 : 0u) * TWC + jl;
 #pragma unroll
             for (int i = 0; i < NR; ++i)
