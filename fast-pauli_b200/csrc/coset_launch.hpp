@@ -73,47 +73,24 @@ int get_coset_plan(DeviceOp<T> const &op, int n_qubits, int rank, int reserve_lo
                 d.dir->zl[g] = h.szl[g];
             }
         }
-        if (rank == 8 && n_qubits <= 30 && h.basis.r == 8 && h.gxl.size() == static_cast<size_t>(kPairMasks) &&
-            h.sz.size() <= static_cast<size_t>(kPairMaxStrings))
+        uint64_t nb3[8], nb2[8];
+        if (rank == 8 && n_qubits <= 30 && h.sz.size() <= static_cast<size_t>(kPairMaxStrings) && pair_basis<T>(h, nb3, nb2))
         {
-            // eight x-masks: if they are independent they ARE a basis of the pass' span; K3j re-chooses the local
-            // coordinates from them so that masks (0,1), (2,3), (4,5) differ in one of the three row bits a thread owns
-            uint64_t m[kPairMasks];
-            for (int g = 0; g < kPairMasks; ++g)
+            // eight independent x-masks: K3j re-chooses the local coordinates from them (coset_plan.hpp: pair_basis)
+            d.pair = std::make_shared<PairStrings<T>>();
+            std::memset(d.pair.get(), 0, sizeof(PairStrings<T>));
+            for (int k = 0; k < kPairMasks; ++k)
             {
-                m[g] = 0;
-                for (int k = 0; k < 8; ++k)
-                    if ((h.gxl[g] >> k) & 1u)
-                        m[g] ^= h.basis.b[k];
+                d.pair->basis[0][k] = nb3[k];
+                d.pair->basis[1][k] = nb2[k];
             }
-            uint32_t red[kPairMasks], rk = 0; // GF(2) rank of the local coordinates
-            for (int g = 0; g < kPairMasks; ++g)
+            for (size_t i = 0; i < h.sz.size(); ++i)
             {
-                uint32_t v = h.gxl[g];
-                for (uint32_t j = 0; j < rk; ++j)
-                    v = std::min(v, v ^ red[j]);
-                if (v)
-                    red[rk++] = v;
+                d.pair->c[i] = Cx<T>{h.sc[i].real(), h.sc[i].imag()};
+                d.pair->z[i] = static_cast<uint32_t>(h.sz[i]);
             }
-            if (rk == kPairMasks)
-            {
-                d.pair = std::make_shared<PairStrings<T>>();
-                std::memset(d.pair.get(), 0, sizeof(PairStrings<T>));
-                uint64_t const nb3[kPairMasks] = {m[0], m[2], m[4], m[6], m[7], m[0] ^ m[1], m[2] ^ m[3], m[4] ^ m[5]};
-                uint64_t const nb2[kPairMasks] = {m[0], m[2], m[4], m[5], m[6], m[7], m[0] ^ m[1], m[2] ^ m[3]};
-                for (int k = 0; k < kPairMasks; ++k)
-                {
-                    d.pair->basis[0][k] = nb3[k];
-                    d.pair->basis[1][k] = nb2[k];
-                }
-                for (size_t i = 0; i < h.sz.size(); ++i)
-                {
-                    d.pair->c[i] = Cx<T>{h.sc[i].real(), h.sc[i].imag()};
-                    d.pair->z[i] = static_cast<uint32_t>(h.sz[i]);
-                }
-                for (size_t g = 0; g <= h.gxl.size(); ++g)
-                    d.pair->gs[g] = static_cast<uint8_t>(h.gstart[g]);
-            }
+            for (size_t g = 0; g <= h.gxl.size(); ++g)
+                d.pair->gs[g] = static_cast<uint8_t>(h.gstart[g]);
         }
         CosetChunk *chunks = nullptr;
         uint32_t *gxl = nullptr, *gstart = nullptr, *szl = nullptr, *sidx = nullptr;
@@ -594,33 +571,9 @@ int try_single_state(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out
         if (op.single_state_tried == 0)
         {
             op.single_state_tried = -1;
-            // the operator on the upper bits: (x >> 4, z >> 4) with the low nibbles kept per string
-            struct Rs
-            {
-                uint64_t x, z;
-                uint8_t xlo, zlo;
-                std::complex<T> c;
-            };
-            std::vector<Rs> rs;
-            for (size_t g = 0; g + 1 < op.host.gstart.size(); ++g)
-                for (uint32_t t = op.host.gstart[g]; t < op.host.gstart[g + 1]; ++t)
-                    rs.push_back(Rs{op.host.gx[g] >> 4, op.host.sz[t] >> 4, static_cast<uint8_t>(op.host.gx[g] & 15u),
-                                    static_cast<uint8_t>(op.host.sz[t] & 15u), op.host.sc[t]});
-            std::stable_sort(rs.begin(), rs.end(), [](Rs const &a, Rs const &b) { return a.x != b.x ? a.x < b.x : a.z < b.z; });
-            PackedOp<T> r;
-            r.n_qubits = nr;
-            r.n_strings_in = rs.size();
-            for (size_t i = 0; i < rs.size(); ++i)
-            {
-                if (i == 0 || rs[i].x != rs[i - 1].x)
-                {
-                    r.gx.push_back(rs[i].x);
-                    r.gstart.push_back(static_cast<uint32_t>(i));
-                }
-                r.sz.push_back(rs[i].z);
-                r.sc.push_back(rs[i].c);
-            }
-            r.gstart.push_back(static_cast<uint32_t>(rs.size()));
+            // the operator on the upper bits with the low nibbles kept per string (coset_plan.hpp: single_state_reshape)
+            SingleStateOp<T> const ss = single_state_reshape<T>(op.host, n_qubits);
+            PackedOp<T> const &r = ss.r;
             std::vector<CosetPassHost<T>> host = plan_coset<T>(r, nr, 8, 0);
             std::vector<typename DeviceOp<T>::SingleStatePass> plan(host.size());
             // every pass re-streams the state: only worth it while the passes stay few (the general path needs one
@@ -647,8 +600,8 @@ int try_single_state(fp_ctx *ctx, DeviceOp<T> const &op, int n_qubits, void *out
                         d.strs.z[t] = h.sz[t];
                         d.strs.xl[t] = h.gxl[g];
                         d.strs.zl[t] = h.szl[t];
-                        d.strs.xlo[t] = rs[h.sidx[t]].xlo;
-                        d.strs.zlo[t] = rs[h.sidx[t]].zlo;
+                        d.strs.xlo[t] = ss.xlo[h.sidx[t]];
+                        d.strs.zlo[t] = ss.zlo[h.sidx[t]];
                     }
             }
             if (ok)

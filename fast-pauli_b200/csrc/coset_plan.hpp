@@ -259,4 +259,89 @@ inline std::vector<CosetPassHost<T>> plan_coset(PackedOp<T> const &op, int n_qub
     return passes;
 }
 
+// ---------------------------------------------------------------- K3j (coset4.cuh): paired-mask basis of a pass
+// A pass of exactly eight INDEPENDENT x-masks m_0..m_7 (plan order): the masks themselves span the pass, so the local
+// coordinates can be re-chosen such that masks (0,1), (2,3) [and (4,5)] differ in one of the row bits a lane owns:
+//   nb2 (two pairs):   b_0..5 = m_0, m_2, m_4, m_5, m_6, m_7    b_6 = m_0^m_1   b_7 = m_2^m_3
+//   nb3 (three pairs): b_0..4 = m_0, m_2, m_4, m_6, m_7         b_5 = m_0^m_1   b_6 = m_2^m_3   b_7 = m_4^m_5
+// i.e. in the new coordinates  m_{2p} = e_p,  m_{2p+1} = e_p ^ e_{8-RB+p}  (p < RB),  m_{2RB+q} = e_{RB+q}.
+// Returns false when the pass is not of that kind.
+template <typename T> inline bool pair_basis(CosetPassHost<T> const &h, uint64_t (&nb3)[8], uint64_t (&nb2)[8])
+{
+    if (h.basis.r != 8 || h.gxl.size() != 8)
+        return false;
+    uint64_t m[8];
+    for (int g = 0; g < 8; ++g)
+    {
+        m[g] = 0;
+        for (int k = 0; k < 8; ++k)
+            if ((h.gxl[g] >> k) & 1u)
+                m[g] ^= h.basis.b[k];
+    }
+    uint32_t red[8], rk = 0; // GF(2) rank of the local coordinates
+    for (int g = 0; g < 8; ++g)
+    {
+        uint32_t v = h.gxl[g];
+        for (uint32_t j = 0; j < rk; ++j)
+            v = std::min(v, v ^ red[j]);
+        if (v)
+            red[rk++] = v;
+    }
+    if (rk != 8)
+        return false;
+    uint64_t const a3[8] = {m[0], m[2], m[4], m[6], m[7], m[0] ^ m[1], m[2] ^ m[3], m[4] ^ m[5]};
+    uint64_t const a2[8] = {m[0], m[2], m[4], m[5], m[6], m[7], m[0] ^ m[1], m[2] ^ m[3]};
+    for (int k = 0; k < 8; ++k)
+    {
+        nb3[k] = a3[k];
+        nb2[k] = a2[k];
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------- single states (K3i, coset3.cuh)
+// One state of 2^n amplitudes viewed as 2^(n-4) rows x 16 columns (the column is the 4 lowest index bits): the operator
+// on the upper n-4 bits, (x >> 4, z >> 4), with every string's low nibbles kept beside it (column permutation j -> j ^ xlo,
+// column sign (-1)^popc(j & zlo)).  Strings are sorted by (x >> 4, z >> 4) and grouped by x >> 4; no merging (two
+// strings that differ only in their low nibbles stay two strings).
+template <typename T> struct SingleStateOp
+{
+    PackedOp<T> r;            // gx, gstart, sz, sc on n - 4 qubits
+    std::vector<uint8_t> xlo; // [S]
+    std::vector<uint8_t> zlo; // [S]
+};
+
+template <typename T> inline SingleStateOp<T> single_state_reshape(PackedOp<T> const &op, int n_qubits)
+{
+    struct Rs
+    {
+        uint64_t x, z;
+        uint8_t xlo, zlo;
+        std::complex<T> c;
+    };
+    std::vector<Rs> rs;
+    for (size_t g = 0; g + 1 < op.gstart.size(); ++g)
+        for (uint32_t t = op.gstart[g]; t < op.gstart[g + 1]; ++t)
+            rs.push_back(Rs{op.gx[g] >> 4, op.sz[t] >> 4, static_cast<uint8_t>(op.gx[g] & 15u),
+                            static_cast<uint8_t>(op.sz[t] & 15u), op.sc[t]});
+    std::stable_sort(rs.begin(), rs.end(), [](Rs const &a, Rs const &b) { return a.x != b.x ? a.x < b.x : a.z < b.z; });
+    SingleStateOp<T> o;
+    o.r.n_qubits = n_qubits - 4;
+    o.r.n_strings_in = rs.size();
+    for (size_t i = 0; i < rs.size(); ++i)
+    {
+        if (i == 0 || rs[i].x != rs[i - 1].x)
+        {
+            o.r.gx.push_back(rs[i].x);
+            o.r.gstart.push_back(static_cast<uint32_t>(i));
+        }
+        o.r.sz.push_back(rs[i].z);
+        o.r.sc.push_back(rs[i].c);
+        o.xlo.push_back(rs[i].xlo);
+        o.zlo.push_back(rs[i].zlo);
+    }
+    o.r.gstart.push_back(static_cast<uint32_t>(rs.size()));
+    return o;
+}
+
 } // namespace fpk
